@@ -1,0 +1,442 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of the parity oracle.
+
+Two libraries live here:
+
+* ``libem2oracle.so``  -- plain-C restatement of the reference hot path (``em2_oracle.c``), each
+  function citing the reference file:line it follows.  Always buildable (``make -C oracle``).
+* ``_ref/libem2ref.so`` -- the reference's OWN sources compiled unmodified from
+  ``/root/reference/src`` plus ``ref_driver.cpp`` (``make -C oracle ref``).  Present whenever it was
+  built in the authoring container; it travels to the GPU box as a prebuilt file.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package, and only as the checker.  Nothing under ``expressionmatrix2_b200/``
+imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "libem2oracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libem2ref.so")
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+i64p = C.POINTER(C.c_int64)
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement and, when /root/reference is present, the reference itself."""
+    args = ["make", "-C", _HERE, "all"]
+    if force:
+        subprocess.check_call(["make", "-C", _HERE, "clean"])
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# C restatement
+# ----------------------------------------------------------------------------------------------
+_olib = None
+
+
+def olib():
+    global _olib
+    if _olib is None:
+        if not os.path.exists(_ORACLE_SO):
+            build()
+        L = C.CDLL(_ORACLE_SO)
+        L.em2o_normal_stream.argtypes = [C.c_uint32, C.c_uint64, f64p]
+        L.em2o_generate_lsh_vectors.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, f64p]
+        L.em2o_cell_sums.argtypes = [C.c_uint64, u64p, f32p, f64p, f64p]
+        L.em2o_signatures.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, f32p, f64p, f64p, C.c_uint64, u64p,
+                                      C.c_double, u64p, f64p]
+        L.em2o_similarity_table.argtypes = [C.c_uint64, f64p]
+        L.em2o_mismatch_max.argtypes = [C.c_uint64, C.c_double]
+        L.em2o_mismatch_max.restype = C.c_int64
+        L.em2o_mismatch_counts.argtypes = [u64p, C.c_uint64, C.c_uint64, u32p, u32p, u32p]
+        L.em2o_mismatch_row.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint32, u32p]
+        L.em2o_mismatch_checksum.argtypes = [u64p, C.c_uint64, C.c_uint64, u64p, u64p]
+        L.em2o_topk.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64,
+                                u32p, f32p, u32p]
+        L.em2o_topk.restype = C.c_double
+        L.em2o_pair_loop.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, u64p, u64p]
+        L.em2o_pair_loop.restype = C.c_double
+        L.em2o_exact_similarities.argtypes = [C.c_uint64, u64p, u32p, f32p, f64p, f64p, C.c_uint64, u32p, u32p, f64p]
+        L.em2o_exact_rows.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, f32p, f64p, f64p, C.c_uint64,
+                                      C.c_uint64, f64p]
+        L.em2o_murmur64a.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.em2o_murmur64a.restype = C.c_uint64
+        _olib = L
+    return _olib
+
+
+def word_count(lsh_count: int) -> int:
+    return (lsh_count - 1) // 64 + 1
+
+
+def normal_stream(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, np.float64)
+    olib().em2o_normal_stream(seed, n, _ptr(out, f64p))
+    return out
+
+
+def generate_lsh_vectors(gene_count: int, lsh_count: int, seed: int) -> np.ndarray:
+    U = np.empty((gene_count, lsh_count), np.float64)
+    olib().em2o_generate_lsh_vectors(gene_count, lsh_count, seed, _ptr(U, f64p))
+    return U
+
+
+def cell_sums(toc, counts):
+    toc = _c(toc, np.uint64)
+    counts = _c(counts, np.float32)
+    n = len(toc) - 1
+    s1 = np.empty(n, np.float64)
+    s2 = np.empty(n, np.float64)
+    olib().em2o_cell_sums(n, _ptr(toc, u64p), _ptr(counts, f32p), _ptr(s1, f64p), _ptr(s2, f64p))
+    return s1, s2
+
+
+def signatures(toc, gene_ids, counts, sum1, U, eps: float = 1e-12, want_scalars: bool = False):
+    toc = _c(toc, np.uint64)
+    gene_ids = _c(gene_ids, np.uint32)
+    counts = _c(counts, np.float32)
+    sum1 = _c(sum1, np.float64)
+    U = _c(U, np.float64)
+    n = len(toc) - 1
+    G, L = U.shape
+    W = word_count(L)
+    sig = np.zeros((n, W), np.uint64)
+    nz = C.c_uint64(0)
+    scal = np.empty((n, L), np.float64) if want_scalars else None
+    olib().em2o_signatures(n, G, _ptr(toc, u64p), _ptr(gene_ids, u32p), _ptr(counts, f32p), _ptr(sum1, f64p),
+                           _ptr(U, f64p), L, _ptr(sig, u64p), eps, C.byref(nz),
+                           _ptr(scal, f64p) if want_scalars else None)
+    if want_scalars:
+        return sig, int(nz.value), scal
+    return sig, int(nz.value)
+
+
+def similarity_table(lsh_count: int) -> np.ndarray:
+    t = np.empty(lsh_count + 1, np.float64)
+    olib().em2o_similarity_table(lsh_count, _ptr(t, f64p))
+    return t
+
+
+def mismatch_max(lsh_count: int, threshold: float) -> int:
+    return int(olib().em2o_mismatch_max(lsh_count, threshold))
+
+
+def mismatch_counts(sig, c0, c1) -> np.ndarray:
+    sig = _c(sig, np.uint64)
+    c0 = _c(c0, np.uint32)
+    c1 = _c(c1, np.uint32)
+    out = np.empty(len(c0), np.uint32)
+    olib().em2o_mismatch_counts(_ptr(sig, u64p), sig.shape[1], len(c0), _ptr(c0, u32p), _ptr(c1, u32p),
+                                _ptr(out, u32p))
+    return out
+
+
+def mismatch_row(sig, cell0: int) -> np.ndarray:
+    sig = _c(sig, np.uint64)
+    out = np.empty(sig.shape[0], np.uint32)
+    olib().em2o_mismatch_row(_ptr(sig, u64p), sig.shape[1], sig.shape[0], cell0, _ptr(out, u32p))
+    return out
+
+
+def mismatch_checksum(sig):
+    sig = _c(sig, np.uint64)
+    a = C.c_uint64(0)
+    b = C.c_uint64(0)
+    olib().em2o_mismatch_checksum(_ptr(sig, u64p), sig.shape[1], sig.shape[0], C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def topk(sig, lsh_count: int, k: int, threshold: float, row_begin: int = 0, row_end: int | None = None):
+    """Deterministic top-k oracle. Returns (ids [R,k] u32, sims [R,k] f32, used [R] u32, seconds)."""
+    sig = _c(sig, np.uint64)
+    n = sig.shape[0]
+    row_end = n if row_end is None else row_end
+    R = row_end - row_begin
+    ids = np.zeros((R, k), np.uint32)
+    sims = np.zeros((R, k), np.float32)
+    used = np.zeros(R, np.uint32)
+    t = olib().em2o_topk(_ptr(sig, u64p), n, lsh_count, k, threshold, row_begin, row_end, _ptr(ids, u32p),
+                         _ptr(sims, f32p), _ptr(used, u32p))
+    return ids, sims, used, float(t)
+
+
+def pair_loop(sig, lsh_count: int, threshold: float, row_begin: int, row_end: int):
+    sig = _c(sig, np.uint64)
+    pairs = C.c_uint64(0)
+    passed = C.c_uint64(0)
+    t = olib().em2o_pair_loop(_ptr(sig, u64p), sig.shape[0], lsh_count, threshold, row_begin, row_end,
+                              C.byref(pairs), C.byref(passed))
+    return float(t), int(pairs.value), int(passed.value)
+
+
+def exact_similarities(gene_count, toc, gene_ids, counts, sum1, sum2, c0, c1) -> np.ndarray:
+    toc = _c(toc, np.uint64)
+    gene_ids = _c(gene_ids, np.uint32)
+    counts = _c(counts, np.float32)
+    sum1 = _c(sum1, np.float64)
+    sum2 = _c(sum2, np.float64)
+    c0 = _c(c0, np.uint32)
+    c1 = _c(c1, np.uint32)
+    out = np.empty(len(c0), np.float64)
+    olib().em2o_exact_similarities(gene_count, _ptr(toc, u64p), _ptr(gene_ids, u32p), _ptr(counts, f32p),
+                                   _ptr(sum1, f64p), _ptr(sum2, f64p), len(c0), _ptr(c0, u32p), _ptr(c1, u32p),
+                                   _ptr(out, f64p))
+    return out
+
+
+def exact_rows(gene_count, toc, gene_ids, counts, sum1, sum2, row_begin, row_end) -> np.ndarray:
+    toc = _c(toc, np.uint64)
+    gene_ids = _c(gene_ids, np.uint32)
+    counts = _c(counts, np.float32)
+    sum1 = _c(sum1, np.float64)
+    sum2 = _c(sum2, np.float64)
+    n = len(toc) - 1
+    out = np.empty((row_end - row_begin, n), np.float64)
+    olib().em2o_exact_rows(n, gene_count, _ptr(toc, u64p), _ptr(gene_ids, u32p), _ptr(counts, f32p),
+                           _ptr(sum1, f64p), _ptr(sum2, f64p), row_begin, row_end, _ptr(out, f64p))
+    return out
+
+
+def murmur64a(data: bytes, seed: int = 231) -> int:
+    buf = C.create_string_buffer(data, len(data))
+    return int(olib().em2o_murmur64a(buf, len(data), seed))
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference itself (oracle/_ref)
+# ----------------------------------------------------------------------------------------------
+def have_ref() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+_rlib = None
+
+
+def rlib():
+    global _rlib
+    if _rlib is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libem2ref.so is not built (run `make -C oracle ref` where "
+                               "/root/reference exists)")
+        L = C.CDLL(_REF_SO)
+        L.em2ref_last_error.restype = C.c_char_p
+        L.em2ref_open_csr.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u64p, u32p, f32p, C.c_uint64, C.c_uint32,
+                                      C.POINTER(C.c_void_p)]
+        L.em2ref_open_signatures.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u64p, C.POINTER(C.c_void_p)]
+        L.em2ref_close.argtypes = [C.c_void_p]
+        L.em2ref_word_count.argtypes = [C.c_void_p]
+        L.em2ref_word_count.restype = C.c_uint64
+        L.em2ref_signature_seconds.argtypes = [C.c_void_p]
+        L.em2ref_signature_seconds.restype = C.c_double
+        L.em2ref_lsh_ctor_seconds.argtypes = [C.c_void_p]
+        L.em2ref_lsh_ctor_seconds.restype = C.c_double
+        L.em2ref_get_signatures.argtypes = [C.c_void_p, u64p]
+        L.em2ref_get_lsh_vectors.argtypes = [C.c_void_p, f64p]
+        L.em2ref_get_sums.argtypes = [C.c_void_p, f64p, f64p]
+        L.em2ref_get_similarity_table.argtypes = [C.c_void_p, f64p]
+        L.em2ref_mismatch_counts.argtypes = [C.c_void_p, C.c_uint64, u32p, u32p, u32p]
+        L.em2ref_mismatch_row.argtypes = [C.c_void_p, C.c_uint32, u32p]
+        L.em2ref_exact_similarity.argtypes = [C.c_void_p, C.c_uint64, u32p, u32p, f64p]
+        L.em2ref_find_similar_pairs4_loop.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_uint32, C.c_uint32,
+                                                      u32p, f32p, u32p, f64p, u64p]
+        L.em2ref_topk_deterministic.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_uint32, C.c_uint32,
+                                                u32p, f32p, u32p, f64p]
+        L.em2ref_write_similar_pairs.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                 u32p, f32p, u32p]
+        L.em2ref_read_similar_pairs.argtypes = [C.c_char_p, C.c_char_p, u64p, u64p, u32p, f32p, u32p]
+        L.em2ref_keep_best_less.argtypes = [C.c_uint64, i64p, C.c_uint64, i64p, u64p]
+        L.em2ref_normal_stream.argtypes = [C.c_uint32, C.c_uint64, f64p]
+        L.em2ref_murmur64a.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.em2ref_murmur64a.restype = C.c_uint64
+        _rlib = L
+    return _rlib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("reference oracle: " + rlib().em2ref_last_error().decode())
+
+
+class Reference:
+    """The reference's own Lsh / ExpressionMatrixSubset / SimilarPairs objects behind a handle."""
+
+    def __init__(self, handle, tmpdir, cell_count, lsh_count, gene_count=None):
+        self._h = handle
+        self._tmp = tmpdir
+        self.cell_count = cell_count
+        self.lsh_count = lsh_count
+        self.gene_count = gene_count
+
+    @classmethod
+    def from_csr(cls, toc, gene_ids, counts, gene_count: int, lsh_count: int, seed: int = 231) -> "Reference":
+        toc = _c(toc, np.uint64)
+        gene_ids = _c(gene_ids, np.uint32)
+        counts = _c(counts, np.float32)
+        tmp = tempfile.TemporaryDirectory(prefix="em2ref-")
+        h = C.c_void_p()
+        _check(rlib().em2ref_open_csr(tmp.name.encode(), len(toc) - 1, gene_count, _ptr(toc, u64p),
+                                      _ptr(gene_ids, u32p), _ptr(counts, f32p), lsh_count, seed, C.byref(h)))
+        return cls(h, tmp, len(toc) - 1, lsh_count, gene_count)
+
+    @classmethod
+    def from_signatures(cls, sig, lsh_count: int) -> "Reference":
+        sig = _c(sig, np.uint64)
+        tmp = tempfile.TemporaryDirectory(prefix="em2ref-")
+        h = C.c_void_p()
+        _check(rlib().em2ref_open_signatures(tmp.name.encode(), sig.shape[0], lsh_count, _ptr(sig, u64p),
+                                             C.byref(h)))
+        return cls(h, tmp, sig.shape[0], lsh_count)
+
+    def close(self):
+        if self._h is not None:
+            _check(rlib().em2ref_close(self._h))
+            self._h = None
+            self._tmp.cleanup()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def signature_seconds(self) -> float:
+        return float(rlib().em2ref_signature_seconds(self._h))
+
+    @property
+    def lsh_ctor_seconds(self) -> float:
+        return float(rlib().em2ref_lsh_ctor_seconds(self._h))
+
+    def signatures(self) -> np.ndarray:
+        W = int(rlib().em2ref_word_count(self._h))
+        out = np.empty((self.cell_count, W), np.uint64)
+        _check(rlib().em2ref_get_signatures(self._h, _ptr(out, u64p)))
+        return out
+
+    def lsh_vectors(self) -> np.ndarray:
+        out = np.empty((self.gene_count, self.lsh_count), np.float64)
+        _check(rlib().em2ref_get_lsh_vectors(self._h, _ptr(out, f64p)))
+        return out
+
+    def sums(self):
+        s1 = np.empty(self.cell_count, np.float64)
+        s2 = np.empty(self.cell_count, np.float64)
+        _check(rlib().em2ref_get_sums(self._h, _ptr(s1, f64p), _ptr(s2, f64p)))
+        return s1, s2
+
+    def similarity_table(self) -> np.ndarray:
+        out = np.empty(self.lsh_count + 1, np.float64)
+        _check(rlib().em2ref_get_similarity_table(self._h, _ptr(out, f64p)))
+        return out
+
+    def mismatch_counts(self, c0, c1) -> np.ndarray:
+        c0 = _c(c0, np.uint32)
+        c1 = _c(c1, np.uint32)
+        out = np.empty(len(c0), np.uint32)
+        _check(rlib().em2ref_mismatch_counts(self._h, len(c0), _ptr(c0, u32p), _ptr(c1, u32p), _ptr(out, u32p)))
+        return out
+
+    def mismatch_row(self, cell0: int) -> np.ndarray:
+        out = np.empty(self.cell_count, np.uint32)
+        _check(rlib().em2ref_mismatch_row(self._h, cell0, _ptr(out, u32p)))
+        return out
+
+    def exact_similarity(self, c0, c1) -> np.ndarray:
+        c0 = _c(c0, np.uint32)
+        c1 = _c(c1, np.uint32)
+        out = np.empty(len(c0), np.float64)
+        _check(rlib().em2ref_exact_similarity(self._h, len(c0), _ptr(c0, u32p), _ptr(c1, u32p), _ptr(out, f64p)))
+        return out
+
+    def find_similar_pairs4_loop(self, k: int, threshold: float, row_begin: int = 0, row_end: int | None = None,
+                                 want_pairs: bool = True):
+        """Literal findSimilarPairs4 pair loop. Returns dict(ids, sims, used, seconds, pairs)."""
+        n = self.cell_count
+        row_end = n if row_end is None else row_end
+        secs = C.c_double(0)
+        visited = C.c_uint64(0)
+        if want_pairs:
+            ids = np.zeros((n, k), np.uint32)
+            sims = np.zeros((n, k), np.float32)
+            used = np.zeros(n, np.uint32)
+            _check(rlib().em2ref_find_similar_pairs4_loop(self._h, k, threshold, row_begin, row_end, _ptr(ids, u32p),
+                                                          _ptr(sims, f32p), _ptr(used, u32p), C.byref(secs),
+                                                          C.byref(visited)))
+        else:
+            ids = sims = used = None
+            _check(rlib().em2ref_find_similar_pairs4_loop(self._h, k, threshold, row_begin, row_end, None, None,
+                                                          None, C.byref(secs), C.byref(visited)))
+        return dict(ids=ids, sims=sims, used=used, seconds=float(secs.value), pairs=int(visited.value))
+
+    def topk_deterministic(self, k: int, threshold: float, row_begin: int = 0, row_end: int | None = None):
+        n = self.cell_count
+        row_end = n if row_end is None else row_end
+        R = row_end - row_begin
+        ids = np.zeros((R, k), np.uint32)
+        sims = np.zeros((R, k), np.float32)
+        used = np.zeros(R, np.uint32)
+        secs = C.c_double(0)
+        _check(rlib().em2ref_topk_deterministic(self._h, k, threshold, row_begin, row_end, _ptr(ids, u32p),
+                                                _ptr(sims, f32p), _ptr(used, u32p), C.byref(secs)))
+        return ids, sims, used, float(secs.value)
+
+
+def ref_normal_stream(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, np.float64)
+    _check(rlib().em2ref_normal_stream(seed, n, _ptr(out, f64p)))
+    return out
+
+
+def ref_murmur64a(data: bytes, seed: int = 231) -> int:
+    buf = C.create_string_buffer(data, len(data))
+    return int(rlib().em2ref_murmur64a(buf, len(data), seed))
+
+
+def ref_keep_best_less(values, k: int) -> np.ndarray:
+    v = _c(values, np.int64)
+    out = np.empty(len(v), np.int64)
+    cnt = C.c_uint64(0)
+    _check(rlib().em2ref_keep_best_less(len(v), _ptr(v, i64p), k, _ptr(out, i64p), C.byref(cnt)))
+    return out[: cnt.value]
+
+
+def ref_write_similar_pairs(directory: str, name: str, gene_count: int, ids, sims, used) -> None:
+    ids = _c(ids, np.uint32)
+    sims = _c(sims, np.float32)
+    used = _c(used, np.uint32)
+    n, k = ids.shape
+    _check(rlib().em2ref_write_similar_pairs(directory.encode(), name.encode(), n, gene_count, k, _ptr(ids, u32p),
+                                             _ptr(sims, f32p), _ptr(used, u32p)))
+
+
+def ref_read_similar_pairs(directory: str, name: str):
+    k = C.c_uint64(0)
+    n = C.c_uint64(0)
+    _check(rlib().em2ref_read_similar_pairs(directory.encode(), name.encode(), C.byref(k), C.byref(n), None, None,
+                                            None))
+    ids = np.zeros((n.value, k.value), np.uint32)
+    sims = np.zeros((n.value, k.value), np.float32)
+    used = np.zeros(n.value, np.uint32)
+    _check(rlib().em2ref_read_similar_pairs(directory.encode(), name.encode(), C.byref(k), C.byref(n),
+                                            _ptr(ids, u32p), _ptr(sims, f32p), _ptr(used, u32p)))
+    return ids, sims, used
