@@ -1,0 +1,257 @@
+"""expressionmatrix2_b200 -- B200-native LSH cell-similarity engine, drop-in for the hot path of
+chanzuckerberg/ExpressionMatrix2 (findSimilarPairs4: signatures -> Hamming scan -> top-k -> SimilarPairs).
+
+This module is the thin Python face of ``libem2b200.so`` (C-ABI in ``include/em2b200.h``; CUDA kernels
+in ``csrc/``).  There is no CPU fallback: if the shared library is missing, or no sm_100 device is
+present, the calls raise.
+
+The reference-compatible Python module (``ExpressionMatrix2`` with ``ExpressionMatrix.findSimilarPairs4``
+etc., mirroring reference src/PythonModule.cpp:776-824, 945-953) is built from ``host/`` -- see
+``expressionmatrix2_b200.hostmodule``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .synthetic import PAIR_DTYPE, to_pairs  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libem2b200.so")
+
+VARIANT_AUTO, VARIANT_POPC, VARIANT_MMA_I8 = 0, 1, 2
+SIMPAIR_DTYPE = np.dtype([("cell", "<u4"), ("similarity", "<f4")])  # SimilarPairs::Pair
+
+
+class Em2Error(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_double), ("sums_ms", C.c_double), ("signatures_ms", C.c_double), ("encode_ms", C.c_double),
+        ("scan_ms", C.c_double), ("finalize_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
+        ("near_zero_projections", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("kernel_launches", C.c_uint64), ("candidates_appended", C.c_uint64), ("variant_used", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+_u64p = C.POINTER(C.c_uint64)
+_lib = None
+
+
+def lib():
+    """Load libem2b200.so (built in-tree by ``python -m expressionmatrix2_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Em2Error(f"{LIB_PATH} is missing: build it with `python -m expressionmatrix2_b200.build` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_double
+    L.em2_abi_version.restype = i32
+    L.em2_create.argtypes = [i32, C.POINTER(vp)]
+    L.em2_destroy.argtypes = [vp]
+    L.em2_destroy.restype = None
+    L.em2_last_error.argtypes = [vp]
+    L.em2_last_error.restype = C.c_char_p
+    L.em2_device_name.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.em2_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.em2_generate_lsh_vectors.argtypes = [u64, u64, C.c_uint32, vp]
+    L.em2_similarity_table.argtypes = [u64, vp]
+    L.em2_mismatch_max.argtypes = [u64, dbl]
+    L.em2_mismatch_max.restype = i64
+    L.em2_compute_signatures.argtypes = [vp, u64, u64, vp, vp, vp, u64, vp, vp, vp]
+    L.em2_find_similar_pairs.argtypes = [vp, vp, u64, u64, u64, u64, u64, dbl, i32, vp, vp]
+    L.em2_lsh_similar_pairs.argtypes = [vp, u64, u64, vp, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
+    L.em2_exact_similar_pairs.argtypes = [vp, u64, u64, vp, vp, u64, dbl, vp, vp]
+    L.em2_cell_sums_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.em2_signatures_device.argtypes = [vp, u64, u64, vp, vp, vp, vp, vp, u64, u64, vp, vp, vp]
+    L.em2_scan_topk_device.argtypes = [vp, vp, u64, u64, u64, u64, u64, i64, vp, i32, vp, vp, vp]
+    L.em2_mismatch_counts_device.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp]
+    L.em2_mismatch_block_device.argtypes = [vp, vp, u64, u64, u64, u64, i32, vp, vp]
+    if L.em2_abi_version() != 1:
+        raise Em2Error("libem2b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def word_count(lsh_count: int) -> int:
+    return (lsh_count - 1) // 64 + 1
+
+
+# --------------------------------------------------------------------------------------------------
+# host helpers of the path (no GPU needed)
+# --------------------------------------------------------------------------------------------------
+def generate_lsh_vectors(gene_count: int, lsh_count: int, seed: int = 231) -> np.ndarray:
+    """Hyperplanes double[G][L] (reference Lsh::generateLshVectors, src/Lsh.cpp:68-113)."""
+    U = np.empty((gene_count, lsh_count), np.float64)
+    rc = lib().em2_generate_lsh_vectors(gene_count, lsh_count, seed, U.ctypes.data)
+    if rc:
+        raise Em2Error("em2_generate_lsh_vectors: invalid argument")
+    return U
+
+
+def similarity_table(lsh_count: int) -> np.ndarray:
+    t = np.empty(lsh_count + 1, np.float64)
+    rc = lib().em2_similarity_table(lsh_count, t.ctypes.data)
+    if rc:
+        raise Em2Error("em2_similarity_table: invalid argument")
+    return t
+
+
+def mismatch_max(lsh_count: int, similarity_threshold: float) -> int:
+    return int(lib().em2_mismatch_max(lsh_count, similarity_threshold))
+
+
+def _ptr(x):
+    """Raw address of a numpy array, a torch tensor, or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+def _as_pairs(counts, gene_ids=None) -> np.ndarray:
+    if gene_ids is not None:
+        return to_pairs(np.asarray(gene_ids, np.uint32), np.asarray(counts, np.float32))
+    counts = np.ascontiguousarray(counts)
+    if counts.dtype != PAIR_DTYPE:
+        raise TypeError("counts must have dtype PAIR_DTYPE (pair<GeneId,float>) or be given with gene_ids")
+    return counts
+
+
+class Engine:
+    """One context on one GPU (em2_context).  Not re-entrant."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.em2_create(device, C.byref(h))
+        if rc:
+            raise Em2Error(f"em2_create failed ({rc}): " + self._L.em2_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.em2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise Em2Error(f"{what} failed ({rc}): " + self._L.em2_last_error(self._h).decode())
+
+    @property
+    def device_name(self) -> str:
+        buf = C.create_string_buffer(256)
+        self._check(self._L.em2_device_name(self._h, buf, 256), "em2_device_name")
+        return buf.value.decode()
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._L.em2_get_stats(self._h, C.byref(s)), "em2_get_stats")
+        return s.as_dict()
+
+    # ---- blocking calls on host buffers -----------------------------------------------------------
+    def compute_signatures(self, toc, counts, lsh_vectors, gene_ids=None, want_sums: bool = False):
+        """counts: PAIR_DTYPE array, or float counts with gene_ids.  Returns uint64 [N, W] (and sums)."""
+        toc = np.ascontiguousarray(toc, np.uint64)
+        pairs = _as_pairs(counts, gene_ids)
+        U = np.ascontiguousarray(lsh_vectors, np.float64)
+        n = len(toc) - 1
+        G, Lc = U.shape
+        sig = np.empty((n, word_count(Lc)), np.uint64)
+        s1 = np.empty(n, np.float64) if want_sums else None
+        s2 = np.empty(n, np.float64) if want_sums else None
+        self._check(self._L.em2_compute_signatures(self._h, n, G, _ptr(toc), _ptr(pairs), _ptr(U), Lc, _ptr(sig),
+                                                   _ptr(s1), _ptr(s2)), "em2_compute_signatures")
+        return (sig, s1, s2) if want_sums else sig
+
+    def find_similar_pairs(self, signatures, lsh_count: int, k: int, similarity_threshold: float,
+                           variant: int = VARIANT_AUTO, row_begin: int = 0, row_end: int | None = None):
+        """Returns (ids uint32 [R,k], sims float32 [R,k], used uint32 [R])."""
+        sig = np.ascontiguousarray(signatures, np.uint64)
+        n = sig.shape[0]
+        row_end = n if row_end is None else row_end
+        R = row_end - row_begin
+        out = np.zeros((R, k), SIMPAIR_DTYPE)
+        used = np.zeros(R, np.uint32)
+        self._check(self._L.em2_find_similar_pairs(self._h, _ptr(sig), n, lsh_count, row_begin, row_end, k,
+                                                   similarity_threshold, variant, _ptr(out), _ptr(used)),
+                    "em2_find_similar_pairs")
+        return np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used
+
+    def lsh_similar_pairs(self, toc, counts, lsh_vectors, k: int, similarity_threshold: float, gene_ids=None,
+                          variant: int = VARIANT_AUTO, want_signatures: bool = False):
+        toc = np.ascontiguousarray(toc, np.uint64)
+        pairs = _as_pairs(counts, gene_ids)
+        U = np.ascontiguousarray(lsh_vectors, np.float64)
+        n = len(toc) - 1
+        G, Lc = U.shape
+        out = np.zeros((n, k), SIMPAIR_DTYPE)
+        used = np.zeros(n, np.uint32)
+        sig = np.empty((n, word_count(Lc)), np.uint64) if want_signatures else None
+        self._check(self._L.em2_lsh_similar_pairs(self._h, n, G, _ptr(toc), _ptr(pairs), _ptr(U), Lc, k,
+                                                  similarity_threshold, variant, _ptr(out), _ptr(used), _ptr(sig)),
+                    "em2_lsh_similar_pairs")
+        res = (np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used)
+        return res + (sig,) if want_signatures else res
+
+    def exact_similar_pairs(self, toc, counts, gene_count: int, k: int, similarity_threshold: float, gene_ids=None):
+        toc = np.ascontiguousarray(toc, np.uint64)
+        pairs = _as_pairs(counts, gene_ids)
+        n = len(toc) - 1
+        out = np.zeros((n, k), SIMPAIR_DTYPE)
+        used = np.zeros(n, np.uint32)
+        self._check(self._L.em2_exact_similar_pairs(self._h, n, gene_count, _ptr(toc), _ptr(pairs), k,
+                                                    similarity_threshold, _ptr(out), _ptr(used)),
+                    "em2_exact_similar_pairs")
+        return np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used
+
+    # ---- device-resident calls (torch CUDA tensors or raw device pointers) ------------------------
+    def cell_sums_device(self, n, d_toc, d_counts, d_sum1, d_sum2=None, stream=None):
+        self._check(self._L.em2_cell_sums_device(self._h, n, _ptr(d_toc), _ptr(d_counts), _ptr(d_sum1), _ptr(d_sum2),
+                                                 stream), "em2_cell_sums_device")
+
+    def signatures_device(self, n, gene_count, d_toc, d_counts, d_sum1, d_sum2, d_U, ld, lsh_count, d_sig,
+                          d_near_zero=None, stream=None):
+        self._check(self._L.em2_signatures_device(self._h, n, gene_count, _ptr(d_toc), _ptr(d_counts), _ptr(d_sum1),
+                                                  _ptr(d_sum2), _ptr(d_U), ld, lsh_count, _ptr(d_sig),
+                                                  _ptr(d_near_zero), stream), "em2_signatures_device")
+
+    def scan_topk_device(self, d_sig, n, lsh_count, row_begin, row_end, k, mismatch_max_, d_lut, d_pairs, d_used,
+                         variant: int = VARIANT_AUTO, stream=None):
+        self._check(self._L.em2_scan_topk_device(self._h, _ptr(d_sig), n, lsh_count, row_begin, row_end, k,
+                                                 mismatch_max_, _ptr(d_lut), variant, _ptr(d_pairs), _ptr(d_used),
+                                                 stream), "em2_scan_topk_device")
+
+    def mismatch_counts_device(self, d_sig, lsh_count, pair_count, d_c0, d_c1, d_out, stream=None):
+        self._check(self._L.em2_mismatch_counts_device(self._h, _ptr(d_sig), lsh_count, pair_count, _ptr(d_c0),
+                                                       _ptr(d_c1), _ptr(d_out), stream),
+                    "em2_mismatch_counts_device")
+
+    def mismatch_block_device(self, d_sig, n, lsh_count, row_begin, row_end, d_out, variant: int = VARIANT_POPC,
+                              stream=None):
+        self._check(self._L.em2_mismatch_block_device(self._h, _ptr(d_sig), n, lsh_count, row_begin, row_end,
+                                                      variant, _ptr(d_out), stream), "em2_mismatch_block_device")

@@ -1,0 +1,455 @@
+// C-ABI of libem2b200 (include/em2b200.h): context management, the blocking host-buffer calls and
+// the thin *_device wrappers.  No CPU fallback lives here: every compute entry point launches the
+// CUDA kernels of this library or fails.
+#include "common.cuh"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace em2 {
+
+static thread_local std::string g_createError;
+
+int fail(em2_context* ctx, int code, const std::string& message)
+{
+    if (ctx) ctx->error = message;
+    else g_createError = message;
+    return code;
+}
+
+int cudaFail(em2_context* ctx, cudaError_t e, const char* what, const char* file, int line)
+{
+    std::string m = std::string("CUDA error ") + std::to_string(int(e)) + " (" + cudaGetErrorName(e) + ": " +
+                    cudaGetErrorString(e) + ") from " + what + " at " + file + ":" + std::to_string(line);
+    cudaGetLastError();   // clear the sticky-less error state
+    return fail(ctx, e == cudaErrorMemoryAllocation ? EM2_ERR_OOM : EM2_ERR_CUDA, m);
+}
+
+int reserve(em2_context* ctx, int which, size_t bytes, void** out)
+{
+    DeviceBuffer& b = ctx->scratch[which];
+    if (bytes == 0) bytes = 16;
+    if (b.bytes < bytes) {
+        if (b.ptr) {
+            EM2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            EM2_CUDA(ctx, cudaDeviceSynchronize());
+            EM2_CUDA(ctx, cudaFree(b.ptr));
+            b.ptr = nullptr;
+            b.bytes = 0;
+        }
+        const size_t want = roundUp(bytes, 1 << 20);
+        EM2_CUDA(ctx, cudaMalloc(&b.ptr, want));
+        b.bytes = want;
+    }
+    *out = b.ptr;
+    return EM2_OK;
+}
+
+int reservePinned(em2_context* ctx, int which, size_t bytes, void** out)
+{
+    PinnedBuffer& b = ctx->pinned[which];
+    if (b.bytes < bytes) {
+        if (b.ptr) EM2_CUDA(ctx, cudaFreeHost(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+        EM2_CUDA(ctx, cudaMallocHost(&b.ptr, bytes));
+        b.bytes = bytes;
+    }
+    *out = b.ptr;
+    return EM2_OK;
+}
+
+namespace {
+
+struct StageTimer {
+    em2_context* ctx;
+    int next = 0;
+    explicit StageTimer(em2_context* c) : ctx(c) {}
+    int mark()   // records an event on the context stream, returns its index
+    {
+        cudaEventRecord(ctx->ev[next], ctx->stream);
+        return next++;
+    }
+    double ms(int a, int b)
+    {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
+        return double(t);
+    }
+};
+
+double nowMs()
+{
+    return 1e-6 * double(std::chrono::duration_cast<std::chrono::nanoseconds>(
+                             std::chrono::steady_clock::now().time_since_epoch())
+                             .count());
+}
+
+int guardDevice(em2_context* ctx)
+{
+    if (!ctx) return EM2_ERR_INVALID;
+    EM2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return EM2_OK;
+}
+
+void resetStats(em2_context* ctx)
+{
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+}
+
+int uploadLut(em2_context* ctx, uint64_t lshCount, float** dLut)
+{
+    std::vector<double> t(lshCount + 1);
+    em2_similarity_table(lshCount, t.data());
+    void* pin = nullptr;
+    EM2_TRY(reservePinned(ctx, 1, (lshCount + 1) * sizeof(float), &pin));
+    float* f = static_cast<float*>(pin);
+    for (uint64_t m = 0; m <= lshCount; m++) f[m] = float(t[m]);   // SimilarPairs stores float(similarity)
+    void* d = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_LUT, (lshCount + 1) * sizeof(float), &d));
+    EM2_CUDA(ctx, cudaMemcpyAsync(d, f, (lshCount + 1) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (lshCount + 1) * sizeof(float);
+    *dLut = static_cast<float*>(d);
+    return EM2_OK;
+}
+
+}  // namespace
+}  // namespace em2
+
+using namespace em2;
+
+extern "C" {
+
+int em2_abi_version(void) { return EM2_ABI_VERSION; }
+
+int em2_create(int device, em2_context** out)
+{
+    if (!out) return fail(nullptr, EM2_ERR_INVALID, "em2_create: null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, EM2_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                        "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count)
+        return fail(nullptr, EM2_ERR_INVALID, "em2_create: device index out of range");
+    em2_context* ctx = new em2_context;
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {
+        const int rc = cudaFail(nullptr, e, "cudaSetDevice/cudaGetDeviceProperties", __FILE__, __LINE__);
+        delete ctx;
+        return rc;
+    }
+    if (ctx->prop.major != 10) {
+        const std::string m = std::string("device ") + ctx->prop.name + " is sm_" + std::to_string(ctx->prop.major) +
+                              std::to_string(ctx->prop.minor) + "; libem2b200 contains sm_100a code only";
+        delete ctx;
+        return fail(nullptr, EM2_ERR_NO_DEVICE, m);
+    }
+    ctx->smCount = ctx->prop.multiProcessorCount;
+    cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if ((e = cudaGetLastError()) != cudaSuccess) {
+        const int rc = cudaFail(nullptr, e, "stream/event creation", __FILE__, __LINE__);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return EM2_OK;
+}
+
+void em2_destroy(em2_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& b : ctx->scratch)
+        if (b.ptr) cudaFree(b.ptr);
+    for (auto& b : ctx->pinned)
+        if (b.ptr) cudaFreeHost(b.ptr);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    delete ctx;
+}
+
+const char* em2_last_error(const em2_context* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+int em2_device_name(em2_context* ctx, char* buffer, size_t bufferSize)
+{
+    if (!ctx || !buffer || bufferSize == 0) return EM2_ERR_INVALID;
+    std::snprintf(buffer, bufferSize, "%s", ctx->prop.name);
+    return EM2_OK;
+}
+
+int em2_get_stats(const em2_context* ctx, em2_stats* stats)
+{
+    if (!ctx || !stats) return EM2_ERR_INVALID;
+    *stats = ctx->stats;
+    return EM2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident wrappers
+// ------------------------------------------------------------------------------------------------
+int em2_cell_sums_device(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
+                         double* sum1, double* sum2, void* stream)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!toc || !sum1 || (!counts && cellCount)) return fail(ctx, EM2_ERR_INVALID, "em2_cell_sums_device: null pointer");
+    return launchCellSums(ctx, cellCount, toc, counts, sum1, sum2, static_cast<cudaStream_t>(stream));
+}
+
+int em2_signatures_device(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                          const em2_count* counts, const double* sum1, const double* sum2, const double* lshVectors,
+                          uint64_t ld, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero, void* stream)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!toc || !sum1 || !lshVectors || !signatures) return fail(ctx, EM2_ERR_INVALID, "em2_signatures_device: null pointer");
+    if (ld < lshCount) return fail(ctx, EM2_ERR_INVALID, "em2_signatures_device: ld < lshCount");
+    return launchSignatures(ctx, cellCount, geneCount, toc, counts, sum1, sum2, lshVectors, ld, lshCount, signatures,
+                            nearZero, static_cast<cudaStream_t>(stream));
+}
+
+int em2_scan_topk_device(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                         uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax,
+                         const float* similarityTable, int variant, em2_pair* pairs, uint32_t* usedCount, void* stream)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!signatures || !similarityTable || !pairs || !usedCount)
+        return fail(ctx, EM2_ERR_INVALID, "em2_scan_topk_device: null pointer");
+    return launchScanTopK(ctx, signatures, cellCount, lshCount, rowBegin, rowEnd, k, mismatchMax, similarityTable,
+                          variant, pairs, usedCount, static_cast<cudaStream_t>(stream));
+}
+
+int em2_mismatch_counts_device(em2_context* ctx, const uint64_t* signatures, uint64_t lshCount, uint64_t pairCount,
+                               const uint32_t* cell0, const uint32_t* cell1, uint32_t* out, void* stream)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!signatures || !cell0 || !cell1 || !out) return fail(ctx, EM2_ERR_INVALID, "em2_mismatch_counts_device: null pointer");
+    return launchMismatchCounts(ctx, signatures, lshCount, pairCount, cell0, cell1, out, static_cast<cudaStream_t>(stream));
+}
+
+int em2_mismatch_block_device(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                              uint64_t rowBegin, uint64_t rowEnd, int variant, uint16_t* out, void* stream)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!signatures || !out) return fail(ctx, EM2_ERR_INVALID, "em2_mismatch_block_device: null pointer");
+    return launchMismatchBlock(ctx, signatures, cellCount, lshCount, rowBegin, rowEnd, variant, out,
+                               static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// blocking host-buffer calls
+// ------------------------------------------------------------------------------------------------
+static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCount, uint64_t geneCount,
+                              const uint64_t* toc, const em2_count* counts, const double* U, uint64_t lshCount,
+                              uint64_t** dSigOut, double** dSum1Out, double** dSum2Out)
+{
+    const uint64_t nnz = toc[cellCount];
+    const uint64_t W = wordCount(lshCount);
+    void *dToc, *dCounts, *dU, *dSum1, *dSum2, *dSig, *dCounters;
+    EM2_TRY(reserve(ctx, em2_context::S_TOC, (cellCount + 1) * sizeof(uint64_t), &dToc));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTS, nnz * sizeof(em2_count), &dCounts));
+    EM2_TRY(reserve(ctx, em2_context::S_U, geneCount * lshCount * sizeof(double), &dU));
+    EM2_TRY(reserve(ctx, em2_context::S_SUM1, cellCount * sizeof(double), &dSum1));
+    EM2_TRY(reserve(ctx, em2_context::S_SUM2, cellCount * sizeof(double), &dSum2));
+    EM2_TRY(reserve(ctx, em2_context::S_SIG, cellCount * W * sizeof(uint64_t), &dSig));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &dCounters));
+    cudaStream_t s = ctx->stream;
+
+    const int e0 = T.mark();
+    EM2_CUDA(ctx, cudaMemsetAsync(dCounters, 0, 64, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dToc, toc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dCounts, counts, nnz * sizeof(em2_count), cudaMemcpyHostToDevice, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dU, U, geneCount * lshCount * sizeof(double), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += (cellCount + 1) * 8 + nnz * 8 + geneCount * lshCount * 8;
+    const int e1 = T.mark();
+    EM2_TRY(launchCellSums(ctx, cellCount, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+                           static_cast<double*>(dSum1), static_cast<double*>(dSum2), s));
+    const int e2 = T.mark();
+    EM2_TRY(launchSignatures(ctx, cellCount, geneCount, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+                             static_cast<double*>(dSum1), static_cast<double*>(dSum2), static_cast<double*>(dU),
+                             lshCount, lshCount, static_cast<uint64_t*>(dSig), static_cast<uint64_t*>(dCounters), s));
+    const int e3 = T.mark();
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.h2d_ms += T.ms(e0, e1);
+    ctx->stats.sums_ms += T.ms(e1, e2);
+    ctx->stats.signatures_ms += T.ms(e2, e3);
+    *dSigOut = static_cast<uint64_t*>(dSig);
+    *dSum1Out = static_cast<double*>(dSum1);
+    *dSum2Out = static_cast<double*>(dSum2);
+    return EM2_OK;
+}
+
+static int fetchCounters(em2_context* ctx)
+{
+    uint64_t h[8] = {};
+    EM2_CUDA(ctx, cudaMemcpyAsync(h, ctx->scratch[em2_context::S_COUNTERS].ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    EM2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.near_zero_projections = h[0];
+    ctx->stats.candidates_appended = h[1];
+    return EM2_OK;
+}
+
+static int scanToHost(em2_context* ctx, StageTimer& T, const uint64_t* dSig, uint64_t cellCount, uint64_t lshCount,
+                      uint64_t rowBegin, uint64_t rowEnd, uint64_t k, double similarityThreshold, int variant,
+                      em2_pair* pairs, uint32_t* usedCount)
+{
+    const uint64_t rows = rowEnd - rowBegin;
+    cudaStream_t s = ctx->stream;
+    float* dLut = nullptr;
+    EM2_TRY(uploadLut(ctx, lshCount, &dLut));
+    const int64_t mismatchMax = em2_mismatch_max(lshCount, similarityThreshold);
+    void *dPairs, *dUsed;
+    EM2_TRY(reserve(ctx, em2_context::S_PAIRS, rows * k * sizeof(em2_pair), &dPairs));
+    EM2_TRY(reserve(ctx, em2_context::S_USED, rows * sizeof(uint32_t), &dUsed));
+    const int e0 = T.mark();
+    EM2_TRY(launchScanTopK(ctx, dSig, cellCount, lshCount, rowBegin, rowEnd, k, mismatchMax, dLut, variant,
+                           static_cast<em2_pair*>(dPairs), static_cast<uint32_t*>(dUsed), s));
+    const int e1 = T.mark();
+    EM2_CUDA(ctx, cudaMemcpyAsync(pairs, dPairs, rows * k * sizeof(em2_pair), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(usedCount, dUsed, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    const int e2 = T.mark();
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.d2h_bytes += rows * k * sizeof(em2_pair) + rows * sizeof(uint32_t);
+    ctx->stats.scan_ms += T.ms(e0, e1);
+    ctx->stats.d2h_ms += T.ms(e1, e2);
+    return EM2_OK;
+}
+
+int em2_compute_signatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                           const em2_count* counts, const double* lshVectors, uint64_t lshCount,
+                           uint64_t* signatures, double* sum1, double* sum2)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!toc || !lshVectors || !signatures || (!counts && cellCount && toc[cellCount]))
+        return fail(ctx, EM2_ERR_INVALID, "em2_compute_signatures: null pointer");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    if (cellCount == 0) return EM2_OK;
+    StageTimer T(ctx);
+    uint64_t* dSig;
+    double *dSum1, *dSum2;
+    EM2_TRY(signaturesOnDevice(ctx, T, cellCount, geneCount, toc, counts, lshVectors, lshCount, &dSig, &dSum1, &dSum2));
+    const uint64_t W = wordCount(lshCount);
+    const int e0 = T.mark();
+    EM2_CUDA(ctx, cudaMemcpyAsync(signatures, dSig, cellCount * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sum1) EM2_CUDA(ctx, cudaMemcpyAsync(sum1, dSum1, cellCount * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sum2) EM2_CUDA(ctx, cudaMemcpyAsync(sum2, dSum2, cellCount * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const int e1 = T.mark();
+    EM2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_ms += T.ms(e0, e1);
+    ctx->stats.d2h_bytes += cellCount * W * 8 + (sum1 ? cellCount * 8 : 0) + (sum2 ? cellCount * 8 : 0);
+    EM2_TRY(fetchCounters(ctx));
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
+int em2_find_similar_pairs(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                           uint64_t rowBegin, uint64_t rowEnd, uint64_t k, double similarityThreshold, int variant,
+                           em2_pair* pairs, uint32_t* usedCount)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!signatures || !pairs || !usedCount) return fail(ctx, EM2_ERR_INVALID, "em2_find_similar_pairs: null pointer");
+    if (rowEnd > cellCount || rowBegin > rowEnd) return fail(ctx, EM2_ERR_INVALID, "row range outside [0, cellCount]");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    if (rowEnd == rowBegin) return EM2_OK;
+    StageTimer T(ctx);
+    const uint64_t W = wordCount(lshCount);
+    void *dSig, *dCounters;
+    EM2_TRY(reserve(ctx, em2_context::S_SIG, cellCount * W * sizeof(uint64_t), &dSig));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &dCounters));
+    const int e0 = T.mark();
+    EM2_CUDA(ctx, cudaMemsetAsync(dCounters, 0, 64, ctx->stream));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dSig, signatures, cellCount * W * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int e1 = T.mark();
+    ctx->stats.h2d_bytes += cellCount * W * 8;
+    EM2_TRY(scanToHost(ctx, T, static_cast<uint64_t*>(dSig), cellCount, lshCount, rowBegin, rowEnd, k,
+                       similarityThreshold, variant, pairs, usedCount));
+    ctx->stats.h2d_ms += T.ms(e0, e1);
+    EM2_TRY(fetchCounters(ctx));
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
+int em2_lsh_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                          const em2_count* counts, const double* lshVectors, uint64_t lshCount, uint64_t k,
+                          double similarityThreshold, int variant, em2_pair* pairs, uint32_t* usedCount,
+                          uint64_t* signaturesOut)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!toc || !lshVectors || !pairs || !usedCount || (!counts && cellCount && toc[cellCount]))
+        return fail(ctx, EM2_ERR_INVALID, "em2_lsh_similar_pairs: null pointer");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    if (cellCount == 0) return EM2_OK;
+    StageTimer T(ctx);
+    uint64_t* dSig;
+    double *dSum1, *dSum2;
+    EM2_TRY(signaturesOnDevice(ctx, T, cellCount, geneCount, toc, counts, lshVectors, lshCount, &dSig, &dSum1, &dSum2));
+    if (signaturesOut) {
+        const uint64_t W = wordCount(lshCount);
+        EM2_CUDA(ctx, cudaMemcpyAsync(signaturesOut, dSig, cellCount * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += cellCount * W * 8;
+    }
+    EM2_TRY(scanToHost(ctx, T, dSig, cellCount, lshCount, 0, cellCount, k, similarityThreshold, variant, pairs, usedCount));
+    EM2_TRY(fetchCounters(ctx));
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
+int em2_exact_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                            const em2_count* counts, uint64_t k, double similarityThreshold, em2_pair* pairs,
+                            uint32_t* usedCount)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!toc || !pairs || !usedCount || (!counts && cellCount && toc[cellCount]))
+        return fail(ctx, EM2_ERR_INVALID, "em2_exact_similar_pairs: null pointer");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    if (cellCount == 0) return EM2_OK;
+    StageTimer T(ctx);
+    const uint64_t nnz = toc[cellCount];
+    void *dToc, *dCounts, *dSum1, *dSum2, *dPairs, *dUsed;
+    EM2_TRY(reserve(ctx, em2_context::S_TOC, (cellCount + 1) * sizeof(uint64_t), &dToc));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTS, nnz * sizeof(em2_count), &dCounts));
+    EM2_TRY(reserve(ctx, em2_context::S_SUM1, cellCount * sizeof(double), &dSum1));
+    EM2_TRY(reserve(ctx, em2_context::S_SUM2, cellCount * sizeof(double), &dSum2));
+    EM2_TRY(reserve(ctx, em2_context::S_PAIRS, cellCount * k * sizeof(em2_pair), &dPairs));
+    EM2_TRY(reserve(ctx, em2_context::S_USED, cellCount * sizeof(uint32_t), &dUsed));
+    cudaStream_t s = ctx->stream;
+    const int e0 = T.mark();
+    EM2_CUDA(ctx, cudaMemcpyAsync(dToc, toc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dCounts, counts, nnz * sizeof(em2_count), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += (cellCount + 1) * 8 + nnz * 8;
+    const int e1 = T.mark();
+    EM2_TRY(launchCellSums(ctx, cellCount, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+                           static_cast<double*>(dSum1), static_cast<double*>(dSum2), s));
+    const int e2 = T.mark();
+    EM2_TRY(launchExact(ctx, cellCount, geneCount, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+                        static_cast<double*>(dSum1), static_cast<double*>(dSum2), k, similarityThreshold,
+                        static_cast<em2_pair*>(dPairs), static_cast<uint32_t*>(dUsed), s));
+    const int e3 = T.mark();
+    EM2_CUDA(ctx, cudaMemcpyAsync(pairs, dPairs, cellCount * k * sizeof(em2_pair), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(usedCount, dUsed, cellCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    const int e4 = T.mark();
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.h2d_ms = T.ms(e0, e1);
+    ctx->stats.sums_ms = T.ms(e1, e2);
+    ctx->stats.scan_ms = T.ms(e2, e3);
+    ctx->stats.d2h_ms = T.ms(e3, e4);
+    ctx->stats.d2h_bytes += cellCount * k * sizeof(em2_pair) + cellCount * 4;
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Shared declarations of the CUDA side of libem2b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/em2b200.h"
+
+namespace em2 {
+
+// A growable device scratch area owned by the context.
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct PinnedBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace em2
+
+struct em2_context {
+    int device = -1;
+    int smCount = 0;
+    cudaDeviceProp prop{};
+    std::string error;
+    em2_stats stats{};
+    cudaStream_t stream = nullptr;       // stream of the blocking calls
+    cudaStream_t copyStream = nullptr;   // overlapped host<->device staging
+    cudaEvent_t ev[16] = {};
+
+    // Named scratch buffers (grown on demand, never shrunk; freed in em2_destroy).
+    enum Scratch {
+        S_SUMU = 0,      // column sums of the hyperplanes, double[Lpad]
+        S_UPAD,          // hyperplanes re-pitched to a multiple of 128 columns
+        S_CAND,          // candidate keys of the scan, uint64[segments][rows][cap]
+        S_CANDCOUNT,     // uint32[segments][rows]
+        S_COUNTERS,      // small uint64 counters
+        S_TOC, S_COUNTS, S_SUM1, S_SUM2, S_U, S_SIG, S_LUT, S_PAIRS, S_USED,   // staging of the blocking API
+        S_ENC,           // +-1 int8 encoded signatures (MMA variant)
+        S_MISC,
+        S_COUNT
+    };
+    em2::DeviceBuffer scratch[S_COUNT];
+    em2::PinnedBuffer pinned[2];
+};
+
+namespace em2 {
+
+int fail(em2_context* ctx, int code, const std::string& message);
+int cudaFail(em2_context* ctx, cudaError_t e, const char* what, const char* file, int line);
+// Grow-only allocation of a named scratch buffer.
+int reserve(em2_context* ctx, int which, size_t bytes, void** out);
+int reservePinned(em2_context* ctx, int which, size_t bytes, void** out);
+
+#define EM2_CUDA(ctx, call)                                                         \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) return em2::cudaFail(ctx, e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define EM2_TRY(call)                 \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != EM2_OK) return rc__; \
+    } while (0)
+
+inline uint64_t wordCount(uint64_t lshCount) { return (lshCount - 1) / 64 + 1; }
+inline uint64_t roundUp(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+// ---- stage launchers (each returns an em2_status and adds to ctx->stats.kernel_launches) ----------
+int launchCellSums(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
+                   double* sum1, double* sum2, cudaStream_t s);
+int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                     const em2_count* counts, const double* sum1, const double* sum2, const double* U,
+                     uint64_t ld, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero, cudaStream_t s);
+int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                   uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
+                   int variant, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);
+int launchMismatchCounts(em2_context* ctx, const uint64_t* signatures, uint64_t lshCount, uint64_t pairCount,
+                         const uint32_t* c0, const uint32_t* c1, uint32_t* out, cudaStream_t s);
+int launchMismatchBlock(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                        uint64_t rowBegin, uint64_t rowEnd, int variant, uint16_t* out, cudaStream_t s);
+int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                const em2_count* counts, const double* sum1, const double* sum2, uint64_t k,
+                double similarityThreshold, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);
+
+// scan internals shared between the POPC and MMA variants
+struct ScanPlan {
+    uint32_t rowsPerCta;
+    uint32_t rowBlocks;
+    uint32_t segments;     // column segments (grid.y)
+    uint64_t segmentCols;  // columns per segment (multiple of the column tile)
+    uint32_t cap;          // candidate buffer capacity per (segment,row)
+};
+int launchFinalize(em2_context* ctx, const ScanPlan& plan, uint64_t rows, uint64_t k, const uint64_t* cand,
+                   const uint32_t* candCount, const float* lut, em2_pair* pairs, uint32_t* usedCount,
+                   cudaStream_t s);
+int launchScanMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                  uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
+                  em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);
+int launchMismatchBlockMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                           uint64_t rowBegin, uint64_t rowEnd, uint16_t* out, cudaStream_t s);
+
+}  // namespace em2

@@ -1,0 +1,241 @@
+// Signature construction on sm_100a.
+//
+// Replaces, bit for bit, the reference's CPU loops
+//   ExpressionMatrixSubset::computeSums         (reference src/ExpressionMatrixSubset.cpp:47-58)
+//   lshVectorsSums                              (reference src/Lsh.cpp:137-144)
+//   Lsh::computeCellLshSignatures               (reference src/Lsh.cpp:160-207)
+// Bit-exactness rule: every projection s_i is the SAME sequence of IEEE double operations the
+// reference executes (its build is -O3 -msse4.2: separate mulsd/addsd, no FMA):
+//     s_i = (-mean) * sumU_i;   for each stored (gene,count) of the cell, in stored order:
+//     s_i = s_i + double(count) * U[gene][i]
+// so the kernels use __dmul_rn/__dadd_rn (never contracted) and keep one accumulator per
+// (cell, hyperplane) with no cross-thread reduction.  Parallelism is over cells and hyperplanes.
+//
+// Data movement (v1): one warp owns (cell, 128-hyperplane slice).  The cell's CSR entries are staged
+// through shared memory 32 at a time (coalesced 256 B reads); for every entry the warp reads the 1 KB
+// slice row U[gene][slice] with two 512 B LDG.128 requests.  Blocks are ordered slice-major so that
+// the G x 128 x 8 B slice (30 MB at G = 30k) stays L2 resident while all cells pass over it.
+#include "common.cuh"
+
+namespace em2 {
+
+namespace {
+
+constexpr int kSigWarps = 8;          // warps (cells) per block
+constexpr int kSliceCols = 128;       // hyperplanes per warp slice
+constexpr double kNearZeroEps = 1e-12;
+
+// One thread per cell, sequential like the reference (order matters for the rounding of sum1).
+__global__ void cellSumsKernel(uint64_t cellCount, const uint64_t* __restrict__ toc,
+                               const em2_count* __restrict__ counts, double* __restrict__ sum1,
+                               double* __restrict__ sum2)
+{
+    const uint64_t c = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (c >= cellCount) return;
+    double s1 = 0., s2 = 0.;
+    const uint64_t e = toc[c + 1];
+    for (uint64_t j = toc[c]; j < e; j++) {
+        const float x = counts[j].count;
+        s1 = __dadd_rn(s1, double(x));                 // sum.sum1 += count
+        s2 = __dadd_rn(s2, double(__fmul_rn(x, x)));   // sum.sum2 += count*count (float product)
+    }
+    sum1[c] = s1;
+    if (sum2) sum2[c] = s2;
+}
+
+// One thread per hyperplane column, genes in ascending order (src/Lsh.cpp:137-144).
+__global__ void columnSumsKernel(uint64_t geneCount, const double* __restrict__ U, uint64_t ld, uint32_t cols,
+                                 double* __restrict__ sumU)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cols) return;
+    double s = 0.;
+    uint64_t g = 0;
+    for (; g + 8 <= geneCount; g += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __ldg(U + (g + j) * ld + i);
+#pragma unroll
+        for (int j = 0; j < 8; j++) s = __dadd_rn(s, v[j]);
+    }
+    for (; g < geneCount; g++) s = __dadd_rn(s, __ldg(U + g * ld + i));
+    sumU[i] = s;
+}
+
+__device__ __forceinline__ uint64_t spreadBits(uint32_t v)
+{
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+
+__device__ __forceinline__ double2 ldU(const double* p)
+{
+    // read-only, 16-byte vector load
+    return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// grid.x = slices * ceil(cellCount / kSigWarps), slice-major.  U must have `ld` >= slices*128 columns
+// readable (zero padded beyond lshCount), ld even, base 16-byte aligned.
+__global__ void __launch_bounds__(kSigWarps * 32)
+signatureKernel(uint64_t cellCount, uint64_t geneCount, const uint64_t* __restrict__ toc,
+                const em2_count* __restrict__ counts, const double* __restrict__ sum1,
+                const double* __restrict__ sum2, const double* __restrict__ U, uint64_t ld,
+                const double* __restrict__ sumU, uint32_t lshCount, uint32_t wordsPerCell, uint32_t cellBlocks,
+                uint64_t* __restrict__ signatures, unsigned long long* __restrict__ nearZero)
+{
+    __shared__ uint32_t sGene[kSigWarps][32];
+    __shared__ double sCount[kSigWarps][32];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t slice = blockIdx.x / cellBlocks;
+    const uint64_t cell = uint64_t(blockIdx.x % cellBlocks) * kSigWarps + warp;
+    if (cell >= cellCount) return;
+
+    const uint32_t colBase = slice * kSliceCols;
+    const uint32_t c0 = colBase + 2 * lane;        // hyperplanes c0, c0+1
+    const uint32_t c1 = c0 + 64;                   // hyperplanes c1, c1+1
+
+    const double mean = __ddiv_rn(sum1[cell], double(geneCount));      // src/Lsh.cpp:167-168
+    const double negMean = -mean;
+    const double2 su0 = *reinterpret_cast<const double2*>(sumU + c0);
+    const double2 su1 = *reinterpret_cast<const double2*>(sumU + c1);
+    double a0 = __dmul_rn(negMean, su0.x);                               // src/Lsh.cpp:180-182
+    double a1 = __dmul_rn(negMean, su0.y);
+    double a2 = __dmul_rn(negMean, su1.x);
+    double a3 = __dmul_rn(negMean, su1.y);
+
+    const double* Uslice = U + c0;
+    const uint64_t begin = toc[cell];
+    const uint64_t end = toc[cell + 1];
+    for (uint64_t base = begin; base < end; base += 32) {
+        // Stage up to 32 entries of the CSR row (coalesced), padded to a multiple of 4 with
+        // (gene 0, count 0): adding 0*U leaves every accumulator unchanged.
+        const uint64_t left = end - base;
+        const int n = left < 32 ? int(left) : 32;
+        uint32_t g = 0;
+        double c = 0.;
+        if (lane < n) {
+            const em2_count p = counts[base + lane];
+            g = p.gene;
+            c = double(p.count);                                         // src/Lsh.cpp:190
+        }
+        sGene[warp][lane] = g;
+        sCount[warp][lane] = c;
+        __syncwarp();
+        const int n4 = (n + 3) & ~3;
+        for (int j = 0; j < n4; j += 4) {
+            double2 u[4][2];
+            double cnt[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double* row = Uslice + uint64_t(sGene[warp][j + q]) * ld;
+                cnt[q] = sCount[warp][j + q];
+                u[q][0] = ldU(row);
+                u[q][1] = ldU(row + 64);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {                                // src/Lsh.cpp:194-197, in order
+                a0 = __dadd_rn(a0, __dmul_rn(cnt[q], u[q][0].x));
+                a1 = __dadd_rn(a1, __dmul_rn(cnt[q], u[q][0].y));
+                a2 = __dadd_rn(a2, __dmul_rn(cnt[q], u[q][1].x));
+                a3 = __dadd_rn(a3, __dmul_rn(cnt[q], u[q][1].y));
+            }
+        }
+        __syncwarp();
+    }
+
+    // Sign bits -> two 64-bit words, first hyperplane in the most significant bit
+    // (src/Lsh.cpp:201-206, src/BitSet.hpp:48-62).  Columns >= lshCount never set a bit.
+    const bool p0 = (c0 < lshCount) && (a0 > 0.);
+    const bool p1 = (c0 + 1 < lshCount) && (a1 > 0.);
+    const bool p2 = (c1 < lshCount) && (a2 > 0.);
+    const bool p3 = (c1 + 1 < lshCount) && (a3 > 0.);
+    const uint32_t b0 = __ballot_sync(0xffffffffu, p0);
+    const uint32_t b1 = __ballot_sync(0xffffffffu, p1);
+    const uint32_t b2 = __ballot_sync(0xffffffffu, p2);
+    const uint32_t b3 = __ballot_sync(0xffffffffu, p3);
+
+    if (nearZero != nullptr && sum2 != nullptr) {
+        const double scale = sqrt(sum2[cell]);
+        int nz = 0;
+        nz += (c0 < lshCount) && (fabs(a0) < kNearZeroEps * (scale + fabs(__dmul_rn(mean, su0.x))));
+        nz += (c0 + 1 < lshCount) && (fabs(a1) < kNearZeroEps * (scale + fabs(__dmul_rn(mean, su0.y))));
+        nz += (c1 < lshCount) && (fabs(a2) < kNearZeroEps * (scale + fabs(__dmul_rn(mean, su1.x))));
+        nz += (c1 + 1 < lshCount) && (fabs(a3) < kNearZeroEps * (scale + fabs(__dmul_rn(mean, su1.y))));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        if (lane == 0 && nz) atomicAdd(nearZero, (unsigned long long)nz);
+    }
+
+    if (lane == 0) {
+        const uint32_t w0 = slice * 2;
+        if (w0 < wordsPerCell)
+            signatures[cell * wordsPerCell + w0] = __brevll(spreadBits(b0) | (spreadBits(b1) << 1));
+        if (w0 + 1 < wordsPerCell)
+            signatures[cell * wordsPerCell + w0 + 1] = __brevll(spreadBits(b2) | (spreadBits(b3) << 1));
+    }
+}
+
+}  // namespace
+
+int launchCellSums(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
+                   double* sum1, double* sum2, cudaStream_t s)
+{
+    if (cellCount == 0) return EM2_OK;
+    const int threads = 128;
+    const unsigned blocks = unsigned((cellCount + threads - 1) / threads);
+    cellSumsKernel<<<blocks, threads, 0, s>>>(cellCount, toc, counts, sum1, sum2);
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+    return EM2_OK;
+}
+
+int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                     const em2_count* counts, const double* sum1, const double* sum2, const double* U,
+                     uint64_t ld, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero, cudaStream_t s)
+{
+    if (cellCount == 0) return EM2_OK;
+    if (lshCount == 0 || lshCount > 65535) return fail(ctx, EM2_ERR_INVALID, "lshCount must be in [1, 65535]");
+    if (geneCount == 0) return fail(ctx, EM2_ERR_INVALID, "geneCount must be positive");
+    const uint64_t W = wordCount(lshCount);
+    const uint64_t Lpad = roundUp(lshCount, kSliceCols);
+    const uint32_t slices = uint32_t(Lpad / kSliceCols);
+
+    // The kernel wants `Lpad` readable, zero padded columns with an even pitch and 16-byte alignment.
+    const double* Uk = U;
+    uint64_t ldk = ld;
+    if (ld < Lpad || (ld & 1) || (reinterpret_cast<uintptr_t>(U) & 15)) {
+        void* p = nullptr;
+        EM2_TRY(reserve(ctx, em2_context::S_UPAD, geneCount * Lpad * sizeof(double), &p));
+        EM2_CUDA(ctx, cudaMemsetAsync(p, 0, geneCount * Lpad * sizeof(double), s));
+        EM2_CUDA(ctx, cudaMemcpy2DAsync(p, Lpad * sizeof(double), U, ld * sizeof(double), lshCount * sizeof(double),
+                                        geneCount, cudaMemcpyDeviceToDevice, s));
+        Uk = static_cast<const double*>(p);
+        ldk = Lpad;
+    }
+
+    void* sumU = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_SUMU, Lpad * sizeof(double), &sumU));
+    columnSumsKernel<<<unsigned((Lpad + 127) / 128), 128, 0, s>>>(geneCount, Uk, ldk, uint32_t(Lpad),
+                                                                 static_cast<double*>(sumU));
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+
+    const uint64_t cellBlocks = (cellCount + kSigWarps - 1) / kSigWarps;
+    const uint64_t blocks = cellBlocks * slices;
+    if (blocks > 0x7fffffffull) return fail(ctx, EM2_ERR_INVALID, "too many cells for one signature launch");
+    signatureKernel<<<unsigned(blocks), kSigWarps * 32, 0, s>>>(
+        cellCount, geneCount, toc, counts, sum1, sum2, Uk, ldk, static_cast<const double*>(sumU), uint32_t(lshCount),
+        uint32_t(W), uint32_t(cellBlocks), signatures, reinterpret_cast<unsigned long long*>(nearZero));
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+    return EM2_OK;
+}
+
+}  // namespace em2

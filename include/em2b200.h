@@ -1,0 +1,186 @@
+/*
+ * em2b200.h -- C-ABI of the B200-native LSH cell-similarity engine (libem2b200.so).
+ *
+ * This is the drop-in boundary for the hot path of chanzuckerberg/ExpressionMatrix2:
+ *     signature construction -> all-pairs Hamming scan -> per-cell top-k -> SimilarPairs payload.
+ * The reference has no FFI for this path; the seam it DOES have is the host/device interface of its
+ * OpenCL prototype,
+ *     Lsh::initializeGpu / getGpuName / loadSignaturesToGpu / setupGpuKernelN / gpuKernelN /
+ *     cleanupGpuKernelN            (reference src/Lsh.hpp:214-265, src/LshGpu.cpp:47-369)
+ * called from ExpressionMatrix::findSimilarPairs4Gpu (src/ExpressionMatrixLshGpu.cpp:15-99).
+ * The entry points below replace that seam, coarser (whole job instead of per block) and extended
+ * upward to the signature stage, which the reference only has on the CPU (src/Lsh.cpp:118-224).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; no exceptions cross this boundary.
+ *   - every call returns an int status (EM2_OK == 0); em2_last_error() gives the message.  The C++
+ *     host layer turns a failure into std::runtime_error, as CZI_ASSERT / LshGpu.cpp:200-204 do.
+ *   - there is NO CPU fallback: without a CUDA device em2_create fails with EM2_ERR_NO_DEVICE.
+ *   - calls are blocking unless named *_device (those enqueue on the given stream and return).
+ *   - a context is not re-entrant; use one context per GPU / per host thread.
+ *   - the caller owns every buffer it passes; the library keeps no pointer after a call returns
+ *     (host buffers are typically mmap regions of the reference's MemoryMapped::Vector files).
+ *
+ * Data layouts (bit-compatible with the reference's files)
+ *   expression counts : toc uint64[N+1] + em2_count[nnz] (pair<GeneId,float>, AoS, genes ascending per
+ *                       cell; src/MemoryMappedVectorOfVectors.hpp:189-190, src/ExpressionMatrix.cpp:265-277)
+ *   hyperplanes       : double [G][L] row-major (src/Lsh.hpp:105-113)
+ *   signatures        : uint64 [N][W], W = (L-1)/64+1, bit p at word p>>6, bit 63-(p&63)
+ *                       (src/BitSet.hpp:48-62, src/Lsh.cpp:57,127,148)
+ *   similar pairs     : em2_pair[N][k] (pair<CellId,float>) + uint32 usedCount[N]
+ *                       (src/SimilarPairs.hpp:53-56,165-203), each row ordered by (similarity desc,
+ *                       cell id asc) == SimilarPairs::sort() order (src/orderPairs.hpp:44-52)
+ */
+#ifndef EM2B200_H
+#define EM2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EM2_ABI_VERSION 1
+
+enum em2_status {
+    EM2_OK = 0,
+    EM2_ERR_INVALID = 1,   /* bad argument */
+    EM2_ERR_CUDA = 2,      /* CUDA runtime / kernel failure */
+    EM2_ERR_NO_DEVICE = 3, /* no usable sm_100 device: there is no CPU fallback */
+    EM2_ERR_OOM = 4
+};
+
+/* Hamming-scan variants (BASELINE.json north_star item 2). */
+enum em2_variant {
+    EM2_VARIANT_AUTO = 0,   /* library picks */
+    EM2_VARIANT_POPC = 1,   /* XOR + carry-save + POPC on the integer pipes */
+    EM2_VARIANT_MMA_I8 = 2  /* tcgen05.mma kind::i8 on +-1 encoded signatures, Hamming = (L - dot)/2 */
+};
+
+typedef struct em2_context em2_context;
+
+/* pair<GeneId,float>: one stored expression count (reference src/ExpressionMatrixSubset.hpp:37). */
+typedef struct em2_count {
+    uint32_t gene;
+    float count;
+} em2_count;
+
+/* SimilarPairs::Pair = pair<CellId,float> (reference src/SimilarPairs.hpp:53-56). */
+typedef struct em2_pair {
+    uint32_t cell;
+    float similarity;
+} em2_pair;
+
+/* Per-stage device timings (CUDA events) and counters of the last blocking call on a context.
+ * Replaces the reference's chrono brackets (src/Lsh.cpp:160,209-222, src/ExpressionMatrixLsh.cpp:217,270-274). */
+typedef struct em2_stats {
+    double h2d_ms;            /* host -> device copies                                   */
+    double sums_ms;           /* per-cell sums + hyperplane column sums                  */
+    double signatures_ms;     /* signature kernel                                        */
+    double encode_ms;         /* +-1 int8 expansion (MMA variant only)                   */
+    double scan_ms;           /* Hamming scan + fused candidate selection                */
+    double finalize_ms;       /* final ordering + similarity lookup                      */
+    double d2h_ms;            /* device -> host copies                                   */
+    double total_ms;          /* wall clock of the call                                  */
+    uint64_t near_zero_projections; /* projections with |s| < eps*(sqrt(sum2)+|mean*sumU|), eps = 1e-12 */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t kernel_launches; /* kernels of this library launched by the call            */
+    uint64_t candidates_appended; /* scan-stage candidates that passed the running bound  */
+    int32_t variant_used;     /* em2_variant actually run                                */
+    int32_t reserved;
+} em2_stats;
+
+/* ------------------------------------------------------------------------------------------------
+ * Context.  Replaces Lsh::initializeGpu / getGpuName / cleanupGpu (src/Lsh.hpp:214-225,
+ * src/LshGpu.cpp:47-72): choose a device, own all device memory and streams.
+ * ---------------------------------------------------------------------------------------------- */
+int em2_abi_version(void);
+int em2_create(int device, em2_context** ctx);
+void em2_destroy(em2_context* ctx);
+/* ctx may be NULL: returns the message of the last failed em2_create on this thread. */
+const char* em2_last_error(const em2_context* ctx);
+int em2_device_name(em2_context* ctx, char* buffer, size_t bufferSize);
+int em2_get_stats(const em2_context* ctx, em2_stats* stats);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-side helpers of the path (cheap, O(G*L) or O(L); kept on the host by design).
+ * ---------------------------------------------------------------------------------------------- */
+/* Lsh::generateLshVectors (src/Lsh.cpp:68-113): G*L normals from mt19937(seed), gene outer / vector
+ * inner, each hyperplane (column) scaled to unit norm.  U is double[G*L] row-major. */
+int em2_generate_lsh_vectors(uint64_t geneCount, uint64_t lshCount, uint32_t seed, double* U);
+/* Lsh::computeSimilarityTable (src/Lsh.cpp:229-249): table[m] = cos(m*pi/L), m = 0..L. */
+int em2_similarity_table(uint64_t lshCount, double* table /* [lshCount+1] */);
+/* Largest mismatch count whose similarity passes findSimilarPairs4's strict filter
+ * `similarity > similarityThreshold` (src/ExpressionMatrixLsh.cpp:244); -1 if none passes. */
+int64_t em2_mismatch_max(uint64_t lshCount, double similarityThreshold);
+
+/* ------------------------------------------------------------------------------------------------
+ * Blocking calls on HOST buffers (what the C++ Lsh / ExpressionMatrix layer calls).
+ * ---------------------------------------------------------------------------------------------- */
+/* ExpressionMatrixSubset::computeSums + Lsh::computeCellLshSignatures
+ * (src/ExpressionMatrixSubset.cpp:47-58, src/Lsh.cpp:118-224).
+ * signatures: uint64[cellCount*W], fully overwritten.  sum1/sum2 (optional, may be NULL): per-cell
+ * sums as the reference computes them. */
+int em2_compute_signatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                           const em2_count* counts, const double* lshVectors, uint64_t lshCount,
+                           uint64_t* signatures, double* sum1, double* sum2);
+
+/* The pair loop of findSimilarPairs4 + SimilarPairs::copy + sort
+ * (src/ExpressionMatrixLsh.cpp:199-286, src/SimilarPairs.cpp:369-405) with the deterministic
+ * selection of the reference's GPU host path (src/ExpressionMatrixLshGpu.cpp:132-157):
+ * for every cell in [rowBegin,rowEnd), the k cells (other than itself) of smallest
+ * (mismatch, cellId) among those with table[mismatch] > similarityThreshold.
+ * pairs: em2_pair[(rowEnd-rowBegin)*k]; usedCount: uint32[rowEnd-rowBegin].  Unused slots are zeroed. */
+int em2_find_similar_pairs(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                           uint64_t rowBegin, uint64_t rowEnd, uint64_t k, double similarityThreshold,
+                           int variant, em2_pair* pairs, uint32_t* usedCount);
+
+/* Whole job, counts -> similar pairs, signatures never leave the device (optionally also returned). */
+int em2_lsh_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                          const em2_count* counts, const double* lshVectors, uint64_t lshCount, uint64_t k,
+                          double similarityThreshold, int variant, em2_pair* pairs, uint32_t* usedCount,
+                          uint64_t* signaturesOut /* may be NULL */);
+
+/* Exact path (findSimilarPairs0, src/ExpressionMatrixFindSimilarPairs.cpp:16-88 with
+ * ExpressionMatrixSubset::computeCellSimilarity, src/ExpressionMatrixSubset.cpp:83-133):
+ * Pearson correlation over all genes, deterministic top-k by (similarity desc, cellId asc) among
+ * pairs with similarity > threshold. */
+int em2_exact_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                            const em2_count* counts, uint64_t k, double similarityThreshold, em2_pair* pairs,
+                            uint32_t* usedCount);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident calls: every pointer is a DEVICE pointer on the context's device, work is enqueued
+ * on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and the call returns
+ * without synchronising.  These are what bench.py times for the HBM-resident figure and what the
+ * multi-GPU driver uses around its NCCL all-gather.
+ * ---------------------------------------------------------------------------------------------- */
+/* sum1/sum2: device double[cellCount] outputs (sum2 may be NULL). */
+int em2_cell_sums_device(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
+                         double* sum1, double* sum2, void* stream);
+/* lshVectors: device double[geneCount*ld], ld >= lshCount (elements).  sum1 from em2_cell_sums_device.
+ * signatures: device uint64[cellCount*W]. nearZero: device uint64 counter (may be NULL), accumulated. */
+int em2_signatures_device(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                          const em2_count* counts, const double* sum1, const double* sum2,
+                          const double* lshVectors, uint64_t ld, uint64_t lshCount, uint64_t* signatures,
+                          uint64_t* nearZero, void* stream);
+/* signatures: device uint64[cellCount*W] of ALL cells (columns); rows [rowBegin,rowEnd) are scanned.
+ * similarityTable: device float[lshCount+1].  pairs/usedCount as in em2_find_similar_pairs. */
+int em2_scan_topk_device(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                         uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax,
+                         const float* similarityTable, int variant, em2_pair* pairs, uint32_t* usedCount,
+                         void* stream);
+/* Hamming distances of explicit pairs (Lsh::computeMismatchCount, src/Lsh.cpp:266-274), for tests. */
+int em2_mismatch_counts_device(em2_context* ctx, const uint64_t* signatures, uint64_t lshCount, uint64_t pairCount,
+                               const uint32_t* cell0, const uint32_t* cell1, uint32_t* out, void* stream);
+/* Hamming distances from the variant's own arithmetic for a full block of rows x all columns
+ * (uint16 out[(rowEnd-rowBegin)*cellCount]); used by the parity tests to check the MMA path bit-exactly. */
+int em2_mismatch_block_device(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                              uint64_t rowBegin, uint64_t rowEnd, int variant, uint16_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EM2B200_H */

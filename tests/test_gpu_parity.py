@@ -1,0 +1,178 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI, against the
+oracle on the same seeded inputs and against the golden fixtures generated from the reference build.
+
+Bars: signatures bit-exact, Hamming distances bit-exact, neighbour lists exactly equal to the
+deterministic oracle (ids, order, usedCount), similarity floats 0 ULP."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+import expressionmatrix2_b200 as em2  # noqa: E402
+from expressionmatrix2_b200 import synthetic  # noqa: E402
+
+VARIANTS = [em2.VARIANT_POPC]
+
+
+def _check_lists(got, want):
+    ids, sims, used = got
+    wids, wsims, wused = want
+    assert np.array_equal(used, wused)
+    assert np.array_equal(ids, wids)
+    assert np.array_equal(sims.view(np.uint32), wsims.view(np.uint32))   # 0 ULP
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_signatures_bit_exact(engine, name):
+    g = load_golden(name)
+    U = em2.generate_lsh_vectors(int(g["gene_count"]), int(g["lsh_count"]), int(g["seed"]))
+    sig, s1, s2 = engine.compute_signatures(g["toc"], g["counts"], U, gene_ids=g["genes"], want_sums=True)
+    assert np.array_equal(s1, g["sum1"]) and np.array_equal(s2, g["sum2"])
+    assert np.array_equal(sig, g["signatures"])
+    assert engine.stats()["near_zero_projections"] == 0
+    assert engine.stats()["kernel_launches"] >= 3
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_neighbour_lists(engine, name, variant):
+    g = load_golden(name)
+    L = int(g["lsh_count"])
+    for i in range(int(g["combos"])):
+        k, thr = int(g[f"combo{i}_k"]), float(g[f"combo{i}_thr"])
+        got = engine.find_similar_pairs(g["signatures"], L, k, thr, variant=variant)
+        _check_lists(got, (g[f"combo{i}_ids"], g[f"combo{i}_sims"], g[f"combo{i}_used"]))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_whole_job(engine, name):
+    """counts -> similar pairs in one call, signatures staying on the device."""
+    g = load_golden(name)
+    L = int(g["lsh_count"])
+    U = em2.generate_lsh_vectors(int(g["gene_count"]), L, int(g["seed"]))
+    k, thr = int(g["combo0_k"]), float(g["combo0_thr"])
+    ids, sims, used, sig = engine.lsh_similar_pairs(g["toc"], g["counts"], U, k, thr, gene_ids=g["genes"],
+                                                    want_signatures=True)
+    assert np.array_equal(sig, g["signatures"])
+    _check_lists((ids, sims, used), (g["combo0_ids"], g["combo0_sims"], g["combo0_used"]))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_hamming_bit_exact(engine, name):
+    import torch
+    g = load_golden(name)
+    L = int(g["lsh_count"])
+    sig = torch.from_numpy(g["signatures"].view(np.int64)).cuda()
+    c0 = torch.from_numpy(g["pair_c0"].view(np.int32)).cuda()
+    c1 = torch.from_numpy(g["pair_c1"].view(np.int32)).cuda()
+    out = torch.zeros(len(g["pair_c0"]), dtype=torch.int32, device="cuda")
+    engine.mismatch_counts_device(sig, L, len(g["pair_c0"]), c0, c1, out,
+                                  stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), g["pair_mismatch"])
+    n = g["signatures"].shape[0]
+    block = torch.zeros((1, n), dtype=torch.int16, device="cuda")
+    engine.mismatch_block_device(sig, n, L, 0, 1, block, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(block.cpu().numpy().view(np.uint16)[0].astype(np.uint32), g["row0_mismatch"])
+
+
+@pytest.mark.parametrize("N,G,dens,L,mode", [
+    (1500, 700, 0.05, 1024, "clustered"),
+    (1100, 500, 0.03, 512, "iid"),
+    (900, 333, 0.07, 200, "clustered"),     # L not a multiple of 64 or 128
+    (700, 300, 0.05, 1, "iid"),             # one hyperplane
+    (640, 256, 0.05, 4096, "clustered"),    # L > 1024: shared-memory row panel
+])
+def test_signatures_and_lists_vs_oracle(engine, oracle, N, G, dens, L, mode):
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, dens, seed=N + L, mode=mode, clusters=7)
+    U = em2.generate_lsh_vectors(G, L, 231)
+    s1, _ = oracle.cell_sums(toc, counts)
+    want_sig, _ = oracle.signatures(toc, genes, counts, s1, U)
+    sig = engine.compute_signatures(toc, counts, U, gene_ids=genes)
+    assert np.array_equal(sig, want_sig)
+    for k, thr in ((50, 0.2), (10, -1.0), (100, 0.0)):
+        want = oracle.topk(want_sig, L, k, thr)[:3]
+        for variant in VARIANTS:
+            _check_lists(engine.find_similar_pairs(sig, L, k, thr, variant=variant), want)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ties_and_duplicates(engine, oracle, variant):
+    """Heavy ties: many identical signatures and iid bits at small L (distances collide constantly);
+    the (mismatch, id) tie-break must reproduce the oracle exactly, including at the k-th place."""
+    rng = np.random.default_rng(3)
+    base = synthetic.gen_signatures(40, 64, seed=1)
+    sig = base[rng.integers(0, 40, 3000)]            # 3000 cells, only 40 distinct signatures
+    for k, thr in ((50, -1.0), (7, 0.9), (100, 0.2)):
+        _check_lists(engine.find_similar_pairs(sig, 64, k, thr, variant=variant), oracle.topk(sig, 64, k, thr)[:3])
+    sig = synthetic.gen_signatures(5000, 128, seed=2)   # iid: all distances near 64
+    for k, thr in ((50, -1.0), (20, 0.2)):
+        _check_lists(engine.find_similar_pairs(sig, 128, k, thr, variant=variant), oracle.topk(sig, 128, k, thr)[:3])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_row_blocks_and_ragged_sizes(engine, oracle, variant):
+    """Row-block calls (the multi-GPU partition) and sizes that are not multiples of any tile."""
+    sig = synthetic.gen_signatures(2049, 1024, seed=11, clusters=13)
+    want_ids, want_sims, want_used, _ = oracle.topk(sig, 1024, 50, 0.2)
+    parts = [(0, 700), (700, 701), (701, 2049)]
+    for b, e in parts:
+        got = engine.find_similar_pairs(sig, 1024, 50, 0.2, variant=variant, row_begin=b, row_end=e)
+        _check_lists(got, (want_ids[b:e], want_sims[b:e], want_used[b:e]))
+    # empty row range and k larger than the number of other cells
+    ids, sims, used = engine.find_similar_pairs(sig, 1024, 5, 0.2, variant=variant, row_begin=5, row_end=5)
+    assert ids.shape == (0, 5)
+    small = sig[:7]
+    _check_lists(engine.find_similar_pairs(small, 1024, 50, -1.0, variant=variant), oracle.topk(small, 1024, 50, -1.0)[:3])
+    one = sig[:1]
+    ids, sims, used = engine.find_similar_pairs(one, 1024, 3, -1.0, variant=variant)
+    assert used[0] == 0
+    # a threshold nothing passes
+    ids, sims, used = engine.find_similar_pairs(sig[:300], 1024, 10, 1.0, variant=variant)
+    assert np.all(used == 0) and np.all(ids == 0)
+
+
+def test_empty_and_degenerate_cells(engine, oracle):
+    toc = np.array([0, 0, 3, 3, 8, 8], np.uint64)
+    genes = np.array([0, 2, 4, 0, 1, 2, 3, 4], np.uint32)
+    counts = np.array([1, 2, 3, 1, 1, 1, 1, 1], np.float32)
+    U = em2.generate_lsh_vectors(5, 70, 3)
+    s1, _ = oracle.cell_sums(toc, counts)
+    want, _ = oracle.signatures(toc, genes, counts, s1, U)
+    sig = engine.compute_signatures(toc, counts, U, gene_ids=genes)
+    assert np.array_equal(sig, want)
+    _check_lists(engine.find_similar_pairs(sig, 70, 3, -1.0), oracle.topk(sig, 70, 3, -1.0)[:3])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_size_independent_properties_at_scale(engine, oracle, variant):
+    """At a size the oracle cannot finish in seconds (65k cells): properties that need no full oracle.
+    (1) sampled rows equal the oracle's rows; (2) lists are sorted by (similarity desc, id asc), contain
+    no self and no duplicates; (3) every stored similarity equals table[hamming(row, id)];
+    (4) planted duplicates are found with similarity 1; (5) idempotence."""
+    N, L, k = 65536 + 77, 1024, 50
+    sig = synthetic.gen_signatures(N, L, seed=21, clusters=200)
+    sig[N - 1] = sig[5]
+    sig[N - 2] = sig[5]
+    ids, sims, used = engine.find_similar_pairs(sig, L, k, 0.2, variant=variant)
+    ids2, sims2, used2 = engine.find_similar_pairs(sig, L, k, 0.2, variant=variant)
+    assert np.array_equal(ids, ids2) and np.array_equal(sims, sims2) and np.array_equal(used, used2)
+    rows = np.r_[0, 5, 4097, N - 2, N - 1, np.random.default_rng(0).integers(0, N, 40)]
+    for r in rows:
+        wi, ws, wu, _ = oracle.topk(sig, L, k, 0.2, int(r), int(r) + 1)
+        _check_lists((ids[r:r + 1], sims[r:r + 1], used[r:r + 1]), (wi, ws, wu))
+    assert ids[5, 0] == N - 2 and ids[5, 1] == N - 1 and sims[5, 0] == 1.0 and sims[5, 1] == 1.0
+    table = oracle.similarity_table(L).astype(np.float32)
+    sample = np.random.default_rng(1).integers(0, N, 2000)
+    for r in sample:
+        u = int(used[r])
+        row_ids, row_sims = ids[r, :u], sims[r, :u]
+        assert r not in row_ids and len(set(row_ids.tolist())) == u
+        m = oracle.mismatch_counts(sig, np.full(u, r, np.uint32), row_ids)
+        assert np.array_equal(table[m], row_sims)
+        key = m.astype(np.uint64) << np.uint64(32) | row_ids.astype(np.uint64)
+        assert np.all(np.diff(key.astype(np.int64)) > 0)
+        assert np.all(ids[r, u:] == 0)
