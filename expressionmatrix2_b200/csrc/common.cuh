@@ -98,6 +98,8 @@ struct ScanPlan {
     uint64_t segmentCols;  // columns per segment (multiple of the column tile)
     uint32_t cap;          // candidate buffer capacity per (segment,row)
 };
+ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount, uint64_t k, uint32_t tileCols,
+                      uint32_t rowsPerCta, uint32_t ctasPerSm);
 int launchFinalize(em2_context* ctx, const ScanPlan& plan, uint64_t rows, uint64_t k, const uint64_t* cand,
                    const uint32_t* candCount, const float* lut, em2_pair* pairs, uint32_t* usedCount,
                    cudaStream_t s);

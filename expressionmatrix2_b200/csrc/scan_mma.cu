@@ -1,14 +1,473 @@
-// tcgen05 int8 variant of the Hamming scan -- placeholder until the kernel lands (fails loudly).
+// All-pairs Hamming scan with fused per-cell top-k -- tcgen05 int8 tensor-core variant (sm_100a).
+//
+// Hamming distance is a dense contraction: with signature bits encoded as +-1 int8,
+//     dot(x, y) = K - 2 * hamming(x, y)      (K = bit count padded to a multiple of 128; pad bits agree)
+// so the all-pairs scan is the int8 GEMM  D = E * E^T  with exact s32 accumulation, and the top-k
+// selection is its epilogue.  Same selection semantics and candidate machinery as the XOR/POPC variant
+// (scan_popc.cu, topk.cuh); Hamming distances are bit-exact because every partial sum is an integer
+// far below 2^31.
+//
+// Replaces (reference): countMismatches src/BitSet.hpp:277-288 + the findSimilarPairs4 pair loop
+// src/ExpressionMatrixLsh.cpp:218-269.  Nothing here is derived from src/Lsh.cl.
+//
+// Kernel structure (one persistent CTA per SM, 192 threads, warp specialised):
+//   warps 0-3  epilogue : thread t owns accumulator row t (TMEM lane t).  tcgen05.ld 32 columns at a
+//                         time, one compare per candidate against the row's running bound
+//                         (dot > K - 2*tau  <=>  hamming < tau), rare survivors appended to the
+//                         row's candidate buffer (topk.cuh).
+//   warp 4     producer : TMA (cp.async.bulk.tensor, 128B swizzle).  The A operand -- 128 query rows x
+//                         K bytes -- is loaded ONCE per work item and stays resident in shared memory
+//                         (row stationary); the B operand streams 256-column x 128-byte K-chunks
+//                         through a ring of stages.
+//   warp 5     MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=32,
+//                         accumulators in TMEM, double buffered (2 x 256 columns = all 512), so the
+//                         epilogue of tile t overlaps the MMAs of tile t+1.  tcgen05.commit releases
+//                         shared-memory stages and publishes accumulators through mbarriers.
+// Work item = (128-row block, column segment); items are dealt round-robin to the persistent CTAs.
 #include "common.cuh"
+#include "topk.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+
 namespace em2 {
-int launchScanMma(em2_context* ctx, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, int64_t,
-                  const float*, em2_pair*, uint32_t*, cudaStream_t)
+
+namespace {
+
+constexpr int kRowsPerItem = 128;     // UMMA M
+constexpr int kTileN = 256;           // UMMA N
+constexpr int kChunkBytes = 128;      // K bytes per TMA box / swizzle atom
+constexpr int kUmmaK = 32;            // K per tcgen05.mma for 8-bit operands
+constexpr int kThreads = 192;
+constexpr int kMaxPanels = 8;         // K <= 1024
+constexpr uint32_t kPanelBytes = kRowsPerItem * kChunkBytes;   // 16 KB
+constexpr uint32_t kStageBytes = kTileN * kChunkBytes;         // 32 KB
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
 {
-    return fail(ctx, EM2_ERR_INVALID, "EM2_VARIANT_MMA_I8 is not available in this build");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
 }
-int launchMismatchBlockMma(em2_context* ctx, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint16_t*,
-                           cudaStream_t)
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
 {
-    return fail(ctx, EM2_ERR_INVALID, "EM2_VARIANT_MMA_I8 is not available in this build");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbarArrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smemAddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tmaLoad2d(void* smemDst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smemAddr(smemDst)), "l"(map), "r"(smemAddr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05FenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05FenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05Commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mmaI8(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmemD),
+        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor: K-major, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart
+// (encoding per the PTX ISA tcgen05 matrix-descriptor table; version field = 1 on sm_100).
+__device__ __forceinline__ uint64_t makeSmemDesc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= uint64_t((saddr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+    d |= uint64_t(1) << 16;                          // leading byte offset (ignored for swizzled K-major; 1)
+    d |= uint64_t(1024 >> 4) << 32;                  // stride byte offset = 1024 B between 8-row groups
+    d |= uint64_t(1) << 46;                          // descriptor version
+    d |= uint64_t(2) << 61;                          // layout type: SWIZZLE_128B
+    return d;
+}
+
+// Instruction descriptor: kind::i8, A/B signed 8-bit K-major, D s32, M=128, N=256.
+constexpr uint32_t kInstrDesc = (2u << 4)                        // c_format = S32
+                                | (1u << 7)                      // a_format = signed 8-bit
+                                | (1u << 10)                     // b_format = signed 8-bit
+                                | (uint32_t(kTileN >> 3) << 17)  // n_dim
+                                | (uint32_t(kRowsPerItem >> 4) << 24);   // m_dim
+
+struct MmaParams {
+    uint64_t cellCount;      // N (columns)
+    uint64_t rowBegin, rows; // scanned rows [rowBegin, rowBegin + rows)
+    uint32_t K;              // padded bit count == bytes per encoded row
+    uint32_t panels;         // K / 128
+    uint32_t stages;         // B ring depth
+    uint32_t segments;
+    uint64_t segmentCols;
+    uint32_t rowBlocks;
+    uint32_t k, cap, tau0;
+    uint64_t* cand;
+    uint32_t* candCount;
+    unsigned long long* appendedTotal;
+    uint16_t* dump;          // optional: all distances of the scanned rows (tests)
+};
+
+template <bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1)
+scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const MmaParams p)
+{
+    extern __shared__ uint8_t smemRaw[];
+    // carve: [A panels][B stages][barriers]; 1024-byte alignment for the 128B swizzle
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = base;
+    uint8_t* smB = smA + size_t(p.panels) * kPanelBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + size_t(p.stages) * kStageBytes);
+    uint64_t* aFull = bars + 0;
+    uint64_t* aEmpty = bars + 1;
+    uint64_t* accFull = bars + 2;    // [2]
+    uint64_t* accEmpty = bars + 4;   // [2]
+    uint64_t* bFull = bars + 6;      // [stages]
+    uint64_t* bEmpty = bFull + p.stages;
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bEmpty + p.stages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbarInit(aFull, 1);
+        mbarInit(aEmpty, 1);
+        for (int i = 0; i < 2; i++) {
+            mbarInit(accFull + i, 1);
+            mbarInit(accEmpty + i, 128);
+        }
+        for (uint32_t i = 0; i < p.stages; i++) {
+            mbarInit(bFull + i, 1);
+            mbarInit(bEmpty + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smemAddr(tmemSlot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05FenceBefore();
+    __syncthreads();
+    tcgen05FenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+
+    const uint32_t items = p.rowBlocks * p.segments;
+    const uint32_t tilesPerSeg = uint32_t((p.segmentCols + kTileN - 1) / kTileN);
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t itemIter = 0, bIter = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+                const uint32_t rb = item / p.segments, seg = item % p.segments;
+                const int32_t row0 = int32_t(p.rowBegin + uint64_t(rb) * kRowsPerItem);
+                mbarWait(aEmpty, (itemIter & 1) ^ 1);
+                mbarExpectTx(aFull, p.panels * kPanelBytes);
+                for (uint32_t pn = 0; pn < p.panels; pn++)
+                    tmaLoad2d(smA + size_t(pn) * kPanelBytes, &mapA, aFull, int32_t(pn * kChunkBytes), row0);
+                const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
+                const uint64_t colEnd = min(colBegin + p.segmentCols, p.cellCount);
+                const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
+                for (uint32_t t = 0; t < tiles; t++) {
+                    const int32_t col0 = int32_t(colBegin + uint64_t(t) * kTileN);
+                    for (uint32_t kc = 0; kc < p.panels; kc++, bIter++) {
+                        const uint32_t s = bIter % p.stages;
+                        mbarWait(bEmpty + s, ((bIter / p.stages) & 1) ^ 1);
+                        mbarExpectTx(bFull + s, kStageBytes);
+                        tmaLoad2d(smB + size_t(s) * kStageBytes, &mapB, bFull + s, int32_t(kc * kChunkBytes), col0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t itemIter = 0, bIter = 0, tileIter = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+                const uint32_t seg = item % p.segments;
+                const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
+                const uint64_t colEnd = min(colBegin + p.segmentCols, p.cellCount);
+                const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
+                mbarWait(aFull, itemIter & 1);
+                tcgen05FenceAfter();
+                for (uint32_t t = 0; t < tiles; t++, tileIter++) {
+                    const uint32_t buf = tileIter & 1;
+                    mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
+                    tcgen05FenceAfter();
+                    const uint32_t tmemD = tmemBase + buf * kTileN;
+                    for (uint32_t kc = 0; kc < p.panels; kc++, bIter++) {
+                        const uint32_t s = bIter % p.stages;
+                        mbarWait(bFull + s, (bIter / p.stages) & 1);
+                        tcgen05FenceAfter();
+                        const uint32_t aAddr = smemAddr(smA + size_t(kc) * kPanelBytes);
+                        const uint32_t bAddr = smemAddr(smB + size_t(s) * kStageBytes);
+#pragma unroll
+                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++) {
+                            mmaI8(tmemD, makeSmemDesc(aAddr + ks * kUmmaK), makeSmemDesc(bAddr + ks * kUmmaK), kInstrDesc,
+                                  (kc | uint32_t(ks)) != 0u);
+                        }
+                        tcgen05Commit(bEmpty + s);           // stage reusable once these MMAs have read it
+                    }
+                    tcgen05Commit(accFull + buf);            // accumulator complete
+                }
+                tcgen05Commit(aEmpty);                       // A panels reusable
+            }
+        }
+    } else {
+        // ===================== epilogue: thread == accumulator row =====================
+        const uint32_t dotK = p.K;
+        uint32_t tileIter = 0;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const uint32_t rb = item / p.segments, seg = item % p.segments;
+            const uint64_t localRow = uint64_t(rb) * kRowsPerItem + threadIdx.x;
+            const bool valid = localRow < p.rows;
+            const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
+            const uint64_t colEndLong = min(colBegin + p.segmentCols, p.cellCount);
+            const uint32_t colEnd = uint32_t(colEndLong);
+            const uint32_t tiles = uint32_t((colEndLong - colBegin + kTileN - 1) / kTileN);
+            RowState st;
+            st.rowId = valid ? uint32_t(p.rowBegin + localRow) : 0xffffffffu;
+            st.count = 0;
+            st.appended = 0;
+            st.tau = valid ? p.tau0 : 0;
+            st.buf = p.cand + (uint64_t(seg) * p.rows + (valid ? localRow : 0)) * p.cap;
+            int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.tau);      // hamming < tau  <=>  dot > K - 2 tau
+            for (uint32_t t = 0; t < tiles; t++, tileIter++) {
+                const uint32_t buf = tileIter & 1;
+                mbarWait(accFull + buf, (tileIter >> 1) & 1);
+                tcgen05FenceAfter();
+                const uint32_t idBase = uint32_t(colBegin) + t * kTileN;
+                const uint32_t taddr = tmemBase + buf * kTileN + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+                for (int c = 0; c < kTileN; c += 32) {
+                    uint32_t v[32];
+                    tmemLoad32(taddr + c, v);
+                    tmemLoadWait();
+                    if (DUMP) {
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const uint32_t id = idBase + c + j;
+                                if (id < colEnd)
+                                    p.dump[localRow * p.cellCount + id] = uint16_t((int32_t(dotK) - int32_t(v[j])) >> 1);
+                            }
+                        }
+                    } else {
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) any |= (int32_t(v[j]) > dotThr);
+                        if (any) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (int32_t(v[j]) > dotThr) {
+                                    const uint32_t ham = uint32_t(int32_t(dotK) - int32_t(v[j])) >> 1;
+                                    consider(st, ham, idBase + c + j, colEnd, p.k, p.cap);
+                                    dotThr = int32_t(dotK) - 2 * int32_t(st.tau);
+                                }
+                            }
+                        }
+                    }
+                }
+                tcgen05FenceBefore();
+                mbarArrive(accEmpty + buf);
+            }
+            if (!DUMP && valid) {
+                p.candCount[uint64_t(seg) * p.rows + localRow] = st.count;
+                if (p.appendedTotal && st.appended) atomicAdd(p.appendedTotal, (unsigned long long)st.appended);
+            }
+        }
+    }
+
+    tcgen05FenceBefore();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmemBase) : "memory");
+    }
+}
+
+// +-1 int8 expansion of the packed signatures: E[n][p] = bit p set ? +1 : -1, p < K; bits at and
+// beyond lshCount (zero in the packed words, or beyond them) encode as -1 in every row.
+__global__ void encodeKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCount, uint32_t K,
+                             uint8_t* __restrict__ enc)
+{
+    const uint32_t groupsPerRow = K / 16;      // 16 bits -> 16 bytes per thread
+    const uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (idx >= cellCount * groupsPerRow) return;
+    const uint64_t row = idx / groupsPerRow;
+    const uint32_t g = uint32_t(idx - row * groupsPerRow);
+    const uint32_t w = g >> 2;
+    uint32_t bits = 0;
+    if (w < W) bits = uint32_t(sig[row * W + w] >> (48 - 16 * (g & 3))) & 0xFFFFu;   // MSB-first
+    uint32_t out[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t bit = (bits >> (15 - (4 * q + b))) & 1u;
+            word |= (bit ? 0x01u : 0xFFu) << (8 * b);
+        }
+        out[q] = word;
+    }
+    *reinterpret_cast<uint4*>(enc + row * K + size_t(g) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int makeMap(em2_context* ctx, CUtensorMap* map, void* base, uint64_t rows, uint32_t K, uint32_t boxRows)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        EM2_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+        if (!f || q != cudaDriverEntryPointSuccess) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    const cuuint64_t dims[2] = {K, rows};
+    const cuuint64_t strides[1] = {K};
+    const cuuint32_t box[2] = {uint32_t(kChunkBytes), boxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+    return EM2_OK;
+}
+
+int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount, uint64_t rowBegin,
+           uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut, em2_pair* pairs, uint32_t* usedCount,
+           uint16_t* dump, cudaStream_t s)
+{
+    const uint64_t rows = rowEnd - rowBegin;
+    const uint32_t W = uint32_t(wordCount(lshCount));
+    const uint32_t K = uint32_t(roundUp(lshCount, kChunkBytes));
+    if (K > kMaxPanels * kChunkBytes)
+        return fail(ctx, EM2_ERR_INVALID, "EM2_VARIANT_MMA_I8 supports lshCount <= 1024 (use EM2_VARIANT_POPC)");
+    if (cellCount > 0x7fffff00ull) return fail(ctx, EM2_ERR_INVALID, "cellCount too large for the MMA variant");
+
+    // 1. encode
+    void* enc = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_ENC, cellCount * K, &enc));
+    {
+        const uint64_t threads = cellCount * (K / 16);
+        encodeKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(signatures, W, cellCount, K, static_cast<uint8_t*>(enc));
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+    }
+
+    // 2. plan + scratch
+    MmaParams p{};
+    const uint32_t panels = K / kChunkBytes;
+    const size_t avail = 227 * 1024 - 1024 - 256 - size_t(panels) * kPanelBytes;
+    p.stages = uint32_t(std::min<size_t>(6, avail / kStageBytes));
+    ScanPlan plan = makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kRowsPerItem, 1);
+    if (dump) {
+        plan.segments = 1;
+        plan.segmentCols = roundUp(cellCount, kTileN);
+    }
+    void* cand = nullptr;
+    void* candCount = nullptr;
+    void* counters = nullptr;
+    if (!dump) {
+        EM2_TRY(reserve(ctx, em2_context::S_CAND, size_t(plan.segments) * rows * plan.cap * sizeof(uint64_t), &cand));
+        EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(plan.segments) * rows * sizeof(uint32_t), &candCount));
+    }
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
+    p.cellCount = cellCount;
+    p.rowBegin = rowBegin;
+    p.rows = rows;
+    p.K = K;
+    p.panels = panels;
+    p.segments = plan.segments;
+    p.segmentCols = plan.segmentCols;
+    p.rowBlocks = plan.rowBlocks;
+    p.k = uint32_t(k);
+    p.cap = plan.cap;
+    p.tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
+    p.cand = static_cast<uint64_t*>(cand);
+    p.candCount = static_cast<uint32_t*>(candCount);
+    p.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
+    p.dump = dump;
+
+    CUtensorMap mapA, mapB;
+    EM2_TRY(makeMap(ctx, &mapA, enc, cellCount, K, kRowsPerItem));
+    EM2_TRY(makeMap(ctx, &mapB, enc, cellCount, K, kTileN));
+
+    const size_t smem = 1024 + size_t(panels) * kPanelBytes + size_t(p.stages) * kStageBytes + 256;
+    const uint32_t items = plan.rowBlocks * plan.segments;
+    const unsigned grid = unsigned(std::min<uint32_t>(items, uint32_t(ctx->smCount)));
+    if (dump) {
+        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        scanMmaKernel<true><<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+    } else {
+        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        scanMmaKernel<false><<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+    }
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+    if (dump) return EM2_OK;
+    return launchFinalize(ctx, plan, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s);
+}
+
+}  // namespace
+
+int launchScanMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                  uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
+                  em2_pair* pairs, uint32_t* usedCount, cudaStream_t s)
+{
+    return runMma(ctx, signatures, cellCount, lshCount, rowBegin, rowEnd, k, mismatchMax, lut, pairs, usedCount,
+                  nullptr, s);
+}
+
+int launchMismatchBlockMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                           uint64_t rowBegin, uint64_t rowEnd, uint16_t* out, cudaStream_t s)
+{
+    return runMma(ctx, signatures, cellCount, lshCount, rowBegin, rowEnd, 1, int64_t(lshCount), nullptr, nullptr,
+                  nullptr, out, s);
+}
+
 }  // namespace em2

@@ -24,6 +24,7 @@
 //   * the finalize kernel orders each row's survivors by (mismatch, id), looks up cos(pi m/L) in the
 //     host-computed float table (bit-identical similarities) and writes the SimilarPairs payload.
 #include "common.cuh"
+#include "topk.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -114,57 +115,6 @@ template <int W32, int CSA> __device__ __forceinline__ uint32_t hammingRow(const
             twos += __popc(c[t]);
         }
         return ones + 2 * twos + 4 * fours;
-    }
-}
-
-// Exact in-place prune of a per-row candidate buffer to its k smallest (mismatch, id) keys.
-// Invariant kept: among entries with equal mismatch count, ids are in increasing order (appends arrive
-// in increasing id; the compaction below is stable), so "the r smallest ids among the ties" are simply
-// the first r ties.
-__device__ __noinline__ void pruneCandidates(uint64_t* buf, uint32_t& count, uint32_t k, uint32_t& tau)
-{
-    uint32_t lo = 0, hi = tau - 1;          // every stored mismatch count is < tau
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        uint32_t c = 0;
-        for (uint32_t i = 0; i < count; i++) c += (uint32_t(buf[i] >> 32) <= mid);
-        if (c >= k) hi = mid;
-        else lo = mid + 1;
-    }
-    const uint32_t h = lo;
-    uint32_t less = 0;
-    for (uint32_t i = 0; i < count; i++) less += (uint32_t(buf[i] >> 32) < h);
-    uint32_t r = k - less;                  // ties at h that still fit
-    uint32_t j = 0;
-    for (uint32_t i = 0; i < count; i++) {
-        const uint64_t key = buf[i];
-        const uint32_t m = uint32_t(key >> 32);
-        bool keep = m < h;
-        if (m == h && r > 0) {
-            keep = true;
-            r--;
-        }
-        if (keep) buf[j++] = key;
-    }
-    count = j;
-    tau = h;                                // later ids are larger: ties at h can no longer enter
-}
-
-struct RowState {
-    uint64_t* buf;
-    uint32_t count;
-    uint32_t tau;
-    uint32_t rowId;
-    uint32_t appended;
-};
-
-__device__ __forceinline__ void consider(RowState& st, uint32_t ham, uint32_t id, uint32_t colEnd, uint32_t k,
-                                         uint32_t cap)
-{
-    if (ham < st.tau && id < colEnd && id != st.rowId) {
-        st.buf[st.count++] = (uint64_t(ham) << 32) | id;
-        st.appended++;
-        if (st.count == cap) pruneCandidates(st.buf, st.count, k, st.tau);
     }
 }
 
