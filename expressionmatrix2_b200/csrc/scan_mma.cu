@@ -11,18 +11,20 @@
 // src/ExpressionMatrixLsh.cpp:218-269.  Nothing here is derived from src/Lsh.cl.
 //
 // Kernel structure (one persistent CTA per SM, 192 threads, warp specialised):
-//   warps 0-3  epilogue : thread t owns accumulator row t (TMEM lane t).  tcgen05.ld 32 columns at a
-//                         time, one compare per candidate against the row's running bound
-//                         (dot > K - 2*tau  <=>  hamming < tau), rare survivors appended to the
-//                         row's candidate buffer (topk.cuh).
-//   warp 4     producer : TMA (cp.async.bulk.tensor, 128B swizzle).  The A operand -- 128 query rows x
-//                         K bytes -- is loaded ONCE per work item and stays resident in shared memory
-//                         (row stationary); the B operand streams 256-column x 128-byte K-chunks
-//                         through a ring of stages.
-//   warp 5     MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=32,
-//                         accumulators in TMEM, double buffered (2 x 256 columns = all 512), so the
-//                         epilogue of tile t overlaps the MMAs of tile t+1.  tcgen05.commit releases
-//                         shared-memory stages and publishes accumulators through mbarriers.
+//   warps 0-3  epilogue : thread t owns query row t of the work item == TMEM lane t.  At the start of an
+//                         item it writes its row's K encoded bytes into TMEM (tcgen05.st): the A operand
+//                         is ROW STATIONARY IN TENSOR MEMORY (128 lanes x 256 columns) for the whole
+//                         sweep and never touches shared memory again.  Per column tile it reads the
+//                         accumulator with tcgen05.ld, 32 columns at a time: one compare per candidate
+//                         against the row's running bound (dot > K - 2*tau  <=>  hamming < tau), rare
+//                         survivors appended to the row's candidate buffer (topk.cuh).
+//   warp 4     producer : TMA (cp.async.bulk.tensor, 128B swizzle) streams the B operand -- 128 columns
+//                         x 128-byte K-chunks (16 KB) -- through a deep ring (all of shared memory).
+//   warp 5     MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (A from TMEM, B from
+//                         shared memory), M=128 N=128 K=32; accumulators in TMEM, double buffered
+//                         (2 x 128 columns), so the epilogue of tile t overlaps the MMAs of tile t+1.
+//                         tcgen05.commit releases shared-memory stages and publishes accumulators
+//                         through mbarriers.  TMEM map: [0,128) acc0, [128,256) acc1, [256,512) A.
 // Work item = (128-row block, column segment); items are dealt round-robin to the persistent CTAs.
 #include "common.cuh"
 #include "topk.cuh"
@@ -36,13 +38,16 @@ namespace em2 {
 namespace {
 
 constexpr int kRowsPerItem = 128;     // UMMA M
-constexpr int kTileN = 256;           // UMMA N
+constexpr int kTileN = 128;           // UMMA N
 constexpr int kChunkBytes = 128;      // K bytes per TMA box / swizzle atom
 constexpr int kUmmaK = 32;            // K per tcgen05.mma for 8-bit operands
 constexpr int kThreads = 192;
 constexpr int kMaxPanels = 8;         // K <= 1024
-constexpr uint32_t kPanelBytes = kRowsPerItem * kChunkBytes;   // 16 KB
-constexpr uint32_t kStageBytes = kTileN * kChunkBytes;         // 32 KB
+constexpr uint32_t kChunkTileBytes = kTileN * kChunkBytes;     // 16 KB: one K-chunk of a column tile
+constexpr int kChunksPerStage = 2;                             // a ring stage carries two K-chunks (32 KB)
+constexpr uint32_t kStageBytes = kChunksPerStage * kChunkTileBytes;
+constexpr int kStages = 6;                                     // 192 KB ring
+constexpr uint32_t kTmemA = 256;      // first TMEM column of the A operand
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -87,17 +92,30 @@ __device__ __forceinline__ void tcgen05Commit(uint64_t* bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smemAddr(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mmaI8(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void mmaI8(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmemD),
-        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+        "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tmemStore32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+          "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmemStoreWait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -111,6 +129,21 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// v[j] for a run-time j without spilling the array to local memory: a 5-level select tree (31 SEL).
+__device__ __forceinline__ int32_t pick32(const uint32_t (&v)[32], int j)
+{
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = (j & 16) ? v[16 + i] : v[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = (j & 8) ? a[8 + i] : a[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) c[i] = (j & 4) ? b[4 + i] : b[i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) d[i] = (j & 2) ? c[2 + i] : c[i];
+    return int32_t((j & 1) ? d[1] : d[0]);
+}
 
 // Shared-memory matrix descriptor: K-major, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart
 // (encoding per the PTX ISA tcgen05 matrix-descriptor table; version field = 1 on sm_100).
@@ -150,33 +183,29 @@ struct MmaParams {
 
 template <bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
-scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const MmaParams p)
+scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restrict__ enc, const MmaParams p)
 {
     extern __shared__ uint8_t smemRaw[];
-    // carve: [A panels][B stages][barriers]; 1024-byte alignment for the 128B swizzle
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smA = base;
-    uint8_t* smB = smA + size_t(p.panels) * kPanelBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + size_t(p.stages) * kStageBytes);
-    uint64_t* aFull = bars + 0;
-    uint64_t* aEmpty = bars + 1;
+    // carve: [B stages][barriers]; 1024-byte alignment for the 128B swizzle
+    uint8_t* smB = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + size_t(kStages) * kStageBytes);
+    uint64_t* aFull = bars + 0;      // epilogue threads -> MMA: the A operand of this item is in TMEM
     uint64_t* accFull = bars + 2;    // [2]
     uint64_t* accEmpty = bars + 4;   // [2]
     uint64_t* bFull = bars + 6;      // [stages]
-    uint64_t* bEmpty = bFull + p.stages;
-    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bEmpty + p.stages);
+    uint64_t* bEmpty = bFull + kStages;
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bEmpty + kStages);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        mbarInit(aFull, 1);
-        mbarInit(aEmpty, 1);
+        mbarInit(aFull, 128);
         for (int i = 0; i < 2; i++) {
             mbarInit(accFull + i, 1);
             mbarInit(accEmpty + i, 128);
         }
-        for (uint32_t i = 0; i < p.stages; i++) {
+        for (uint32_t i = 0; i < kStages; i++) {
             mbarInit(bFull + i, 1);
             mbarInit(bEmpty + i, 1);
         }
@@ -193,29 +222,31 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t tmemBase = *tmemSlot;
 
     const uint32_t items = p.rowBlocks * p.segments;
-    const uint32_t tilesPerSeg = uint32_t((p.segmentCols + kTileN - 1) / kTileN);
 
     if (warp == 4) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (B operand) =====================
         if (lane == 0) {
-            uint32_t itemIter = 0, bIter = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
-                const uint32_t rb = item / p.segments, seg = item % p.segments;
-                const int32_t row0 = int32_t(p.rowBegin + uint64_t(rb) * kRowsPerItem);
-                mbarWait(aEmpty, (itemIter & 1) ^ 1);
-                mbarExpectTx(aFull, p.panels * kPanelBytes);
-                for (uint32_t pn = 0; pn < p.panels; pn++)
-                    tmaLoad2d(smA + size_t(pn) * kPanelBytes, &mapA, aFull, int32_t(pn * kChunkBytes), row0);
+            uint32_t stage = 0, phase = 0;
+            const uint32_t stagesPerTile = (p.panels + kChunksPerStage - 1) / kChunksPerStage;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const uint32_t seg = item % p.segments;
                 const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
                 const uint64_t colEnd = min(colBegin + p.segmentCols, p.cellCount);
                 const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
                 for (uint32_t t = 0; t < tiles; t++) {
                     const int32_t col0 = int32_t(colBegin + uint64_t(t) * kTileN);
-                    for (uint32_t kc = 0; kc < p.panels; kc++, bIter++) {
-                        const uint32_t s = bIter % p.stages;
-                        mbarWait(bEmpty + s, ((bIter / p.stages) & 1) ^ 1);
-                        mbarExpectTx(bFull + s, kStageBytes);
-                        tmaLoad2d(smB + size_t(s) * kStageBytes, &mapB, bFull + s, int32_t(kc * kChunkBytes), col0);
+                    for (uint32_t j = 0; j < stagesPerTile; j++) {
+                        const uint32_t kc0 = j * kChunksPerStage;
+                        const uint32_t chunks = min(uint32_t(kChunksPerStage), p.panels - kc0);
+                        mbarWait(bEmpty + stage, phase ^ 1);
+                        mbarExpectTx(bFull + stage, chunks * kChunkTileBytes);
+                        uint8_t* dst = smB + size_t(stage) * kStageBytes;
+                        for (uint32_t c = 0; c < chunks; c++)
+                            tmaLoad2d(dst + c * kChunkTileBytes, &mapB, bFull + stage, int32_t((kc0 + c) * kChunkBytes), col0);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
             }
@@ -223,7 +254,8 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t itemIter = 0, bIter = 0, tileIter = 0;
+            uint32_t itemIter = 0, tileIter = 0, stage = 0, phase = 0;
+            const uint32_t stagesPerTile = (p.panels + kChunksPerStage - 1) / kChunksPerStage;
             for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
                 const uint32_t seg = item % p.segments;
                 const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
@@ -236,27 +268,34 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
                     tcgen05FenceAfter();
                     const uint32_t tmemD = tmemBase + buf * kTileN;
-                    for (uint32_t kc = 0; kc < p.panels; kc++, bIter++) {
-                        const uint32_t s = bIter % p.stages;
-                        mbarWait(bFull + s, (bIter / p.stages) & 1);
+                    uint32_t aCol = tmemBase + kTmemA;
+                    uint32_t first = 0;                      // 0 on the tile's first MMA: overwrite the accumulator
+                    for (uint32_t j = 0; j < stagesPerTile; j++) {
+                        const uint32_t chunks = min(uint32_t(kChunksPerStage), p.panels - j * kChunksPerStage);
+                        mbarWait(bFull + stage, phase);
                         tcgen05FenceAfter();
-                        const uint32_t aAddr = smemAddr(smA + size_t(kc) * kPanelBytes);
-                        const uint32_t bAddr = smemAddr(smB + size_t(s) * kStageBytes);
+                        uint32_t bAddr = smemAddr(smB + size_t(stage) * kStageBytes);
+                        for (uint32_t c = 0; c < chunks; c++, bAddr += kChunkTileBytes) {
 #pragma unroll
-                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++) {
-                            mmaI8(tmemD, makeSmemDesc(aAddr + ks * kUmmaK), makeSmemDesc(bAddr + ks * kUmmaK), kInstrDesc,
-                                  (kc | uint32_t(ks)) != 0u);
+                            for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++, aCol += kUmmaK / 4) {
+                                mmaI8(tmemD, aCol, makeSmemDesc(bAddr + ks * kUmmaK), kInstrDesc, first);
+                                first = 1;
+                            }
                         }
-                        tcgen05Commit(bEmpty + s);           // stage reusable once these MMAs have read it
+                        tcgen05Commit(bEmpty + stage);       // stage reusable once these MMAs have read it
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
-                    tcgen05Commit(accFull + buf);            // accumulator complete
-                }
-                tcgen05Commit(aEmpty);                       // A panels reusable
+                    tcgen05Commit(accFull + buf);            // accumulator complete (and, on the item's last
+                }                                            // tile, every read of the A operand is done)
             }
         }
     } else {
-        // ===================== epilogue: thread == accumulator row =====================
+        // ===================== epilogue: thread == query row == TMEM lane =====================
         const uint32_t dotK = p.K;
+        const uint32_t laneField = uint32_t(warp * 32) << 16;
         uint32_t tileIter = 0;
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
             const uint32_t rb = item / p.segments, seg = item % p.segments;
@@ -266,6 +305,28 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const uint64_t colEndLong = min(colBegin + p.segmentCols, p.cellCount);
             const uint32_t colEnd = uint32_t(colEndLong);
             const uint32_t tiles = uint32_t((colEndLong - colBegin + kTileN - 1) / kTileN);
+
+            // A operand: this thread's encoded row -> TMEM lane, columns [kTmemA, kTmemA + K/4).
+            // The previous item's MMAs have all completed (its last accFull was waited on below).
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(enc + (p.rowBegin + (valid ? localRow : 0)) * uint64_t(p.K));
+                for (uint32_t c = 0; c < p.K / 4; c += 32) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const uint4 x = valid ? __ldg(src + c / 4 + q) : make_uint4(0, 0, 0, 0);
+                        v[4 * q] = x.x;
+                        v[4 * q + 1] = x.y;
+                        v[4 * q + 2] = x.z;
+                        v[4 * q + 3] = x.w;
+                    }
+                    tmemStore32(tmemBase + laneField + kTmemA + c, v);
+                }
+                tmemStoreWait();
+                tcgen05FenceBefore();
+                mbarArrive(aFull);
+            }
+
             RowState st;
             st.rowId = valid ? uint32_t(p.rowBegin + localRow) : 0xffffffffu;
             st.count = 0;
@@ -278,7 +339,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 mbarWait(accFull + buf, (tileIter >> 1) & 1);
                 tcgen05FenceAfter();
                 const uint32_t idBase = uint32_t(colBegin) + t * kTileN;
-                const uint32_t taddr = tmemBase + buf * kTileN + (uint32_t(warp * 32) << 16);
+                const uint32_t taddr = tmemBase + buf * kTileN + laneField;
 #pragma unroll 1
                 for (int c = 0; c < kTileN; c += 32) {
                     uint32_t v[32];
@@ -294,18 +355,22 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             }
                         }
                     } else {
-                        bool any = false;
+                        int32_t mx = int32_t(v[0]);
 #pragma unroll
-                        for (int j = 0; j < 32; j++) any |= (int32_t(v[j]) > dotThr);
-                        if (any) {
+                        for (int j = 1; j < 32; j++) mx = max(mx, int32_t(v[j]));
+                        if (mx > dotThr) {
+                            // Rare per lane, but some lane of the warp is here most of the time: keep it
+                            // straight-line.  Bit mask of the passing columns, then one candidate per set bit.
+                            uint32_t mask = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if (int32_t(v[j]) > dotThr) {
-                                    const uint32_t ham = uint32_t(int32_t(dotK) - int32_t(v[j])) >> 1;
-                                    consider(st, ham, idBase + c + j, colEnd, p.k, p.cap);
-                                    dotThr = int32_t(dotK) - 2 * int32_t(st.tau);
-                                }
-                            }
+                            for (int j = 0; j < 32; j++) mask |= uint32_t(int32_t(v[j]) > dotThr) << j;
+                            do {
+                                const int j = __ffs(int(mask)) - 1;
+                                mask &= mask - 1;
+                                const int32_t val = pick32(v, j);
+                                consider(st, uint32_t(int32_t(dotK) - val) >> 1, idBase + c + j, colEnd, p.k, p.cap);
+                            } while (mask);
+                            dotThr = int32_t(dotK) - 2 * int32_t(st.tau);
                         }
                     }
                 }
@@ -402,8 +467,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     // 2. plan + scratch
     MmaParams p{};
     const uint32_t panels = K / kChunkBytes;
-    const size_t avail = 227 * 1024 - 1024 - 256 - size_t(panels) * kPanelBytes;
-    p.stages = uint32_t(std::min<size_t>(6, avail / kStageBytes));
+    p.stages = kStages;
     ScanPlan plan = makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kRowsPerItem, 1);
     if (dump) {
         plan.segments = 1;
@@ -433,19 +497,18 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     p.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
     p.dump = dump;
 
-    CUtensorMap mapA, mapB;
-    EM2_TRY(makeMap(ctx, &mapA, enc, cellCount, K, kRowsPerItem));
+    CUtensorMap mapB;
     EM2_TRY(makeMap(ctx, &mapB, enc, cellCount, K, kTileN));
 
-    const size_t smem = 1024 + size_t(panels) * kPanelBytes + size_t(p.stages) * kStageBytes + 256;
+    const size_t smem = 1024 + size_t(kStages) * kStageBytes + 512;
     const uint32_t items = plan.rowBlocks * plan.segments;
     const unsigned grid = unsigned(std::min<uint32_t>(items, uint32_t(ctx->smCount)));
     if (dump) {
         EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        scanMmaKernel<true><<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+        scanMmaKernel<true><<<grid, kThreads, smem, s>>>(mapB, static_cast<const uint8_t*>(enc), p);
     } else {
         EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        scanMmaKernel<false><<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+        scanMmaKernel<false><<<grid, kThreads, smem, s>>>(mapB, static_cast<const uint8_t*>(enc), p);
     }
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());

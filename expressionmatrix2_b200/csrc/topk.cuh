@@ -8,8 +8,9 @@ namespace em2 {
 // Exact in-place prune of a per-row candidate buffer to its k smallest (mismatch, id) keys.
 // Invariant kept: among entries with equal mismatch count, ids are in increasing order (appends arrive
 // in increasing id; the compaction below is stable), so "the r smallest ids among the ties" are simply
-// the first r ties.
-static __device__ __noinline__ void pruneCandidates(uint64_t* buf, uint32_t& count, uint32_t k, uint32_t& tau)
+// the first r ties.  Returns (new count, new tau); state is passed by value so that it stays in registers
+// at the (rare) call sites.
+static __device__ __noinline__ uint2 pruneCandidates(uint64_t* buf, uint32_t count, uint32_t k, uint32_t tau)
 {
     uint32_t lo = 0, hi = tau - 1;          // every stored mismatch count is < tau
     while (lo < hi) {
@@ -34,8 +35,7 @@ static __device__ __noinline__ void pruneCandidates(uint64_t* buf, uint32_t& cou
         }
         if (keep) buf[j++] = key;
     }
-    count = j;
-    tau = h;                                // later ids are larger: ties at h can no longer enter
+    return make_uint2(j, h);                // later ids are larger: ties at h can no longer enter
 }
 
 struct RowState {
@@ -47,12 +47,16 @@ struct RowState {
 };
 
 static __device__ __forceinline__ void consider(RowState& st, uint32_t ham, uint32_t id, uint32_t colEnd, uint32_t k,
-                                         uint32_t cap)
+                                                uint32_t cap)
 {
     if (ham < st.tau && id < colEnd && id != st.rowId) {
         st.buf[st.count++] = (uint64_t(ham) << 32) | id;
         st.appended++;
-        if (st.count == cap) pruneCandidates(st.buf, st.count, k, st.tau);
+        if (st.count == cap) {
+            const uint2 r = pruneCandidates(st.buf, st.count, k, st.tau);
+            st.count = r.x;
+            st.tau = r.y;
+        }
     }
 }
 
