@@ -41,7 +41,9 @@ constexpr int kRowsPerItem = 128;     // UMMA M
 constexpr int kTileN = 128;           // UMMA N
 constexpr int kChunkBytes = 128;      // K bytes per TMA box / swizzle atom
 constexpr int kUmmaK = 32;            // K per tcgen05.mma for 8-bit operands
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;          // two column sub-streams per row: 2 epilogue warps per SM sub-partition
+constexpr int kSubStreams = kEpiWarps / 4;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kMaxPanels = 8;         // K <= 1024
 constexpr uint32_t kChunkTileBytes = kTileN * kChunkBytes;     // 16 KB: one K-chunk of a column tile
 constexpr int kChunksPerStage = 2;                             // a ring stage carries two K-chunks (32 KB)
@@ -200,10 +202,10 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        mbarInit(aFull, 128);
+        mbarInit(aFull, kEpiWarps * 32);
         for (int i = 0; i < 2; i++) {
             mbarInit(accFull + i, 1);
-            mbarInit(accEmpty + i, 128);
+            mbarInit(accEmpty + i, kEpiWarps * 32);
         }
         for (uint32_t i = 0; i < kStages; i++) {
             mbarInit(bFull + i, 1);
@@ -212,7 +214,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smemAddr(tmemSlot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -223,7 +225,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
 
     const uint32_t items = p.rowBlocks * p.segments;
 
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         // ===================== TMA producer (B operand) =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -251,7 +253,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kEpiWarps + 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t itemIter = 0, tileIter = 0, stage = 0, phase = 0;
@@ -294,12 +296,18 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
         }
     } else {
         // ===================== epilogue: thread == query row == TMEM lane =====================
+        // thread -> (row = TMEM lane, column sub-stream): warps 0-3 take columns [0,64) of every tile,
+        // warps 4-7 columns [64,128); each (row, sub-stream) has its own bound and candidate buffer, so
+        // ids stay increasing within a stream (topk.cuh) and the finalize kernel merges the streams.
         const uint32_t dotK = p.K;
-        const uint32_t laneField = uint32_t(warp * 32) << 16;
+        const uint32_t rowInItem = threadIdx.x & (kRowsPerItem - 1);
+        const uint32_t sub = threadIdx.x / kRowsPerItem;
+        constexpr int kSubCols = kTileN / kSubStreams;
+        const uint32_t laneField = uint32_t((warp & 3) * 32) << 16;
         uint32_t tileIter = 0;
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
             const uint32_t rb = item / p.segments, seg = item % p.segments;
-            const uint64_t localRow = uint64_t(rb) * kRowsPerItem + threadIdx.x;
+            const uint64_t localRow = uint64_t(rb) * kRowsPerItem + rowInItem;
             const bool valid = localRow < p.rows;
             const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
             const uint64_t colEndLong = min(colBegin + p.segmentCols, p.cellCount);
@@ -310,7 +318,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             // The previous item's MMAs have all completed (its last accFull was waited on below).
             {
                 const uint4* src = reinterpret_cast<const uint4*>(enc + (p.rowBegin + (valid ? localRow : 0)) * uint64_t(p.K));
-                for (uint32_t c = 0; c < p.K / 4; c += 32) {
+                for (uint32_t c = sub * 32; c < p.K / 4; c += 32 * kSubStreams) {   // sub-streams share the copy
                     uint32_t v[32];
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
@@ -332,16 +340,16 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             st.count = 0;
             st.appended = 0;
             st.tau = valid ? p.tau0 : 0;
-            st.buf = p.cand + (uint64_t(seg) * p.rows + (valid ? localRow : 0)) * p.cap;
+            st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * p.rows + (valid ? localRow : 0)) * p.cap;
             int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.tau);      // hamming < tau  <=>  dot > K - 2 tau
             for (uint32_t t = 0; t < tiles; t++, tileIter++) {
                 const uint32_t buf = tileIter & 1;
                 mbarWait(accFull + buf, (tileIter >> 1) & 1);
                 tcgen05FenceAfter();
-                const uint32_t idBase = uint32_t(colBegin) + t * kTileN;
-                const uint32_t taddr = tmemBase + buf * kTileN + laneField;
+                const uint32_t idBase = uint32_t(colBegin) + t * kTileN + sub * kSubCols;
+                const uint32_t taddr = tmemBase + buf * kTileN + sub * kSubCols + laneField;
 #pragma unroll 1
-                for (int c = 0; c < kTileN; c += 32) {
+                for (int c = 0; c < kSubCols; c += 32) {
                     uint32_t v[32];
                     tmemLoad32(taddr + c, v);
                     tmemLoadWait();
@@ -378,7 +386,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                 mbarArrive(accEmpty + buf);
             }
             if (!DUMP && valid) {
-                p.candCount[uint64_t(seg) * p.rows + localRow] = st.count;
+                p.candCount[uint64_t(seg * kSubStreams + sub) * p.rows + localRow] = st.count;
                 if (p.appendedTotal && st.appended) atomicAdd(p.appendedTotal, (unsigned long long)st.appended);
             }
         }
@@ -386,7 +394,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
 
     tcgen05FenceBefore();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmemBase) : "memory");
     }
 }
@@ -477,8 +485,8 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     void* candCount = nullptr;
     void* counters = nullptr;
     if (!dump) {
-        EM2_TRY(reserve(ctx, em2_context::S_CAND, size_t(plan.segments) * rows * plan.cap * sizeof(uint64_t), &cand));
-        EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(plan.segments) * rows * sizeof(uint32_t), &candCount));
+        EM2_TRY(reserve(ctx, em2_context::S_CAND, size_t(plan.segments) * kSubStreams * rows * plan.cap * sizeof(uint64_t), &cand));
+        EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(plan.segments) * kSubStreams * rows * sizeof(uint32_t), &candCount));
     }
     EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
     p.cellCount = cellCount;
@@ -513,7 +521,9 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
     if (dump) return EM2_OK;
-    return launchFinalize(ctx, plan, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s);
+    ScanPlan merged = plan;                    // every (segment, sub-stream) buffer is one list to merge
+    merged.segments = plan.segments * kSubStreams;
+    return launchFinalize(ctx, merged, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s);
 }
 
 }  // namespace

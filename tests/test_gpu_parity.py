@@ -13,7 +13,11 @@ pytestmark = pytest.mark.gpu
 import expressionmatrix2_b200 as em2  # noqa: E402
 from expressionmatrix2_b200 import synthetic  # noqa: E402
 
-VARIANTS = [em2.VARIANT_POPC]
+VARIANTS = [em2.VARIANT_POPC, em2.VARIANT_MMA_I8]
+
+
+def _variants_for(L):
+    return [v for v in VARIANTS if v != em2.VARIANT_MMA_I8 or L <= 1024]
 
 
 def _check_lists(got, want):
@@ -40,6 +44,8 @@ def test_golden_signatures_bit_exact(engine, name):
 def test_golden_neighbour_lists(engine, name, variant):
     g = load_golden(name)
     L = int(g["lsh_count"])
+    if variant not in _variants_for(L):
+        pytest.skip("the MMA variant covers lshCount <= 1024")
     for i in range(int(g["combos"])):
         k, thr = int(g[f"combo{i}_k"]), float(g[f"combo{i}_thr"])
         got = engine.find_similar_pairs(g["signatures"], L, k, thr, variant=variant)
@@ -73,10 +79,28 @@ def test_golden_hamming_bit_exact(engine, name):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint32), g["pair_mismatch"])
     n = g["signatures"].shape[0]
-    block = torch.zeros((1, n), dtype=torch.int16, device="cuda")
-    engine.mismatch_block_device(sig, n, L, 0, 1, block, stream=torch.cuda.current_stream().cuda_stream)
+    for variant in _variants_for(L):
+        block = torch.zeros((1, n), dtype=torch.int16, device="cuda")
+        engine.mismatch_block_device(sig, n, L, 0, 1, block, variant=variant,
+                                     stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(block.cpu().numpy().view(np.uint16)[0].astype(np.uint32), g["row0_mismatch"])
+
+
+@pytest.mark.parametrize("L", [64, 200, 512, 1024])
+def test_mma_distances_equal_popc_distances(engine, oracle, L):
+    """Every distance of a 300-row block from the tcgen05 arithmetic equals the reference popcount."""
+    import torch
+    N = 3001
+    sig = synthetic.gen_signatures(N, L, seed=L, clusters=11)
+    d_sig = torch.from_numpy(sig.view(np.int64)).cuda()
+    out = torch.zeros((300, N), dtype=torch.int16, device="cuda")
+    engine.mismatch_block_device(d_sig, N, L, 1500, 1800, out, variant=em2.VARIANT_MMA_I8,
+                                 stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert np.array_equal(block.cpu().numpy().view(np.uint16)[0].astype(np.uint32), g["row0_mismatch"])
+    got = out.cpu().numpy().view(np.uint16)
+    for r in (0, 17, 299):
+        assert np.array_equal(got[r].astype(np.uint32), oracle.mismatch_row(sig, 1500 + r))
 
 
 @pytest.mark.parametrize("N,G,dens,L,mode", [
@@ -95,7 +119,7 @@ def test_signatures_and_lists_vs_oracle(engine, oracle, N, G, dens, L, mode):
     assert np.array_equal(sig, want_sig)
     for k, thr in ((50, 0.2), (10, -1.0), (100, 0.0)):
         want = oracle.topk(want_sig, L, k, thr)[:3]
-        for variant in VARIANTS:
+        for variant in _variants_for(L) + [em2.VARIANT_AUTO]:
             _check_lists(engine.find_similar_pairs(sig, L, k, thr, variant=variant), want)
 
 
