@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace em2 {
 
@@ -44,11 +45,13 @@ constexpr int kUmmaK = 32;            // K per tcgen05.mma for 8-bit operands
 constexpr int kEpiWarps = 8;          // two column sub-streams per row: 2 epilogue warps per SM sub-partition
 constexpr int kSubStreams = kEpiWarps / 4;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr uint32_t kRingBytes = 32 * kEpiThreads * 4;          // per-thread ring of 32 passing columns
 constexpr int kMaxPanels = 8;         // K <= 1024
 constexpr uint32_t kChunkTileBytes = kTileN * kChunkBytes;     // 16 KB: one K-chunk of a column tile
 constexpr int kChunksPerStage = 2;                             // a ring stage carries two K-chunks (32 KB)
 constexpr uint32_t kStageBytes = kChunksPerStage * kChunkTileBytes;
-constexpr int kStages = 6;                                     // 192 KB ring
+constexpr int kStages = 5;                                     // 160 KB ring
 constexpr uint32_t kTmemA = 256;      // first TMEM column of the A operand
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -183,7 +186,7 @@ struct MmaParams {
     uint16_t* dump;          // optional: all distances of the scanned rows (tests)
 };
 
-template <bool DUMP>
+template <bool DUMP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restrict__ enc, const MmaParams p)
 {
@@ -197,6 +200,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
     uint64_t* bFull = bars + 6;      // [stages]
     uint64_t* bEmpty = bFull + kStages;
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bEmpty + kStages);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(bars) + 128;   // [32][kEpiThreads], after 512 B of barriers
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -366,18 +370,41 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                         int32_t mx = int32_t(v[0]);
 #pragma unroll
                         for (int j = 1; j < 32; j++) mx = max(mx, int32_t(v[j]));
-                        if (mx > dotThr) {
-                            // Rare per lane, but some lane of the warp is here most of the time: keep it
-                            // straight-line.  Bit mask of the passing columns, then one candidate per set bit.
-                            uint32_t mask = 0;
+                        if (EPI == 0) {
+                            // lanes with a passing column diverge; straight-line mask + select tree
+                            if (mx > dotThr) {
+                                uint32_t mask = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) mask |= uint32_t(int32_t(v[j]) > dotThr) << j;
-                            do {
-                                const int j = __ffs(int(mask)) - 1;
-                                mask &= mask - 1;
-                                const int32_t val = pick32(v, j);
-                                consider(st, uint32_t(int32_t(dotK) - val) >> 1, idBase + c + j, colEnd, p.k, p.cap);
-                            } while (mask);
+                                for (int j = 0; j < 32; j++) mask |= uint32_t(int32_t(v[j]) > dotThr) << j;
+                                do {
+                                    const int j = __ffs(int(mask)) - 1;
+                                    mask &= mask - 1;
+                                    const int32_t val = pick32(v, j);
+                                    consider(st, uint32_t(int32_t(dotK) - val) >> 1, idBase + c + j, colEnd);
+                                } while (mask);
+                            }
+                            if (__any_sync(0xffffffffu, mx > dotThr)) {
+                                warpPruneIfNeeded(st, p.k, p.cap);
+                                dotThr = int32_t(dotK) - 2 * int32_t(st.tau);
+                            }
+                        } else if (__any_sync(0xffffffffu, mx > dotThr)) {
+                            // Some row of this warp has a passing column (common with clustered data).
+                            // Keep the warp converged: every lane pushes its passing columns into its
+                            // private shared-memory ring with predicated stores, then drains the ring.
+                            uint32_t n = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (int32_t(v[j]) > dotThr) {
+                                    ring[n * kEpiThreads + threadIdx.x] = (v[j] << 5) | uint32_t(j);
+                                    n++;
+                                }
+                            }
+                            for (uint32_t i = 0; i < n; i++) {
+                                const uint32_t e = ring[i * kEpiThreads + threadIdx.x];
+                                const int32_t val = int32_t(e) >> 5;
+                                consider(st, uint32_t(int32_t(dotK) - val) >> 1, idBase + c + (e & 31u), colEnd);
+                            }
+                            warpPruneIfNeeded(st, p.k, p.cap);
                             dotThr = int32_t(dotK) - 2 * int32_t(st.tau);
                         }
                     }
@@ -508,16 +535,18 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     CUtensorMap mapB;
     EM2_TRY(makeMap(ctx, &mapB, enc, cellCount, K, kTileN));
 
-    const size_t smem = 1024 + size_t(kStages) * kStageBytes + 512;
+    const size_t smem = 1024 + size_t(kStages) * kStageBytes + 512 + kRingBytes;
     const uint32_t items = plan.rowBlocks * plan.segments;
     const unsigned grid = unsigned(std::min<uint32_t>(items, uint32_t(ctx->smCount)));
-    if (dump) {
-        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        scanMmaKernel<true><<<grid, kThreads, smem, s>>>(mapB, static_cast<const uint8_t*>(enc), p);
-    } else {
-        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        scanMmaKernel<false><<<grid, kThreads, smem, s>>>(mapB, static_cast<const uint8_t*>(enc), p);
-    }
+    static const int epi = [] { const char* e = std::getenv("EM2_MMA_EPI"); return e ? std::atoi(e) : 0; }();
+    auto go = [&](auto kernel) -> int {
+        EM2_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kernel<<<grid, kThreads, smem, s>>>(mapB, static_cast<const uint8_t*>(enc), p);
+        return EM2_OK;
+    };
+    if (dump) EM2_TRY(go(scanMmaKernel<true, 0>));
+    else if (epi == 0) EM2_TRY(go(scanMmaKernel<false, 0>));
+    else EM2_TRY(go(scanMmaKernel<false, 1>));
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
     if (dump) return EM2_OK;

@@ -203,11 +203,15 @@ scanPopcRegsKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCo
             const uint32_t h2 = hammingRow<W32, CSA>(a, panel + (c + 2) * W32);
             const uint32_t h3 = hammingRow<W32, CSA>(a, panel + (c + 3) * W32);
             const uint32_t hmin = min(min(h0, h1), min(h2, h3));
-            if (hmin < st.tau) {
-                consider(st, h0, idBase + c + 0, colEnd, k, cap);
-                consider(st, h1, idBase + c + 1, colEnd, k, cap);
-                consider(st, h2, idBase + c + 2, colEnd, k, cap);
-                consider(st, h3, idBase + c + 3, colEnd, k, cap);
+            const bool hit = hmin < st.tau;
+            if (__any_sync(0xffffffffu, hit)) {
+              if (hit) {
+                consider(st, h0, idBase + c + 0, colEnd);
+                consider(st, h1, idBase + c + 1, colEnd);
+                consider(st, h2, idBase + c + 2, colEnd);
+                consider(st, h3, idBase + c + 3, colEnd);
+              }
+              warpPruneIfNeeded(st, k, cap);
             }
         }
     }
@@ -303,11 +307,15 @@ scanPopcSmemKernel(const uint64_t* __restrict__ sig, uint32_t W, uint32_t W32 /*
                 h3 += __popc(xor3(r0 ^ v3.x, r1 ^ v3.y, r2 ^ v3.z)) + 2 * __popc(maj3(r0 ^ v3.x, r1 ^ v3.y, r2 ^ v3.z)) + __popc(r3 ^ v3.w);
             }
             const uint32_t hmin = min(min(h0, h1), min(h2, h3));
-            if (hmin < st.tau) {
-                consider(st, h0, idBase + c + 0, colEnd, k, cap);
-                consider(st, h1, idBase + c + 1, colEnd, k, cap);
-                consider(st, h2, idBase + c + 2, colEnd, k, cap);
-                consider(st, h3, idBase + c + 3, colEnd, k, cap);
+            const bool hit = hmin < st.tau;
+            if (__any_sync(0xffffffffu, hit)) {
+              if (hit) {
+                consider(st, h0, idBase + c + 0, colEnd);
+                consider(st, h1, idBase + c + 1, colEnd);
+                consider(st, h2, idBase + c + 2, colEnd);
+                consider(st, h3, idBase + c + 3, colEnd);
+              }
+              warpPruneIfNeeded(st, k, cap);
             }
         }
     }
@@ -450,7 +458,7 @@ ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount,
     p.segments = best;
     p.segmentCols = roundUp((cellCount + best - 1) / best, tileCols);
     p.segments = uint32_t((cellCount + p.segmentCols - 1) / p.segmentCols);
-    p.cap = uint32_t(std::max<uint64_t>(2 * k, k + 32));
+    p.cap = candidateCapacity(uint32_t(k));
     return p;
 }
 

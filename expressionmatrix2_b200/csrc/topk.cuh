@@ -1,61 +1,102 @@
-// Per-row candidate state shared by the two Hamming-scan variants: the running bound tau, the
+// Per-row streaming selection shared by the two Hamming-scan variants: the running bound tau, the
 // append-only candidate buffer in global memory and its exact in-place prune.
+//
+// Each (row, column stream) -- one thread -- appends the composite keys (mismatch << 32 | cellId) of
+// accepted candidates to a private region of global memory (L1/L2 resident, touched only on the rare
+// accepted candidate).  When a region runs out of slack it is pruned in place to its k best keys and tau
+// becomes the k-th best mismatch count.  Columns of a stream are visited in increasing cell id, so a new
+// candidate's id is larger than every kept id: it can displace a kept key only if its mismatch count is
+// STRICTLY smaller than the k-th best.  The hot-path filter is therefore the single compare `ham < tau`,
+// and ties at the k-th place resolve to the smaller id, exactly as the (mismatch asc, id asc) order of the
+// reference's deterministic selection (reference src/ExpressionMatrixLshGpu.cpp:148-149) requires.
+//
+// The prune is WARP-COOPERATIVE: at a point where the warp is converged, lanes whose buffers are nearly
+// full are served one after the other by all 32 lanes (count by ballot/reduce, stable compaction by
+// ballot prefix sums), ~400 issue slots instead of ~5000 for a single-thread prune under divergence.
+// (Measured alternatives: single-thread prune -- 1.5-4x slower scans on clustered data; a k-entry max-heap
+// with an exact bound -- 40% fewer accepted candidates but a 6-level dependent sift through L1 each.)
 #pragma once
 #include <cstdint>
 
 namespace em2 {
 
-// Exact in-place prune of a per-row candidate buffer to its k smallest (mismatch, id) keys.
-// Invariant kept: among entries with equal mismatch count, ids are in increasing order (appends arrive
-// in increasing id; the compaction below is stable), so "the r smallest ids among the ties" are simply
-// the first r ties.  Returns (new count, new tau); state is passed by value so that it stays in registers
-// at the (rare) call sites.
-static __device__ __noinline__ uint2 pruneCandidates(uint64_t* buf, uint32_t count, uint32_t k, uint32_t tau)
+constexpr uint32_t kPruneSlack = 32;    // appends a thread may make between two prune points
+
+struct RowState {
+    uint64_t* buf;
+    uint32_t count;
+    uint32_t tau;       // accept iff ham < tau
+    uint32_t rowId;
+    uint32_t appended;
+};
+
+// capacity of a candidate region for a given k
+__host__ __device__ inline uint32_t candidateCapacity(uint32_t k) { return 2 * k + kPruneSlack; }
+
+// Plain append; the caller guarantees at most kPruneSlack appends between two warpPruneIfNeeded() calls.
+static __device__ __forceinline__ void consider(RowState& st, uint32_t ham, uint32_t id, uint32_t colEnd)
 {
+    if (ham < st.tau && id < colEnd && id != st.rowId) {
+        st.buf[st.count++] = (uint64_t(ham) << 32) | id;
+        st.appended++;
+    }
+}
+
+// Exact in-place prune of ONE candidate region to its k smallest (mismatch, id) keys, executed by the
+// whole (converged) warp; buf/count/tau are warp-uniform.  Invariant kept: among entries with equal
+// mismatch count ids are in increasing order (appends arrive in increasing id; the compaction is stable),
+// so "the r smallest ids among the ties" are simply the first r ties.  Returns the new bound; the new count
+// is k.
+static __device__ __noinline__ uint32_t warpPrune(uint64_t* buf, uint32_t count, uint32_t k, uint32_t tau)
+{
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t lo = 0, hi = tau - 1;          // every stored mismatch count is < tau
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         uint32_t c = 0;
-        for (uint32_t i = 0; i < count; i++) c += (uint32_t(buf[i] >> 32) <= mid);
+        for (uint32_t i = lane; i < count; i += 32) c += (uint32_t(buf[i] >> 32) <= mid);
+        c = __reduce_add_sync(0xffffffffu, c);
         if (c >= k) hi = mid;
         else lo = mid + 1;
     }
     const uint32_t h = lo;
     uint32_t less = 0;
-    for (uint32_t i = 0; i < count; i++) less += (uint32_t(buf[i] >> 32) < h);
-    uint32_t r = k - less;                  // ties at h that still fit
-    uint32_t j = 0;
-    for (uint32_t i = 0; i < count; i++) {
-        const uint64_t key = buf[i];
+    for (uint32_t i = lane; i < count; i += 32) less += (uint32_t(buf[i] >> 32) < h);
+    less = __reduce_add_sync(0xffffffffu, less);
+    const uint32_t r = k - less;            // ties at h that still fit
+    uint32_t out = 0, tiesBefore = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < count; base += 32) {
+        const uint32_t i = base + lane;
+        const uint64_t key = i < count ? buf[i] : ~0ull;
         const uint32_t m = uint32_t(key >> 32);
-        bool keep = m < h;
-        if (m == h && r > 0) {
-            keep = true;
-            r--;
-        }
-        if (keep) buf[j++] = key;
+        const bool tie = (i < count) && (m == h);
+        const uint32_t tieMask = __ballot_sync(0xffffffffu, tie);
+        const bool keep = (i < count) && (m < h || (tie && tiesBefore + __popc(tieMask & lt) < r));
+        const uint32_t keepMask = __ballot_sync(0xffffffffu, keep);
+        if (keep) buf[out + __popc(keepMask & lt)] = key;      // out + rank <= i: never overtakes the reads
+        out += __popc(keepMask);
+        tiesBefore += __popc(tieMask);
     }
-    return make_uint2(j, h);                // later ids are larger: ties at h can no longer enter
+    __syncwarp();
+    return h;                               // later ids are larger: ties at h can no longer enter
 }
 
-struct RowState {
-    uint64_t* buf;
-    uint32_t count;
-    uint32_t tau;
-    uint32_t rowId;
-    uint32_t appended;
-};
-
-static __device__ __forceinline__ void consider(RowState& st, uint32_t ham, uint32_t id, uint32_t colEnd, uint32_t k,
-                                                uint32_t cap)
+// Call with the warp converged.  Serves every lane whose region has less than kPruneSlack free slots.
+static __device__ __forceinline__ void warpPruneIfNeeded(RowState& st, uint32_t k, uint32_t cap)
 {
-    if (ham < st.tau && id < colEnd && id != st.rowId) {
-        st.buf[st.count++] = (uint64_t(ham) << 32) | id;
-        st.appended++;
-        if (st.count == cap) {
-            const uint2 r = pruneCandidates(st.buf, st.count, k, st.tau);
-            st.count = r.x;
-            st.tau = r.y;
+    uint32_t need = __ballot_sync(0xffffffffu, st.count + kPruneSlack > cap);
+    if (need) __syncwarp();                 // the owners' appends become visible to the helping lanes
+    while (need) {
+        const int src = __ffs(int(need)) - 1;
+        need &= need - 1;
+        const uint64_t b = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(st.buf), src);
+        const uint32_t c = __shfl_sync(0xffffffffu, st.count, src);
+        const uint32_t t = __shfl_sync(0xffffffffu, st.tau, src);
+        const uint32_t h = warpPrune(reinterpret_cast<uint64_t*>(b), c, k, t);
+        if (int(threadIdx.x & 31) == src) {
+            st.count = k;
+            st.tau = h;
         }
     }
 }
