@@ -1,0 +1,234 @@
+#include "ExpressionMatrix.hpp"
+
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <ctime>
+#include <iostream>
+
+#include "Gpu.hpp"
+#include "Lsh.hpp"
+#include "SimilarPairs.hpp"
+
+using namespace ChanZuckerberg::ExpressionMatrix2;
+
+namespace {
+
+bool pathExists(const std::string& p)
+{
+    struct stat st;
+    return ::stat(p.c_str(), &st) == 0;
+}
+
+std::vector<std::string> listDirectory(const std::string& dir)
+{
+    std::vector<std::string> out;
+    DIR* d = ::opendir(dir.c_str());
+    if (!d) throw std::runtime_error("Error opening directory " + dir);
+    while (dirent* e = ::readdir(d)) out.push_back(e->d_name);
+    ::closedir(d);
+    return out;
+}
+
+// "2017-Nov-01 12:00:00.000000 " like the reference's timestamp manipulator (src/timestamp.hpp:9-13)
+std::ostream& timestamp(std::ostream& s)
+{
+    const auto now = std::chrono::system_clock::now();
+    const std::time_t t = std::chrono::system_clock::to_time_t(now);
+    std::tm tmv;
+    localtime_r(&t, &tmv);
+    char buf[64];
+    std::strftime(buf, sizeof(buf), "%Y-%b-%d %H:%M:%S", &tmv);
+    char out[96];
+    std::snprintf(out, sizeof(out), "%s.%06ld ", buf,
+                  long(std::chrono::duration_cast<std::chrono::microseconds>(now.time_since_epoch()).count() % 1000000));
+    return s << out;
+}
+
+bool startsWith(const std::string& s, const std::string& p) { return s.compare(0, p.size(), p) == 0; }
+bool endsWith(const std::string& s, const std::string& p)
+{
+    return s.size() >= p.size() && s.compare(s.size() - p.size(), p.size(), p) == 0;
+}
+
+}  // namespace
+
+ExpressionMatrix::ExpressionMatrix(const std::string& dir, bool allowReadOnly) : directoryName(dir)
+{
+    if (pathExists(dir)) {
+        cellExpressionCounts.accessExistingReadWrite(dir + "/CellExpressionCounts", allowReadOnly);
+        for (const std::string& f : listDirectory(dir)) {
+            if (startsWith(f, "CellSet-")) {
+                auto cs = std::make_shared<CellSet>();
+                cs->accessExistingReadWrite(dir + "/" + f, allowReadOnly);
+                cellSets[f.substr(8)] = cs;
+            } else if (startsWith(f, "GeneSet-") && endsWith(f, "-GlobalIds")) {
+                const std::string name = f.substr(8, f.size() - 8 - 10);
+                geneSets[name].accessExisting(dir + "/GeneSet-" + name, allowReadOnly);
+            }
+        }
+        if (!cellSets.count("AllCells")) throw std::runtime_error("Cell set \"AllCells\" is missing.");
+        if (!geneSets.count("AllGenes")) throw std::runtime_error("Gene set \"AllGenes\" is missing.");
+        geneCount_ = geneSets["AllGenes"].size();
+    } else {
+        if (::mkdir(dir.c_str(), 0755) != 0) throw std::runtime_error("Could not create directory " + dir);
+        cellExpressionCounts.createNew(dir + "/CellExpressionCounts");
+        auto all = std::make_shared<CellSet>();
+        all->createNew(dir + "/CellSet-AllCells", 0);
+        cellSets["AllCells"] = all;
+        geneSets["AllGenes"].createNew(dir + "/GeneSet-AllGenes");
+    }
+}
+
+void ExpressionMatrix::addGenes(GeneId count)
+{
+    GeneSet& all = geneSets["AllGenes"];
+    for (GeneId i = 0; i < count; i++) all.addGene(geneCount_++);
+}
+
+CellId ExpressionMatrix::addCell(std::vector<std::pair<GeneId, float>> counts)
+{
+    std::sort(counts.begin(), counts.end());
+    for (size_t i = 0; i < counts.size(); i++) {
+        if (counts[i].first >= geneCount_) throw std::runtime_error("addCell: gene id out of range");
+        if (i && counts[i].first == counts[i - 1].first) throw std::runtime_error("addCell: duplicate gene id");
+    }
+    const CellId id = cellCount();
+    cellExpressionCounts.appendVector(counts.begin(), counts.end());
+    cellSets["AllCells"]->push_back(id);
+    return id;
+}
+
+void ExpressionMatrix::addCells(const uint64_t* toc, const GeneId* geneIds, const float* counts, size_t n)
+{
+    std::vector<std::pair<GeneId, float>> row;
+    for (size_t c = 0; c < n; c++) {
+        row.clear();
+        for (uint64_t j = toc[c]; j < toc[c + 1]; j++) row.push_back(std::make_pair(geneIds[j], counts[j]));
+        addCell(row);
+    }
+}
+
+void ExpressionMatrix::createGeneSet(const std::string& name, std::vector<GeneId> ids)
+{
+    if (geneSets.count(name)) throw std::runtime_error("Gene set " + name + " already exists.");
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    GeneSet& gs = geneSets[name];
+    gs.createNew(directoryName + "/GeneSet-" + name);
+    for (GeneId g : ids) {
+        if (g >= geneCount_) throw std::runtime_error("createGeneSet: gene id out of range");
+        gs.addGene(g);
+    }
+}
+
+void ExpressionMatrix::createCellSet(const std::string& name, std::vector<CellId> ids)
+{
+    if (cellSets.count(name)) throw std::runtime_error("Cell set " + name + " already exists.");
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    auto cs = std::make_shared<CellSet>();
+    cs->createNew(directoryName + "/CellSet-" + name, ids.size());
+    for (size_t i = 0; i < ids.size(); i++) {
+        if (ids[i] >= cellCount()) throw std::runtime_error("createCellSet: cell id out of range");
+        (*cs)[i] = ids[i];
+    }
+    cellSets[name] = cs;
+}
+
+const GeneSet& ExpressionMatrix::findGeneSet(const std::string& name)
+{
+    const auto it = geneSets.find(name);
+    if (it == geneSets.end()) throw std::runtime_error("Gene set " + name + " does not exist.");
+    if (it->second.size() == 0) throw std::runtime_error("Gene set " + name + " is empty.");
+    return it->second;
+}
+
+const CellSet& ExpressionMatrix::findCellSet(const std::string& name)
+{
+    const auto it = cellSets.find(name);
+    if (it == cellSets.end()) throw std::runtime_error("Cell set " + name + " does not exist.");
+    if (it->second->size() == 0) throw std::runtime_error("Cell set " + name + " is empty.");
+    return *it->second;
+}
+
+void ExpressionMatrix::findSimilarPairs4(std::ostream& out, const std::string& geneSetName,
+                                         const std::string& cellSetName, const std::string& similarPairsName,
+                                         size_t k, double similarityThreshold, size_t lshCount, unsigned int seed)
+{
+    out << timestamp << "ExpressionMatrix::findSimilarPairs4 begins." << std::endl;
+    const GeneSet& geneSet = findGeneSet(geneSetName);
+    const CellSet& cellSet = findCellSet(cellSetName);
+    const CellId n = CellId(cellSet.size());
+
+    out << timestamp << "Creating expression matrix subset." << std::endl;
+    ExpressionMatrixSubset subset(directoryName + "/tmp-ExpressionMatrixSubset-" + similarPairsName, geneSet, cellSet,
+                                  cellExpressionCounts);
+
+    out << timestamp << "Computing cell LSH signatures on " << Gpu::instance().name() << "." << std::endl;
+    Lsh lsh(directoryName + "/tmp-Lsh-" + similarPairsName, subset, lshCount, seed);
+    lastSignatureMs = Gpu::instance().stats().signatures_ms;
+    out << "Computation of LSH cell signatures took " << 1e-3 * lastSignatureMs << " s on the device; "
+        << lsh.nearZeroProjections << " projections inside the rounding band." << std::endl;
+
+    out << timestamp << "Initializing SimilarPairs object." << std::endl;
+    SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
+
+    out << timestamp << "Begin computing similarities for all cell pairs." << std::endl;
+    lsh.findSimilarPairs(similarPairs, k, similarityThreshold, scanVariant);
+    lastScanMs = Gpu::instance().stats().scan_ms;
+    out << "Time for all pairs: " << 1e-3 * lastScanMs << " s." << std::endl;
+    if (n > 1) out << "Time per pair: " << 1e-3 * lastScanMs / (0.5 * double(n) * double(n - 1)) << " s." << std::endl;
+    out << timestamp << "ExpressionMatrix::findSimilarPairs4 ends." << std::endl;
+    lsh.remove();
+}
+
+void ExpressionMatrix::findSimilarPairs4(const std::string& geneSetName, const std::string& cellSetName,
+                                         const std::string& similarPairsName, size_t k, double similarityThreshold,
+                                         size_t lshCount, unsigned int seed)
+{
+    findSimilarPairs4(std::cout, geneSetName, cellSetName, similarPairsName, k, similarityThreshold, lshCount, seed);
+}
+
+void ExpressionMatrix::computeLshSignatures(const std::string& geneSetName, const std::string& cellSetName,
+                                            const std::string& lshName, size_t lshCount, unsigned int seed)
+{
+    const GeneSet& geneSet = findGeneSet(geneSetName);
+    const CellSet& cellSet = findCellSet(cellSetName);
+    ExpressionMatrixSubset subset(directoryName + "/tmp-ExpressionMatrixSubset-" + lshName, geneSet, cellSet,
+                                  cellExpressionCounts);
+    Lsh lsh(directoryName + "/Lsh-" + lshName, subset, lshCount, seed);
+    lastSignatureMs = Gpu::instance().stats().signatures_ms;
+}
+
+void ExpressionMatrix::findSimilarPairs0(std::ostream& out, const std::string& geneSetName,
+                                         const std::string& cellSetName, const std::string& similarPairsName,
+                                         size_t k, double similarityThreshold)
+{
+    if (similarityThreshold > 1.) throw std::runtime_error("similarityThreshold must not exceed 1.");
+    const GeneSet& geneSet = findGeneSet(geneSetName);
+    const CellSet& cellSet = findCellSet(cellSetName);
+    SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
+    ExpressionMatrixSubset subset(directoryName + "/tmp-ExpressionMatrixSubset-" + similarPairsName, geneSet, cellSet,
+                                  cellExpressionCounts);
+    out << timestamp << "Begin computing similarities for all cell pairs." << std::endl;
+    const size_t n = subset.cellCount();
+    std::vector<uint32_t> used(n);
+    Gpu& gpu = Gpu::instance();
+    gpu.check(em2_exact_similar_pairs(gpu.context(), n, subset.geneCount(), subset.toc(),
+                                      reinterpret_cast<const em2_count*>(subset.data()), k, similarityThreshold,
+                                      reinterpret_cast<em2_pair*>(similarPairs.begin(0)), used.data()),
+              "em2_exact_similar_pairs");
+    similarPairs.setUsedCounts(used);
+    lastScanMs = gpu.stats().scan_ms;
+    out << "Time for all pairs: " << 1e-3 * lastScanMs << " s." << std::endl;
+    if (n > 1) out << "Time per pair: " << 1e-3 * lastScanMs / (0.5 * double(n) * double(n - 1)) << " s." << std::endl;
+}
+
+void ExpressionMatrix::findSimilarPairs0(const std::string& geneSetName, const std::string& cellSetName,
+                                         const std::string& similarPairsName, size_t k, double similarityThreshold)
+{
+    findSimilarPairs0(std::cout, geneSetName, cellSetName, similarPairsName, k, similarityThreshold);
+}

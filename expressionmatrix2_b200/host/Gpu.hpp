@@ -1,0 +1,28 @@
+// Process-wide handle on the CUDA engine (libem2b200, include/em2b200.h).  The host classes call the
+// C-ABI through this and turn a non-zero status into std::runtime_error, like the reference turns
+// cl::Error into runtime_error (reference src/LshGpu.cpp:38-43,200-204).  There is no CPU fallback.
+#pragma once
+#include <stdexcept>
+#include <string>
+
+#include "../../include/em2b200.h"
+
+namespace ChanZuckerberg {
+namespace ExpressionMatrix2 {
+
+class Gpu {
+public:
+    static Gpu& instance();              // device = $EM2_DEVICE or 0; throws without an sm_100 GPU
+    em2_context* context() { return ctx_; }
+    std::string name();
+    em2_stats stats();
+    void check(int status, const char* what);
+    ~Gpu();
+
+private:
+    Gpu();
+    em2_context* ctx_ = nullptr;
+};
+
+}  // namespace ExpressionMatrix2
+}  // namespace ChanZuckerberg
