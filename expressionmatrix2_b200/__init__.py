@@ -34,7 +34,8 @@ class Stats(C.Structure):
         ("h2d_ms", C.c_double), ("sums_ms", C.c_double), ("signatures_ms", C.c_double), ("encode_ms", C.c_double),
         ("scan_ms", C.c_double), ("finalize_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
         ("near_zero_projections", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("kernel_launches", C.c_uint64), ("candidates_appended", C.c_uint64), ("variant_used", C.c_int32),
+        ("kernel_launches", C.c_uint64), ("candidates_appended", C.c_uint64), ("filter_cells", C.c_uint64),
+        ("filter_uncertain", C.c_uint64), ("variant_used", C.c_int32),
         ("reserved", C.c_int32),
     ]
 
@@ -64,6 +65,7 @@ def lib():
     L.em2_last_error.restype = C.c_char_p
     L.em2_device_name.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.em2_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.em2_set_option.argtypes = [vp, C.c_char_p, i64]
     L.em2_generate_lsh_vectors.argtypes = [u64, u64, C.c_uint32, vp]
     L.em2_similarity_table.argtypes = [u64, vp]
     L.em2_mismatch_max.argtypes = [u64, dbl]
@@ -167,6 +169,9 @@ class Engine:
         buf = C.create_string_buffer(256)
         self._check(self._L.em2_device_name(self._h, buf, 256), "em2_device_name")
         return buf.value.decode()
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self._L.em2_set_option(self._h, name.encode(), value), "em2_set_option")
 
     def stats(self) -> dict:
         s = Stats()

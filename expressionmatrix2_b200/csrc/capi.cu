@@ -196,6 +196,16 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats)
     return EM2_OK;
 }
 
+int em2_set_option(em2_context* ctx, const char* name, int64_t value)
+{
+    if (!ctx || !name) return EM2_ERR_INVALID;
+    const std::string n(name);
+    if (n == "signature_mode" && value >= 0 && value <= 2) ctx->signatureMode = int(value);
+    else if (n == "popc_csa" && value >= 0 && value <= 2) ctx->popcCsa = int(value);
+    else return fail(ctx, EM2_ERR_INVALID, "em2_set_option: unknown option or value out of range: " + n);
+    return EM2_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // device-resident wrappers
 // ------------------------------------------------------------------------------------------------
@@ -296,6 +306,8 @@ static int fetchCounters(em2_context* ctx)
     EM2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.near_zero_projections = h[0];
     ctx->stats.candidates_appended = h[1];
+    ctx->stats.filter_cells = h[2];
+    ctx->stats.filter_uncertain = h[3];
     return EM2_OK;
 }
 

@@ -43,9 +43,14 @@ struct em2_context {
         S_COUNTERS,      // small uint64 counters
         S_TOC, S_COUNTS, S_SUM1, S_SUM2, S_U, S_SIG, S_LUT, S_PAIRS, S_USED,   // staging of the blocking API
         S_ENC,           // +-1 int8 encoded signatures (MMA variant)
+        S_DENSE,         // dense uint8 counts of the signature filter path
+        S_UQ,            // quantised, transposed hyperplanes (two int8 digits) + per-column scale
+        S_FLAGS,         // per-cell eligibility flags / fallback list / uncertain list
         S_MISC,
         S_COUNT
     };
+    int signatureMode = 0;   // 0 auto, 1 FP64 kernel only, 2 force the tensor-core filter path
+    int popcCsa = 1;         // carry-save levels of the POPC scan
     em2::DeviceBuffer scratch[S_COUNT];
     em2::PinnedBuffer pinned[2];
 };
@@ -79,6 +84,17 @@ int launchCellSums(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, co
 int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                      const em2_count* counts, const double* sum1, const double* sum2, const double* U,
                      uint64_t ld, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero, cudaStream_t s);
+// Tensor-core filter + exact fix-up signature path (sig_filter.cu); same contract as launchSignatures.
+int launchSignaturesFiltered(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                             const em2_count* counts, const double* sum1, const double* sum2, const double* U,
+                             uint64_t ld, const double* sumU, uint64_t lshCount, uint64_t* signatures,
+                             uint64_t* nearZero, cudaStream_t s);
+// FP64 kernel on an explicit list of cells (cellList == nullptr: all cells).
+int launchSignaturesFp64(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                         const em2_count* counts, const double* sum1, const double* sum2, const double* U,
+                         uint64_t ld, const double* sumU, uint64_t lshCount, uint64_t* signatures,
+                         uint64_t* nearZero, const uint32_t* cellList, const uint32_t* cellListCount,
+                         uint64_t maxListed, cudaStream_t s);
 int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                    uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
                    int variant, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);

@@ -400,15 +400,6 @@ __global__ void mismatchBlockKernel(const uint64_t* __restrict__ sig, uint32_t W
     out[r * cellCount + col] = uint16_t(m);
 }
 
-int csaLevels()
-{
-    static int v = [] {
-        const char* e = std::getenv("EM2_POPC_CSA");
-        return e ? std::max(0, std::min(2, std::atoi(e))) : 1;
-    }();
-    return v;
-}
-
 template <int W32>
 int launchRegs(em2_context* ctx, const ScanPlan& plan, const uint64_t* sig, uint32_t W, uint64_t cellCount,
                uint64_t rowBegin, uint64_t rowEnd, uint32_t k, uint32_t tau0, uint64_t* cand, uint32_t* candCount,
@@ -422,7 +413,7 @@ int launchRegs(em2_context* ctx, const ScanPlan& plan, const uint64_t* sig, uint
                                                 tau0, cand, candCount, appended);
         return EM2_OK;
     };
-    switch (csaLevels()) {
+    switch (ctx->popcCsa) {
     case 0: EM2_TRY(go(scanPopcRegsKernel<W32, 0>)); break;
     case 2: EM2_TRY(go(scanPopcRegsKernel<W32, 2>)); break;
     default: EM2_TRY(go(scanPopcRegsKernel<W32, 1>)); break;

@@ -88,6 +88,8 @@ typedef struct em2_stats {
     uint64_t d2h_bytes;
     uint64_t kernel_launches; /* kernels of this library launched by the call            */
     uint64_t candidates_appended; /* scan-stage candidates that passed the running bound  */
+    uint64_t filter_cells;        /* cells whose signatures came from the tensor-core filter path */
+    uint64_t filter_uncertain;    /* projections the filter could not decide (recomputed exactly in FP64) */
     int32_t variant_used;     /* em2_variant actually run                                */
     int32_t reserved;
 } em2_stats;
@@ -103,6 +105,9 @@ void em2_destroy(em2_context* ctx);
 const char* em2_last_error(const em2_context* ctx);
 int em2_device_name(em2_context* ctx, char* buffer, size_t bufferSize);
 int em2_get_stats(const em2_context* ctx, em2_stats* stats);
+/* Tuning / test knobs.  Names: "signature_mode" (0 = automatic, 1 = FP64 kernel only, 2 = force the
+ * tensor-core filter + exact fix-up path), "popc_csa" (carry-save levels of the POPC scan, 0..2). */
+int em2_set_option(em2_context* ctx, const char* name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-side helpers of the path (cheap, O(G*L) or O(L); kept on the host by design).

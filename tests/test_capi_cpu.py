@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(em2):
 
 def test_struct_layouts_match_reference_types(em2):
     assert em2.PAIR_DTYPE.itemsize == 8 and em2.SIMPAIR_DTYPE.itemsize == 8   # pair<uint32,float>
-    assert ctypes.sizeof(em2.Stats) == 8 * 8 + 5 * 8 + 8
+    assert ctypes.sizeof(em2.Stats) == 8 * 8 + 7 * 8 + 8
 
 
 @pytest.mark.parametrize("name", golden_cases())
