@@ -227,6 +227,7 @@ def run_b200(args, w):
     ltoc, lgenes, lcounts = part.slice_csr(toc, genes, counts)
     lpairs = em2.to_pairs(lgenes, lcounts)
     rows = part.rows
+    nnz_local = int(ltoc[-1])
     eng = em2.Engine(local_rank)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -251,7 +252,8 @@ def run_b200(args, w):
         mark(0)
         eng.cell_sums_device(rows, d_toc, d_counts, d_sum1, d_sum2, stream=stream)
         mark(1)
-        eng.signatures_device(rows, G, d_toc, d_counts, d_sum1, d_sum2, d_U, L, L, d_sig_local, d_nz, stream=stream)
+        eng.signatures_device(rows, G, d_toc, d_counts, d_sum1, d_sum2, d_U, L, L, d_sig_local, d_nz, stream=stream,
+                              nnz=nnz_local)
         mark(2)
         full = all_gather_signatures(d_sig_local, part) if world > 1 else d_sig_local
         mark(3)

@@ -75,7 +75,7 @@ def lib():
     L.em2_lsh_similar_pairs.argtypes = [vp, u64, u64, vp, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_exact_similar_pairs.argtypes = [vp, u64, u64, vp, vp, u64, dbl, vp, vp]
     L.em2_cell_sums_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
-    L.em2_signatures_device.argtypes = [vp, u64, u64, vp, vp, vp, vp, vp, u64, u64, vp, vp, vp]
+    L.em2_signatures_device.argtypes = [vp, u64, u64, vp, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp]
     L.em2_scan_topk_device.argtypes = [vp, vp, u64, u64, u64, u64, u64, i64, vp, i32, vp, vp, vp]
     L.em2_mismatch_counts_device.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp]
     L.em2_mismatch_block_device.argtypes = [vp, vp, u64, u64, u64, u64, i32, vp, vp]
@@ -240,9 +240,10 @@ class Engine:
                                                  stream), "em2_cell_sums_device")
 
     def signatures_device(self, n, gene_count, d_toc, d_counts, d_sum1, d_sum2, d_U, ld, lsh_count, d_sig,
-                          d_near_zero=None, stream=None):
+                          d_near_zero=None, stream=None, nnz: int = 0):
+        """nnz (= toc[n], a host-side hint) lets the library choose the tensor-core filter path; 0 = FP64 kernel."""
         self._check(self._L.em2_signatures_device(self._h, n, gene_count, _ptr(d_toc), _ptr(d_counts), _ptr(d_sum1),
-                                                  _ptr(d_sum2), _ptr(d_U), ld, lsh_count, _ptr(d_sig),
+                                                  _ptr(d_sum2), _ptr(d_U), ld, lsh_count, nnz, _ptr(d_sig),
                                                   _ptr(d_near_zero), stream), "em2_signatures_device")
 
     def scan_topk_device(self, d_sig, n, lsh_count, row_begin, row_end, k, mismatch_max_, d_lut, d_pairs, d_used,

@@ -2,6 +2,7 @@
 // the thin *_device wrappers.  No CPU fallback lives here: every compute entry point launches the
 // CUDA kernels of this library or fails.
 #include "common.cuh"
+#include "tc05.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -58,6 +59,32 @@ int reservePinned(em2_context* ctx, int which, size_t bytes, void** out)
         b.bytes = bytes;
     }
     *out = b.ptr;
+    return EM2_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int makeTensorMapU8(em2_context* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t widthBytes,
+                    uint64_t pitchBytes, uint32_t boxRows)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        EM2_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+        if (!f || q != cudaDriverEntryPointSuccess) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    const cuuint64_t dims[2] = {widthBytes, rows};
+    const cuuint64_t strides[1] = {pitchBytes};
+    const cuuint32_t box[2] = {128u, boxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
     return EM2_OK;
 }
 
@@ -202,6 +229,9 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     const std::string n(name);
     if (n == "signature_mode" && value >= 0 && value <= 2) ctx->signatureMode = int(value);
     else if (n == "popc_csa" && value >= 0 && value <= 2) ctx->popcCsa = int(value);
+    else if (n == "filter_counts_signed" && value >= 0 && value <= 1) ctx->filterCountsSigned = int(value);
+    else if (n == "exact_matrix_bytes" && value >= 0) ctx->exactMatrixBytes = uint64_t(value);
+    else if (n == "filter_uncertain_cap" && value >= 0 && value <= (1 << 28)) ctx->filterUncertainCap = uint32_t(value);
     else return fail(ctx, EM2_ERR_INVALID, "em2_set_option: unknown option or value out of range: " + n);
     return EM2_OK;
 }
@@ -219,13 +249,14 @@ int em2_cell_sums_device(em2_context* ctx, uint64_t cellCount, const uint64_t* t
 
 int em2_signatures_device(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                           const em2_count* counts, const double* sum1, const double* sum2, const double* lshVectors,
-                          uint64_t ld, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero, void* stream)
+                          uint64_t ld, uint64_t lshCount, uint64_t nnz, uint64_t* signatures, uint64_t* nearZero,
+                          void* stream)
 {
     EM2_TRY(guardDevice(ctx));
     if (!toc || !sum1 || !lshVectors || !signatures) return fail(ctx, EM2_ERR_INVALID, "em2_signatures_device: null pointer");
     if (ld < lshCount) return fail(ctx, EM2_ERR_INVALID, "em2_signatures_device: ld < lshCount");
-    return launchSignatures(ctx, cellCount, geneCount, toc, counts, sum1, sum2, lshVectors, ld, lshCount, signatures,
-                            nearZero, static_cast<cudaStream_t>(stream));
+    return launchSignatures(ctx, cellCount, geneCount, toc, counts, sum1, sum2, lshVectors, ld, lshCount, nnz,
+                            signatures, nearZero, static_cast<cudaStream_t>(stream));
 }
 
 int em2_scan_topk_device(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
@@ -287,7 +318,7 @@ static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCoun
     const int e2 = T.mark();
     EM2_TRY(launchSignatures(ctx, cellCount, geneCount, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
                              static_cast<double*>(dSum1), static_cast<double*>(dSum2), static_cast<double*>(dU),
-                             lshCount, lshCount, static_cast<uint64_t*>(dSig), static_cast<uint64_t*>(dCounters), s));
+                             lshCount, lshCount, nnz, static_cast<uint64_t*>(dSig), static_cast<uint64_t*>(dCounters), s));
     const int e3 = T.mark();
     EM2_CUDA(ctx, cudaStreamSynchronize(s));
     ctx->stats.h2d_ms += T.ms(e0, e1);

@@ -51,6 +51,9 @@ struct em2_context {
     };
     int signatureMode = 0;   // 0 auto, 1 FP64 kernel only, 2 force the tensor-core filter path
     int popcCsa = 1;         // carry-save levels of the POPC scan
+    uint32_t filterUncertainCap = 0;   // test knob: capacity of the uncertain list (0 = automatic)
+    uint64_t exactMatrixBytes = 0;     // test knob: budget of the exact path's similarity matrix (0 = 8 GiB)
+    int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM
     em2::DeviceBuffer scratch[S_COUNT];
     em2::PinnedBuffer pinned[2];
 };
@@ -81,20 +84,26 @@ inline uint64_t roundUp(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 // ---- stage launchers (each returns an em2_status and adds to ctx->stats.kernel_launches) ----------
 int launchCellSums(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
                    double* sum1, double* sum2, cudaStream_t s);
+// Signature stage dispatcher: FP64 kernel, or the tensor-core filter path (sig_filter.cu) when it pays.
+// nnzHint = number of stored counts (0 = unknown: the automatic choice then stays with the FP64 kernel).
 int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                      const em2_count* counts, const double* sum1, const double* sum2, const double* U,
-                     uint64_t ld, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero, cudaStream_t s);
-// Tensor-core filter + exact fix-up signature path (sig_filter.cu); same contract as launchSignatures.
+                     uint64_t ld, uint64_t lshCount, uint64_t nnzHint, uint64_t* signatures, uint64_t* nearZero,
+                     cudaStream_t s);
+// Tensor-core filter + exact fix-up (sig_filter.cu).  Upadded/ldPadded: hyperplanes in the FP64 kernel's layout.
 int launchSignaturesFiltered(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                              const em2_count* counts, const double* sum1, const double* sum2, const double* U,
-                             uint64_t ld, const double* sumU, uint64_t lshCount, uint64_t* signatures,
-                             uint64_t* nearZero, cudaStream_t s);
-// FP64 kernel on an explicit list of cells (cellList == nullptr: all cells).
+                             uint64_t ld, const double* Upadded, uint64_t ldPadded, uint64_t lshCount,
+                             uint64_t* signatures, uint64_t* nearZero, cudaStream_t s);
+// FP64 kernel on a cell range, or on a device-resident list of cells, optionally predicated on a device counter.
 int launchSignaturesFp64(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
-                         const em2_count* counts, const double* sum1, const double* sum2, const double* U,
-                         uint64_t ld, const double* sumU, uint64_t lshCount, uint64_t* signatures,
-                         uint64_t* nearZero, const uint32_t* cellList, const uint32_t* cellListCount,
-                         uint64_t maxListed, cudaStream_t s);
+                         const em2_count* counts, const double* sum1, const double* sum2, const double* Uk,
+                         uint64_t ldk, const double* sumU, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero,
+                         const uint32_t* cellList, const uint32_t* cellListCount, uint64_t maxListed,
+                         const uint32_t* runIfCount, uint32_t runIfCap, uint64_t rangeBegin, uint64_t rangeCells,
+                         cudaStream_t s);
+int launchColumnStats(em2_context* ctx, uint64_t geneCount, const double* U, uint64_t ld, uint64_t lshCount,
+                      uint64_t cols, double* sumU, double* scale, double* e1, double* e2, cudaStream_t s);
 int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                    uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
                    int variant, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);

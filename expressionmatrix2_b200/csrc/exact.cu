@@ -1,9 +1,481 @@
-// Exact (Pearson) all-pairs path -- placeholder until the kernel lands (fails loudly).
+// Exact (Pearson) all-pairs similarity with per-cell top-k on sm_100a -- BASELINE config 5.
+//
+// Replaces ExpressionMatrix::findSimilarPairs0 (reference src/ExpressionMatrixFindSimilarPairs.cpp:16-88):
+// for every cell pair, ExpressionMatrixSubset::computeCellSimilarity (src/ExpressionMatrixSubset.cpp:83-133)
+//     scalarProduct = sum over shared genes of float(x_a * x_b), accumulated in double
+//     r = (n*scalarProduct - sum1_a*sum1_b) / sqrt((n*sum2_a - sum1_a^2) * (n*sum2_b - sum1_b^2))
+// kept when r > similarityThreshold, k best per cell (SimilarPairs::add, src/SimilarPairs.cpp:168-231),
+// rows finally sorted by (similarity desc, cell id asc) (SimilarPairs::sort, src/orderPairs.hpp:44-52).
+//
+// Expression counts are non-negative integers (UMI counts), so the scalar product of two cells is an
+// integer and the all-pairs scalar products are the Gram matrix X X^T of the dense count matrix.  The
+// tensor cores compute it EXACTLY: counts are split into base-256 digits (one uint8 plane for counts <= 255,
+// two for counts <= 65535), tcgen05.mma kind::i8 (u8 x u8 -> s32) accumulates the digit Gram matrices
+// LL, HL+LH and HH in TMEM, and the epilogue recombines them as 65536 HH + 256 (HL+LH) + LL in double --
+// the same value the reference's merge loop produces while every product x_a*x_b is below 2^24 (counts <=
+// 4095; above that the reference rounds each product to float and agreement is to ~1e-7 relative).  The
+// epilogue then evaluates r with the reference's operation sequence (separate multiplies, subtract, sqrt,
+// divide, round-to-nearest doubles) and stores float(r) -- or a "rejected" marker when !(r > threshold) --
+// into a rows x N float matrix in HBM (a chunk of rows at a time); `exactSelectKernel` makes one pass over
+// each row to pick the k largest (float similarity desc, id asc), which is the file order after sort().
+//
+// GEMM kernel: persistent CTA per SM, warps 0-3 epilogue (thread = row cell = TMEM lane), warp 4 TMA producer,
+// warp 5 MMA issuer; tile 128 x 128 cells, K = genes in 128-byte chunks, both operands are row blocks of the
+// SAME dense planes (128B-swizzled TMA boxes).  Tiles are visited in 12 x 12 super-tiles so that the ~148
+// CTAs running at any moment share 24 row/column panels through L2 instead of streaming 148 distinct ones.
 #include "common.cuh"
+#include "tc05.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 namespace em2 {
-int launchExact(em2_context* ctx, uint64_t, uint64_t, const uint64_t*, const em2_count*, const double*,
-                const double*, uint64_t, double, em2_pair*, uint32_t*, cudaStream_t)
+
+namespace {
+
+using namespace tc05;
+
+constexpr int kXTile = 128;           // cells per tile side (UMMA M and N)
+constexpr int kXChunk = 128;          // genes per pipeline stage
+constexpr uint32_t kXPlaneBytes = kXTile * kXChunk;   // 16 KB: one operand tile of one digit plane
+constexpr int kXThreads = 192;
+constexpr int kXSuper = 12;
+constexpr float kRejected = -2.f;     // marker in the similarity matrix (r >= -1 always)
+
+// max count, integrality, max sum2, max nnz: decides the digit count on the host.
+__global__ void exactScanKernel(uint64_t cellCount, uint64_t geneCount, const uint64_t* __restrict__ toc,
+                                const em2_count* __restrict__ counts, const double* __restrict__ sum2,
+                                unsigned long long* __restrict__ out /* [0]=max count, [1]=bad flag, [2]=max sum2 bits, [3]=max nnz */)
 {
-    return fail(ctx, EM2_ERR_INVALID, "the exact path is not available in this build");
+    const uint64_t nnz = toc[cellCount];
+    uint32_t mx = 0, bad = 0;
+    for (uint64_t e = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; e < nnz; e += uint64_t(gridDim.x) * blockDim.x) {
+        const em2_count p = counts[e];
+        const float c = p.count;
+        if (!(c >= 0.f) || c > 65535.f || c != truncf(c) || p.gene >= geneCount) bad = 1;
+        else mx = max(mx, uint32_t(c));
+    }
+    double s2 = 0.;
+    uint64_t nz = 0;
+    for (uint64_t c = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; c < cellCount; c += uint64_t(gridDim.x) * blockDim.x) {
+        s2 = fmax(s2, sum2[c]);
+        nz = max(nz, toc[c + 1] - toc[c]);
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    for (int o = 16; o > 0; o >>= 1) {
+        s2 = fmax(s2, __shfl_xor_sync(0xffffffffu, s2, o));
+        nz = max(nz, __shfl_xor_sync(0xffffffffu, nz, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out + 0, (unsigned long long)mx);
+        if (bad) atomicOr(out + 1, 1ull);
+        atomicMax(out + 2, (unsigned long long)__double_as_longlong(s2));   // non-negative doubles order like integers
+        atomicMax(out + 3, (unsigned long long)nz);
+    }
 }
+
+// Dense digit planes lo[c][g] = count & 255, hi[c][g] = count >> 8 (one warp per cell) and the per-cell
+// variance term v = n*sum2 - sum1*sum1 (src/ExpressionMatrixSubset.cpp:118-121).
+__global__ void __launch_bounds__(256)
+exactDensifyKernel(uint64_t cellCount, uint64_t geneCount, uint64_t gPad, const uint64_t* __restrict__ toc,
+                   const em2_count* __restrict__ counts, const double* __restrict__ sum1,
+                   const double* __restrict__ sum2, uint8_t* __restrict__ lo, uint8_t* __restrict__ hi,
+                   double* __restrict__ var)
+{
+    const uint64_t cell = blockIdx.x * uint64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= cellCount) return;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t o = uint64_t(lane) * 16; o < gPad; o += 512) {
+        *reinterpret_cast<uint4*>(lo + cell * gPad + o) = z;
+        if (hi) *reinterpret_cast<uint4*>(hi + cell * gPad + o) = z;
+    }
+    __syncwarp();
+    const uint64_t end = toc[cell + 1];
+    for (uint64_t e = toc[cell] + lane; e < end; e += 32) {
+        const em2_count p = counts[e];
+        const uint32_t c = uint32_t(p.count);
+        lo[cell * gPad + p.gene] = uint8_t(c & 255u);
+        if (hi) hi[cell * gPad + p.gene] = uint8_t(c >> 8);
+    }
+    if (lane == 0) {
+        const double n = double(geneCount), s1 = sum1[cell];
+        var[cell] = __dsub_rn(__dmul_rn(n, sum2[cell]), __dmul_rn(s1, s1));
+    }
+}
+
+struct ExactParams {
+    uint64_t cellCount;          // N (columns)
+    uint64_t rowBegin, rows;     // rows of this chunk
+    uint64_t geneCount;
+    uint32_t kChunks;
+    uint32_t rowBlocks, colTiles, superCols, items;
+    uint32_t idesc;
+    uint64_t ldOut;              // floats per row of the similarity matrix
+    double threshold;
+    const double* sum1;
+    const double* var;
+    float* out;
+};
+
+__device__ __forceinline__ bool itemToTile(const ExactParams& p, uint32_t item, uint32_t& rb, uint32_t& ct)
+{
+    const uint32_t super = item / (kXSuper * kXSuper), within = item % (kXSuper * kXSuper);
+    rb = (super / p.superCols) * kXSuper + within / kXSuper;
+    ct = (super % p.superCols) * kXSuper + within % kXSuper;
+    return rb < p.rowBlocks && ct < p.colTiles;
+}
+
+template <int DIGITS>
+__global__ void __launch_bounds__(kXThreads, 1)
+exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant__ CUtensorMap mapHi, const ExactParams p)
+{
+    constexpr int kStages = DIGITS == 1 ? 6 : 3;
+    constexpr uint32_t kStageBytes = 2 * DIGITS * kXPlaneBytes;       // A planes then B planes
+    constexpr int kAccBufs = DIGITS == 1 ? 2 : 1;                     // TMEM: 2 x 128 columns, or HH | X | LL
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(kStages) * kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* accFull = bars + 2 * kStages;
+    uint64_t* accEmpty = accFull + 2;
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(accEmpty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; i++) {
+            mbarInit(full + i, 1);
+            mbarInit(empty + i, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbarInit(accFull + i, 1);
+            mbarInit(accEmpty + i, 128);
+        }
+        mbarInitFence();
+    }
+    if (warp == 4) tmemAlloc(tmemSlot, 512);
+    fenceBefore();
+    __syncthreads();
+    fenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            prefetchMap(&mapLo);
+            if (DIGITS == 2) prefetchMap(&mapHi);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+                uint32_t rb, ct;
+                if (!itemToTile(p, item, rb, ct)) continue;
+                const int32_t rowA = int32_t(p.rowBegin + uint64_t(rb) * kXTile);
+                const int32_t rowB = int32_t(ct * kXTile);
+                for (uint32_t kc = 0; kc < p.kChunks; kc++) {
+                    mbarWait(empty + stage, phase ^ 1);
+                    mbarExpectTx(full + stage, kStageBytes);
+                    uint8_t* dst = ring + size_t(stage) * kStageBytes;
+                    const int32_t k0 = int32_t(kc * kXChunk);
+                    if (DIGITS == 1) {
+                        tmaLoad2d(dst, &mapLo, full + stage, k0, rowA);
+                        tmaLoad2d(dst + kXPlaneBytes, &mapLo, full + stage, k0, rowB);
+                    } else {
+                        tmaLoad2d(dst, &mapHi, full + stage, k0, rowA);
+                        tmaLoad2d(dst + kXPlaneBytes, &mapLo, full + stage, k0, rowA);
+                        tmaLoad2d(dst + 2 * kXPlaneBytes, &mapHi, full + stage, k0, rowB);
+                        tmaLoad2d(dst + 3 * kXPlaneBytes, &mapLo, full + stage, k0, rowB);
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, tileIter = 0;
+            for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+                uint32_t rb, ct;
+                if (!itemToTile(p, item, rb, ct)) continue;
+                const uint32_t buf = tileIter % kAccBufs;
+                const uint32_t use = tileIter / kAccBufs;
+                mbarWait(accEmpty + buf, (use & 1) ^ 1);
+                fenceAfter();
+                const uint32_t tmemD = tmemBase + buf * kXTile;
+                uint32_t accumulate = 0;
+                for (uint32_t kc = 0; kc < p.kChunks; kc++) {
+                    mbarWait(full + stage, phase);
+                    fenceAfter();
+                    const uint32_t base = smemAddr(ring + size_t(stage) * kStageBytes);
+#pragma unroll
+                    for (int ks = 0; ks < kXChunk / 32; ks++) {
+                        if (DIGITS == 1) {
+                            mmaI8Ss(tmemD, makeSmemDesc(base + ks * 32), makeSmemDesc(base + kXPlaneBytes + ks * 32), p.idesc,
+                                    accumulate);
+                        } else {
+                            const uint64_t aHi = makeSmemDesc(base + ks * 32), aLo = makeSmemDesc(base + kXPlaneBytes + ks * 32);
+                            const uint64_t bHi = makeSmemDesc(base + 2 * kXPlaneBytes + ks * 32);
+                            const uint64_t bLo = makeSmemDesc(base + 3 * kXPlaneBytes + ks * 32);
+                            mmaI8Ss(tmemBase, aHi, bHi, p.idesc, accumulate);                  // HH
+                            mmaI8Ss(tmemBase + kXTile, aHi, bLo, p.idesc, accumulate);         // X  = HL
+                            mmaI8Ss(tmemBase + kXTile, aLo, bHi, p.idesc, 1);                  //    + LH
+                            mmaI8Ss(tmemBase + 2 * kXTile, aLo, bLo, p.idesc, accumulate);     // LL
+                        }
+                        accumulate = 1;
+                    }
+                    commit(empty + stage);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                commit(accFull + buf);
+                tileIter++;
+            }
+        }
+    } else {
+        // ===================== epilogue: thread == row cell == TMEM lane =====================
+        const uint32_t laneField = uint32_t(warp * 32) << 16;
+        const double n = double(p.geneCount);
+        uint32_t tileIter = 0;
+        for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+            uint32_t rb, ct;
+            if (!itemToTile(p, item, rb, ct)) continue;
+            const uint64_t localRow = uint64_t(rb) * kXTile + threadIdx.x;
+            const bool valid = localRow < p.rows;
+            const uint64_t a = p.rowBegin + (valid ? localRow : 0);
+            const double s1a = p.sum1[a], va = p.var[a];
+            const uint32_t buf = tileIter % kAccBufs;
+            const uint32_t use = tileIter / kAccBufs;
+            mbarWait(accFull + buf, use & 1);
+            fenceAfter();
+            const uint32_t taddr = tmemBase + buf * kXTile + laneField;
+            float* outRow = p.out + localRow * p.ldOut + uint64_t(ct) * kXTile;
+#pragma unroll 1
+            for (int q = 0; q < kXTile / 32; q++) {
+                uint32_t ll[32], xx[32], hh[32];
+                if (DIGITS == 1) {
+                    tmemLoad32(taddr + q * 32, ll);
+                } else {
+                    tmemLoad32(taddr + q * 32, hh);
+                    tmemLoad32(taddr + kXTile + q * 32, xx);
+                    tmemLoad32(taddr + 2 * kXTile + q * 32, ll);
+                }
+                tmemLoadWait();
+                const uint64_t bBase = uint64_t(ct) * kXTile + q * 32;
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    float r4[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) {
+                        const int j = j4 + jj;
+                        const uint64_t b = bBase + j;
+                        float res = kRejected;
+                        if (b < p.cellCount && b != a) {
+                            double sp = double(ll[j]);                                        // u8 x u8 sums are non-negative
+                            if (DIGITS == 2) sp = fma(fma(double(hh[j]), 256., double(xx[j])), 256., sp);   // exact
+                            const double num = __dsub_rn(__dmul_rn(n, sp), __dmul_rn(s1a, __ldg(p.sum1 + b)));
+                            const double den = __dsqrt_rn(__dmul_rn(va, __ldg(p.var + b)));
+                            const double r = __ddiv_rn(num, den);
+                            if (r > p.threshold) res = float(r);
+                        }
+                        r4[jj] = res;
+                    }
+                    if (valid) {
+                        if (bBase + j4 + 3 < p.ldOut)
+                            *reinterpret_cast<float4*>(outRow + q * 32 + j4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                    }
+                }
+            }
+            fenceBefore();
+            mbarArrive(accEmpty + buf);
+            tileIter++;
+        }
+    }
+    fenceBefore();
+    __syncthreads();
+    if (warp == 4) tmemDealloc(tmemBase, 512);
+}
+
+// ---- selection -------------------------------------------------------------------------------------
+// key = (~orderable(similarity) << 32) | cellId : ascending key == (similarity desc, id asc)
+__device__ __forceinline__ uint32_t orderable(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fromOrderable(uint32_t o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+constexpr int kSelWarps = 4;
+
+// One warp per row: stream the row, keep keys below the running bound in a shared-memory buffer, prune the
+// buffer to its k smallest keys (rank by counting; keys are unique) whenever it is nearly full.
+__global__ void __launch_bounds__(kSelWarps * 32)
+exactSelectKernel(uint64_t rows, uint64_t cellCount, uint64_t ldOut, const float* __restrict__ sim, uint32_t k,
+                  uint32_t cap, em2_pair* __restrict__ pairs, uint32_t* __restrict__ usedCount)
+{
+    extern __shared__ __align__(16) uint64_t sbuf[];        // kSelWarps x 2 x cap
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t row = uint64_t(blockIdx.x) * kSelWarps + warp;
+    if (row >= rows) return;
+    uint64_t* buf = sbuf + size_t(warp) * 2 * cap;
+    uint64_t* tmp = buf + cap;
+    uint32_t count = 0;
+    uint64_t bound = ~0ull;                                  // accept keys < bound
+    const float* src = sim + row * ldOut;
+    const uint32_t lt = (1u << lane) - 1u;
+
+    auto prune = [&]() {
+        __syncwarp();
+        // rank by counting; survivors land sorted in tmp, then copy back
+        for (uint32_t e = lane; e < count; e += 32) {
+            const uint64_t key = buf[e];
+            uint32_t rank = 0;
+            for (uint32_t f = 0; f < count; f++) rank += (buf[f] < key);
+            if (rank < k) tmp[rank] = key;
+        }
+        __syncwarp();
+        const uint32_t kept = count < k ? count : k;
+        for (uint32_t e = lane; e < kept; e += 32) buf[e] = tmp[e];
+        __syncwarp();
+        count = kept;
+        if (kept == k) bound = buf[k - 1];
+    };
+
+    for (uint64_t base = 0; base < cellCount; base += 32) {
+        const uint64_t id = base + lane;
+        uint64_t key = ~0ull;
+        if (id < cellCount) {
+            const float f = __ldg(src + id);
+            if (f != kRejected) key = (uint64_t(~orderable(f)) << 32) | id;
+        }
+        const bool pass = key < bound;
+        const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+        if (mask) {
+            if (pass) buf[count + __popc(mask & lt)] = key;
+            count += __popc(mask);
+            if (count + 32 > cap) prune();
+        }
+    }
+    prune();
+    for (uint32_t e = lane; e < k; e += 32) {
+        em2_pair out;
+        if (e < count) {
+            out.cell = uint32_t(buf[e]);
+            out.similarity = fromOrderable(~uint32_t(buf[e] >> 32));
+        } else {
+            out.cell = 0;
+            out.similarity = 0.f;
+        }
+        pairs[row * k + e] = out;
+    }
+    if (lane == 0) usedCount[row] = count;
+}
+
+}  // namespace
+
+int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc, const em2_count* counts,
+                const double* sum1, const double* sum2, uint64_t k, double similarityThreshold, em2_pair* pairs,
+                uint32_t* usedCount, cudaStream_t s)
+{
+    if (k == 0 || k > 1024) return fail(ctx, EM2_ERR_INVALID, "k must be in [1, 1024]");
+    if (cellCount > 0x7fffff00ull || geneCount > 0x7fffff00ull) return fail(ctx, EM2_ERR_INVALID, "matrix too large for the exact path");
+    if (!(similarityThreshold <= 1.)) return fail(ctx, EM2_ERR_INVALID, "similarityThreshold must be <= 1");   // CZI_ASSERT, FindSimilarPairs.cpp:27
+    const uint64_t gPad = roundUp(geneCount, kXChunk);
+
+    // ---- what do the counts look like? ---------------------------------------------------------------
+    void* misc = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_MISC, 64, &misc));
+    EM2_CUDA(ctx, cudaMemsetAsync(misc, 0, 64, s));
+    exactScanKernel<<<ctx->smCount * 4, 256, 0, s>>>(cellCount, geneCount, toc, counts, sum2, static_cast<unsigned long long*>(misc));
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+    unsigned long long h[4];
+    EM2_CUDA(ctx, cudaMemcpyAsync(h, misc, sizeof(h), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    if (h[1])
+        return fail(ctx, EM2_ERR_INVALID,
+                    "em2_exact_similar_pairs: the tensor-core exact path needs integer-valued counts in [0, 65535] "
+                    "(raw UMI counts) and gene ids below geneCount");
+    const int digits = h[0] <= 255 ? 1 : 2;
+    double maxSum2;
+    std::memcpy(&maxSum2, &h[2], 8);
+    const double llBound = digits == 1 ? maxSum2 : std::min(maxSum2, 65025. * double(h[3]));
+    if (llBound >= 2147483648. || maxSum2 / 128. >= 2147483648.)
+        return fail(ctx, EM2_ERR_INVALID, "em2_exact_similar_pairs: a cell's sum of squared counts overflows the s32 accumulators");
+
+    // ---- dense digit planes ----------------------------------------------------------------------------
+    void *lo = nullptr, *hi = nullptr, *var = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_DENSE, cellCount * gPad * digits, &lo));
+    if (digits == 2) hi = static_cast<uint8_t*>(lo) + cellCount * gPad;
+    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, cellCount * sizeof(double), &var));
+    exactDensifyKernel<<<unsigned((cellCount + 7) / 8), 256, 0, s>>>(cellCount, geneCount, gPad, toc, counts, sum1, sum2,
+                                                                    static_cast<uint8_t*>(lo), static_cast<uint8_t*>(hi),
+                                                                    static_cast<double*>(var));
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+
+    // ---- row chunks: GEMM + epilogue into the similarity matrix, then selection --------------------------
+    const uint64_t ldOut = roundUp(cellCount, kXTile);
+    const uint64_t budget = ctx->exactMatrixBytes ? ctx->exactMatrixBytes : (8ull << 30);
+    uint64_t chunkRows = std::max<uint64_t>(kXTile, budget / (ldOut * sizeof(float)) / kXTile * kXTile);
+    chunkRows = std::min<uint64_t>(chunkRows, roundUp(cellCount, kXTile));
+    void* simMatrix = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_CAND, chunkRows * ldOut * sizeof(float), &simMatrix));
+
+    CUtensorMap mapLo, mapHi;
+    EM2_TRY(makeTensorMapU8(ctx, &mapLo, lo, cellCount, gPad, gPad, kXTile));
+    EM2_TRY(makeTensorMapU8(ctx, &mapHi, digits == 2 ? hi : lo, cellCount, gPad, gPad, kXTile));
+    const int stages = digits == 1 ? 6 : 3;
+    const size_t smemGemm = 1024 + size_t(stages) * 2 * digits * kXPlaneBytes + 256;
+    const uint32_t cap = uint32_t(2 * k + 64);
+    const size_t smemSel = size_t(kSelWarps) * 2 * cap * sizeof(uint64_t);
+    EM2_CUDA(ctx, cudaFuncSetAttribute(exactSelectKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemSel)));
+
+    for (uint64_t begin = 0; begin < cellCount; begin += chunkRows) {
+        const uint64_t rows = std::min(chunkRows, cellCount - begin);
+        ExactParams p{};
+        p.cellCount = cellCount;
+        p.rowBegin = begin;
+        p.rows = rows;
+        p.geneCount = geneCount;
+        p.kChunks = uint32_t(gPad / kXChunk);
+        p.rowBlocks = uint32_t((rows + kXTile - 1) / kXTile);
+        p.colTiles = uint32_t(ldOut / kXTile);
+        const uint32_t superRows = (p.rowBlocks + kXSuper - 1) / kXSuper;
+        p.superCols = (p.colTiles + kXSuper - 1) / kXSuper;
+        p.items = superRows * p.superCols * kXSuper * kXSuper;
+        p.idesc = instrDescI8(false, false, kXTile, kXTile);
+        p.ldOut = ldOut;
+        p.threshold = similarityThreshold;
+        p.sum1 = sum1;
+        p.var = static_cast<const double*>(var);
+        p.out = static_cast<float*>(simMatrix);
+        const unsigned grid = unsigned(std::min<uint32_t>(p.items, uint32_t(ctx->smCount)));
+        if (digits == 1) {
+            EM2_CUDA(ctx, cudaFuncSetAttribute(exactGemmKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemGemm)));
+            exactGemmKernel<1><<<grid, kXThreads, smemGemm, s>>>(mapLo, mapHi, p);
+        } else {
+            EM2_CUDA(ctx, cudaFuncSetAttribute(exactGemmKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemGemm)));
+            exactGemmKernel<2><<<grid, kXThreads, smemGemm, s>>>(mapLo, mapHi, p);
+        }
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+        exactSelectKernel<<<unsigned((rows + kSelWarps - 1) / kSelWarps), kSelWarps * 32, smemSel, s>>>(
+            rows, cellCount, ldOut, static_cast<const float*>(simMatrix), uint32_t(k), cap, pairs + begin * k, usedCount + begin);
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->stats.variant_used = EM2_VARIANT_MMA_I8;
+    return EM2_OK;
+}
+
 }  // namespace em2

@@ -27,9 +27,8 @@
 //                         through mbarriers.  TMEM map: [0,128) acc0, [128,256) acc1, [256,512) A.
 // Work item = (128-row block, column segment); items are dealt round-robin to the persistent CTAs.
 #include "common.cuh"
+#include "tc05.cuh"
 #include "topk.cuh"
-
-#include <cuda.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -37,6 +36,8 @@
 namespace em2 {
 
 namespace {
+
+using namespace tc05;
 
 constexpr int kRowsPerItem = 128;     // UMMA M
 constexpr int kTileN = 128;           // UMMA N
@@ -54,87 +55,6 @@ constexpr uint32_t kStageBytes = kChunksPerStage * kChunkTileBytes;
 constexpr int kStages = 5;                                     // 160 KB ring
 constexpr uint32_t kTmemA = 256;      // first TMEM column of the A operand
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(smemAddr(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tmaLoad2d(void* smemDst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smemAddr(smemDst)), "l"(map), "r"(smemAddr(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05FenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05FenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05Commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smemAddr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mmaI8(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmemD),
-        "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmemStore32(uint32_t taddr, const uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
-          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
-          "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmemStoreWait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // v[j] for a run-time j without spilling the array to local memory: a 5-level select tree (31 SEL).
 __device__ __forceinline__ int32_t pick32(const uint32_t (&v)[32], int j)
 {
@@ -148,19 +68,6 @@ __device__ __forceinline__ int32_t pick32(const uint32_t (&v)[32], int j)
 #pragma unroll
     for (int i = 0; i < 2; i++) d[i] = (j & 2) ? c[2 + i] : c[i];
     return int32_t((j & 1) ? d[1] : d[0]);
-}
-
-// Shared-memory matrix descriptor: K-major, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart
-// (encoding per the PTX ISA tcgen05 matrix-descriptor table; version field = 1 on sm_100).
-__device__ __forceinline__ uint64_t makeSmemDesc(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= uint64_t((saddr & 0x3FFFF) >> 4);          // start address, bits [0,14)
-    d |= uint64_t(1) << 16;                          // leading byte offset (ignored for swizzled K-major; 1)
-    d |= uint64_t(1024 >> 4) << 32;                  // stride byte offset = 1024 B between 8-row groups
-    d |= uint64_t(1) << 46;                          // descriptor version
-    d |= uint64_t(2) << 61;                          // layout type: SWIZZLE_128B
-    return d;
 }
 
 // Instruction descriptor: kind::i8, A/B signed 8-bit K-major, D s32, M=128, N=256.
@@ -222,9 +129,9 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smemAddr(tmemSlot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    tcgen05FenceBefore();
+    fenceBefore();
     __syncthreads();
-    tcgen05FenceAfter();
+    fenceAfter();
     const uint32_t tmemBase = *tmemSlot;
 
     const uint32_t items = p.rowBlocks * p.segments;
@@ -268,33 +175,33 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                 const uint64_t colEnd = min(colBegin + p.segmentCols, p.cellCount);
                 const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
                 mbarWait(aFull, itemIter & 1);
-                tcgen05FenceAfter();
+                fenceAfter();
                 for (uint32_t t = 0; t < tiles; t++, tileIter++) {
                     const uint32_t buf = tileIter & 1;
                     mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
-                    tcgen05FenceAfter();
+                    fenceAfter();
                     const uint32_t tmemD = tmemBase + buf * kTileN;
                     uint32_t aCol = tmemBase + kTmemA;
                     uint32_t first = 0;                      // 0 on the tile's first MMA: overwrite the accumulator
                     for (uint32_t j = 0; j < stagesPerTile; j++) {
                         const uint32_t chunks = min(uint32_t(kChunksPerStage), p.panels - j * kChunksPerStage);
                         mbarWait(bFull + stage, phase);
-                        tcgen05FenceAfter();
+                        fenceAfter();
                         uint32_t bAddr = smemAddr(smB + size_t(stage) * kStageBytes);
                         for (uint32_t c = 0; c < chunks; c++, bAddr += kChunkTileBytes) {
 #pragma unroll
                             for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++, aCol += kUmmaK / 4) {
-                                mmaI8(tmemD, aCol, makeSmemDesc(bAddr + ks * kUmmaK), kInstrDesc, first);
+                                mmaI8Ts(tmemD, aCol, makeSmemDesc(bAddr + ks * kUmmaK), kInstrDesc, first);
                                 first = 1;
                             }
                         }
-                        tcgen05Commit(bEmpty + stage);       // stage reusable once these MMAs have read it
+                        commit(bEmpty + stage);       // stage reusable once these MMAs have read it
                         if (++stage == kStages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    tcgen05Commit(accFull + buf);            // accumulator complete (and, on the item's last
+                    commit(accFull + buf);            // accumulator complete (and, on the item's last
                 }                                            // tile, every read of the A operand is done)
             }
         }
@@ -335,7 +242,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                     tmemStore32(tmemBase + laneField + kTmemA + c, v);
                 }
                 tmemStoreWait();
-                tcgen05FenceBefore();
+                fenceBefore();
                 mbarArrive(aFull);
             }
 
@@ -349,7 +256,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             for (uint32_t t = 0; t < tiles; t++, tileIter++) {
                 const uint32_t buf = tileIter & 1;
                 mbarWait(accFull + buf, (tileIter >> 1) & 1);
-                tcgen05FenceAfter();
+                fenceAfter();
                 const uint32_t idBase = uint32_t(colBegin) + t * kTileN + sub * kSubCols;
                 const uint32_t taddr = tmemBase + buf * kTileN + sub * kSubCols + laneField;
 #pragma unroll 1
@@ -409,7 +316,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                         }
                     }
                 }
-                tcgen05FenceBefore();
+                fenceBefore();
                 mbarArrive(accEmpty + buf);
             }
             if (!DUMP && valid) {
@@ -419,7 +326,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
         }
     }
 
-    tcgen05FenceBefore();
+    fenceBefore();
     __syncthreads();
     if (warp == kEpiWarps) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmemBase) : "memory");
@@ -451,31 +358,6 @@ __global__ void encodeKernel(const uint64_t* __restrict__ sig, uint32_t W, uint6
         out[q] = word;
     }
     *reinterpret_cast<uint4*>(enc + row * K + size_t(g) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int makeMap(em2_context* ctx, CUtensorMap* map, void* base, uint64_t rows, uint32_t K, uint32_t boxRows)
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        EM2_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
-        if (!f || q != cudaDriverEntryPointSuccess) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
-        fn = reinterpret_cast<EncodeTiledFn>(f);
-    }
-    const cuuint64_t dims[2] = {K, rows};
-    const cuuint64_t strides[1] = {K};
-    const cuuint32_t box[2] = {uint32_t(kChunkBytes), boxRows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
-    return EM2_OK;
 }
 
 int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount, uint64_t rowBegin,
@@ -533,7 +415,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     p.dump = dump;
 
     CUtensorMap mapB;
-    EM2_TRY(makeMap(ctx, &mapB, enc, cellCount, K, kTileN));
+    EM2_TRY(makeTensorMapU8(ctx, &mapB, enc, cellCount, K, K, kTileN));
 
     const size_t smem = 1024 + size_t(kStages) * kStageBytes + 512 + kRingBytes;
     const uint32_t items = plan.rowBlocks * plan.segments;

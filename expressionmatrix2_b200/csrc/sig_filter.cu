@@ -1,0 +1,535 @@
+// Signature construction, tensor-core FILTER path (sm_100a): the sign of every projection is decided by an
+// exact-integer tcgen05 GEMM with a rigorous error bound; the few projections the bound cannot decide are
+// recomputed with the reference's own FP64 operation sequence.  The resulting signature bits are identical
+// to Lsh::computeCellLshSignatures (reference src/Lsh.cpp:160-207) -- this path only changes HOW MUCH FP64
+// work is needed, never the answer.
+//
+// Why: the FP64 kernel (signatures.cu) needs one 8-byte hyperplane element per multiply-add and is bound by
+// the L1 data pipe.  Expression counts are small non-negative integers (UMI counts), so
+//     s_i = sum_g c_g U[g][i] - mean * sumU_i
+// can be bracketed as follows.  Quantise every hyperplane column to 22-bit fixed point,
+//     U[g][i] = scale_i * q[g][i] + eps,   |eps| <= scale_i / 2,   q = (128 d2 + d1) * 128 + d0,  d* int8,
+// expand the cell's counts to a dense uint8 row, and let the tensor cores compute the three EXACT integer
+// sums  S_j = sum_g c_g d_j[g][i]  (kind::i8, s32 accumulators).  Then
+//     s~_i = scale_i * ((128 S_2 + S_1) * 128 + S_0) - mean * sumU_i
+// differs from the value the reference computes by at most
+//     B_i = sum1 * scale_i / 2                                   (quantisation, sum1 = sum_g c_g)
+//         + (nnz + 16) * 2^-52 * (sum1 * max_g|U[g][i]| + |mean * sumU_i|)   (FP64 rounding of both sides)
+// so whenever |s~_i| > B_i the reference's sign is the sign of s~_i.  Otherwise (a few per 100,000
+// projections at 30k genes, 5 % density; 0.35 % with two digits, which is why there are three) the pair
+// (cell, i) goes to a list and `fixupKernel` evaluates the
+// reference's sequence  s = (-mean) * sumU_i;  s = s + double(c) * U[g][i]  in stored gene order with
+// __dmul_rn/__dadd_rn.  Cells with a count that is not an integer in [0, 255] (or an enormous sum) are not
+// eligible; they are listed and computed entirely by the FP64 kernel.  If the uncertain list overflows, the
+// FP64 kernel recomputes every cell (device-side predicate, no host round trip).
+//
+// GEMM: persistent CTA per SM, warp specialised -- warps 0-3 epilogue (thread = cell = TMEM lane), warp 4
+// TMA producer, warp 5 MMA issuer.  Tile = 128 cells x 128 hyperplanes x 3 digits (UMMA M=128, one N=256
+// and one N=128 instruction per 32 genes), K = genes in 128-byte chunks, both operands by TMA (128B swizzle)
+// through a 3-stage ring of 64 KB stages, accumulators in 384 TMEM columns (the epilogue is ~1 % of a tile's
+// 235-chunk main loop, so it is not double buffered).
+#include "common.cuh"
+#include "tc05.cuh"
+
+#include <algorithm>
+
+namespace em2 {
+
+namespace {
+
+using namespace tc05;
+
+constexpr int kFM = 128;              // cells per tile (UMMA M)
+constexpr int kFHyper = 128;          // hyperplanes per tile
+constexpr int kFDigits = 3;
+constexpr int kFN = kFDigits * kFHyper;   // accumulator columns: digit d of hyperplane j at column d*128 + j (d = 0 highest)
+constexpr int kFChunk = 128;          // genes (K bytes) per pipeline stage
+constexpr int kFStages = 3;
+constexpr uint32_t kFABytes = kFM * kFChunk;
+constexpr uint32_t kFBBytes = kFN * kFChunk;
+constexpr uint32_t kFStageBytes = kFABytes + kFBBytes;     // 64 KB
+constexpr int kFThreads = 192;
+constexpr double kQuantMax = 2080768.;   // |q| <= 127 * 128 * 128
+constexpr double kNearZeroEps = 1e-12;
+constexpr double kMaxSum1 = 1.6e7;    // keeps |sum c * qh| <= 127 * sum1 below 2^31
+
+// Per hyperplane column: sum over genes in ascending order (src/Lsh.cpp:137-144), max |U|, and the
+// constants of the filter bound.  The sum is a G-long dependent chain of FP64 adds per column, so the
+// kernel is organised around keeping that chain fed: a block owns 32 columns, all 8 warps stream 128-gene
+// tiles into a double-buffered shared-memory panel with cp.async, warp 0 runs the 32 chains from there.
+constexpr int kCsRows = 128;
+
+__device__ __forceinline__ void cpAsync8(void* smemDst, const void* gmemSrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smemAddr(smemDst)), "l"(gmemSrc) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+columnStatsKernel(uint64_t geneCount, const double* __restrict__ U, uint64_t ld, uint32_t lshCount, uint32_t cols,
+                  double* __restrict__ sumU, double* __restrict__ scale, double* __restrict__ e1,
+                  double* __restrict__ e2)
+{
+    extern __shared__ __align__(16) double panel[];      // [2][kCsRows][32]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * 32 + tx;
+    const bool active = i < lshCount;
+    const uint32_t tiles = uint32_t((geneCount + kCsRows - 1) / kCsRows);
+    auto issue = [&](uint32_t t) {
+        double* dst = panel + size_t(t & 1) * kCsRows * 32;
+        if (active) {
+            for (int r = ty; r < kCsRows; r += 8) {
+                const uint64_t g = uint64_t(t) * kCsRows + r;
+                if (g < geneCount) cpAsync8(dst + r * 32 + tx, U + g * ld + i);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    double s = 0., m = 0.;
+    if (tiles) issue(0);
+    for (uint32_t t = 0; t < tiles; t++) {
+        if (t + 1 < tiles) issue(t + 1);
+        else asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
+        if (ty == 0 && active) {
+            const double* src = panel + size_t(t & 1) * kCsRows * 32 + tx;
+            const int rows = int(min(uint64_t(kCsRows), geneCount - uint64_t(t) * kCsRows));
+            if (rows == kCsRows) {
+#pragma unroll 16
+                for (int r = 0; r < kCsRows; r++) {
+                    const double v = src[r * 32];
+                    s = __dadd_rn(s, v);
+                    m = fmax(m, fabs(v));
+                }
+            } else {
+                for (int r = 0; r < rows; r++) {
+                    const double v = src[r * 32];
+                    s = __dadd_rn(s, v);
+                    m = fmax(m, fabs(v));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (ty != 0 || i >= cols) return;
+    sumU[i] = s;
+    if (scale) {
+        const double sc = m > 0. ? m / kQuantMax : 1.;
+        scale[i] = sc;
+        e1[i] = 0.5 * sc * (1. + 1e-6);
+        e2[i] = 2.220446049250313e-16 * (m + fabs(s) / double(geneCount));
+    }
+}
+
+// Quantise + transpose the hyperplanes into the GEMM's B operand: int8 [nBlocks*384][Gpad], row
+// nb*384 + d*128 + j = digit d (0 = highest) of hyperplane nb*128 + j, genes contiguous.  Block = 128 genes x 32 hyperplanes.  The buffer is zeroed beforehand (pads stay 0).
+__global__ void __launch_bounds__(256)
+quantizeKernel(uint64_t geneCount, const double* __restrict__ U, uint64_t ld, uint32_t lshCount,
+               const double* __restrict__ scale, uint64_t gPad, int8_t* __restrict__ Uq)
+{
+    __shared__ int8_t sDig[kFDigits][32][132];
+    const uint64_t g0 = uint64_t(blockIdx.x) * 128;
+    const uint32_t i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t i = i0 + tx;
+    const double inv = (i < lshCount) ? 1. / scale[i] : 0.;
+    const double sc = (i < lshCount) ? scale[i] : 1.;
+    for (int r = ty; r < 128; r += 8) {
+        const uint64_t g = g0 + r;
+        int q = 0;
+        if (g < geneCount && i < lshCount) {
+            const double u = __ldg(U + g * ld + i);
+            // nearest integer to u/scale: the product with the reciprocal can be off by one ulp, which
+            // moves the quantisation error by at most 1e-12 * scale -- inside e1's safety factor.
+            q = __double2int_rn(u * inv);
+            // keep the invariant |u - sc*q| <= sc/2 (1 + 1e-6) under every rounding
+            if (fabs(u - sc * double(q)) > 0.5 * sc * (1. + 5e-7)) q = __double2int_rn(u / sc);
+        }
+        const int d2 = (q + 8192) >> 14;        // floor: q - 16384 d2 in [-8192, 8191], |d2| <= 127
+        const int rem = q - 16384 * d2;
+        const int d1 = (rem + 64) >> 7;         // in [-64, 64]
+        sDig[0][tx][r] = int8_t(d2);
+        sDig[1][tx][r] = int8_t(d1);
+        sDig[2][tx][r] = int8_t(rem - 128 * d1);   // in [-64, 63]
+    }
+    __syncthreads();
+    // write: warp w handles hyperplanes w, w+8, ...; lane writes 4 consecutive genes
+    for (int c = ty; c < 32; c += 8) {
+        const uint32_t ic = i0 + c;
+        if (ic >= lshCount) continue;
+        const uint32_t nb = ic / kFHyper, j = ic % kFHyper;
+#pragma unroll
+        for (int d = 0; d < kFDigits; d++) {
+            int8_t* row = Uq + (uint64_t(nb) * kFN + d * kFHyper + j) * gPad + g0;
+            *reinterpret_cast<uint32_t*>(row + 4 * tx) = *reinterpret_cast<const uint32_t*>(&sDig[d][c][4 * tx]);
+        }
+    }
+}
+
+// Dense uint8 expansion of a chunk of cells (the GEMM's A operand) + eligibility.  One warp per cell.
+__global__ void __launch_bounds__(256)
+densifyKernel(uint64_t chunkBegin, uint32_t chunkCells, uint64_t geneCount, uint64_t gPad,
+              const uint64_t* __restrict__ toc, const em2_count* __restrict__ counts,
+              const double* __restrict__ sum1, float maxCount, uint8_t* __restrict__ dense,
+              uint8_t* __restrict__ flags, uint32_t* __restrict__ fallbackList, uint32_t* __restrict__ fallbackCount)
+{
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= chunkCells) return;
+    const uint64_t cell = chunkBegin + w;
+    uint8_t* row = dense + uint64_t(w) * gPad;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t o = uint64_t(lane) * 16; o < gPad; o += 512) *reinterpret_cast<uint4*>(row + o) = z;
+    __syncwarp();
+    bool ok = sum1[cell] < kMaxSum1;
+    const uint64_t end = toc[cell + 1];
+    for (uint64_t e = toc[cell] + lane; e < end; e += 32) {
+        const em2_count p = counts[e];
+        const float c = p.count;
+        ok = ok && (c >= 0.f) && (c <= maxCount) && (c == truncf(c)) && (p.gene < geneCount);
+        if (p.gene < geneCount) row[p.gene] = uint8_t(min(255u, __float2uint_rz(fmaxf(c, 0.f))));
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        flags[w] = ok ? 1 : 0;
+        if (!ok) fallbackList[atomicAdd(fallbackCount, 1u)] = uint32_t(cell);
+    }
+}
+
+struct FilterParams {
+    uint64_t chunkBegin;
+    uint32_t chunkCells;
+    uint64_t geneCount;
+    uint32_t kChunks;          // ceil(G / 128)
+    uint32_t mBlocks, nBlocks;
+    uint32_t lshCount, wordsPerCell;
+    uint32_t idesc256, idesc128;
+    const uint64_t* toc;
+    const double* sum1;
+    const uint8_t* flags;
+    const double *sumU, *scale, *e1, *e2;
+    uint64_t* signatures;
+    uint64_t* uncertain;       // (cell << 32 | hyperplane)
+    uint32_t* uncertainCount;
+    uint32_t uncertainCap;
+};
+
+__global__ void __launch_bounds__(kFThreads, 1)
+sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const FilterParams p)
+{
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(kFStages) * kFStageBytes);
+    uint64_t* full = bars;                   // [stages]  TMA -> MMA
+    uint64_t* empty = bars + kFStages;       // [stages]  MMA -> TMA
+    uint64_t* accFull = bars + 2 * kFStages; // MMA -> epilogue
+    uint64_t* accEmpty = accFull + 1;        // epilogue -> MMA
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(accEmpty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kFStages; i++) {
+            mbarInit(full + i, 1);
+            mbarInit(empty + i, 1);
+        }
+        mbarInit(accFull, 1);
+        mbarInit(accEmpty, 128);
+        mbarInitFence();
+    }
+    if (warp == 4) tmemAlloc(tmemSlot, 512);
+    fenceBefore();
+    __syncthreads();
+    fenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    const uint32_t items = p.mBlocks * p.nBlocks;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            prefetchMap(&mapA);
+            prefetchMap(&mapB);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const int32_t rowA = int32_t((item / p.nBlocks) * kFM);
+                const int32_t rowB = int32_t((item % p.nBlocks) * kFN);
+                for (uint32_t kc = 0; kc < p.kChunks; kc++) {
+                    mbarWait(empty + stage, phase ^ 1);
+                    mbarExpectTx(full + stage, kFStageBytes);
+                    uint8_t* dst = ring + size_t(stage) * kFStageBytes;
+                    tmaLoad2d(dst, &mapA, full + stage, int32_t(kc * kFChunk), rowA);
+#pragma unroll
+                    for (int d = 0; d < kFDigits; d++)
+                        tmaLoad2d(dst + kFABytes + d * kFHyper * kFChunk, &mapB, full + stage, int32_t(kc * kFChunk),
+                                  rowB + d * kFHyper);
+                    if (++stage == kFStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, tileIter = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, tileIter++) {
+                mbarWait(accEmpty, (tileIter & 1) ^ 1);
+                fenceAfter();
+                const uint32_t tmemD = tmemBase;
+                uint32_t accumulate = 0;
+                for (uint32_t kc = 0; kc < p.kChunks; kc++) {
+                    mbarWait(full + stage, phase);
+                    fenceAfter();
+                    const uint32_t aAddr = smemAddr(ring + size_t(stage) * kFStageBytes);
+                    const uint32_t bAddr = aAddr + kFABytes;
+#pragma unroll
+                    for (int ks = 0; ks < kFChunk / 32; ks++) {
+                        const uint64_t descA = makeSmemDesc(aAddr + ks * 32);
+                        mmaI8Ss(tmemD, descA, makeSmemDesc(bAddr + ks * 32), p.idesc256, accumulate);
+                        mmaI8Ss(tmemD + 256, descA, makeSmemDesc(bAddr + 256 * kFChunk + ks * 32), p.idesc128, accumulate);
+                        accumulate = 1;
+                    }
+                    commit(empty + stage);
+                    if (++stage == kFStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                commit(accFull);
+            }
+        }
+    } else {
+        // ===================== epilogue: thread == cell == TMEM lane =====================
+        const uint32_t laneField = uint32_t(warp * 32) << 16;
+        uint32_t tileIter = 0;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, tileIter++) {
+            const uint32_t mb = item / p.nBlocks, nb = item % p.nBlocks;
+            const uint32_t wLocal = mb * kFM + threadIdx.x;
+            const bool valid = wLocal < p.chunkCells && p.flags[wLocal] != 0;
+            const uint64_t cell = p.chunkBegin + (wLocal < p.chunkCells ? wLocal : 0);
+            const double s1 = p.sum1[cell];
+            const double mean = __ddiv_rn(s1, double(p.geneCount));           // src/Lsh.cpp:167-168
+            const double terms = double(p.toc[cell + 1] - p.toc[cell] + 16);
+            mbarWait(accFull, tileIter & 1);
+            fenceAfter();
+            const uint32_t taddr = tmemBase + laneField;
+            uint32_t masks[4];
+#pragma unroll 1
+            for (int q = 0; q < 4; q++) {
+                uint32_t d2[32], d1[32], d0[32];
+                tmemLoad32(taddr + q * 32, d2);
+                tmemLoad32(taddr + kFHyper + q * 32, d1);
+                tmemLoad32(taddr + 2 * kFHyper + q * 32, d0);
+                tmemLoadWait();
+                uint32_t mask = 0;
+                const uint32_t iBase = nb * kFHyper + q * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t i = iBase + j;
+                    const double acc = fma(fma(double(int32_t(d2[j])), 128., double(int32_t(d1[j]))), 128.,
+                                           double(int32_t(d0[j])));                  // exact integer < 2^53
+                    const double sh = __dsub_rn(__dmul_rn(acc, __ldg(p.scale + i)), __dmul_rn(mean, __ldg(p.sumU + i)));
+                    const double bound = s1 * (__ldg(p.e1 + i) + terms * __ldg(p.e2 + i));
+                    if (fabs(sh) > bound) {
+                        mask |= uint32_t(sh > 0.) << (31 - j);
+                    } else if (valid && i < p.lshCount) {
+                        const uint32_t slot = atomicAdd(p.uncertainCount, 1u);
+                        if (slot < p.uncertainCap) p.uncertain[slot] = (cell << 32) | i;
+                    }
+                }
+                masks[q] = mask;
+            }
+            fenceBefore();
+            mbarArrive(accEmpty);
+            if (valid) {
+                const uint32_t w0 = nb * 2;
+                uint64_t* out = p.signatures + cell * p.wordsPerCell;
+                if (w0 < p.wordsPerCell) out[w0] = (uint64_t(masks[0]) << 32) | masks[1];
+                if (w0 + 1 < p.wordsPerCell) out[w0 + 1] = (uint64_t(masks[2]) << 32) | masks[3];
+            }
+        }
+    }
+    fenceBefore();
+    __syncthreads();
+    if (warp == 4) tmemDealloc(tmemBase, 512);
+}
+
+// Exact FP64 evaluation of the listed (cell, hyperplane) projections: the reference's operation sequence
+// (src/Lsh.cpp:180-198).  One warp per entry: lanes fetch 32 stored counts and their hyperplane elements and
+// form the 32 products in parallel; the additions run in stored order.
+__global__ void __launch_bounds__(256)
+fixupKernel(uint64_t geneCount, const uint64_t* __restrict__ toc, const em2_count* __restrict__ counts,
+            const double* __restrict__ sum1, const double* __restrict__ sum2, const double* __restrict__ U, uint64_t ld,
+            const double* __restrict__ sumU, uint32_t wordsPerCell, const uint64_t* __restrict__ entries,
+            const uint32_t* __restrict__ entryCount, uint32_t cap, uint64_t* __restrict__ signatures,
+            unsigned long long* __restrict__ nearZero)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = min(*entryCount, cap);
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
+        const uint64_t entry = entries[e];
+        const uint64_t cell = entry >> 32;
+        const uint32_t i = uint32_t(entry);
+        const double mean = __ddiv_rn(sum1[cell], double(geneCount));
+        double s = __dmul_rn(-mean, sumU[i]);
+        const uint64_t end = toc[cell + 1];
+        for (uint64_t base = toc[cell]; base < end; base += 32) {
+            double prod = 0.;
+            if (base + lane < end) {
+                const em2_count c = counts[base + lane];
+                prod = __dmul_rn(double(c.count), __ldg(U + uint64_t(c.gene) * ld + i));
+            }
+            const int nv = int(min(uint64_t(32), end - base));
+            for (int j = 0; j < nv; j++) s = __dadd_rn(s, __shfl_sync(0xffffffffu, prod, j));
+        }
+        if (lane == 0) {
+            if (s > 0.) atomicOr(reinterpret_cast<unsigned long long*>(signatures + cell * wordsPerCell + (i >> 6)),
+                                 1ull << (63 - (i & 63)));
+            if (nearZero && sum2 &&
+                fabs(s) < kNearZeroEps * (sqrt(sum2[cell]) + fabs(__dmul_rn(mean, sumU[i]))))
+                atomicAdd(nearZero, 1ull);
+        }
+    }
+}
+
+__global__ void recordFilterCounters(const uint32_t* uncertainCount, const uint32_t* fallbackCount, uint32_t chunkCells,
+                                     unsigned long long* counters)
+{
+    if (counters) {
+        atomicAdd(counters + 2, (unsigned long long)(chunkCells - *fallbackCount));
+        atomicAdd(counters + 3, (unsigned long long)(*uncertainCount));
+    }
+}
+
+}  // namespace
+
+int launchColumnStats(em2_context* ctx, uint64_t geneCount, const double* U, uint64_t ld, uint64_t lshCount,
+                      uint64_t cols, double* sumU, double* scale, double* e1, double* e2, cudaStream_t s)
+{
+    const size_t smem = 2 * size_t(kCsRows) * 32 * sizeof(double);
+    EM2_CUDA(ctx, cudaFuncSetAttribute(columnStatsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    columnStatsKernel<<<unsigned((cols + 31) / 32), 256, smem, s>>>(geneCount, U, ld, uint32_t(lshCount), uint32_t(cols),
+                                                                    sumU, scale, e1, e2);
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+    return EM2_OK;
+}
+
+int launchSignaturesFiltered(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                             const em2_count* counts, const double* sum1, const double* sum2, const double* U,
+                             uint64_t ld, const double* Upadded, uint64_t ldPadded, uint64_t lshCount,
+                             uint64_t* signatures, uint64_t* nearZero, cudaStream_t s)
+{
+    const uint64_t W = wordCount(lshCount);
+    const uint64_t gPad = roundUp(geneCount, kFChunk);
+    const uint32_t nBlocks = uint32_t((lshCount + kFHyper - 1) / kFHyper);
+    const uint64_t Lpad = uint64_t(nBlocks) * kFHyper;
+    if (geneCount > 0x7fffff00ull) return fail(ctx, EM2_ERR_INVALID, "geneCount too large");
+
+    // ---- per-hyperplane constants + quantised operand ---------------------------------------------
+    void* stats = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_SUMU, 4 * Lpad * sizeof(double), &stats));
+    double* sumU = static_cast<double*>(stats);
+    double* scale = sumU + Lpad;
+    double* e1 = scale + Lpad;
+    double* e2 = e1 + Lpad;
+    EM2_TRY(launchColumnStats(ctx, geneCount, U, ld, lshCount, Lpad, sumU, scale, e1, e2, s));
+    void* uq = nullptr;
+    const size_t uqBytes = size_t(nBlocks) * kFN * gPad;
+    EM2_TRY(reserve(ctx, em2_context::S_UQ, uqBytes, &uq));
+    EM2_CUDA(ctx, cudaMemsetAsync(uq, 0, uqBytes, s));
+    {
+        const dim3 grid(unsigned(gPad / 128), unsigned((lshCount + 31) / 32));
+        quantizeKernel<<<grid, 256, 0, s>>>(geneCount, U, ld, uint32_t(lshCount), scale, gPad, static_cast<int8_t*>(uq));
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+    }
+
+    // ---- chunks of cells ---------------------------------------------------------------------------
+    const uint64_t denseBudget = 6ull << 30;
+    uint64_t chunkMax = std::max<uint64_t>(kFM, denseBudget / gPad / kFM * kFM);
+    chunkMax = std::min<uint64_t>(chunkMax, roundUp(cellCount, kFM));
+    void *dense, *lists;
+    EM2_TRY(reserve(ctx, em2_context::S_DENSE, chunkMax * gPad, &dense));
+    const uint32_t uncertainCap = ctx->filterUncertainCap ? ctx->filterUncertainCap :
+        uint32_t(std::min<uint64_t>(std::max<uint64_t>(1u << 20, chunkMax * lshCount / 32), 1u << 28));
+    // layout of S_FLAGS: [counters: 2 x u32 (+pad to 16)] [flags: chunkMax bytes] [fallback list: chunkMax u32] [uncertain: cap u64]
+    const size_t offFlags = 16, offFallback = roundUp(offFlags + chunkMax, 16), offUncertain = roundUp(offFallback + 4 * chunkMax, 16);
+    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, offUncertain + size_t(uncertainCap) * 8, &lists));
+    uint8_t* base = static_cast<uint8_t*>(lists);
+    uint32_t* uncertainCount = reinterpret_cast<uint32_t*>(base);
+    uint32_t* fallbackCount = uncertainCount + 1;
+    uint8_t* dFlags = base + offFlags;
+    uint32_t* fallbackList = reinterpret_cast<uint32_t*>(base + offFallback);
+    uint64_t* uncertain = reinterpret_cast<uint64_t*>(base + offUncertain);
+
+    const bool unsignedCounts = ctx->filterCountsSigned == 0;
+    const size_t smem = 1024 + size_t(kFStages) * kFStageBytes + 256;
+    EM2_CUDA(ctx, cudaFuncSetAttribute(sigFilterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CUtensorMap mapB;
+    EM2_TRY(makeTensorMapU8(ctx, &mapB, uq, uint64_t(nBlocks) * kFN, gPad, gPad, 128));
+
+    for (uint64_t begin = 0; begin < cellCount; begin += chunkMax) {
+        const uint32_t chunkCells = uint32_t(std::min<uint64_t>(chunkMax, cellCount - begin));
+        EM2_CUDA(ctx, cudaMemsetAsync(base, 0, 16, s));
+        densifyKernel<<<(chunkCells + 7) / 8, 256, 0, s>>>(begin, chunkCells, geneCount, gPad, toc, counts, sum1,
+                                                           unsignedCounts ? 255.f : 127.f, static_cast<uint8_t*>(dense),
+                                                           dFlags, fallbackList, fallbackCount);
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+
+        FilterParams p{};
+        p.chunkBegin = begin;
+        p.chunkCells = chunkCells;
+        p.geneCount = geneCount;
+        p.kChunks = uint32_t(gPad / kFChunk);
+        p.mBlocks = (chunkCells + kFM - 1) / kFM;
+        p.nBlocks = nBlocks;
+        p.lshCount = uint32_t(lshCount);
+        p.wordsPerCell = uint32_t(W);
+        p.idesc256 = instrDescI8(!unsignedCounts, true, kFM, 256);
+        p.idesc128 = instrDescI8(!unsignedCounts, true, kFM, 128);
+        p.toc = toc;
+        p.sum1 = sum1;
+        p.flags = dFlags;
+        p.sumU = sumU;
+        p.scale = scale;
+        p.e1 = e1;
+        p.e2 = e2;
+        p.signatures = signatures;
+        p.uncertain = uncertain;
+        p.uncertainCount = uncertainCount;
+        p.uncertainCap = uncertainCap;
+        CUtensorMap mapA;
+        EM2_TRY(makeTensorMapU8(ctx, &mapA, dense, chunkCells, gPad, gPad, kFM));
+        const uint32_t items = p.mBlocks * p.nBlocks;
+        const unsigned grid = std::min<uint32_t>(items, uint32_t(ctx->smCount));
+        sigFilterKernel<<<grid, kFThreads, smem, s>>>(mapA, mapB, p);
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+
+        fixupKernel<<<ctx->smCount * 8, 256, 0, s>>>(geneCount, toc, counts, sum1, sum2, U, ld, sumU, uint32_t(W), uncertain,
+                                                     uncertainCount, uncertainCap, signatures,
+                                                     reinterpret_cast<unsigned long long*>(nearZero));
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+
+        // cells the filter could not take (non-integer / large counts): the FP64 kernel on the list;
+        // and, should the uncertain list have overflowed, the FP64 kernel on the whole chunk.
+        EM2_TRY(launchSignaturesFp64(ctx, cellCount, geneCount, toc, counts, sum1, sum2, Upadded, ldPadded, sumU, lshCount,
+                                     signatures, nearZero, fallbackList, fallbackCount, chunkCells, nullptr, 0, begin,
+                                     chunkCells, s));
+        EM2_TRY(launchSignaturesFp64(ctx, cellCount, geneCount, toc, counts, sum1, sum2, Upadded, ldPadded, sumU, lshCount,
+                                     signatures, nearZero, nullptr, nullptr, 0, uncertainCount, uncertainCap, begin,
+                                     chunkCells, s));
+        recordFilterCounters<<<1, 1, 0, s>>>(uncertainCount, fallbackCount, chunkCells,
+                                             reinterpret_cast<unsigned long long*>(ctx->scratch[em2_context::S_COUNTERS].ptr));
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+    }
+    return EM2_OK;
+}
+
+}  // namespace em2

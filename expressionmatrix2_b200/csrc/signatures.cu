@@ -17,6 +17,8 @@
 // the G x 128 x 8 B slice (30 MB at G = 30k) stays L2 resident while all cells pass over it.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace em2 {
 
 namespace {
@@ -43,25 +45,6 @@ __global__ void cellSumsKernel(uint64_t cellCount, const uint64_t* __restrict__ 
     if (sum2) sum2[c] = s2;
 }
 
-// One thread per hyperplane column, genes in ascending order (src/Lsh.cpp:137-144).
-__global__ void columnSumsKernel(uint64_t geneCount, const double* __restrict__ U, uint64_t ld, uint32_t cols,
-                                 double* __restrict__ sumU)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cols) return;
-    double s = 0.;
-    uint64_t g = 0;
-    for (; g + 8 <= geneCount; g += 8) {
-        double v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = __ldg(U + (g + j) * ld + i);
-#pragma unroll
-        for (int j = 0; j < 8; j++) s = __dadd_rn(s, v[j]);
-    }
-    for (; g < geneCount; g++) s = __dadd_rn(s, __ldg(U + g * ld + i));
-    sumU[i] = s;
-}
-
 __device__ __forceinline__ uint64_t spreadBits(uint32_t v)
 {
     uint64_t x = v;
@@ -79,23 +62,34 @@ __device__ __forceinline__ double2 ldU(const double* p)
     return __ldg(reinterpret_cast<const double2*>(p));
 }
 
-// grid.x = slices * ceil(cellCount / kSigWarps), slice-major.  U must have `ld` >= slices*128 columns
-// readable (zero padded beyond lshCount), ld even, base 16-byte aligned.
-__global__ void __launch_bounds__(kSigWarps * 32)
-signatureKernel(uint64_t cellCount, uint64_t geneCount, const uint64_t* __restrict__ toc,
+// Work unit = (128-hyperplane slice, group of kSigWarps cells), slice-major; blocks take units grid-stride
+// (the plain launch has one block per unit).  U must have `ld` >= slices*128 columns readable (zero padded
+// beyond lshCount), ld even, base 16-byte aligned.  Cells are [rangeBegin, rangeBegin + rangeCells), or, when
+// `cellList` is given, the first *cellListCount entries of that list.  With `runIfCount` the whole launch is
+// a no-op unless *runIfCount > runIfCap (device-side predicate of the filter path's overflow rescue).
+__global__ void __launch_bounds__(kSigWarps * 32, 4)
+signatureKernel(uint64_t rangeBegin, uint64_t rangeCells, uint64_t geneCount, const uint64_t* __restrict__ toc,
                 const em2_count* __restrict__ counts, const double* __restrict__ sum1,
                 const double* __restrict__ sum2, const double* __restrict__ U, uint64_t ld,
-                const double* __restrict__ sumU, uint32_t lshCount, uint32_t wordsPerCell, uint32_t cellBlocks,
-                uint64_t* __restrict__ signatures, unsigned long long* __restrict__ nearZero)
+                const double* __restrict__ sumU, uint32_t lshCount, uint32_t wordsPerCell, uint32_t slices,
+                uint64_t* __restrict__ signatures, unsigned long long* __restrict__ nearZero,
+                const uint32_t* __restrict__ cellList, const uint32_t* __restrict__ cellListCount,
+                const uint32_t* __restrict__ runIfCount, uint32_t runIfCap)
 {
     __shared__ uint32_t sGene[kSigWarps][32];
     __shared__ double sCount[kSigWarps][32];
 
+    if (runIfCount != nullptr && *runIfCount <= runIfCap) return;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t slice = blockIdx.x / cellBlocks;
-    const uint64_t cell = uint64_t(blockIdx.x % cellBlocks) * kSigWarps + warp;
-    if (cell >= cellCount) return;
+    const uint64_t nCells = cellList ? min(uint64_t(*cellListCount), rangeCells) : rangeCells;
+    const uint64_t cellBlocks = (nCells + kSigWarps - 1) / kSigWarps;
+    const uint64_t units = cellBlocks * slices;
+  for (uint64_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const uint32_t slice = uint32_t(unit / cellBlocks);
+    const uint64_t idx = (unit % cellBlocks) * kSigWarps + warp;
+    if (idx >= nCells) continue;
+    const uint64_t cell = cellList ? uint64_t(cellList[idx]) : rangeBegin + idx;
 
     const uint32_t colBase = slice * kSliceCols;
     const uint32_t c0 = colBase + 2 * lane;        // hyperplanes c0, c0+1
@@ -180,6 +174,8 @@ signatureKernel(uint64_t cellCount, uint64_t geneCount, const uint64_t* __restri
         if (w0 + 1 < wordsPerCell)
             signatures[cell * wordsPerCell + w0 + 1] = __brevll(spreadBits(b2) | (spreadBits(b3) << 1));
     }
+    __syncwarp();
+  }
 }
 
 }  // namespace
@@ -196,18 +192,41 @@ int launchCellSums(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, co
     return EM2_OK;
 }
 
+int launchSignaturesFp64(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                         const em2_count* counts, const double* sum1, const double* sum2, const double* Uk,
+                         uint64_t ldk, const double* sumU, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero,
+                         const uint32_t* cellList, const uint32_t* cellListCount, uint64_t maxListed,
+                         const uint32_t* runIfCount, uint32_t runIfCap, uint64_t rangeBegin, uint64_t rangeCells,
+                         cudaStream_t s)
+{
+    (void)cellCount;
+    const uint64_t W = wordCount(lshCount);
+    const uint32_t slices = uint32_t(roundUp(lshCount, kSliceCols) / kSliceCols);
+    const uint64_t cells = cellList ? maxListed : rangeCells;
+    if (cells == 0) return EM2_OK;
+    uint64_t blocks = (cells + kSigWarps - 1) / kSigWarps * slices;
+    // device-sized work (a list, or a predicate that is normally false): a persistent grid is enough
+    if (cellList || runIfCount) blocks = std::min<uint64_t>(blocks, uint64_t(ctx->smCount) * 8);
+    if (blocks > 0x7fffffffull) return fail(ctx, EM2_ERR_INVALID, "too many cells for one signature launch");
+    signatureKernel<<<unsigned(blocks), kSigWarps * 32, 0, s>>>(
+        rangeBegin, cells, geneCount, toc, counts, sum1, sum2, Uk, ldk, sumU, uint32_t(lshCount), uint32_t(W), slices,
+        signatures, reinterpret_cast<unsigned long long*>(nearZero), cellList, cellListCount, runIfCount, runIfCap);
+    ctx->stats.kernel_launches++;
+    EM2_CUDA(ctx, cudaGetLastError());
+    return EM2_OK;
+}
+
 int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                      const em2_count* counts, const double* sum1, const double* sum2, const double* U,
-                     uint64_t ld, uint64_t lshCount, uint64_t* signatures, uint64_t* nearZero, cudaStream_t s)
+                     uint64_t ld, uint64_t lshCount, uint64_t nnzHint, uint64_t* signatures, uint64_t* nearZero,
+                     cudaStream_t s)
 {
     if (cellCount == 0) return EM2_OK;
     if (lshCount == 0 || lshCount > 65535) return fail(ctx, EM2_ERR_INVALID, "lshCount must be in [1, 65535]");
     if (geneCount == 0) return fail(ctx, EM2_ERR_INVALID, "geneCount must be positive");
-    const uint64_t W = wordCount(lshCount);
     const uint64_t Lpad = roundUp(lshCount, kSliceCols);
-    const uint32_t slices = uint32_t(Lpad / kSliceCols);
 
-    // The kernel wants `Lpad` readable, zero padded columns with an even pitch and 16-byte alignment.
+    // The FP64 kernel wants `Lpad` readable, zero padded columns with an even pitch and 16-byte alignment.
     const double* Uk = U;
     uint64_t ldk = ld;
     if (ld < Lpad || (ld & 1) || (reinterpret_cast<uintptr_t>(U) & 15)) {
@@ -220,22 +239,25 @@ int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, c
         ldk = Lpad;
     }
 
+    // Path choice (both are bit-identical): the tensor-core filter does G*2L int8 MACs per cell
+    // at ~1.2e15/s, the FP64 kernel nnz*L at ~2.9e12/s, so the filter wins above ~0.5 % density; it also
+    // needs enough cells to fill the GPU with 128 x 128 tiles.
+    bool filter = false;
+    if (ctx->signatureMode == 2) filter = true;
+    else if (ctx->signatureMode == 0 && nnzHint != 0) {
+        const double density = double(nnzHint) / (double(cellCount) * double(geneCount));
+        filter = density >= 0.012 && cellCount >= 4096 && geneCount >= 1024 && lshCount >= 128;
+    }
+    if (filter)
+        return launchSignaturesFiltered(ctx, cellCount, geneCount, toc, counts, sum1, sum2, U, ld, Uk, ldk, lshCount,
+                                        signatures, nearZero, s);
+
     void* sumU = nullptr;
     EM2_TRY(reserve(ctx, em2_context::S_SUMU, Lpad * sizeof(double), &sumU));
-    columnSumsKernel<<<unsigned((Lpad + 127) / 128), 128, 0, s>>>(geneCount, Uk, ldk, uint32_t(Lpad),
-                                                                 static_cast<double*>(sumU));
-    ctx->stats.kernel_launches++;
-    EM2_CUDA(ctx, cudaGetLastError());
-
-    const uint64_t cellBlocks = (cellCount + kSigWarps - 1) / kSigWarps;
-    const uint64_t blocks = cellBlocks * slices;
-    if (blocks > 0x7fffffffull) return fail(ctx, EM2_ERR_INVALID, "too many cells for one signature launch");
-    signatureKernel<<<unsigned(blocks), kSigWarps * 32, 0, s>>>(
-        cellCount, geneCount, toc, counts, sum1, sum2, Uk, ldk, static_cast<const double*>(sumU), uint32_t(lshCount),
-        uint32_t(W), uint32_t(cellBlocks), signatures, reinterpret_cast<unsigned long long*>(nearZero));
-    ctx->stats.kernel_launches++;
-    EM2_CUDA(ctx, cudaGetLastError());
-    return EM2_OK;
+    EM2_TRY(launchColumnStats(ctx, geneCount, Uk, ldk, Lpad, Lpad, static_cast<double*>(sumU), nullptr, nullptr, nullptr, s));
+    return launchSignaturesFp64(ctx, cellCount, geneCount, toc, counts, sum1, sum2, Uk, ldk,
+                                static_cast<const double*>(sumU), lshCount, signatures, nearZero, nullptr, nullptr, 0,
+                                nullptr, 0, 0, cellCount, s);
 }
 
 }  // namespace em2

@@ -106,7 +106,10 @@ const char* em2_last_error(const em2_context* ctx);
 int em2_device_name(em2_context* ctx, char* buffer, size_t bufferSize);
 int em2_get_stats(const em2_context* ctx, em2_stats* stats);
 /* Tuning / test knobs.  Names: "signature_mode" (0 = automatic, 1 = FP64 kernel only, 2 = force the
- * tensor-core filter + exact fix-up path), "popc_csa" (carry-save levels of the POPC scan, 0..2). */
+ * tensor-core filter + exact fix-up path), "popc_csa" (carry-save levels of the POPC scan, 0..2),
+ * "filter_counts_signed" (1: the filter GEMM takes counts as s8 <= 127 instead of u8 <= 255),
+ * "filter_uncertain_cap" (capacity of the filter's uncertain list; 0 = automatic), "exact_matrix_bytes"
+ * (budget of the exact path's row-chunk similarity matrix; 0 = 8 GiB). */
 int em2_set_option(em2_context* ctx, const char* name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -166,11 +169,13 @@ int em2_exact_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneC
 int em2_cell_sums_device(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
                          double* sum1, double* sum2, void* stream);
 /* lshVectors: device double[geneCount*ld], ld >= lshCount (elements).  sum1 from em2_cell_sums_device.
+ * nnz: number of stored counts, toc[cellCount] (a hint for the choice between the FP64 kernel and the
+ * tensor-core filter path -- both give identical bits; 0 = unknown).
  * signatures: device uint64[cellCount*W]. nearZero: device uint64 counter (may be NULL), accumulated. */
 int em2_signatures_device(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                           const em2_count* counts, const double* sum1, const double* sum2,
-                          const double* lshVectors, uint64_t ld, uint64_t lshCount, uint64_t* signatures,
-                          uint64_t* nearZero, void* stream);
+                          const double* lshVectors, uint64_t ld, uint64_t lshCount, uint64_t nnz,
+                          uint64_t* signatures, uint64_t* nearZero, void* stream);
 /* signatures: device uint64[cellCount*W] of ALL cells (columns); rows [rowBegin,rowEnd) are scanned.
  * similarityTable: device float[lshCount+1].  pairs/usedCount as in em2_find_similar_pairs. */
 int em2_scan_topk_device(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,

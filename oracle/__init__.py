@@ -217,6 +217,36 @@ def exact_rows(gene_count, toc, gene_ids, counts, sum1, sum2, row_begin, row_end
     return out
 
 
+def exact_topk(gene_count, toc, gene_ids, counts, k: int, threshold: float, row_begin: int = 0,
+               row_end: int | None = None):
+    """Deterministic top-k of the exact path (findSimilarPairs0, src/ExpressionMatrixFindSimilarPairs.cpp:60-80 +
+    SimilarPairs::add/sort): per cell, among other cells with r > threshold (double compare), the k largest
+    by (float(r) desc, cell id asc) -- SimilarPairs stores float similarities (src/SimilarPairs.hpp:53-56) and
+    sort() orders by (similarity desc, id asc) (src/orderPairs.hpp:44-52).
+    Returns (ids uint32[rows,k], sims float32[rows,k], used uint32[rows], r float64[rows,N])."""
+    n = len(toc) - 1
+    row_end = n if row_end is None else row_end
+    s1, s2 = cell_sums(toc, counts)
+    r = exact_rows(gene_count, toc, gene_ids, counts, s1, s2, row_begin, row_end)
+    rows = row_end - row_begin
+    ids = np.zeros((rows, k), np.uint32)
+    sims = np.zeros((rows, k), np.float32)
+    used = np.zeros(rows, np.uint32)
+    cols = np.arange(n)
+    for i in range(rows):
+        row = r[i]
+        with np.errstate(invalid="ignore"):
+            ok = (row > threshold) & (cols != row_begin + i)
+        cand = cols[ok]
+        f = row[ok].astype(np.float32)
+        order = np.lexsort((cand, -f.astype(np.float64)))[:k]
+        u = len(order)
+        ids[i, :u] = cand[order]
+        sims[i, :u] = f[order]
+        used[i] = u
+    return ids, sims, used, r
+
+
 def murmur64a(data: bytes, seed: int = 231) -> int:
     buf = C.create_string_buffer(data, len(data))
     return int(olib().em2o_murmur64a(buf, len(data), seed))

@@ -200,3 +200,142 @@ def test_size_independent_properties_at_scale(engine, oracle, variant):
         key = m.astype(np.uint64) << np.uint64(32) | row_ids.astype(np.uint64)
         assert np.all(np.diff(key.astype(np.int64)) > 0)
         assert np.all(ids[r, u:] == 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core signature filter path (sig_filter.cu): same bits as the FP64 kernel and the oracle
+# ---------------------------------------------------------------------------------------------------
+def _with_mode(engine, mode, fn, **opts):
+    engine.set_option("signature_mode", mode)
+    for k, v in opts.items():
+        engine.set_option(k, v)
+    try:
+        return fn()
+    finally:
+        engine.set_option("signature_mode", 0)
+        for k in opts:
+            engine.set_option(k, 0)
+
+
+@pytest.mark.parametrize("N,G,dens,L,mode", [
+    (1500, 700, 0.05, 1024, "clustered"),
+    (900, 333, 0.07, 200, "clustered"),      # neither G nor L a multiple of 128
+    (700, 300, 0.05, 1, "iid"),
+    (1300, 2100, 0.02, 384, "iid"),
+])
+def test_filter_signatures_bit_exact(engine, oracle, N, G, dens, L, mode):
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, dens, seed=N + L, mode=mode, clusters=7)
+    U = em2.generate_lsh_vectors(G, L, 231)
+    s1, _ = oracle.cell_sums(toc, counts)
+    want, _ = oracle.signatures(toc, genes, counts, s1, U)
+    sig = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes))
+    st = engine.stats()
+    assert np.array_equal(sig, want)
+    assert st["filter_cells"] == N and st["near_zero_projections"] == 0
+    assert st["filter_uncertain"] < 0.01 * N * L + 16
+    sig_s8 = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes),
+                        filter_counts_signed=1)
+    assert np.array_equal(sig_s8, want)
+
+
+def test_filter_ineligible_cells_and_overflow(engine, oracle):
+    """Cells with non-integer or large counts fall back to the FP64 kernel cell by cell; an overflowing
+    uncertain list triggers the device-side full FP64 recompute.  Bits never change."""
+    N, G, L = 1200, 640, 256
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, 0.05, seed=5, mode="clustered", clusters=5)
+    counts[::97] = 300.0
+    counts[5::1013] = 2.5
+    toc = toc.copy()
+    U = em2.generate_lsh_vectors(G, L, 231)
+    s1, _ = oracle.cell_sums(toc, counts)
+    want, _ = oracle.signatures(toc, genes, counts, s1, U)
+    sig = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes))
+    st = engine.stats()
+    assert np.array_equal(sig, want)
+    assert 0 < st["filter_cells"] < N
+    sig = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes),
+                     filter_uncertain_cap=1)
+    assert np.array_equal(sig, want)
+
+
+def test_filter_equals_fp64_at_scale(engine, oracle):
+    """20k cells x 30k genes (bench density): automatic mode takes the filter path; every word equals the
+    FP64 kernel's, and sampled cells equal the oracle."""
+    N, G, m, L = 20000, 30000, 1500, 1024
+    toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, m, seed=12345)
+    U = em2.generate_lsh_vectors(G, L, 231)
+    auto = engine.compute_signatures(toc, counts, U, gene_ids=genes)
+    st = engine.stats()
+    assert st["filter_cells"] == N
+    fp64 = _with_mode(engine, 1, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes))
+    assert engine.stats()["filter_cells"] == 0
+    assert np.array_equal(auto, fp64)
+    e = int(toc[64])
+    s1, _ = oracle.cell_sums(toc[:65], counts[:e])
+    want, _ = oracle.signatures(toc[:65], genes[:e], counts[:e], s1, U)
+    assert np.array_equal(auto[:64], want)
+
+
+# ---------------------------------------------------------------------------------------------------
+# exact (Pearson) path -- BASELINE config 5
+# ---------------------------------------------------------------------------------------------------
+def _check_exact(engine, oracle, toc, genes, counts, G, k, thr, bit_exact=True):
+    ids, sims, used = engine.exact_similar_pairs(toc, counts, G, k, thr, gene_ids=genes)
+    wids, wsims, wused, r = oracle.exact_topk(G, toc, genes, counts, k, thr)
+    if bit_exact:
+        assert np.array_equal(used, wused)
+        assert np.array_equal(ids, wids)
+        assert np.array_equal(sims.view(np.uint32), wsims.view(np.uint32))     # 0 ULP
+    else:
+        # tolerance of SURVEY 8c: |r_gpu - r_ref| <= 1e-5; lists may differ only inside that band
+        for c in range(len(used)):
+            u = int(used[c])
+            assert np.all(np.abs(sims[c, :u].astype(np.float64) - r[c, ids[c, :u]]) <= 1e-5)
+            assert abs(u - int(wused[c])) <= 1 or thr < -0.5
+            if u and wused[c]:
+                assert abs(float(sims[c, u - 1]) - float(wsims[c, int(wused[c]) - 1])) <= 2e-5
+    return ids, sims, used
+
+
+@pytest.mark.parametrize("N,G,dens,k,thr", [
+    (700, 500, 0.05, 20, 0.2),
+    (1031, 777, 0.03, 50, -1.0),     # ragged sizes, pure top-k
+    (300, 130, 0.10, 5, 0.5),
+])
+def test_exact_path_bit_exact_small_counts(engine, oracle, N, G, dens, k, thr):
+    """Integer counts <= 255: one digit plane; scalar products, r and the lists are bit-identical to the
+    reference's CPU loop (oracle restatement of ExpressionMatrixSubset::computeCellSimilarity)."""
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, dens, seed=N, mode="clustered", clusters=6)
+    _check_exact(engine, oracle, toc, genes, counts, G, k, thr)
+    assert engine.stats()["kernel_launches"] >= 4
+
+
+def test_exact_path_two_digit_counts_and_row_chunks(engine, oracle):
+    """Counts up to 4095 need two digit planes (HH, HL+LH, LL accumulators); a tiny matrix budget forces
+    several row chunks.  Still bit-exact."""
+    N, G = 900, 400
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, 0.06, seed=9, mode="clustered", clusters=4)
+    rng = np.random.default_rng(1)
+    big = rng.integers(0, len(counts), len(counts) // 20)
+    counts[big] = rng.integers(256, 4096, len(big)).astype(np.float32)
+    engine.set_option("exact_matrix_bytes", 300 * 1024 * 4)
+    try:
+        _check_exact(engine, oracle, toc, genes, counts, G, 30, 0.1)
+    finally:
+        engine.set_option("exact_matrix_bytes", 0)
+
+
+def test_exact_path_degenerate_cells(engine, oracle):
+    """Empty cells and constant cells have zero variance: r is NaN in the reference and never stored."""
+    toc = np.array([0, 0, 3, 3, 8, 10, 13], np.uint64)
+    genes = np.array([0, 2, 4, 0, 1, 2, 3, 4, 1, 3, 0, 2, 4], np.uint32)
+    counts = np.array([1, 2, 3, 1, 1, 1, 1, 1, 4, 2, 2, 4, 6], np.float32)
+    _check_exact(engine, oracle, toc, genes, counts, 5, 3, -1.0)
+
+
+def test_exact_path_rejects_non_integer_counts(engine):
+    toc = np.array([0, 2, 4], np.uint64)
+    genes = np.array([0, 1, 0, 1], np.uint32)
+    counts = np.array([1.5, 2, 3, 4], np.float32)
+    with pytest.raises(em2.Em2Error):
+        engine.exact_similar_pairs(toc, counts, 2, 1, 0.0, gene_ids=genes)
