@@ -36,6 +36,15 @@ WORKLOADS = {
                note="BASELINE configs[0]: 10k x 20k, 5% density"),
     "c2": dict(cells=100_000, genes=30_000, nnz_per_cell=1500, lsh=1024, k=50, thr=0.2,
                note="BASELINE configs[1]: 100k x 30k, 5% density"),
+    "c3": dict(cells=1_300_000, genes=28_000, nnz_per_cell=2000, lsh=1024, k=50, thr=0.2, per_rank_generation=True,
+               note="BASELINE configs[2]: 1.3M x 28k (10x mouse-brain shape, ~2.0k nnz/cell assumed), meant for 8 GPUs"),
+    "c4": dict(kind="sig", cells=1_000_000, genes=0, lsh=1024, k=50, thr=0.2, clusters=500,
+               note="BASELINE configs[3]: 1M cells, signatures-only synthetic (500 planted clusters, 12% bit flips); "
+                    "--lsh 256/1024/4096 and --variant popc/mma give the sweep"),
+    "c4s": dict(kind="sig", cells=200_000, genes=0, lsh=1024, k=50, thr=0.2, clusters=100,
+                note="reduced c4 for quick checks (NOT a bench line)"),
+    "c5": dict(kind="exact", cells=50_000, genes=20_000, nnz_per_cell=1000, lsh=0, k=50, thr=0.2,
+               note="BASELINE configs[4]: exact Pearson brute force on 50k cells x 20k genes @ 5%"),
     "c2s": dict(cells=20_000, genes=30_000, nnz_per_cell=1500, lsh=1024, k=50, thr=0.2,
                 note="reduced c2 for quick checks (NOT a bench line)"),
 }
@@ -115,83 +124,113 @@ def make_workload(w, seed=12345):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation (oracle/_ref), bounded sample per step
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(w, toc, genes, counts, signatures, sig_cells=1024, loop_rows=2048):
+def cpu_sample(w, toc, genes, counts, signatures, sig_cells=1024, loop_rows=2048, lsh=None):
     """Times the reference's two instrumented regions on a bounded sample of the workload:
     Lsh::computeCellLshSignatures on the first `sig_cells` cells (its own timer, Lsh.cpp:160,209) and the
     findSimilarPairs4 pair loop (ExpressionMatrixLsh.cpp:217,270) for the last `loop_rows` cells against
-    all earlier cells.  Returns the extrapolated whole-job figures."""
+    all earlier cells.  Returns the extrapolated whole-job figures.  toc=None: signatures-only workload
+    (config 4), only the pair loop is timed."""
     import oracle
-    N, L, k, thr = w["cells"], w["lsh"], w["k"], w["thr"]
+    N, L, k, thr = w["cells"], lsh or w["lsh"], w["k"], w["thr"]
     kind = "reference" if oracle.have_ref() else "port"
     sig_cells = min(sig_cells, N)
-    loop_rows = min(loop_rows, N)
+    loop_rows = min(loop_rows if N < 500_000 else 1024, N)
     t0 = time.time()
-    e = int(toc[sig_cells])
+    t_sig, ref_sig = 0.0, None
+    if toc is not None:
+        e = int(toc[sig_cells])
+        if kind == "reference":
+            with oracle.Reference.from_csr(toc[: sig_cells + 1], genes[:e], counts[:e], w["genes"], L, 231) as R:
+                t_sig = R.signature_seconds
+                ref_sig = R.signatures()
+        else:
+            U = oracle.generate_lsh_vectors(w["genes"], L, 231)
+            s1, _ = oracle.cell_sums(toc[: sig_cells + 1], counts[:e])
+            t1 = time.time()
+            ref_sig, _ = oracle.signatures(toc[: sig_cells + 1], genes[:e], counts[:e], s1, U)
+            t_sig = time.time() - t1
     if kind == "reference":
-        with oracle.Reference.from_csr(toc[: sig_cells + 1], genes[:e], counts[:e], w["genes"], L, 231) as R:
-            t_sig = R.signature_seconds
-            ref_sig = R.signatures()
         with oracle.Reference.from_signatures(signatures, L) as R:
             r = R.find_similar_pairs4_loop(k, thr, N - loop_rows, N, want_pairs=False)
             t_loop, pairs = r["seconds"], r["pairs"]
     else:
-        U = oracle.generate_lsh_vectors(w["genes"], L, 231)
-        s1, _ = oracle.cell_sums(toc[: sig_cells + 1], counts[:e])
-        t1 = time.time()
-        ref_sig, _ = oracle.signatures(toc[: sig_cells + 1], genes[:e], counts[:e], s1, U)
-        t_sig = time.time() - t1
         t_loop, pairs, _ = oracle.pair_loop(signatures, L, thr, N - loop_rows, N)
     total_pairs = N * (N - 1) / 2
     sig_s_per_cell = t_sig / sig_cells
     ns_per_pair = 1e9 * t_loop / max(pairs, 1)
     full_seconds = sig_s_per_cell * N + ns_per_pair * 1e-9 * total_pairs
-    return dict(kind=kind, cores=1, value=total_pairs / full_seconds, unit="cell-pairs/s",
-                sample=f"signatures of the first {sig_cells} cells + findSimilarPairs4 pair loop for the last "
-                       f"{loop_rows} cells x all earlier cells ({pairs} pairs), extrapolated to the whole job",
-                signature_s_per_cell=sig_s_per_cell, ns_per_pair=ns_per_pair, extrapolated_job_seconds=full_seconds,
-                sample_seconds=time.time() - t0, sample_signatures_match_gpu=bool(
-                    np.array_equal(ref_sig, signatures[:sig_cells])))
+    what = (f"signatures of the first {sig_cells} cells + " if toc is not None else "")
+    out = dict(value=total_pairs / full_seconds, unit="cell-pairs/s", cores=1, kind=kind,
+               sample=what + f"findSimilarPairs4 pair loop for the last {loop_rows} cells x all earlier cells "
+                             f"({pairs} pairs), extrapolated to the whole job",
+               ns_per_pair=ns_per_pair, signature_s_per_cell=sig_s_per_cell, extrapolated_job_seconds=full_seconds,
+               sample_seconds=time.time() - t0)
+    if ref_sig is not None:
+        out["sample_signatures_match_gpu"] = bool(np.array_equal(ref_sig, signatures[:sig_cells]))
+    return out
 
 
 def run_reference(args, w):
+    """The reference's own CPU code (oracle/_ref; the C port when the reference build is absent) on a bounded sample
+    of the same workload per step, one core (the reference is single threaded)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
+    from expressionmatrix2_b200 import synthetic
     oracle.build()
-    toc, genes, counts, U = make_workload(w)
-    # the pair loop needs the signatures of every cell: computed once with the C restatement's
-    # arithmetic on all host cores would take minutes at 100k cells, so use random-projection-free
-    # synthetic signatures of identical shape for the loop timing when no GPU is present.
+    kind = w.get("kind", "lsh")
+    N, L = w["cells"], args.lsh or w["lsh"]
     try:
         import torch
         have_gpu = torch.cuda.is_available()
     except Exception:
         have_gpu = False
-    if have_gpu:
-        import expressionmatrix2_b200 as em2
-        with em2.Engine(0) as eng:
-            signatures = eng.compute_signatures(toc, counts, U, gene_ids=genes)
-        sig_note = "signatures of all cells from the GPU path (bit-exact vs the reference on the sampled cells)"
-    else:
-        from expressionmatrix2_b200 import synthetic
-        signatures = synthetic.gen_signatures(w["cells"], w["lsh"], seed=1, clusters=64)
-        sig_note = "synthetic signatures (no GPU visible)"
     samples = []
-    for i in range(args.warmup + args.steps):
-        t0 = time.time()
-        s = cpu_sample(w, toc, genes, counts, signatures)
-        s["wall_ms"] = 1e3 * (time.time() - t0)
-        if i >= args.warmup:
-            samples.append(s)
-    value = float(np.median([s["value"] for s in samples]))
+    if kind == "exact":
+        G = w["genes"]
+        toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, w["nnz_per_cell"], seed=12345)
+        s1, s2 = oracle.cell_sums(toc, counts)
+        for i in range(args.warmup + args.steps):
+            t0 = time.time()
+            oracle.exact_rows(G, toc, genes, counts, s1, s2, 4 * i, 4 * i + 4)
+            dt = time.time() - t0
+            if i >= args.warmup:
+                samples.append(dict(value=4 * N / dt, wall_ms=1e3 * dt, kind="port", ns_per_pair=1e9 * dt / (4 * N),
+                                    signature_s_per_cell=0.0, extrapolated_job_seconds=N * (N - 1) / 2 / (4 * N / dt),
+                                    sample=f"computeCellSimilarity for 4 cells against all {N} cells ({4 * N} pairs)"))
+        sig_note = "n/a (exact path)"
+        metric = "cell-pairs/sec (exact Pearson, top-50)"
+    else:
+        toc = genes = counts = None
+        if kind == "lsh":
+            toc, genes, counts, U = make_workload(w)
+        # the pair loop needs the signatures of every cell: the GPU path supplies them when a GPU is present
+        # (they are checked bit-exact against the reference on the sampled cells); synthetic ones otherwise.
+        if kind == "lsh" and have_gpu:
+            import expressionmatrix2_b200 as em2
+            with em2.Engine(0) as eng:
+                signatures = eng.compute_signatures(toc, counts, U, gene_ids=genes)
+            sig_note = "signatures of all cells from the GPU path (bit-exact vs the reference on the sampled cells)"
+        else:
+            signatures = synthetic.gen_signatures(N, L, seed=1000, clusters=w.get("clusters", 64), centre_seed=77)
+            sig_note = "synthetic signatures" + ("" if kind == "sig" else " (no GPU visible)")
+        for i in range(args.warmup + args.steps):
+            t0 = time.time()
+            sm = cpu_sample(w, toc, genes, counts, signatures, lsh=L)
+            sm["wall_ms"] = 1e3 * (time.time() - t0)
+            if i >= args.warmup:
+                samples.append(sm)
+        metric = "cell-pairs/sec (1024-bit LSH, top-50)"
+    value = float(np.median([sm["value"] for sm in samples]))
     best = samples[0]
-    line = dict(impl="reference", metric="cell-pairs/sec (1024-bit LSH, top-50)", value=value, unit="cell-pairs/s",
+    line = dict(impl="reference", metric=metric, value=value, unit="cell-pairs/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=float(np.mean([s["wall_ms"] for s in samples])), higher_is_better=True,
-                scaling="strong", vs_baseline=None, dtype="u64 popcount + f64 projections", data="synthetic",
-                config=dict(workload=args.workload, **{k: w[k] for k in ("cells", "genes", "nnz_per_cell", "lsh", "k", "thr")},
-                            note=w["note"], signatures=sig_note),
+                ms_per_step=float(np.mean([sm["wall_ms"] for sm in samples])), higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="u64 popcount + f64 projections" if kind != "exact" else "f32 products, f64 sums",
+                data="synthetic",
+                config=dict(workload=args.workload, cells=N, genes=w["genes"], nnz_per_cell=w.get("nnz_per_cell"), lsh=L,
+                            k=w["k"], thr=w["thr"], note=w["note"], signatures=sig_note),
                 cpu_baseline=dict(kind=best["kind"], cores=1, value=value, unit="cell-pairs/s", sample=best["sample"],
                                   ns_per_pair=best["ns_per_pair"], signature_s_per_cell=best["signature_s_per_cell"],
                                   extrapolated_job_seconds=best["extrapolated_job_seconds"]),
@@ -203,12 +242,14 @@ def run_reference(args, w):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args, w):
+INT8_PEAK_NOTE = ("2 x bf16_tflops of MEASURED_PEAKS.json ({src}); tools/mma_peak.cu measured 4216 TOP/s (kind::i8, A in "
+                  "TMEM, N=256), 3407 (operands in shared memory, N=256) and 2971 (A in TMEM, N=128 -- the scan's shape) "
+                  "issue-rate peaks on this pool")
+
+
+def _setup_dist():
     import torch
     import torch.distributed as dist
-    import expressionmatrix2_b200 as em2
-    from expressionmatrix2_b200.parallel import Partition, all_gather_signatures
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -218,48 +259,13 @@ def run_b200(args, w):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    variant = dict(auto=em2.VARIANT_AUTO, popc=em2.VARIANT_POPC, mma=em2.VARIANT_MMA_I8)[args.variant]
+    return world, rank, local_rank, dev
 
-    N, G, L, k, thr = w["cells"], w["genes"], w["lsh"], w["k"], w["thr"]
-    W = em2.word_count(L)
-    toc, genes, counts, U = make_workload(w)
-    part = Partition(N, world, rank)
-    ltoc, lgenes, lcounts = part.slice_csr(toc, genes, counts)
-    lpairs = em2.to_pairs(lgenes, lcounts)
-    rows = part.rows
-    nnz_local = int(ltoc[-1])
-    eng = em2.Engine(local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
 
-    # ---- resident buffers ------------------------------------------------------------------------
-    d_toc = torch.from_numpy(ltoc.view(np.int64)).to(dev)
-    d_counts = torch.from_numpy(lpairs.view(np.int64)).to(dev)
-    d_U = torch.from_numpy(U).to(dev)
-    d_sum1 = torch.empty(rows, dtype=torch.float64, device=dev)
-    d_sum2 = torch.empty(rows, dtype=torch.float64, device=dev)
-    d_sig_local = torch.zeros((part.shard, W), dtype=torch.int64, device=dev)
-    d_lut = torch.from_numpy(em2.similarity_table(L).astype(np.float32)).to(dev)
-    d_pairs = torch.zeros((rows, k, 2), dtype=torch.int32, device=dev)
-    d_used = torch.zeros(rows, dtype=torch.int32, device=dev)
-    d_nz = torch.zeros(8, dtype=torch.int64, device=dev)
-    mm = em2.mismatch_max(L, thr)
-    stage_names = ["sums", "signatures", "allgather", "scan_topk"]
-
-    def step(events=None):
-        def mark(i):
-            if events is not None:
-                events[i].record()
-        mark(0)
-        eng.cell_sums_device(rows, d_toc, d_counts, d_sum1, d_sum2, stream=stream)
-        mark(1)
-        eng.signatures_device(rows, G, d_toc, d_counts, d_sum1, d_sum2, d_U, L, L, d_sig_local, d_nz, stream=stream,
-                              nnz=nnz_local)
-        mark(2)
-        full = all_gather_signatures(d_sig_local, part) if world > 1 else d_sig_local
-        mark(3)
-        eng.scan_topk_device(full, N, L, part.row_begin, part.row_end, k, mm, d_lut, d_pairs, d_used,
-                             variant=variant, stream=stream)
-        mark(4)
+def _timed_steps(args, world, dev, local_rank, step, n_marks):
+    """W warm-up steps, then exactly K steps bracketed by barrier + synchronize; CUDA events; max over ranks."""
+    import torch
+    import torch.distributed as dist
 
     def barrier():
         torch.cuda.synchronize()
@@ -270,10 +276,9 @@ def run_b200(args, w):
     for _ in range(args.warmup):
         step()
     barrier()
-    launches0 = eng.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_begin.record()
@@ -283,73 +288,23 @@ def run_b200(args, w):
     barrier()
     clocks = sampler.stop()
     total_ms = t_begin.elapsed_time(t_end)
-    launches = eng.stats()["kernel_launches"] - launches0
-    stage_ms = {n: float(np.mean([ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)]))
-                for j, n in enumerate(stage_names)}
+    stage = [float(np.mean([ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)])) for j in range(n_marks - 1)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    pairs_total = N * (N - 1) / 2
-    value = pairs_total / (ms_per_step * 1e-3)
+    return float(t.item()) / args.steps, stage, clocks, barrier
 
-    # ---- e2e: host buffers -> host lists ----------------------------------------------------------
-    h_pairs = torch.empty((rows, k, 2), dtype=torch.int32).pin_memory()
-    h_used = torch.empty(rows, dtype=torch.int32).pin_memory()
-    if world == 1:
-        # through the reference-facing blocking C-ABI call; host inputs live in pinned memory
-        p_toc = torch.from_numpy(toc.view(np.int64)).pin_memory()
-        p_counts = torch.from_numpy(lpairs.view(np.int64)).pin_memory()
-        p_U = torch.from_numpy(U).pin_memory()
-        n_toc, n_counts, n_U = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE), p_U.numpy()
-        e2e_ms, st = [], None
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            ids, sims, used = eng.lsh_similar_pairs(n_toc, n_counts, n_U, k, thr, variant=variant)
-            if i >= args.warmup:
-                e2e_ms.append(1e3 * (time.perf_counter() - t0))
-            st = eng.stats()
-        e2e_t = float(np.mean(e2e_ms))
-        h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
-        e2e_stats = {k2: st[k2] for k2 in ("h2d_ms", "sums_ms", "signatures_ms", "scan_ms", "d2h_ms")}
-    else:
-        p_toc = torch.from_numpy(ltoc.view(np.int64)).pin_memory()
-        p_counts = torch.from_numpy(lpairs.view(np.int64)).pin_memory()
-        p_U = torch.from_numpy(U).pin_memory()
-        e2e_ms = []
-        for i in range(args.warmup + args.steps):
-            barrier()
-            t0 = time.perf_counter()
-            d_toc.copy_(p_toc, non_blocking=True)
-            d_counts.copy_(p_counts, non_blocking=True)
-            d_U.copy_(p_U, non_blocking=True)
-            step()
-            h_pairs.copy_(d_pairs, non_blocking=True)
-            h_used.copy_(d_used, non_blocking=True)
-            barrier()
-            if i >= args.warmup:
-                e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        tt = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t = float(tt.item())
-        h2d = p_toc.numel() * 8 + p_counts.numel() * 8 + p_U.numel() * 8
-        d2h = h_pairs.numel() * 4 + h_used.numel() * 4
-        e2e_stats = {}
 
-    # ---- roofline of the dominant kernel (the scan) ------------------------------------------------
-    peaks = load_peaks()
-    scan_s = stage_ms["scan_topk"] * 1e-3
+def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total, scan_ms, local_rank):
+    scan_s = scan_ms * 1e-3
     ordered = rows * N                      # pair evaluations this GPU executed per launch
     alg_pairs = pairs_total / world         # algorithmic units per GPU per launch
-    variant_used = eng.stats()["variant_used"] or (em2.VARIANT_POPC if variant != em2.VARIANT_MMA_I8 else variant)
     if variant_used == em2.VARIANT_MMA_I8:
         peak = 2.0 * peaks["bf16_tflops"]   # int8 tensor peak = 2x the measured dense bf16 figure
+        K = (L + 127) // 128 * 128
         roof = dict(bound="tensor", unit="TOP/s", achieved=alg_pairs * 2 * L / scan_s / 1e12, peak=peak,
-                    peak_source=f"2 x bf16_tflops of MEASURED_PEAKS.json ({peaks['source']}); tools/mma_peak.cu "
-                                "measured 4216 TOP/s (kind::i8, A in TMEM, N=256) and 2971 TOP/s (N=128, this "
-                                "kernel's shape) on this pool",
-                    executed=ordered * 2 * L / scan_s / 1e12)
+                    peak_source=INT8_PEAK_NOTE.format(src=peaks["source"]),
+                    executed=ordered * 2 * K / scan_s / 1e12)
     else:
         mb = os.path.join(ROOT, "expressionmatrix2_b200", "build", "microbench")
         popc_peak = None
@@ -364,46 +319,266 @@ def run_b200(args, w):
                     executed=ordered * 2 * W / scan_s / 1e9)
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["executed_frac"] = roof["executed"] / roof["peak"]
-    roof["kernel"] = "scan_topk"
-    roof["kernel_ms"] = stage_ms["scan_topk"]
+    roof["kernel"] = "scan_topk (encode + scanMmaKernel/scanPopc*Kernel + finalize)"
+    roof["kernel_ms"] = scan_ms
     roof["traffic"] = None
+    roof["note"] = ("achieved = algorithmic ops (one evaluation per UNORDERED pair, 2L bit-ops each); executed = what the "
+                    "row-block design runs (every ordered pair): executed_frac is the kernel-quality figure, frac is capped "
+                    "at half of it")
     alg_bytes = N * L / 8 + rows * L / 8 + rows * (8 * k + 4)
     roof["hbm"] = dict(bound="hbm", unit="GB/s", algorithmic_bytes=alg_bytes, achieved=alg_bytes / scan_s / 1e9,
                        peak=peaks["hbm_gbs"], frac=alg_bytes / scan_s / 1e9 / peaks["hbm_gbs"],
                        note="compulsory bytes only; the scan is compute bound by construction")
-    nnz_local = int(ltoc[-1])
-    sig_s = stage_ms["signatures"] * 1e-3
-    sig_bytes = 8 * nnz_local + 8 * (rows + 1) + 8 * rows + 8 * G * L + rows * L / 8
-    sig_roof = dict(kernel="signatures", kernel_ms=stage_ms["signatures"], flops=2.0 * nnz_local * L,
-                    achieved_gflops=2.0 * nnz_local * L / sig_s / 1e9, algorithmic_bytes=sig_bytes,
-                    achieved_gbs=sig_bytes / sig_s / 1e9, hbm_frac=sig_bytes / sig_s / 1e9 / peaks["hbm_gbs"])
+    return roof
+
+
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+    import expressionmatrix2_b200 as em2
+    from expressionmatrix2_b200 import synthetic
+    from expressionmatrix2_b200.parallel import Partition, all_gather_signatures
+
+    world, rank, local_rank, dev = _setup_dist()
+    variant = dict(auto=em2.VARIANT_AUTO, popc=em2.VARIANT_POPC, mma=em2.VARIANT_MMA_I8)[args.variant]
+    kind = w.get("kind", "lsh")
+    N, G, k, thr = w["cells"], w["genes"], w["k"], w["thr"]
+    L = args.lsh or w["lsh"]
+    W = em2.word_count(L)
+    part = Partition(N, world, rank)
+    rows = part.rows
+    eng = em2.Engine(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    peaks = load_peaks()
+    pairs_total = N * (N - 1) / 2
+    cfg = dict(workload=args.workload, cells=N, genes=G, nnz_per_cell=w.get("nnz_per_cell"), lsh=L, k=k, thr=thr,
+               note=w["note"])
+    line = dict(metric="cell-pairs/sec (1024-bit LSH, top-50)", unit="cell-pairs/s", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, higher_is_better=True, scaling="strong", vs_baseline=None, data="synthetic")
+
+    if kind == "exact":
+        # ---------------- config 5: exact Pearson brute force (single GPU; N>1 = replicas of the row blocks) ------
+        if world > 1:
+            raise SystemExit("the exact workload (config 5) is a single-GPU validation run")
+        toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, w["nnz_per_cell"], seed=12345)
+        lpairs = em2.to_pairs(genes, counts)
+        p_toc = torch.from_numpy(toc.view(np.int64)).pin_memory()
+        p_counts = torch.from_numpy(lpairs.view(np.int64)).pin_memory()
+        h_pairs = torch.empty((N, k, 2), dtype=torch.int32).pin_memory()
+        h_used = torch.empty(N, dtype=torch.int32).pin_memory()
+        n_toc, n_counts = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE)
+        sampler = ClockSampler(local_rank)
+        ms, st = [], None
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                sampler.start()
+            t0 = time.perf_counter()
+            eng.exact_similar_pairs_into(n_toc, n_counts, G, k, thr, h_pairs.numpy().view(em2.SIMPAIR_DTYPE).reshape(N, k),
+                                         h_used.numpy().view(np.uint32))
+            if i >= args.warmup:
+                ms.append(1e3 * (time.perf_counter() - t0))
+            st = eng.stats()
+        clocks = sampler.stop()
+        e2e_t = float(np.mean(ms))
+        dev_ms = st["sums_ms"] + st["scan_ms"]
+        Gpad = (G + 127) // 128 * 128
+        peak = 2.0 * peaks["bf16_tflops"]
+        roof = dict(bound="tensor", unit="TOP/s", achieved=pairs_total * 2 * G / (st["scan_ms"] * 1e-3) / 1e12,
+                    executed=float(N) * N * 2 * Gpad / (st["scan_ms"] * 1e-3) / 1e12, peak=peak,
+                    peak_source=INT8_PEAK_NOTE.format(src=peaks["source"]), kernel="exactGemmKernel + exactSelectKernel",
+                    kernel_ms=st["scan_ms"], traffic=None)
+        roof["frac"] = roof["achieved"] / peak
+        roof["executed_frac"] = roof["executed"] / peak
+        line.update(metric="cell-pairs/sec (exact Pearson, top-50)", value=pairs_total / (dev_ms * 1e-3), ms_per_step=dev_ms,
+                    dtype="u8 x u8 -> s32 tcgen05 (scalar products), f64 (correlation)", config=dict(cfg, variant="exact"),
+                    stage_ms=dict(sums=st["sums_ms"], exact=st["scan_ms"]), roofline=roof,
+                    e2e=dict(value=pairs_total / (e2e_t * 1e-3), unit="cell-pairs/s", ms=e2e_t, h2d_bytes_per_step=int(st["h2d_bytes"]),
+                             d2h_bytes_per_step=int(st["d2h_bytes"]), api="em2_exact_similar_pairs (C-ABI, host buffers)"),
+                    gpu_launches=int(st["kernel_launches"]) * args.steps, clocks=clocks)
+        if not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            s1, s2 = oracle.cell_sums(toc, counts)
+            t0 = time.time()
+            r = oracle.exact_rows(G, toc, genes, counts, s1, s2, 0, 4)
+            dt = time.time() - t0
+            ids_np = h_pairs.numpy().view(em2.SIMPAIR_DTYPE).reshape(N, k)
+            wi, ws, wu, _ = oracle.exact_topk(G, toc, genes, counts, k, thr, 0, 4)
+            line["cpu_baseline"] = dict(value=4 * N / dt, unit="cell-pairs/s", cores=1, kind="port",
+                                        sample=f"computeCellSimilarity for cells 0..3 against all {N} cells ({4 * N} pairs)",
+                                        extrapolated_job_seconds=pairs_total / (4 * N / dt),
+                                        sample_rows_match_gpu=bool(np.array_equal(wi, ids_np["cell"][:4]) and
+                                                                   np.array_equal(ws.view(np.uint32), ids_np["similarity"][:4].view(np.uint32))))
+        print(json.dumps(line))
+        eng.close()
+        return
+
+    # ---------------- LSH workloads: "lsh" (counts -> lists) and "sig" (signatures-only scan, config 4) -----------
+    d_lut = torch.from_numpy(em2.similarity_table(L).astype(np.float32)).to(dev)
+    d_pairs = torch.zeros((rows, k, 2), dtype=torch.int32, device=dev)
+    d_used = torch.zeros(rows, dtype=torch.int32, device=dev)
+    d_sig_local = torch.zeros((part.shard, W), dtype=torch.int64, device=dev)
+    mm = em2.mismatch_max(L, thr)
+    if kind == "lsh":
+        if w.get("per_rank_generation"):
+            # each rank synthesises only its own cells (the 1.3M-cell CSR is 21 GB)
+            ltoc, lgenes, lcounts = synthetic.gen_expression_matrix_fast(rows, G, w["nnz_per_cell"], seed=12345 + rank)
+            toc = genes = counts = None
+        else:
+            toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, w["nnz_per_cell"], seed=12345)
+            ltoc, lgenes, lcounts = part.slice_csr(toc, genes, counts)
+        U = em2.generate_lsh_vectors(G, L, 231)
+        lpairs = em2.to_pairs(lgenes, lcounts)
+        nnz_local = int(ltoc[-1])
+        d_toc = torch.from_numpy(ltoc.view(np.int64)).to(dev)
+        d_counts = torch.from_numpy(lpairs.view(np.int64)).to(dev)
+        d_U = torch.from_numpy(U).to(dev)
+        d_sum1 = torch.empty(rows, dtype=torch.float64, device=dev)
+        d_sum2 = torch.empty(rows, dtype=torch.float64, device=dev)
+        d_nz = torch.zeros(8, dtype=torch.int64, device=dev)
+        stage_names = ["sums", "signatures", "allgather", "scan_topk"]
+    else:
+        sig_host = synthetic.gen_signatures(rows, L, seed=1000 + rank, clusters=w.get("clusters", 500), centre_seed=77)
+        p_sig = torch.from_numpy(sig_host.view(np.int64)).pin_memory()
+        d_sig_local[:rows].copy_(p_sig)
+        stage_names = ["allgather", "scan_topk"]
+
+    def step(events=None):
+        def mark(i):
+            if events is not None:
+                events[i].record()
+        j = 0
+        mark(j)
+        if kind == "lsh":
+            eng.cell_sums_device(rows, d_toc, d_counts, d_sum1, d_sum2, stream=stream)
+            j += 1
+            mark(j)
+            eng.signatures_device(rows, G, d_toc, d_counts, d_sum1, d_sum2, d_U, L, L, d_sig_local, d_nz, stream=stream,
+                                  nnz=nnz_local)
+            j += 1
+            mark(j)
+        full = all_gather_signatures(d_sig_local, part) if world > 1 else d_sig_local
+        j += 1
+        mark(j)
+        eng.scan_topk_device(full, N, L, part.row_begin, part.row_end, k, mm, d_lut, d_pairs, d_used,
+                             variant=variant, stream=stream)
+        j += 1
+        mark(j)
+
+    launches0 = eng.stats()["kernel_launches"]
+    ms_per_step, stage, clocks, barrier = _timed_steps(args, world, dev, local_rank, step, len(stage_names) + 1)
+    launches = (eng.stats()["kernel_launches"] - launches0) * args.steps // (args.steps + args.warmup)
+    stage_ms = dict(zip(stage_names, stage))
+    value = pairs_total / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers -> host lists ----------------------------------------------------------
+    h_pairs = torch.empty((rows, k, 2), dtype=torch.int32).pin_memory()
+    h_used = torch.empty(rows, dtype=torch.int32).pin_memory()
+    o_pairs = h_pairs.numpy().view(em2.SIMPAIR_DTYPE).reshape(rows, k)
+    o_used = h_used.numpy().view(np.uint32)
+    e2e_stats = {}
+    if world == 1:
+        # the reference-facing blocking C-ABI call; host buffers in pinned memory (inputs AND outputs)
+        if kind == "lsh":
+            p_toc = torch.from_numpy(ltoc.view(np.int64)).pin_memory()
+            p_counts = torch.from_numpy(lpairs.view(np.int64)).pin_memory()
+            p_U = torch.from_numpy(U).pin_memory()
+            n_toc, n_counts, n_U = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE), p_U.numpy()
+            call = lambda: eng.lsh_similar_pairs_into(n_toc, n_counts, n_U, k, thr, o_pairs, o_used, variant=variant)
+            api = "em2_lsh_similar_pairs (C-ABI, host buffers)"
+        else:
+            n_sig = p_sig.numpy().view(np.uint64)
+            call = lambda: eng.find_similar_pairs_into(n_sig, L, k, thr, o_pairs, o_used, variant=variant)
+            api = "em2_find_similar_pairs (C-ABI, host buffers)"
+        e2e_ms, st = [], None
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            call()
+            if i >= args.warmup:
+                e2e_ms.append(1e3 * (time.perf_counter() - t0))
+            st = eng.stats()
+        e2e_t = float(np.mean(e2e_ms))
+        h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
+        e2e_stats = {k2: st[k2] for k2 in ("h2d_ms", "sums_ms", "signatures_ms", "scan_ms", "d2h_ms")}
+        e2e_stats["note"] = "h2d overlaps sums/signatures (chunked copy stream)"
+    else:
+        api = "device API + pinned host copies per rank"
+        if kind == "lsh":
+            p_toc = torch.from_numpy(ltoc.view(np.int64)).pin_memory()
+            p_counts = torch.from_numpy(lpairs.view(np.int64)).pin_memory()
+            p_U = torch.from_numpy(U).pin_memory()
+        e2e_ms = []
+        for i in range(args.warmup + args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            if kind == "lsh":
+                d_toc.copy_(p_toc, non_blocking=True)
+                d_counts.copy_(p_counts, non_blocking=True)
+                d_U.copy_(p_U, non_blocking=True)
+            else:
+                d_sig_local[:rows].copy_(p_sig, non_blocking=True)
+            step()
+            h_pairs.copy_(d_pairs, non_blocking=True)
+            h_used.copy_(d_used, non_blocking=True)
+            barrier()
+            if i >= args.warmup:
+                e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        tt = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_t = float(tt.item())
+        h2d = (p_toc.numel() * 8 + p_counts.numel() * 8 + p_U.numel() * 8) if kind == "lsh" else p_sig.numel() * 8
+        d2h = h_pairs.numel() * 4 + h_used.numel() * 4
+
+    # ---- rooflines ---------------------------------------------------------------------------------
+    variant_used = eng.stats()["variant_used"] or (em2.VARIANT_POPC if variant != em2.VARIANT_MMA_I8 else variant)
+    roof = _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total,
+                          stage_ms["scan_topk"], local_rank)
+    sig_roof = None
+    if kind == "lsh":
+        sig_s = stage_ms["signatures"] * 1e-3
+        sig_bytes = 8 * nnz_local + 8 * (rows + 1) + 8 * rows + 8 * G * L + rows * L / 8
+        density = nnz_local / (rows * float(G))
+        filtered = density >= 0.012 and rows >= 4096 and G >= 1024 and L >= 128
+        sig_roof = dict(kernel="signatures (columnStats + quantize + densify + sigFilterKernel + fixup)" if filtered
+                        else "signatures (columnStats + signatureKernel, FP64)",
+                        path="tensor-core filter + FP64 fix-up" if filtered else "fp64",
+                        kernel_ms=stage_ms["signatures"], flops=2.0 * nnz_local * L,
+                        achieved_gflops=2.0 * nnz_local * L / sig_s / 1e9, algorithmic_bytes=sig_bytes,
+                        achieved_gbs=sig_bytes / sig_s / 1e9, hbm_frac=sig_bytes / sig_s / 1e9 / peaks["hbm_gbs"])
+        if filtered:
+            Gpad, Lp = (G + 127) // 128 * 128, (L + 127) // 128 * 128
+            ex = 2.0 * rows * Gpad * 3 * Lp
+            sig_roof.update(bound="tensor", executed_int8_tops=ex / sig_s / 1e12, peak=2.0 * peaks["bf16_tflops"],
+                            executed_frac=ex / sig_s / 1e12 / (2.0 * peaks["bf16_tflops"]),
+                            note="executed = dense G x 3L int8 MACs per cell over the whole stage time; the GEMM kernel "
+                                 "alone is ~70% of the stage (profiles/), i.e. ~0.95 of peak")
 
     if rank == 0:
         used_mean = float(d_used.float().mean().item())
-        line = dict(metric="cell-pairs/sec (1024-bit LSH, top-50)", value=value, unit="cell-pairs/s", n_gpus=world,
-                    steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
-                    scaling="strong", vs_baseline=None,
-                    dtype="u64 xor/popc (scan), f64 non-fused mul+add (signatures)", data="synthetic",
-                    config=dict(workload=args.workload, **{k2: w[k2] for k2 in ("cells", "genes", "nnz_per_cell", "lsh", "k", "thr")},
-                                note=w["note"], variant={1: "popc", 2: "mma_i8"}.get(variant_used, "popc"),
+        line.update(value=value, ms_per_step=ms_per_step,
+                    dtype=("s8 tcgen05 / u64 popc (scan), u8 x s8 tcgen05 filter + f64 fix-up (signatures)" if kind == "lsh"
+                           else "s8 tcgen05 / u64 popc (scan)"),
+                    config=dict(cfg, variant={1: "popc", 2: "mma_i8"}.get(variant_used, "popc"),
                                 parallelism=f"cell-row blocks x{world}" + (", 1 NCCL all-gather of signatures" if world > 1 else ""),
-                                l2="inputs (CSR + hyperplanes, >1.4 GB) exceed the 126 MB L2; no flush needed",
+                                l2=("inputs (CSR + hyperplanes, >1.4 GB) exceed the 126 MB L2; no flush needed" if kind == "lsh" else
+                                    "encoded signatures (N x L bytes) exceed the 126 MB L2 for N*L > 1.3e8; candidate buffers are rewritten every step"),
                                 ordered_evaluations_per_s=N * float(N) / (ms_per_step * 1e-3),
                                 mean_neighbours_stored=used_mean),
-                    stage_ms=stage_ms, roofline=roof, signature_roofline=sig_roof,
+                    stage_ms=stage_ms, roofline=roof,
                     e2e=dict(value=pairs_total / (e2e_t * 1e-3), unit="cell-pairs/s", ms=e2e_t,
-                             h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, stage_ms=e2e_stats,
-                             api="em2_lsh_similar_pairs (C-ABI, host buffers)" if world == 1 else
-                                 "device API + pinned host copies per rank"),
+                             h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, stage_ms=e2e_stats, api=api),
                     gpu_launches=int(launches), clocks=clocks)
+        if sig_roof:
+            line["signature_roofline"] = sig_roof
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
-            sig_host = d_sig_local[:rows].cpu().numpy().view(np.uint64)
-            cb = cpu_sample(w, toc, genes, counts, sig_host)
-            line["cpu_baseline"] = {k2: cb[k2] for k2 in ("value", "unit", "cores", "kind", "sample", "ns_per_pair",
-                                                          "signature_s_per_cell", "extrapolated_job_seconds",
-                                                          "sample_seconds", "sample_signatures_match_gpu")}
+            sig_np = d_sig_local[:rows].cpu().numpy().view(np.uint64)
+            if kind == "lsh":
+                cb = cpu_sample(w, toc, genes, counts, sig_np, lsh=L)
+            else:
+                cb = cpu_sample(w, None, None, None, sig_np, lsh=L)
+            line["cpu_baseline"] = cb
         print(json.dumps(line))
     eng.close()
     if world > 1:
@@ -418,6 +593,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "mma"])
+    ap.add_argument("--lsh", type=int, default=0, help="override the workload's LSH bit count (config 4 sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

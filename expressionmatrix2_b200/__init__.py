@@ -223,6 +223,31 @@ class Engine:
         res = (np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used)
         return res + (sig,) if want_signatures else res
 
+    def find_similar_pairs_into(self, signatures, lsh_count: int, k: int, similarity_threshold: float, out_pairs, out_used,
+                                variant: int = VARIANT_AUTO, row_begin: int = 0, row_end: int | None = None) -> None:
+        n = signatures.shape[0]
+        row_end = n if row_end is None else row_end
+        self._check(self._L.em2_find_similar_pairs(self._h, _ptr(signatures), n, lsh_count, row_begin, row_end, k,
+                                                   similarity_threshold, variant, _ptr(out_pairs), _ptr(out_used)),
+                    "em2_find_similar_pairs")
+
+    def lsh_similar_pairs_into(self, toc, pairs, lsh_vectors, k: int, similarity_threshold: float, out_pairs, out_used,
+                               variant: int = VARIANT_AUTO) -> None:
+        """The C-ABI call and nothing else: caller-owned host buffers in (toc uint64[N+1], pairs PAIR_DTYPE[nnz],
+        lsh_vectors float64[G,L]) and out (out_pairs SIMPAIR_DTYPE[N,k], out_used uint32[N]) -- what bench.py times
+        for the end-to-end figure (buffers typically pinned, as the mmap-backed C++ host layer's staging is)."""
+        n = len(toc) - 1
+        G, Lc = lsh_vectors.shape
+        self._check(self._L.em2_lsh_similar_pairs(self._h, n, G, _ptr(toc), _ptr(pairs), _ptr(lsh_vectors), Lc, k,
+                                                  similarity_threshold, variant, _ptr(out_pairs), _ptr(out_used), None),
+                    "em2_lsh_similar_pairs")
+
+    def exact_similar_pairs_into(self, toc, pairs, gene_count: int, k: int, similarity_threshold: float, out_pairs,
+                                 out_used) -> None:
+        self._check(self._L.em2_exact_similar_pairs(self._h, len(toc) - 1, gene_count, _ptr(toc), _ptr(pairs), k,
+                                                    similarity_threshold, _ptr(out_pairs), _ptr(out_used)),
+                    "em2_exact_similar_pairs")
+
     def exact_similar_pairs(self, toc, counts, gene_count: int, k: int, similarity_threshold: float, gene_ids=None):
         toc = np.ascontiguousarray(toc, np.uint64)
         pairs = _as_pairs(counts, gene_ids)

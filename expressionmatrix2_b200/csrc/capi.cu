@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "tc05.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -202,6 +203,8 @@ void em2_destroy(em2_context* ctx)
         if (b.ptr) cudaFreeHost(b.ptr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->pool)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     delete ctx;
@@ -290,10 +293,14 @@ int em2_mismatch_block_device(em2_context* ctx, const uint64_t* signatures, uint
 // ------------------------------------------------------------------------------------------------
 // blocking host-buffer calls
 // ------------------------------------------------------------------------------------------------
+// Counts -> signatures with host inputs.  The CSR payload dominates the transfer (1.2 GB at 100k cells), so it
+// is cut into a few chunks of whole cells: the copy stream moves chunk i+1 over PCIe while the compute stream
+// builds the sums and signatures of chunk i.  Hyperplanes go first (their preparation overlaps chunk 0).
 static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCount, uint64_t geneCount,
                               const uint64_t* toc, const em2_count* counts, const double* U, uint64_t lshCount,
                               uint64_t** dSigOut, double** dSum1Out, double** dSum2Out)
 {
+    (void)T;
     const uint64_t nnz = toc[cellCount];
     const uint64_t W = wordCount(lshCount);
     void *dToc, *dCounts, *dU, *dSum1, *dSum2, *dSig, *dCounters;
@@ -304,26 +311,69 @@ static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCoun
     EM2_TRY(reserve(ctx, em2_context::S_SUM2, cellCount * sizeof(double), &dSum2));
     EM2_TRY(reserve(ctx, em2_context::S_SIG, cellCount * W * sizeof(uint64_t), &dSig));
     EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &dCounters));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->stream, c = ctx->copyStream;
+    constexpr int kMaxChunks = 8;
+    if (!ctx->pool[0])
+        for (auto& ev : ctx->pool) EM2_CUDA(ctx, cudaEventCreate(&ev));
+    cudaEvent_t* ev = ctx->pool;     // [0] copy begin, [1] hyperplanes landed, [2] copy end, [3 + 4i ..] per chunk
 
-    const int e0 = T.mark();
+    // chunk boundaries: whole cells, roughly equal payload
+    const uint64_t chunkBytes = 256ull << 20;
+    const int chunks = int(std::max<uint64_t>(1, std::min<uint64_t>(kMaxChunks, nnz * sizeof(em2_count) / chunkBytes)));
+    uint64_t bound[kMaxChunks + 1];
+    bound[0] = 0;
+    for (int i = 1; i < chunks; i++) {
+        const uint64_t target = nnz / chunks * i;
+        bound[i] = uint64_t(std::lower_bound(toc, toc + cellCount + 1, target) - toc);
+        bound[i] = std::min(std::max(bound[i], bound[i - 1]), cellCount);
+    }
+    bound[chunks] = cellCount;
+
     EM2_CUDA(ctx, cudaMemsetAsync(dCounters, 0, 64, s));
-    EM2_CUDA(ctx, cudaMemcpyAsync(dToc, toc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    EM2_CUDA(ctx, cudaMemcpyAsync(dCounts, counts, nnz * sizeof(em2_count), cudaMemcpyHostToDevice, s));
-    EM2_CUDA(ctx, cudaMemcpyAsync(dU, U, geneCount * lshCount * sizeof(double), cudaMemcpyHostToDevice, s));
+    EM2_CUDA(ctx, cudaEventRecord(ev[0], c));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dToc, toc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dU, U, geneCount * lshCount * sizeof(double), cudaMemcpyHostToDevice, c));
+    EM2_CUDA(ctx, cudaEventRecord(ev[1], c));
     ctx->stats.h2d_bytes += (cellCount + 1) * 8 + nnz * 8 + geneCount * lshCount * 8;
-    const int e1 = T.mark();
-    EM2_TRY(launchCellSums(ctx, cellCount, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
-                           static_cast<double*>(dSum1), static_cast<double*>(dSum2), s));
-    const int e2 = T.mark();
-    EM2_TRY(launchSignatures(ctx, cellCount, geneCount, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
-                             static_cast<double*>(dSum1), static_cast<double*>(dSum2), static_cast<double*>(dU),
-                             lshCount, lshCount, nnz, static_cast<uint64_t*>(dSig), static_cast<uint64_t*>(dCounters), s));
-    const int e3 = T.mark();
+
+    EM2_CUDA(ctx, cudaStreamWaitEvent(s, ev[1], 0));
+    SignaturePlan plan;
+    EM2_CUDA(ctx, cudaEventRecord(ev[3], s));
+    EM2_TRY(prepareSignatures(ctx, cellCount, geneCount, static_cast<const double*>(dU), lshCount, lshCount, nnz, &plan, s));
+    EM2_CUDA(ctx, cudaEventRecord(ev[4], s));
+    for (int i = 0; i < chunks; i++) {
+        const uint64_t b = bound[i], e = bound[i + 1];
+        cudaEvent_t* ce = ev + 5 + 4 * i;      // landed, sums begin, signatures begin, end
+        const uint64_t n0 = toc[b], n1 = toc[e];
+        if (n1 > n0)
+            EM2_CUDA(ctx, cudaMemcpyAsync(static_cast<em2_count*>(dCounts) + n0, counts + n0, (n1 - n0) * sizeof(em2_count),
+                                          cudaMemcpyHostToDevice, c));
+        EM2_CUDA(ctx, cudaEventRecord(ce[0], c));
+        EM2_CUDA(ctx, cudaStreamWaitEvent(s, ce[0], 0));
+        EM2_CUDA(ctx, cudaEventRecord(ce[1], s));
+        EM2_TRY(launchCellSums(ctx, e - b, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+                               static_cast<double*>(dSum1), static_cast<double*>(dSum2), s, b));
+        EM2_CUDA(ctx, cudaEventRecord(ce[2], s));
+        EM2_TRY(launchSignaturesRange(ctx, plan, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+                                      static_cast<double*>(dSum1), static_cast<double*>(dSum2), b, e,
+                                      static_cast<uint64_t*>(dSig), static_cast<uint64_t*>(dCounters), s));
+        EM2_CUDA(ctx, cudaEventRecord(ce[3], s));
+    }
+    EM2_CUDA(ctx, cudaEventRecord(ev[2], c));
+    EM2_CUDA(ctx, cudaStreamSynchronize(c));
     EM2_CUDA(ctx, cudaStreamSynchronize(s));
-    ctx->stats.h2d_ms += T.ms(e0, e1);
-    ctx->stats.sums_ms += T.ms(e1, e2);
-    ctx->stats.signatures_ms += T.ms(e2, e3);
+    auto ms = [](cudaEvent_t a, cudaEvent_t b2) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, a, b2);
+        return double(t);
+    };
+    ctx->stats.h2d_ms += ms(ev[0], ev[2]);
+    ctx->stats.signatures_ms += ms(ev[3], ev[4]);
+    for (int i = 0; i < chunks; i++) {
+        cudaEvent_t* ce = ev + 5 + 4 * i;
+        ctx->stats.sums_ms += ms(ce[1], ce[2]);
+        ctx->stats.signatures_ms += ms(ce[2], ce[3]);
+    }
     *dSigOut = static_cast<uint64_t*>(dSig);
     *dSum1Out = static_cast<double*>(dSum1);
     *dSum2Out = static_cast<double*>(dSum2);

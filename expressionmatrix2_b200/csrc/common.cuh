@@ -33,6 +33,7 @@ struct em2_context {
     cudaStream_t stream = nullptr;       // stream of the blocking calls
     cudaStream_t copyStream = nullptr;   // overlapped host<->device staging
     cudaEvent_t ev[16] = {};
+    cudaEvent_t pool[40] = {};           // per-chunk events of the pipelined host-buffer path (created on first use)
 
     // Named scratch buffers (grown on demand, never shrunk; freed in em2_destroy).
     enum Scratch {
@@ -82,18 +83,40 @@ inline uint64_t wordCount(uint64_t lshCount) { return (lshCount - 1) / 64 + 1; }
 inline uint64_t roundUp(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 // ---- stage launchers (each returns an em2_status and adds to ctx->stats.kernel_launches) ----------
+// sums of cells [cellBegin, cellBegin + cellCount); toc/sum1/sum2 are indexed by absolute cell id
 int launchCellSums(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
-                   double* sum1, double* sum2, cudaStream_t s);
-// Signature stage dispatcher: FP64 kernel, or the tensor-core filter path (sig_filter.cu) when it pays.
-// nnzHint = number of stored counts (0 = unknown: the automatic choice then stays with the FP64 kernel).
+                   double* sum1, double* sum2, cudaStream_t s, uint64_t cellBegin = 0);
+// Signature stage.  prepareSignatures() does the hyperplane-side work once per job (column sums; for the
+// tensor-core filter path also the quantised operand) and picks the path; launchSignaturesRange() then builds the
+// signatures of any range of cells -- the blocking API calls it per chunk while the next chunk's counts are
+// still on their way over PCIe.  nnzHint = number of stored counts (0 = unknown: FP64 kernel).
+struct SignaturePlan {
+    bool filter = false;
+    uint64_t geneCount = 0, lshCount = 0;
+    const double* U = nullptr;        // caller's hyperplanes, pitch ld
+    uint64_t ld = 0;
+    const double* Upadded = nullptr;  // FP64-kernel layout (>= Lpad zero padded columns, even pitch, 16 B aligned)
+    uint64_t ldPadded = 0;
+    double *sumU = nullptr, *scale = nullptr, *e1 = nullptr, *e2 = nullptr;
+    // filter path
+    uint64_t gPad = 0, chunkMax = 0;
+    uint32_t nBlocks = 0, uncertainCap = 0;
+    void *uq = nullptr, *dense = nullptr, *lists = nullptr;
+    size_t offFlags = 0, offFallback = 0, offUncertain = 0;
+};
+int prepareSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const double* U, uint64_t ld,
+                      uint64_t lshCount, uint64_t nnzHint, SignaturePlan* plan, cudaStream_t s);
+int launchSignaturesRange(em2_context* ctx, const SignaturePlan& plan, const uint64_t* toc, const em2_count* counts,
+                          const double* sum1, const double* sum2, uint64_t cellBegin, uint64_t cellEnd,
+                          uint64_t* signatures, uint64_t* nearZero, cudaStream_t s);
+// prepare + whole range
 int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                      const em2_count* counts, const double* sum1, const double* sum2, const double* U,
                      uint64_t ld, uint64_t lshCount, uint64_t nnzHint, uint64_t* signatures, uint64_t* nearZero,
                      cudaStream_t s);
-// Tensor-core filter + exact fix-up (sig_filter.cu).  Upadded/ldPadded: hyperplanes in the FP64 kernel's layout.
-int launchSignaturesFiltered(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
-                             const em2_count* counts, const double* sum1, const double* sum2, const double* U,
-                             uint64_t ld, const double* Upadded, uint64_t ldPadded, uint64_t lshCount,
+int prepareSignaturesFiltered(em2_context* ctx, SignaturePlan& plan, uint64_t cellCountHint, cudaStream_t s);
+int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& plan, const uint64_t* toc, const em2_count* counts,
+                             const double* sum1, const double* sum2, uint64_t cellBegin, uint64_t cellEnd,
                              uint64_t* signatures, uint64_t* nearZero, cudaStream_t s);
 // FP64 kernel on a cell range, or on a device-resident list of cells, optionally predicated on a device counter.
 int launchSignaturesFp64(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
@@ -116,15 +139,45 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
                 double similarityThreshold, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);
 
 // scan internals shared between the POPC and MMA variants
+// Work decomposition of a scan: rows are cut into blocks of rowsPerCta.  The first `mainBlocks` row blocks (a
+// whole number of waves over the GPU) sweep ALL columns as one item each -- one candidate stream per row, so a
+// row's running bound tightens once, not once per segment.  The remaining `tail` row blocks cannot fill a
+// wave; they are cut into `segments` column segments each so that the last wave is short and full.
 struct ScanPlan {
     uint32_t rowsPerCta;
     uint32_t rowBlocks;
-    uint32_t segments;     // column segments (grid.y)
-    uint64_t segmentCols;  // columns per segment (multiple of the column tile)
-    uint32_t cap;          // candidate buffer capacity per (segment,row)
+    uint32_t mainBlocks;   // row blocks [0, mainBlocks): one item, columns [0, N)
+    uint32_t segments;     // column segments of a tail row block (>= 1); candidate streams per row
+    uint64_t segmentCols;  // columns per tail segment (multiple of the column tile)
+    uint32_t items;        // mainBlocks + (rowBlocks - mainBlocks) * segments
+    uint32_t cap;          // candidate buffer capacity per (stream, row)
 };
+struct ScanItem {
+    uint32_t rowBlock, segment;
+    uint64_t colBegin, colEnd;
+};
+__host__ __device__ inline ScanItem decodeScanItem(uint32_t item, uint32_t mainBlocks, uint32_t segments,
+                                                   uint64_t segmentCols, uint64_t cellCount)
+{
+    ScanItem it;
+    if (item < mainBlocks) {
+        it.rowBlock = item;
+        it.segment = 0;
+        it.colBegin = 0;
+        it.colEnd = cellCount;
+    } else {
+        const uint32_t t = item - mainBlocks;
+        it.rowBlock = mainBlocks + t / segments;
+        it.segment = t % segments;
+        it.colBegin = uint64_t(it.segment) * segmentCols;
+        it.colEnd = it.colBegin + segmentCols < cellCount ? it.colBegin + segmentCols : cellCount;
+        if (it.colBegin > cellCount) it.colBegin = cellCount;
+    }
+    return it;
+}
+// streamsPerSegment: candidate streams a kernel keeps per (row, segment) (the MMA variant's column sub-streams).
 ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount, uint64_t k, uint32_t tileCols,
-                      uint32_t rowsPerCta, uint32_t ctasPerSm);
+                      uint32_t rowsPerCta, uint32_t ctasPerSm, uint32_t streamsPerSegment);
 int launchFinalize(em2_context* ctx, const ScanPlan& plan, uint64_t rows, uint64_t k, const uint64_t* cand,
                    const uint32_t* candCount, const float* lut, em2_pair* pairs, uint32_t* usedCount,
                    cudaStream_t s);

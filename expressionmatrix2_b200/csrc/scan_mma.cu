@@ -10,22 +10,24 @@
 // Replaces (reference): countMismatches src/BitSet.hpp:277-288 + the findSimilarPairs4 pair loop
 // src/ExpressionMatrixLsh.cpp:218-269.  Nothing here is derived from src/Lsh.cl.
 //
-// Kernel structure (one persistent CTA per SM, 192 threads, warp specialised):
-//   warps 0-3  epilogue : thread t owns query row t of the work item == TMEM lane t.  At the start of an
-//                         item it writes its row's K encoded bytes into TMEM (tcgen05.st): the A operand
-//                         is ROW STATIONARY IN TENSOR MEMORY (128 lanes x 256 columns) for the whole
-//                         sweep and never touches shared memory again.  Per column tile it reads the
-//                         accumulator with tcgen05.ld, 32 columns at a time: one compare per candidate
-//                         against the row's running bound (dot > K - 2*tau  <=>  hamming < tau), rare
-//                         survivors appended to the row's candidate buffer (topk.cuh).
-//   warp 4     producer : TMA (cp.async.bulk.tensor, 128B swizzle) streams the B operand -- 128 columns
+// Kernel structure (one persistent CTA per SM, 320 threads, warp specialised):
+//   warps 0-7  epilogue : thread = (query row == TMEM lane, column sub-stream).  At the start of an
+//                         item the threads write their row's K encoded bytes into TMEM (tcgen05.st): the A
+//                         operand is ROW STATIONARY IN TENSOR MEMORY (128 lanes x 256 columns) for the whole
+//                         sweep and never touches shared memory again.  Per column tile a thread pulls its 64
+//                         accumulator columns into registers (two tcgen05.ld), hands the TMEM buffer straight
+//                         back to the MMA warp, and only then selects: group maxima against the row's running
+//                         bound (dot > K - 2*lim  <=>  hamming < lim), survivors appended to the row's candidate
+//                         buffer (topk.cuh).  The two sub-streams of a row trade bounds through shared memory.
+//   warp 8     producer : TMA (cp.async.bulk.tensor, 128B swizzle) streams the B operand -- 128 columns
 //                         x 128-byte K-chunks (16 KB) -- through a deep ring (all of shared memory).
-//   warp 5     MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (A from TMEM, B from
+//   warp 9     MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (A from TMEM, B from
 //                         shared memory), M=128 N=128 K=32; accumulators in TMEM, double buffered
 //                         (2 x 128 columns), so the epilogue of tile t overlaps the MMAs of tile t+1.
 //                         tcgen05.commit releases shared-memory stages and publishes accumulators
 //                         through mbarriers.  TMEM map: [0,128) acc0, [128,256) acc1, [256,512) A.
-// Work item = (128-row block, column segment); items are dealt round-robin to the persistent CTAs.
+// Work item = 128-row block x all columns, or x one column segment for the tail row blocks that cannot fill
+// a wave (ScanPlan, common.cuh); items are dealt round-robin to the persistent CTAs.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "topk.cuh"
@@ -47,28 +49,13 @@ constexpr int kEpiWarps = 8;          // two column sub-streams per row: 2 epilo
 constexpr int kSubStreams = kEpiWarps / 4;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr uint32_t kRingBytes = 32 * kEpiThreads * 4;          // per-thread ring of 32 passing columns
+constexpr uint32_t kShareBytes = kEpiThreads * 4;              // bound exchange between a row's two sub-streams
 constexpr int kMaxPanels = 8;         // K <= 1024
 constexpr uint32_t kChunkTileBytes = kTileN * kChunkBytes;     // 16 KB: one K-chunk of a column tile
 constexpr int kChunksPerStage = 2;                             // a ring stage carries two K-chunks (32 KB)
 constexpr uint32_t kStageBytes = kChunksPerStage * kChunkTileBytes;
 constexpr int kStages = 5;                                     // 160 KB ring
 constexpr uint32_t kTmemA = 256;      // first TMEM column of the A operand
-
-// v[j] for a run-time j without spilling the array to local memory: a 5-level select tree (31 SEL).
-__device__ __forceinline__ int32_t pick32(const uint32_t (&v)[32], int j)
-{
-    uint32_t a[16], b[8], c[4], d[2];
-#pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = (j & 16) ? v[16 + i] : v[i];
-#pragma unroll
-    for (int i = 0; i < 8; i++) b[i] = (j & 8) ? a[8 + i] : a[i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) c[i] = (j & 4) ? b[4 + i] : b[i];
-#pragma unroll
-    for (int i = 0; i < 2; i++) d[i] = (j & 2) ? c[2 + i] : c[i];
-    return int32_t((j & 1) ? d[1] : d[0]);
-}
 
 // Instruction descriptor: kind::i8, A/B signed 8-bit K-major, D s32, M=128, N=256.
 constexpr uint32_t kInstrDesc = (2u << 4)                        // c_format = S32
@@ -83,9 +70,8 @@ struct MmaParams {
     uint32_t K;              // padded bit count == bytes per encoded row
     uint32_t panels;         // K / 128
     uint32_t stages;         // B ring depth
-    uint32_t segments;
+    uint32_t mainBlocks, segments, items;   // work decomposition (ScanPlan, common.cuh)
     uint64_t segmentCols;
-    uint32_t rowBlocks;
     uint32_t k, cap, tau0;
     uint64_t* cand;
     uint32_t* candCount;
@@ -93,7 +79,7 @@ struct MmaParams {
     uint16_t* dump;          // optional: all distances of the scanned rows (tests)
 };
 
-template <bool DUMP, int EPI>
+template <bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restrict__ enc, const MmaParams p)
 {
@@ -107,7 +93,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
     uint64_t* bFull = bars + 6;      // [stages]
     uint64_t* bEmpty = bFull + kStages;
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bEmpty + kStages);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(bars) + 128;   // [32][kEpiThreads], after 512 B of barriers
+    uint32_t* tauShare = reinterpret_cast<uint32_t*>(bars) + 128;   // [kSubStreams][kRowsPerItem], after 512 B of barriers
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -134,7 +120,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
     fenceAfter();
     const uint32_t tmemBase = *tmemSlot;
 
-    const uint32_t items = p.rowBlocks * p.segments;
+    const uint32_t items = p.items;
 
     if (warp == kEpiWarps) {
         // ===================== TMA producer (B operand) =====================
@@ -142,9 +128,8 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             uint32_t stage = 0, phase = 0;
             const uint32_t stagesPerTile = (p.panels + kChunksPerStage - 1) / kChunksPerStage;
             for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
-                const uint32_t seg = item % p.segments;
-                const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
-                const uint64_t colEnd = min(colBegin + p.segmentCols, p.cellCount);
+                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
+                const uint64_t colBegin = it.colBegin, colEnd = it.colEnd;
                 const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
                 for (uint32_t t = 0; t < tiles; t++) {
                     const int32_t col0 = int32_t(colBegin + uint64_t(t) * kTileN);
@@ -170,9 +155,8 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             uint32_t itemIter = 0, tileIter = 0, stage = 0, phase = 0;
             const uint32_t stagesPerTile = (p.panels + kChunksPerStage - 1) / kChunksPerStage;
             for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
-                const uint32_t seg = item % p.segments;
-                const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
-                const uint64_t colEnd = min(colBegin + p.segmentCols, p.cellCount);
+                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
+                const uint64_t colBegin = it.colBegin, colEnd = it.colEnd;
                 const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
                 mbarWait(aFull, itemIter & 1);
                 fenceAfter();
@@ -214,16 +198,17 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
         const uint32_t rowInItem = threadIdx.x & (kRowsPerItem - 1);
         const uint32_t sub = threadIdx.x / kRowsPerItem;
         constexpr int kSubCols = kTileN / kSubStreams;
+        static_assert(kSubCols == 64 && kSubStreams == 2, "the epilogue below handles two 32-column chunks per thread");
         const uint32_t laneField = uint32_t((warp & 3) * 32) << 16;
         uint32_t tileIter = 0;
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
-            const uint32_t rb = item / p.segments, seg = item % p.segments;
-            const uint64_t localRow = uint64_t(rb) * kRowsPerItem + rowInItem;
+            const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
+            const uint32_t seg = it.segment;
+            const uint64_t localRow = uint64_t(it.rowBlock) * kRowsPerItem + rowInItem;
             const bool valid = localRow < p.rows;
-            const uint64_t colBegin = uint64_t(seg) * p.segmentCols;
-            const uint64_t colEndLong = min(colBegin + p.segmentCols, p.cellCount);
-            const uint32_t colEnd = uint32_t(colEndLong);
-            const uint32_t tiles = uint32_t((colEndLong - colBegin + kTileN - 1) / kTileN);
+            const uint64_t colBegin = it.colBegin;
+            const uint32_t colEnd = uint32_t(it.colEnd);
+            const uint32_t tiles = uint32_t((it.colEnd - colBegin + kTileN - 1) / kTileN);
 
             // A operand: this thread's encoded row -> TMEM lane, columns [kTmemA, kTmemA + K/4).
             // The previous item's MMAs have all completed (its last accFull was waited on below).
@@ -251,73 +236,77 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             st.count = 0;
             st.appended = 0;
             st.tau = valid ? p.tau0 : 0;
+            st.lim = st.tau;
             st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * p.rows + (valid ? localRow : 0)) * p.cap;
-            int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.tau);      // hamming < tau  <=>  dot > K - 2 tau
+            // The two sub-streams of a row exchange their bounds through shared memory (stale values are only
+            // looser).  The slot is re-initialised per item; the barrier keeps a fast warp from reading the
+            // previous item's value.
+            tauShare[sub * kRowsPerItem + rowInItem] = st.tau;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.lim);      // hamming < lim  <=>  dot > K - 2 lim
+
+            // One 32-column chunk held in registers: group maxima first (the common case is "nothing passes"),
+            // then only the 8-column groups that contain a passing column are examined, with static indexing.
+            auto chunk = [&](const uint32_t (&v)[32], uint32_t id0) {
+                int32_t m[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    m[g] = int32_t(v[8 * g]);
+#pragma unroll
+                    for (int j = 1; j < 8; j++) m[g] = max(m[g], int32_t(v[8 * g + j]));
+                }
+                const int32_t mx = max(max(m[0], m[1]), max(m[2], m[3]));
+                if (mx > dotThr) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        if (m[g] > dotThr) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                if (int32_t(v[8 * g + j]) > dotThr)
+                                    consider(st, uint32_t(int32_t(dotK) - int32_t(v[8 * g + j])) >> 1, id0 + 8 * g + j, colEnd);
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, mx > dotThr)) {
+                    warpPruneIfNeeded(st, p.k, p.cap);
+                    dotThr = int32_t(dotK) - 2 * int32_t(st.lim);
+                }
+            };
+
             for (uint32_t t = 0; t < tiles; t++, tileIter++) {
                 const uint32_t buf = tileIter & 1;
                 mbarWait(accFull + buf, (tileIter >> 1) & 1);
                 fenceAfter();
                 const uint32_t idBase = uint32_t(colBegin) + t * kTileN + sub * kSubCols;
                 const uint32_t taddr = tmemBase + buf * kTileN + sub * kSubCols + laneField;
-#pragma unroll 1
-                for (int c = 0; c < kSubCols; c += 32) {
-                    uint32_t v[32];
-                    tmemLoad32(taddr + c, v);
-                    tmemLoadWait();
-                    if (DUMP) {
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                const uint32_t id = idBase + c + j;
-                                if (id < colEnd)
-                                    p.dump[localRow * p.cellCount + id] = uint16_t((int32_t(dotK) - int32_t(v[j])) >> 1);
-                            }
-                        }
-                    } else {
-                        int32_t mx = int32_t(v[0]);
-#pragma unroll
-                        for (int j = 1; j < 32; j++) mx = max(mx, int32_t(v[j]));
-                        if (EPI == 0) {
-                            // lanes with a passing column diverge; straight-line mask + select tree
-                            if (mx > dotThr) {
-                                uint32_t mask = 0;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) mask |= uint32_t(int32_t(v[j]) > dotThr) << j;
-                                do {
-                                    const int j = __ffs(int(mask)) - 1;
-                                    mask &= mask - 1;
-                                    const int32_t val = pick32(v, j);
-                                    consider(st, uint32_t(int32_t(dotK) - val) >> 1, idBase + c + j, colEnd);
-                                } while (mask);
-                            }
-                            if (__any_sync(0xffffffffu, mx > dotThr)) {
-                                warpPruneIfNeeded(st, p.k, p.cap);
-                                dotThr = int32_t(dotK) - 2 * int32_t(st.tau);
-                            }
-                        } else if (__any_sync(0xffffffffu, mx > dotThr)) {
-                            // Some row of this warp has a passing column (common with clustered data).
-                            // Keep the warp converged: every lane pushes its passing columns into its
-                            // private shared-memory ring with predicated stores, then drains the ring.
-                            uint32_t n = 0;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if (int32_t(v[j]) > dotThr) {
-                                    ring[n * kEpiThreads + threadIdx.x] = (v[j] << 5) | uint32_t(j);
-                                    n++;
-                                }
-                            }
-                            for (uint32_t i = 0; i < n; i++) {
-                                const uint32_t e = ring[i * kEpiThreads + threadIdx.x];
-                                const int32_t val = int32_t(e) >> 5;
-                                consider(st, uint32_t(int32_t(dotK) - val) >> 1, idBase + c + (e & 31u), colEnd);
-                            }
-                            warpPruneIfNeeded(st, p.k, p.cap);
-                            dotThr = int32_t(dotK) - 2 * int32_t(st.tau);
-                        }
-                    }
-                }
+                // Both chunks into registers, then hand the accumulator back at once: selection work (and the
+                // occasional prune) overlaps the MMAs of the next TWO tiles instead of holding a TMEM buffer.
+                uint32_t v0[32], v1[32];
+                tmemLoad32(taddr, v0);
+                tmemLoad32(taddr + 32, v1);
+                tmemLoadWait();
                 fenceBefore();
                 mbarArrive(accEmpty + buf);
+                if (DUMP) {
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const uint32_t id = idBase + j;
+                            if (id < colEnd) p.dump[localRow * p.cellCount + id] = uint16_t((int32_t(dotK) - int32_t(v0[j])) >> 1);
+                            if (id + 32 < colEnd)
+                                p.dump[localRow * p.cellCount + id + 32] = uint16_t((int32_t(dotK) - int32_t(v1[j])) >> 1);
+                        }
+                    }
+                } else {
+                    const uint32_t other = tauShare[(sub ^ 1) * kRowsPerItem + rowInItem];
+                    if (other + 1 < st.lim) {       // a tie with the other stream's k-th best can still win on id
+                        st.lim = other + 1;
+                        dotThr = int32_t(dotK) - 2 * int32_t(st.lim);
+                    }
+                    chunk(v0, idBase);
+                    chunk(v1, idBase + 32);
+                    tauShare[sub * kRowsPerItem + rowInItem] = st.tau;
+                }
             }
             if (!DUMP && valid) {
                 p.candCount[uint64_t(seg * kSubStreams + sub) * p.rows + localRow] = st.count;
@@ -385,10 +374,12 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     MmaParams p{};
     const uint32_t panels = K / kChunkBytes;
     p.stages = kStages;
-    ScanPlan plan = makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kRowsPerItem, 1);
+    ScanPlan plan = makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kRowsPerItem, 1, kSubStreams);
     if (dump) {
+        plan.mainBlocks = plan.rowBlocks;
         plan.segments = 1;
         plan.segmentCols = roundUp(cellCount, kTileN);
+        plan.items = plan.rowBlocks;
     }
     void* cand = nullptr;
     void* candCount = nullptr;
@@ -396,6 +387,8 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     if (!dump) {
         EM2_TRY(reserve(ctx, em2_context::S_CAND, size_t(plan.segments) * kSubStreams * rows * plan.cap * sizeof(uint64_t), &cand));
         EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(plan.segments) * kSubStreams * rows * sizeof(uint32_t), &candCount));
+        if (plan.segments > 1)   // streams a main row block never touches must read as empty
+            EM2_CUDA(ctx, cudaMemsetAsync(candCount, 0, size_t(plan.segments) * kSubStreams * rows * sizeof(uint32_t), s));
     }
     EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
     p.cellCount = cellCount;
@@ -403,9 +396,10 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     p.rows = rows;
     p.K = K;
     p.panels = panels;
+    p.mainBlocks = plan.mainBlocks;
     p.segments = plan.segments;
+    p.items = plan.items;
     p.segmentCols = plan.segmentCols;
-    p.rowBlocks = plan.rowBlocks;
     p.k = uint32_t(k);
     p.cap = plan.cap;
     p.tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
@@ -417,18 +411,16 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     CUtensorMap mapB;
     EM2_TRY(makeTensorMapU8(ctx, &mapB, enc, cellCount, K, K, kTileN));
 
-    const size_t smem = 1024 + size_t(kStages) * kStageBytes + 512 + kRingBytes;
-    const uint32_t items = plan.rowBlocks * plan.segments;
+    const size_t smem = 1024 + size_t(kStages) * kStageBytes + 512 + kShareBytes;
+    const uint32_t items = plan.items;
     const unsigned grid = unsigned(std::min<uint32_t>(items, uint32_t(ctx->smCount)));
-    static const int epi = [] { const char* e = std::getenv("EM2_MMA_EPI"); return e ? std::atoi(e) : 0; }();
     auto go = [&](auto kernel) -> int {
         EM2_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         kernel<<<grid, kThreads, smem, s>>>(mapB, static_cast<const uint8_t*>(enc), p);
         return EM2_OK;
     };
-    if (dump) EM2_TRY(go(scanMmaKernel<true, 0>));
-    else if (epi == 0) EM2_TRY(go(scanMmaKernel<false, 0>));
-    else EM2_TRY(go(scanMmaKernel<false, 1>));
+    if (dump) EM2_TRY(go(scanMmaKernel<true>));
+    else EM2_TRY(go(scanMmaKernel<false>));
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
     if (dump) return EM2_OK;

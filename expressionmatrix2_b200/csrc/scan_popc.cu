@@ -137,7 +137,8 @@ __device__ __forceinline__ void loadTile(uint32_t* panel, const uint64_t* __rest
 template <int W32, int CSA>
 __global__ void __launch_bounds__(kScanThreads)
 scanPopcRegsKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCount, uint64_t rowBegin,
-                   uint64_t rowEnd, uint64_t segmentCols, uint32_t k, uint32_t cap, uint32_t tau0,
+                   uint64_t rowEnd, uint32_t mainBlocks, uint32_t segments, uint64_t segmentCols, uint32_t k,
+                   uint32_t cap, uint32_t tau0,
                    uint64_t* __restrict__ cand, uint32_t* __restrict__ candCount,
                    unsigned long long* __restrict__ appendedTotal)
 {
@@ -145,10 +146,11 @@ scanPopcRegsKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCo
     constexpr int kPanel = kTileCols * W32;
 
     const uint64_t rows = rowEnd - rowBegin;
-    const uint64_t localRow = uint64_t(blockIdx.x) * kScanThreads + threadIdx.x;
+    const ScanItem item = decodeScanItem(blockIdx.x, mainBlocks, segments, segmentCols, cellCount);
+    const uint64_t localRow = uint64_t(item.rowBlock) * kScanThreads + threadIdx.x;
     const bool valid = localRow < rows;
-    const uint64_t colBegin = uint64_t(blockIdx.y) * segmentCols;
-    const uint64_t colEndLong = colBegin + segmentCols < cellCount ? colBegin + segmentCols : cellCount;
+    const uint64_t colBegin = item.colBegin;
+    const uint64_t colEndLong = item.colEnd;
     const uint32_t colEnd = uint32_t(colEndLong);
 
     // zero the pad words once (columns copy only 2*W words of each W32 slot)
@@ -163,7 +165,8 @@ scanPopcRegsKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCo
     st.count = 0;
     st.appended = 0;
     st.tau = valid ? tau0 : 0;
-    st.buf = cand + (uint64_t(blockIdx.y) * rows + (valid ? localRow : 0)) * cap;
+    st.lim = st.tau;
+    st.buf = cand + (uint64_t(item.segment) * rows + (valid ? localRow : 0)) * cap;
     if (valid) {
         const uint32_t* r = reinterpret_cast<const uint32_t*>(sig + (rowBegin + localRow) * W);
 #pragma unroll
@@ -203,7 +206,7 @@ scanPopcRegsKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCo
             const uint32_t h2 = hammingRow<W32, CSA>(a, panel + (c + 2) * W32);
             const uint32_t h3 = hammingRow<W32, CSA>(a, panel + (c + 3) * W32);
             const uint32_t hmin = min(min(h0, h1), min(h2, h3));
-            const bool hit = hmin < st.tau;
+            const bool hit = hmin < st.lim;
             if (__any_sync(0xffffffffu, hit)) {
               if (hit) {
                 consider(st, h0, idBase + c + 0, colEnd);
@@ -217,7 +220,7 @@ scanPopcRegsKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCo
     }
     cpAsyncWait<0>();
     if (valid) {
-        candCount[uint64_t(blockIdx.y) * rows + localRow] = st.count;
+        candCount[uint64_t(item.segment) * rows + localRow] = st.count;
         if (appendedTotal && st.appended) atomicAdd(appendedTotal, (unsigned long long)st.appended);
     }
 }
@@ -227,9 +230,9 @@ scanPopcRegsKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCo
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads)
 scanPopcSmemKernel(const uint64_t* __restrict__ sig, uint32_t W, uint32_t W32 /* = 2W rounded to 4 */,
-                   uint64_t cellCount, uint64_t rowBegin, uint64_t rowEnd, uint64_t segmentCols, uint32_t k,
-                   uint32_t cap, uint32_t tau0, uint64_t* __restrict__ cand, uint32_t* __restrict__ candCount,
-                   unsigned long long* __restrict__ appendedTotal)
+                   uint64_t cellCount, uint64_t rowBegin, uint64_t rowEnd, uint32_t mainBlocks, uint32_t segments,
+                   uint64_t segmentCols, uint32_t k, uint32_t cap, uint32_t tau0, uint64_t* __restrict__ cand,
+                   uint32_t* __restrict__ candCount, unsigned long long* __restrict__ appendedTotal)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* rowPanel = smem;                                   // [W32][kScanThreads]
@@ -238,10 +241,11 @@ scanPopcSmemKernel(const uint64_t* __restrict__ sig, uint32_t W, uint32_t W32 /*
     const uint32_t panelWords = kTileColsS * W32;
 
     const uint64_t rows = rowEnd - rowBegin;
-    const uint64_t localRow = uint64_t(blockIdx.x) * kScanThreads + threadIdx.x;
+    const ScanItem item = decodeScanItem(blockIdx.x, mainBlocks, segments, segmentCols, cellCount);
+    const uint64_t localRow = uint64_t(item.rowBlock) * kScanThreads + threadIdx.x;
     const bool valid = localRow < rows;
-    const uint64_t colBegin = uint64_t(blockIdx.y) * segmentCols;
-    const uint64_t colEndLong = colBegin + segmentCols < cellCount ? colBegin + segmentCols : cellCount;
+    const uint64_t colBegin = item.colBegin;
+    const uint64_t colEndLong = item.colEnd;
     const uint32_t colEnd = uint32_t(colEndLong);
 
     for (uint32_t i = threadIdx.x; i < kStages * panelWords; i += kScanThreads) colPanels[i] = 0;
@@ -257,7 +261,8 @@ scanPopcSmemKernel(const uint64_t* __restrict__ sig, uint32_t W, uint32_t W32 /*
     st.count = 0;
     st.appended = 0;
     st.tau = valid ? tau0 : 0;
-    st.buf = cand + (uint64_t(blockIdx.y) * rows + (valid ? localRow : 0)) * cap;
+    st.lim = st.tau;
+    st.buf = cand + (uint64_t(item.segment) * rows + (valid ? localRow : 0)) * cap;
 
     auto load = [&](uint32_t tile) {
         const uint64_t c0 = colBegin + uint64_t(tile) * kTileColsS;
@@ -307,7 +312,7 @@ scanPopcSmemKernel(const uint64_t* __restrict__ sig, uint32_t W, uint32_t W32 /*
                 h3 += __popc(xor3(r0 ^ v3.x, r1 ^ v3.y, r2 ^ v3.z)) + 2 * __popc(maj3(r0 ^ v3.x, r1 ^ v3.y, r2 ^ v3.z)) + __popc(r3 ^ v3.w);
             }
             const uint32_t hmin = min(min(h0, h1), min(h2, h3));
-            const bool hit = hmin < st.tau;
+            const bool hit = hmin < st.lim;
             if (__any_sync(0xffffffffu, hit)) {
               if (hit) {
                 consider(st, h0, idBase + c + 0, colEnd);
@@ -321,7 +326,7 @@ scanPopcSmemKernel(const uint64_t* __restrict__ sig, uint32_t W, uint32_t W32 /*
     }
     cpAsyncWait<0>();
     if (valid) {
-        candCount[uint64_t(blockIdx.y) * rows + localRow] = st.count;
+        candCount[uint64_t(item.segment) * rows + localRow] = st.count;
         if (appendedTotal && st.appended) atomicAdd(appendedTotal, (unsigned long long)st.appended);
     }
 }
@@ -405,12 +410,11 @@ int launchRegs(em2_context* ctx, const ScanPlan& plan, const uint64_t* sig, uint
                uint64_t rowBegin, uint64_t rowEnd, uint32_t k, uint32_t tau0, uint64_t* cand, uint32_t* candCount,
                unsigned long long* appended, cudaStream_t s)
 {
-    const dim3 grid(plan.rowBlocks, plan.segments);
     const size_t smem = size_t(kStages) * kTileCols * W32 * sizeof(uint32_t);
     auto go = [&](auto kernel) -> int {
         EM2_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kernel<<<grid, kScanThreads, smem, s>>>(sig, W, cellCount, rowBegin, rowEnd, plan.segmentCols, k, plan.cap,
-                                                tau0, cand, candCount, appended);
+        kernel<<<plan.items, kScanThreads, smem, s>>>(sig, W, cellCount, rowBegin, rowEnd, plan.mainBlocks, plan.segments,
+                                                      plan.segmentCols, k, plan.cap, tau0, cand, candCount, appended);
         return EM2_OK;
     };
     switch (ctx->popcCsa) {
@@ -425,31 +429,31 @@ int launchRegs(em2_context* ctx, const ScanPlan& plan, const uint64_t* sig, uint
 
 }  // namespace
 
-// Choose the grid: 256-row blocks x column segments such that the CTA count fills whole waves.
+// See ScanPlan (common.cuh).  Candidate streams cost appends and prunes (each stream has to learn the row's
+// bound on its own), so a row block is cut into column segments only where it is needed to fill the machine.
 ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount, uint64_t k, uint32_t tileCols,
-                      uint32_t rowsPerCta, uint32_t ctasPerSm)
+                      uint32_t rowsPerCta, uint32_t ctasPerSm, uint32_t streamsPerSegment)
 {
     ScanPlan p;
     p.rowsPerCta = rowsPerCta;
     p.rowBlocks = uint32_t((rows + rowsPerCta - 1) / rowsPerCta);
-    const uint64_t slots = uint64_t(ctx->smCount) * ctasPerSm;
-    uint32_t best = 1;
-    double bestEff = 0.;
-    const uint32_t maxSeg = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(32, cellCount / (4 * tileCols))));
-    for (uint32_t s = 1; s <= maxSeg; s++) {
-        const uint64_t total = uint64_t(p.rowBlocks) * s;
-        const uint64_t waves = (total + slots - 1) / slots;
-        const double eff = double(total) / double(waves * slots);
-        if (eff > bestEff + 0.03) {
-            bestEff = eff;
-            best = s;
-        }
-        if (total >= 8 * slots) break;
-    }
-    p.segments = best;
-    p.segmentCols = roundUp((cellCount + best - 1) / best, tileCols);
-    p.segments = uint32_t((cellCount + p.segmentCols - 1) / p.segmentCols);
     p.cap = candidateCapacity(uint32_t(k));
+    const uint32_t slots = uint32_t(ctx->smCount) * ctasPerSm;
+    p.mainBlocks = p.rowBlocks / slots * slots;
+    const uint32_t tail = p.rowBlocks - p.mainBlocks;
+    uint32_t seg = 1;
+    if (tail) {
+        // the finalize kernel stages a row's streams in shared memory: 4 warps x streams x cap keys <= 160 KB
+        const uint32_t maxStreams = std::max<uint32_t>(1, uint32_t((160u << 10) / (size_t(p.cap) * 8 * 4)));
+        const uint32_t maxSeg = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(32, maxStreams / streamsPerSegment),
+                                                                                  cellCount / (4 * tileCols))));
+        seg = std::max<uint32_t>(1, std::min<uint32_t>(slots / tail, maxSeg));
+        // a tail that nearly fills a wave is better left whole
+        if (p.mainBlocks && tail * 10 >= slots * 9) seg = 1;
+    }
+    p.segments = seg;
+    p.segmentCols = roundUp((cellCount + seg - 1) / seg, tileCols);
+    p.items = p.mainBlocks + tail * seg;
     return p;
 }
 
@@ -492,7 +496,7 @@ int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCo
     const uint32_t W = uint32_t(wordCount(lshCount));
     const bool regs = W <= 16;
     const uint32_t tileCols = regs ? kTileCols : 16;
-    ScanPlan plan = makeScanPlan(ctx, rows, cellCount, k, tileCols, kScanThreads, 2);
+    ScanPlan plan = makeScanPlan(ctx, rows, cellCount, k, tileCols, kScanThreads, 2, 1);
     const uint32_t tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
 
     void* cand = nullptr;
@@ -502,6 +506,8 @@ int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCo
     EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(plan.segments) * rows * sizeof(uint32_t), &candCount));
     EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
     unsigned long long* appended = static_cast<unsigned long long*>(counters) + 1;
+    if (plan.segments > 1)   // streams a main row block never touches must read as empty
+        EM2_CUDA(ctx, cudaMemsetAsync(candCount, 0, size_t(plan.segments) * rows * sizeof(uint32_t), s));
 
     if (regs) {
         auto* c = static_cast<uint64_t*>(cand);
@@ -516,9 +522,8 @@ int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCo
         const size_t smem = (size_t(W32) * kScanThreads + size_t(kStages) * 16 * W32) * sizeof(uint32_t);
         if (smem > 227 * 1024) return fail(ctx, EM2_ERR_INVALID, "lshCount too large for the POPC scan (max 6912 bits)");
         EM2_CUDA(ctx, cudaFuncSetAttribute(scanPopcSmemKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        const dim3 grid(plan.rowBlocks, plan.segments);
-        scanPopcSmemKernel<<<grid, kScanThreads, smem, s>>>(signatures, W, W32, cellCount, rowBegin, rowEnd,
-                                                             plan.segmentCols, uint32_t(k), plan.cap, tau0,
+        scanPopcSmemKernel<<<plan.items, kScanThreads, smem, s>>>(signatures, W, W32, cellCount, rowBegin, rowEnd,
+                                                             plan.mainBlocks, plan.segments, plan.segmentCols, uint32_t(k), plan.cap, tau0,
                                                              static_cast<uint64_t*>(cand),
                                                              static_cast<uint32_t*>(candCount), appended);
         ctx->stats.kernel_launches++;

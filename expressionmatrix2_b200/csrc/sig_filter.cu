@@ -417,53 +417,66 @@ int launchColumnStats(em2_context* ctx, uint64_t geneCount, const double* U, uin
     return EM2_OK;
 }
 
-int launchSignaturesFiltered(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
-                             const em2_count* counts, const double* sum1, const double* sum2, const double* U,
-                             uint64_t ld, const double* Upadded, uint64_t ldPadded, uint64_t lshCount,
-                             uint64_t* signatures, uint64_t* nearZero, cudaStream_t s)
+// Hyperplane-side preparation of the filter path (once per job): column constants + quantised operand.
+int prepareSignaturesFiltered(em2_context* ctx, SignaturePlan& pl, uint64_t cellCountHint, cudaStream_t s)
 {
-    const uint64_t W = wordCount(lshCount);
-    const uint64_t gPad = roundUp(geneCount, kFChunk);
-    const uint32_t nBlocks = uint32_t((lshCount + kFHyper - 1) / kFHyper);
-    const uint64_t Lpad = uint64_t(nBlocks) * kFHyper;
+    const uint64_t geneCount = pl.geneCount, lshCount = pl.lshCount;
+    pl.gPad = roundUp(geneCount, kFChunk);
+    pl.nBlocks = uint32_t((lshCount + kFHyper - 1) / kFHyper);
+    const uint64_t Lpad = uint64_t(pl.nBlocks) * kFHyper;
     if (geneCount > 0x7fffff00ull) return fail(ctx, EM2_ERR_INVALID, "geneCount too large");
 
-    // ---- per-hyperplane constants + quantised operand ---------------------------------------------
     void* stats = nullptr;
     EM2_TRY(reserve(ctx, em2_context::S_SUMU, 4 * Lpad * sizeof(double), &stats));
-    double* sumU = static_cast<double*>(stats);
-    double* scale = sumU + Lpad;
-    double* e1 = scale + Lpad;
-    double* e2 = e1 + Lpad;
-    EM2_TRY(launchColumnStats(ctx, geneCount, U, ld, lshCount, Lpad, sumU, scale, e1, e2, s));
-    void* uq = nullptr;
-    const size_t uqBytes = size_t(nBlocks) * kFN * gPad;
-    EM2_TRY(reserve(ctx, em2_context::S_UQ, uqBytes, &uq));
-    EM2_CUDA(ctx, cudaMemsetAsync(uq, 0, uqBytes, s));
+    pl.sumU = static_cast<double*>(stats);
+    pl.scale = pl.sumU + Lpad;
+    pl.e1 = pl.scale + Lpad;
+    pl.e2 = pl.e1 + Lpad;
+    EM2_TRY(launchColumnStats(ctx, geneCount, pl.U, pl.ld, lshCount, Lpad, pl.sumU, pl.scale, pl.e1, pl.e2, s));
+    const size_t uqBytes = size_t(pl.nBlocks) * kFN * pl.gPad;
+    EM2_TRY(reserve(ctx, em2_context::S_UQ, uqBytes, &pl.uq));
+    EM2_CUDA(ctx, cudaMemsetAsync(pl.uq, 0, uqBytes, s));
     {
-        const dim3 grid(unsigned(gPad / 128), unsigned((lshCount + 31) / 32));
-        quantizeKernel<<<grid, 256, 0, s>>>(geneCount, U, ld, uint32_t(lshCount), scale, gPad, static_cast<int8_t*>(uq));
+        const dim3 grid(unsigned(pl.gPad / 128), unsigned((lshCount + 31) / 32));
+        quantizeKernel<<<grid, 256, 0, s>>>(geneCount, pl.U, pl.ld, uint32_t(lshCount), pl.scale, pl.gPad,
+                                            static_cast<int8_t*>(pl.uq));
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
     }
 
-    // ---- chunks of cells ---------------------------------------------------------------------------
+    // scratch of the cell chunks: dense operand, flags, lists
     const uint64_t denseBudget = 6ull << 30;
-    uint64_t chunkMax = std::max<uint64_t>(kFM, denseBudget / gPad / kFM * kFM);
-    chunkMax = std::min<uint64_t>(chunkMax, roundUp(cellCount, kFM));
-    void *dense, *lists;
-    EM2_TRY(reserve(ctx, em2_context::S_DENSE, chunkMax * gPad, &dense));
-    const uint32_t uncertainCap = ctx->filterUncertainCap ? ctx->filterUncertainCap :
-        uint32_t(std::min<uint64_t>(std::max<uint64_t>(1u << 20, chunkMax * lshCount / 32), 1u << 28));
+    pl.chunkMax = std::max<uint64_t>(kFM, denseBudget / pl.gPad / kFM * kFM);
+    pl.chunkMax = std::min<uint64_t>(pl.chunkMax, roundUp(std::max<uint64_t>(cellCountHint, 1), kFM));
+    EM2_TRY(reserve(ctx, em2_context::S_DENSE, pl.chunkMax * pl.gPad, &pl.dense));
+    pl.uncertainCap = ctx->filterUncertainCap ? ctx->filterUncertainCap :
+        uint32_t(std::min<uint64_t>(std::max<uint64_t>(1u << 20, pl.chunkMax * lshCount / 32), 1u << 28));
     // layout of S_FLAGS: [counters: 2 x u32 (+pad to 16)] [flags: chunkMax bytes] [fallback list: chunkMax u32] [uncertain: cap u64]
-    const size_t offFlags = 16, offFallback = roundUp(offFlags + chunkMax, 16), offUncertain = roundUp(offFallback + 4 * chunkMax, 16);
-    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, offUncertain + size_t(uncertainCap) * 8, &lists));
-    uint8_t* base = static_cast<uint8_t*>(lists);
+    pl.offFlags = 16;
+    pl.offFallback = roundUp(pl.offFlags + pl.chunkMax, 16);
+    pl.offUncertain = roundUp(pl.offFallback + 4 * pl.chunkMax, 16);
+    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, pl.offUncertain + size_t(pl.uncertainCap) * 8, &pl.lists));
+    return EM2_OK;
+}
+
+// Signatures of cells [cellBegin, cellEnd) through the filter path.
+int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const uint64_t* toc, const em2_count* counts,
+                             const double* sum1, const double* sum2, uint64_t cellBegin, uint64_t cellEnd,
+                             uint64_t* signatures, uint64_t* nearZero, cudaStream_t s)
+{
+    const uint64_t geneCount = pl.geneCount, lshCount = pl.lshCount, gPad = pl.gPad, chunkMax = pl.chunkMax;
+    const uint64_t W = wordCount(lshCount);
+    const uint32_t nBlocks = pl.nBlocks, uncertainCap = pl.uncertainCap;
+    const double *U = pl.U, *Upadded = pl.Upadded, *sumU = pl.sumU, *scale = pl.scale, *e1 = pl.e1, *e2 = pl.e2;
+    const uint64_t ld = pl.ld, ldPadded = pl.ldPadded;
+    void *uq = pl.uq, *dense = pl.dense;
+    uint8_t* base = static_cast<uint8_t*>(pl.lists);
     uint32_t* uncertainCount = reinterpret_cast<uint32_t*>(base);
     uint32_t* fallbackCount = uncertainCount + 1;
-    uint8_t* dFlags = base + offFlags;
-    uint32_t* fallbackList = reinterpret_cast<uint32_t*>(base + offFallback);
-    uint64_t* uncertain = reinterpret_cast<uint64_t*>(base + offUncertain);
+    uint8_t* dFlags = base + pl.offFlags;
+    uint32_t* fallbackList = reinterpret_cast<uint32_t*>(base + pl.offFallback);
+    uint64_t* uncertain = reinterpret_cast<uint64_t*>(base + pl.offUncertain);
+    const uint64_t cellCount = cellEnd;
 
     const bool unsignedCounts = ctx->filterCountsSigned == 0;
     const size_t smem = 1024 + size_t(kFStages) * kFStageBytes + 256;
@@ -471,8 +484,8 @@ int launchSignaturesFiltered(em2_context* ctx, uint64_t cellCount, uint64_t gene
     CUtensorMap mapB;
     EM2_TRY(makeTensorMapU8(ctx, &mapB, uq, uint64_t(nBlocks) * kFN, gPad, gPad, 128));
 
-    for (uint64_t begin = 0; begin < cellCount; begin += chunkMax) {
-        const uint32_t chunkCells = uint32_t(std::min<uint64_t>(chunkMax, cellCount - begin));
+    for (uint64_t begin = cellBegin; begin < cellEnd; begin += chunkMax) {
+        const uint32_t chunkCells = uint32_t(std::min<uint64_t>(chunkMax, cellEnd - begin));
         EM2_CUDA(ctx, cudaMemsetAsync(base, 0, 16, s));
         densifyKernel<<<(chunkCells + 7) / 8, 256, 0, s>>>(begin, chunkCells, geneCount, gPad, toc, counts, sum1,
                                                            unsignedCounts ? 255.f : 127.f, static_cast<uint8_t*>(dense),

@@ -28,12 +28,13 @@ constexpr int kSliceCols = 128;       // hyperplanes per warp slice
 constexpr double kNearZeroEps = 1e-12;
 
 // One thread per cell, sequential like the reference (order matters for the rounding of sum1).
-__global__ void cellSumsKernel(uint64_t cellCount, const uint64_t* __restrict__ toc,
+__global__ void cellSumsKernel(uint64_t cellBegin, uint64_t cellCount, const uint64_t* __restrict__ toc,
                                const em2_count* __restrict__ counts, double* __restrict__ sum1,
                                double* __restrict__ sum2)
 {
-    const uint64_t c = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if (c >= cellCount) return;
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i >= cellCount) return;
+    const uint64_t c = cellBegin + i;
     double s1 = 0., s2 = 0.;
     const uint64_t e = toc[c + 1];
     for (uint64_t j = toc[c]; j < e; j++) {
@@ -181,12 +182,12 @@ signatureKernel(uint64_t rangeBegin, uint64_t rangeCells, uint64_t geneCount, co
 }  // namespace
 
 int launchCellSums(em2_context* ctx, uint64_t cellCount, const uint64_t* toc, const em2_count* counts,
-                   double* sum1, double* sum2, cudaStream_t s)
+                   double* sum1, double* sum2, cudaStream_t s, uint64_t cellBegin)
 {
     if (cellCount == 0) return EM2_OK;
     const int threads = 128;
     const unsigned blocks = unsigned((cellCount + threads - 1) / threads);
-    cellSumsKernel<<<blocks, threads, 0, s>>>(cellCount, toc, counts, sum1, sum2);
+    cellSumsKernel<<<blocks, threads, 0, s>>>(cellBegin, cellCount, toc, counts, sum1, sum2);
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
     return EM2_OK;
@@ -216,48 +217,69 @@ int launchSignaturesFp64(em2_context* ctx, uint64_t cellCount, uint64_t geneCoun
     return EM2_OK;
 }
 
-int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
-                     const em2_count* counts, const double* sum1, const double* sum2, const double* U,
-                     uint64_t ld, uint64_t lshCount, uint64_t nnzHint, uint64_t* signatures, uint64_t* nearZero,
-                     cudaStream_t s)
+int prepareSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const double* U, uint64_t ld,
+                      uint64_t lshCount, uint64_t nnzHint, SignaturePlan* plan, cudaStream_t s)
 {
-    if (cellCount == 0) return EM2_OK;
     if (lshCount == 0 || lshCount > 65535) return fail(ctx, EM2_ERR_INVALID, "lshCount must be in [1, 65535]");
     if (geneCount == 0) return fail(ctx, EM2_ERR_INVALID, "geneCount must be positive");
     const uint64_t Lpad = roundUp(lshCount, kSliceCols);
+    SignaturePlan& pl = *plan;
+    pl = SignaturePlan();
+    pl.geneCount = geneCount;
+    pl.lshCount = lshCount;
+    pl.U = U;
+    pl.ld = ld;
 
     // The FP64 kernel wants `Lpad` readable, zero padded columns with an even pitch and 16-byte alignment.
-    const double* Uk = U;
-    uint64_t ldk = ld;
+    pl.Upadded = U;
+    pl.ldPadded = ld;
     if (ld < Lpad || (ld & 1) || (reinterpret_cast<uintptr_t>(U) & 15)) {
         void* p = nullptr;
         EM2_TRY(reserve(ctx, em2_context::S_UPAD, geneCount * Lpad * sizeof(double), &p));
         EM2_CUDA(ctx, cudaMemsetAsync(p, 0, geneCount * Lpad * sizeof(double), s));
         EM2_CUDA(ctx, cudaMemcpy2DAsync(p, Lpad * sizeof(double), U, ld * sizeof(double), lshCount * sizeof(double),
                                         geneCount, cudaMemcpyDeviceToDevice, s));
-        Uk = static_cast<const double*>(p);
-        ldk = Lpad;
+        pl.Upadded = static_cast<const double*>(p);
+        pl.ldPadded = Lpad;
     }
 
-    // Path choice (both are bit-identical): the tensor-core filter does G*2L int8 MACs per cell
-    // at ~1.2e15/s, the FP64 kernel nnz*L at ~2.9e12/s, so the filter wins above ~0.5 % density; it also
+    // Path choice (both are bit-identical): the tensor-core filter does G*3L int8 MACs per cell
+    // at ~1.6e15/s, the FP64 kernel nnz*L at ~2.9e12/s, so the filter wins above ~0.5 % density; it also
     // needs enough cells to fill the GPU with 128 x 128 tiles.
-    bool filter = false;
-    if (ctx->signatureMode == 2) filter = true;
-    else if (ctx->signatureMode == 0 && nnzHint != 0) {
+    if (ctx->signatureMode == 2) pl.filter = true;
+    else if (ctx->signatureMode == 0 && nnzHint != 0 && cellCount != 0) {
         const double density = double(nnzHint) / (double(cellCount) * double(geneCount));
-        filter = density >= 0.012 && cellCount >= 4096 && geneCount >= 1024 && lshCount >= 128;
+        pl.filter = density >= 0.012 && cellCount >= 4096 && geneCount >= 1024 && lshCount >= 128;
     }
-    if (filter)
-        return launchSignaturesFiltered(ctx, cellCount, geneCount, toc, counts, sum1, sum2, U, ld, Uk, ldk, lshCount,
-                                        signatures, nearZero, s);
+    if (pl.filter) return prepareSignaturesFiltered(ctx, pl, cellCount, s);
 
     void* sumU = nullptr;
     EM2_TRY(reserve(ctx, em2_context::S_SUMU, Lpad * sizeof(double), &sumU));
-    EM2_TRY(launchColumnStats(ctx, geneCount, Uk, ldk, Lpad, Lpad, static_cast<double*>(sumU), nullptr, nullptr, nullptr, s));
-    return launchSignaturesFp64(ctx, cellCount, geneCount, toc, counts, sum1, sum2, Uk, ldk,
-                                static_cast<const double*>(sumU), lshCount, signatures, nearZero, nullptr, nullptr, 0,
-                                nullptr, 0, 0, cellCount, s);
+    pl.sumU = static_cast<double*>(sumU);
+    return launchColumnStats(ctx, geneCount, pl.Upadded, pl.ldPadded, Lpad, Lpad, pl.sumU, nullptr, nullptr, nullptr, s);
+}
+
+int launchSignaturesRange(em2_context* ctx, const SignaturePlan& pl, const uint64_t* toc, const em2_count* counts,
+                          const double* sum1, const double* sum2, uint64_t cellBegin, uint64_t cellEnd,
+                          uint64_t* signatures, uint64_t* nearZero, cudaStream_t s)
+{
+    if (cellEnd <= cellBegin) return EM2_OK;
+    if (pl.filter)
+        return launchSignaturesFiltered(ctx, pl, toc, counts, sum1, sum2, cellBegin, cellEnd, signatures, nearZero, s);
+    return launchSignaturesFp64(ctx, cellEnd, pl.geneCount, toc, counts, sum1, sum2, pl.Upadded, pl.ldPadded, pl.sumU,
+                                pl.lshCount, signatures, nearZero, nullptr, nullptr, 0, nullptr, 0, cellBegin,
+                                cellEnd - cellBegin, s);
+}
+
+int launchSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                     const em2_count* counts, const double* sum1, const double* sum2, const double* U,
+                     uint64_t ld, uint64_t lshCount, uint64_t nnzHint, uint64_t* signatures, uint64_t* nearZero,
+                     cudaStream_t s)
+{
+    if (cellCount == 0) return EM2_OK;
+    SignaturePlan pl;
+    EM2_TRY(prepareSignatures(ctx, cellCount, geneCount, U, ld, lshCount, nnzHint, &pl, s));
+    return launchSignaturesRange(ctx, pl, toc, counts, sum1, sum2, 0, cellCount, signatures, nearZero, s);
 }
 
 }  // namespace em2

@@ -25,7 +25,9 @@ constexpr uint32_t kPruneSlack = 32;    // appends a thread may make between two
 struct RowState {
     uint64_t* buf;
     uint32_t count;
-    uint32_t tau;       // accept iff ham < tau
+    uint32_t tau;       // this stream's own bound: every stored mismatch count is < tau
+    uint32_t lim;       // filter: accept iff ham < lim; lim <= tau (a kernel may tighten it with bounds
+                        // learned by other streams of the same row)
     uint32_t rowId;
     uint32_t appended;
 };
@@ -36,7 +38,7 @@ __host__ __device__ inline uint32_t candidateCapacity(uint32_t k) { return 2 * k
 // Plain append; the caller guarantees at most kPruneSlack appends between two warpPruneIfNeeded() calls.
 static __device__ __forceinline__ void consider(RowState& st, uint32_t ham, uint32_t id, uint32_t colEnd)
 {
-    if (ham < st.tau && id < colEnd && id != st.rowId) {
+    if (ham < st.lim && id < colEnd && id != st.rowId) {
         st.buf[st.count++] = (uint64_t(ham) << 32) | id;
         st.appended++;
     }
@@ -97,6 +99,7 @@ static __device__ __forceinline__ void warpPruneIfNeeded(RowState& st, uint32_t 
         if (int(threadIdx.x & 31) == src) {
             st.count = k;
             st.tau = h;
+            st.lim = st.lim < h ? st.lim : h;
         }
     }
 }

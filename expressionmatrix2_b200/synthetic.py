@@ -104,20 +104,22 @@ def to_pairs(gene_ids: np.ndarray, counts: np.ndarray) -> np.ndarray:
 
 
 def gen_signatures(cell_count: int, lsh_count: int, seed: int = 12345, clusters: int = 0,
-                   flip_fraction: float = 0.12) -> np.ndarray:
+                   flip_fraction: float = 0.12, centre_seed: int | None = None) -> np.ndarray:
     """Signatures-only synthetic input for scan-only runs: uint64 [N, W], MSB-first bit order.
 
     clusters == 0: iid random bits (all Hamming distances near L/2).
     clusters > 0 : each cell = its cluster centre with each bit flipped with probability
-    `flip_fraction` (planted neighbours)."""
+    `flip_fraction` (planted neighbours).  centre_seed: draw the cluster centres from their own generator, so
+    that shards generated with different `seed`s (one per rank) share the same clusters."""
     rng = np.random.default_rng(seed)
     W = (lsh_count - 1) // 64 + 1
     if clusters <= 0:
         sig = rng.integers(0, 1 << 63, size=(cell_count, W), dtype=np.uint64)
         sig ^= rng.integers(0, 2, size=(cell_count, W), dtype=np.uint64) << np.uint64(63)
     else:
-        centres = rng.integers(0, 1 << 63, size=(clusters, W), dtype=np.uint64)
-        centres ^= rng.integers(0, 2, size=(clusters, W), dtype=np.uint64) << np.uint64(63)
+        crng = rng if centre_seed is None else np.random.default_rng(centre_seed)
+        centres = crng.integers(0, 1 << 63, size=(clusters, W), dtype=np.uint64)
+        centres ^= crng.integers(0, 2, size=(clusters, W), dtype=np.uint64) << np.uint64(63)
         member = rng.integers(0, clusters, size=cell_count)
         sig = centres[member].copy()
         # flip mask with P(bit)=flip_fraction, built from AND/OR of uniform words (p = 1/8 = 0.125 approx)
