@@ -233,6 +233,8 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     if (n == "signature_mode" && value >= 0 && value <= 2) ctx->signatureMode = int(value);
     else if (n == "popc_csa" && value >= 0 && value <= 2) ctx->popcCsa = int(value);
     else if (n == "filter_counts_signed" && value >= 0 && value <= 1) ctx->filterCountsSigned = int(value);
+    else if (n == "cand_cap_extra" && value >= 0 && value <= 14) ctx->candCapExtra = int(value);
+    else if (n == "mma_cta_pair" && value >= 0 && value <= 1) ctx->mmaCtaPair = int(value);
     else if (n == "exact_matrix_bytes" && value >= 0) ctx->exactMatrixBytes = uint64_t(value);
     else if (n == "filter_uncertain_cap" && value >= 0 && value <= (1 << 28)) ctx->filterUncertainCap = uint32_t(value);
     else return fail(ctx, EM2_ERR_INVALID, "em2_set_option: unknown option or value out of range: " + n);

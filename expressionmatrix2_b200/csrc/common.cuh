@@ -54,6 +54,8 @@ struct em2_context {
     int popcCsa = 1;         // carry-save levels of the POPC scan
     uint32_t filterUncertainCap = 0;   // test knob: capacity of the uncertain list (0 = automatic)
     uint64_t exactMatrixBytes = 0;     // test knob: budget of the exact path's similarity matrix (0 = 8 GiB)
+    int candCapExtra = 0;              // candidate regions hold (2 + candCapExtra) * k + 32 keys
+    int mmaCtaPair = 0;                // 1: the MMA scan runs on CTA pairs (cta_group::2, M = 256)
     int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM
     em2::DeviceBuffer scratch[S_COUNT];
     em2::PinnedBuffer pinned[2];
@@ -177,7 +179,7 @@ __host__ __device__ inline ScanItem decodeScanItem(uint32_t item, uint32_t mainB
 }
 // streamsPerSegment: candidate streams a kernel keeps per (row, segment) (the MMA variant's column sub-streams).
 ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount, uint64_t k, uint32_t tileCols,
-                      uint32_t rowsPerCta, uint32_t ctasPerSm, uint32_t streamsPerSegment);
+                      uint32_t rowsPerCta, uint32_t ctasPerSm, uint32_t streamsPerSegment, uint32_t slotsOverride = 0);
 int launchFinalize(em2_context* ctx, const ScanPlan& plan, uint64_t rows, uint64_t k, const uint64_t* cand,
                    const uint32_t* candCount, const float* lut, em2_pair* pairs, uint32_t* usedCount,
                    cudaStream_t s);

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256)
 exactDensifyKernel(uint64_t cellCount, uint64_t geneCount, uint64_t gPad, const uint64_t* __restrict__ toc,
                    const em2_count* __restrict__ counts, const double* __restrict__ sum1,
                    const double* __restrict__ sum2, uint8_t* __restrict__ lo, uint8_t* __restrict__ hi,
-                   double* __restrict__ var)
+                   double* __restrict__ var, float* __restrict__ rinv)
 {
     const uint64_t cell = blockIdx.x * uint64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -102,7 +102,10 @@ exactDensifyKernel(uint64_t cellCount, uint64_t geneCount, uint64_t gPad, const 
     }
     if (lane == 0) {
         const double n = double(geneCount), s1 = sum1[cell];
-        var[cell] = __dsub_rn(__dmul_rn(n, sum2[cell]), __dmul_rn(s1, s1));
+        const double v = __dsub_rn(__dmul_rn(n, sum2[cell]), __dmul_rn(s1, s1));
+        var[cell] = v;
+        // float reciprocal root for the epilogue's cheap pre-filter; NaN for degenerate cells (never rejects)
+        rinv[cell] = v > 0. ? rsqrtf(float(v)) : __int_as_float(0x7fc00000);
     }
 }
 
@@ -117,6 +120,8 @@ struct ExactParams {
     double threshold;
     const double* sum1;
     const double* var;
+    const float* rinv;
+    float thresholdLow;          // float(threshold) - 1e-4: below this the float estimate of r rejects outright
     float* out;
 };
 
@@ -250,6 +255,7 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
             const bool valid = localRow < p.rows;
             const uint64_t a = p.rowBegin + (valid ? localRow : 0);
             const double s1a = p.sum1[a], va = p.var[a];
+            const float rinvA = p.rinv[a];
             const uint32_t buf = tileIter % kAccBufs;
             const uint32_t use = tileIter / kAccBufs;
             mbarWait(accFull + buf, use & 1);
@@ -280,9 +286,14 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
                             double sp = double(ll[j]);                                        // u8 x u8 sums are non-negative
                             if (DIGITS == 2) sp = fma(fma(double(hh[j]), 256., double(xx[j])), 256., sp);   // exact
                             const double num = __dsub_rn(__dmul_rn(n, sp), __dmul_rn(s1a, __ldg(p.sum1 + b)));
-                            const double den = __dsqrt_rn(__dmul_rn(va, __ldg(p.var + b)));
-                            const double r = __ddiv_rn(num, den);
-                            if (r > p.threshold) res = float(r);
+                            // float estimate of r (relative error < 1e-6, |r| <= 1): only candidates within
+                            // 1e-4 of the threshold or above it pay for the exact double sqrt and divide
+                            const float estimate = float(num) * rinvA * __ldg(p.rinv + b);
+                            if (!(estimate < p.thresholdLow)) {
+                                const double den = __dsqrt_rn(__dmul_rn(va, __ldg(p.var + b)));
+                                const double r = __ddiv_rn(num, den);
+                                if (r > p.threshold) res = float(r);
+                            }
                         }
                         r4[jj] = res;
                     }
@@ -416,10 +427,11 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
     void *lo = nullptr, *hi = nullptr, *var = nullptr;
     EM2_TRY(reserve(ctx, em2_context::S_DENSE, cellCount * gPad * digits, &lo));
     if (digits == 2) hi = static_cast<uint8_t*>(lo) + cellCount * gPad;
-    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, cellCount * sizeof(double), &var));
+    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, cellCount * (sizeof(double) + sizeof(float)), &var));
+    float* rinv = reinterpret_cast<float*>(static_cast<double*>(var) + cellCount);
     exactDensifyKernel<<<unsigned((cellCount + 7) / 8), 256, 0, s>>>(cellCount, geneCount, gPad, toc, counts, sum1, sum2,
                                                                     static_cast<uint8_t*>(lo), static_cast<uint8_t*>(hi),
-                                                                    static_cast<double*>(var));
+                                                                    static_cast<double*>(var), rinv);
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
 
@@ -458,6 +470,8 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
         p.threshold = similarityThreshold;
         p.sum1 = sum1;
         p.var = static_cast<const double*>(var);
+        p.rinv = rinv;
+        p.thresholdLow = float(similarityThreshold) - 1e-4f;
         p.out = static_cast<float*>(simMatrix);
         const unsigned grid = unsigned(std::min<uint32_t>(p.items, uint32_t(ctx->smCount)));
         if (digits == 1) {

@@ -56,6 +56,13 @@ constexpr int kChunksPerStage = 2;                             // a ring stage c
 constexpr uint32_t kStageBytes = kChunksPerStage * kChunkTileBytes;
 constexpr int kStages = 5;                                     // 160 KB ring
 constexpr uint32_t kTmemA = 256;      // first TMEM column of the A operand
+// CTA-pair variant (cta_group::2, M = 256): each CTA streams HALF of every B tile (64 columns), so a K-chunk is
+// 8 KB per CTA, a stage 16 KB, and the same 160 KB hold 10 stages.
+constexpr int kPairRows = 2 * kRowsPerItem;
+constexpr uint32_t kPairChunkBytes = (kTileN / 2) * kChunkBytes;
+constexpr uint32_t kPairStageBytes = kChunksPerStage * kPairChunkBytes;
+constexpr int kPairStages = 10;
+constexpr int kMaxStages = 10;
 
 // Instruction descriptor: kind::i8, A/B signed 8-bit K-major, D s32, M=128, N=256.
 constexpr uint32_t kInstrDesc = (2u << 4)                        // c_format = S32
@@ -63,6 +70,7 @@ constexpr uint32_t kInstrDesc = (2u << 4)                        // c_format = S
                                 | (1u << 10)                     // b_format = signed 8-bit
                                 | (uint32_t(kTileN >> 3) << 17)  // n_dim
                                 | (uint32_t(kRowsPerItem >> 4) << 24);   // m_dim
+constexpr uint32_t kInstrDescPair = (kInstrDesc & ~(0x1Fu << 24)) | (uint32_t(kPairRows >> 4) << 24);   // M = 256 over two CTAs
 
 struct MmaParams {
     uint64_t cellCount;      // N (columns)
@@ -79,69 +87,85 @@ struct MmaParams {
     uint16_t* dump;          // optional: all distances of the scanned rows (tests)
 };
 
-template <bool DUMP>
+template <bool DUMP, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restrict__ enc, const MmaParams p)
 {
+    constexpr int kNumStages = PAIR ? kPairStages : kStages;
+    constexpr uint32_t kStageSz = PAIR ? kPairStageBytes : kStageBytes;
+    constexpr uint32_t kChunkSz = PAIR ? kPairChunkBytes : kChunkTileBytes;
     extern __shared__ uint8_t smemRaw[];
     // carve: [B stages][barriers]; 1024-byte alignment for the 128B swizzle
     uint8_t* smB = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + size_t(kStages) * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + size_t(kNumStages) * kStageSz);
     uint64_t* aFull = bars + 0;      // epilogue threads -> MMA: the A operand of this item is in TMEM
     uint64_t* accFull = bars + 2;    // [2]
     uint64_t* accEmpty = bars + 4;   // [2]
     uint64_t* bFull = bars + 6;      // [stages]
-    uint64_t* bEmpty = bFull + kStages;
-    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bEmpty + kStages);
+    uint64_t* bEmpty = bFull + kMaxStages;
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bEmpty + kMaxStages);
     uint32_t* tauShare = reinterpret_cast<uint32_t*>(bars) + 128;   // [kSubStreams][kRowsPerItem], after 512 B of barriers
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // PAIR: the two CTAs of a cluster work on one 256-row item; rank 0 is the leader (it owns the barriers the
+    // MMA thread waits on and issues the MMAs); every CTA runs its own producer and its own epilogue.
+    const uint32_t rank = PAIR ? clusterRank() : 0;
+    const uint32_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+    const uint32_t workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
     if (threadIdx.x == 0) {
-        mbarInit(aFull, kEpiWarps * 32);
+        // PAIR: one arrival per epilogue warp of either CTA; otherwise one per epilogue thread
+        mbarInit(aFull, PAIR ? 2 * kEpiWarps : kEpiWarps * 32);
         for (int i = 0; i < 2; i++) {
             mbarInit(accFull + i, 1);
-            mbarInit(accEmpty + i, kEpiWarps * 32);
+            mbarInit(accEmpty + i, PAIR ? 2 * kEpiWarps : kEpiWarps * 32);
         }
-        for (uint32_t i = 0; i < kStages; i++) {
+        for (uint32_t i = 0; i < kNumStages; i++) {
             mbarInit(bFull + i, 1);
             mbarInit(bEmpty + i, 1);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbarInitFence();
     }
     if (warp == kEpiWarps) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smemAddr(tmemSlot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) tmemAllocPair(tmemSlot, 512);
+        else tmemAlloc(tmemSlot, 512);
     }
     fenceBefore();
-    __syncthreads();
+    if (PAIR) clusterSync();      // barriers of both CTAs are initialised before anyone signals across
+    else __syncthreads();
     fenceAfter();
     const uint32_t tmemBase = *tmemSlot;
 
     const uint32_t items = p.items;
 
     if (warp == kEpiWarps) {
-        // ===================== TMA producer (B operand) =====================
+        // ===================== TMA producer (B operand; PAIR: this CTA's half of every tile) =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const uint32_t stagesPerTile = (p.panels + kChunksPerStage - 1) / kChunksPerStage;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            for (uint32_t item = worker; item < items; item += workers) {
                 const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
                 const uint64_t colBegin = it.colBegin, colEnd = it.colEnd;
                 const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
                 for (uint32_t t = 0; t < tiles; t++) {
-                    const int32_t col0 = int32_t(colBegin + uint64_t(t) * kTileN);
+                    const int32_t col0 = int32_t(colBegin + uint64_t(t) * kTileN + (PAIR ? rank * (kTileN / 2) : 0));
                     for (uint32_t j = 0; j < stagesPerTile; j++) {
                         const uint32_t kc0 = j * kChunksPerStage;
                         const uint32_t chunks = min(uint32_t(kChunksPerStage), p.panels - kc0);
                         mbarWait(bEmpty + stage, phase ^ 1);
-                        mbarExpectTx(bFull + stage, chunks * kChunkTileBytes);
-                        uint8_t* dst = smB + size_t(stage) * kStageBytes;
-                        for (uint32_t c = 0; c < chunks; c++)
-                            tmaLoad2d(dst + c * kChunkTileBytes, &mapB, bFull + stage, int32_t((kc0 + c) * kChunkBytes), col0);
-                        if (++stage == kStages) {
+                        uint8_t* dst = smB + size_t(stage) * kStageSz;
+                        if (PAIR) {
+                            // the leader's barrier collects the bytes of both halves
+                            if (rank == 0) mbarExpectTx(bFull + stage, 2 * chunks * kChunkSz);
+                            for (uint32_t c = 0; c < chunks; c++)
+                                tmaLoad2dPair(dst + c * kChunkSz, &mapB, bFull + stage, int32_t((kc0 + c) * kChunkBytes), col0);
+                        } else {
+                            mbarExpectTx(bFull + stage, chunks * kChunkSz);
+                            for (uint32_t c = 0; c < chunks; c++)
+                                tmaLoad2d(dst + c * kChunkSz, &mapB, bFull + stage, int32_t((kc0 + c) * kChunkBytes), col0);
+                        }
+                        if (++stage == kNumStages) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -150,11 +174,11 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             }
         }
     } else if (warp == kEpiWarps + 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (PAIR: leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
             uint32_t itemIter = 0, tileIter = 0, stage = 0, phase = 0;
             const uint32_t stagesPerTile = (p.panels + kChunksPerStage - 1) / kChunksPerStage;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+            for (uint32_t item = worker; item < items; item += workers, itemIter++) {
                 const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
                 const uint64_t colBegin = it.colBegin, colEnd = it.colEnd;
                 const uint32_t tiles = uint32_t((colEnd - colBegin + kTileN - 1) / kTileN);
@@ -171,22 +195,27 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                         const uint32_t chunks = min(uint32_t(kChunksPerStage), p.panels - j * kChunksPerStage);
                         mbarWait(bFull + stage, phase);
                         fenceAfter();
-                        uint32_t bAddr = smemAddr(smB + size_t(stage) * kStageBytes);
-                        for (uint32_t c = 0; c < chunks; c++, bAddr += kChunkTileBytes) {
+                        uint32_t bAddr = smemAddr(smB + size_t(stage) * kStageSz);
+                        for (uint32_t c = 0; c < chunks; c++, bAddr += kChunkSz) {
 #pragma unroll
                             for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++, aCol += kUmmaK / 4) {
-                                mmaI8Ts(tmemD, aCol, makeSmemDesc(bAddr + ks * kUmmaK), kInstrDesc, first);
+                                if (PAIR) mmaI8TsPair(tmemD, aCol, makeSmemDesc(bAddr + ks * kUmmaK), kInstrDescPair, first);
+                                else mmaI8Ts(tmemD, aCol, makeSmemDesc(bAddr + ks * kUmmaK), kInstrDesc, first);
                                 first = 1;
                             }
                         }
-                        commit(bEmpty + stage);       // stage reusable once these MMAs have read it
-                        if (++stage == kStages) {
+                        // stage reusable once these MMAs have read it (PAIR: in both CTAs)
+                        if (PAIR) commitPair(bEmpty + stage);
+                        else commit(bEmpty + stage);
+                        if (++stage == kNumStages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    commit(accFull + buf);            // accumulator complete (and, on the item's last
-                }                                            // tile, every read of the A operand is done)
+                    // accumulator complete (and, on the item's last tile, every read of the A operand is done)
+                    if (PAIR) commitPair(accFull + buf);
+                    else commit(accFull + buf);
+                }
             }
         }
     } else {
@@ -201,10 +230,11 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
         static_assert(kSubCols == 64 && kSubStreams == 2, "the epilogue below handles two 32-column chunks per thread");
         const uint32_t laneField = uint32_t((warp & 3) * 32) << 16;
         uint32_t tileIter = 0;
-        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+        for (uint32_t item = worker; item < items; item += workers) {
             const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
             const uint32_t seg = it.segment;
-            const uint64_t localRow = uint64_t(it.rowBlock) * kRowsPerItem + rowInItem;
+            const uint64_t localRow = PAIR ? uint64_t(it.rowBlock) * kPairRows + rank * kRowsPerItem + rowInItem
+                                           : uint64_t(it.rowBlock) * kRowsPerItem + rowInItem;
             const bool valid = localRow < p.rows;
             const uint64_t colBegin = it.colBegin;
             const uint32_t colEnd = uint32_t(it.colEnd);
@@ -228,7 +258,12 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                 }
                 tmemStoreWait();
                 fenceBefore();
-                mbarArrive(aFull);
+                if (PAIR) {
+                    __syncwarp();
+                    if (lane == 0) mbarArriveLeader(aFull);
+                } else {
+                    mbarArrive(aFull);
+                }
             }
 
             RowState st;
@@ -286,7 +321,12 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                 tmemLoad32(taddr + 32, v1);
                 tmemLoadWait();
                 fenceBefore();
-                mbarArrive(accEmpty + buf);
+                if (PAIR) {
+                    __syncwarp();
+                    if (lane == 0) mbarArriveLeader(accEmpty + buf);
+                } else {
+                    mbarArrive(accEmpty + buf);
+                }
                 if (DUMP) {
                     if (valid) {
 #pragma unroll
@@ -316,9 +356,12 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
     }
 
     fenceBefore();
-    __syncthreads();
-    if (warp == kEpiWarps) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmemBase) : "memory");
+    if (PAIR) {
+        clusterSync();        // neither CTA may retire while its partner can still signal into it
+        if (warp == kEpiWarps) tmemDeallocPair(tmemBase, 512);
+    } else {
+        __syncthreads();
+        if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
     }
 }
 
@@ -374,7 +417,10 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     MmaParams p{};
     const uint32_t panels = K / kChunkBytes;
     p.stages = kStages;
-    ScanPlan plan = makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kRowsPerItem, 1, kSubStreams);
+    const bool pair = ctx->mmaCtaPair != 0;
+    ScanPlan plan = pair ? makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kPairRows, 1, kSubStreams,
+                                        uint32_t(ctx->smCount / 2))
+                         : makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kRowsPerItem, 1, kSubStreams);
     if (dump) {
         plan.mainBlocks = plan.rowBlocks;
         plan.segments = 1;
@@ -409,18 +455,44 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     p.dump = dump;
 
     CUtensorMap mapB;
-    EM2_TRY(makeTensorMapU8(ctx, &mapB, enc, cellCount, K, K, kTileN));
+    EM2_TRY(makeTensorMapU8(ctx, &mapB, enc, cellCount, K, K, pair ? kTileN / 2 : kTileN));
 
     const size_t smem = 1024 + size_t(kStages) * kStageBytes + 512 + kShareBytes;
+    static_assert(size_t(kStages) * kStageBytes == size_t(kPairStages) * kPairStageBytes, "both variants use the same ring bytes");
     const uint32_t items = plan.items;
-    const unsigned grid = unsigned(std::min<uint32_t>(items, uint32_t(ctx->smCount)));
     auto go = [&](auto kernel) -> int {
         EM2_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kernel<<<grid, kThreads, smem, s>>>(mapB, static_cast<const uint8_t*>(enc), p);
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        if (pair) {
+            // clusters of two CTAs (one TPC); as many pairs as the device can keep resident
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cfg.gridDim = dim3(2 * unsigned(ctx->smCount / 2));
+            int clusters = 0;
+            EM2_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg));
+            if (clusters < 1) return fail(ctx, EM2_ERR_CUDA, "no CTA pair of the MMA scan kernel fits on this device");
+            cfg.gridDim = dim3(2 * std::min<unsigned>(unsigned(clusters), std::min<unsigned>(items, unsigned(ctx->smCount / 2))));
+        } else {
+            cfg.gridDim = dim3(std::min<uint32_t>(items, uint32_t(ctx->smCount)));
+        }
+        EM2_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, mapB, static_cast<const uint8_t*>(enc), p));
         return EM2_OK;
     };
-    if (dump) EM2_TRY(go(scanMmaKernel<true>));
-    else EM2_TRY(go(scanMmaKernel<false>));
+    if (pair) {
+        if (dump) EM2_TRY(go(scanMmaKernel<true, true>));
+        else EM2_TRY(go(scanMmaKernel<false, true>));
+    } else {
+        if (dump) EM2_TRY(go(scanMmaKernel<true, false>));
+        else EM2_TRY(go(scanMmaKernel<false, false>));
+    }
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
     if (dump) return EM2_OK;

@@ -432,13 +432,13 @@ int launchRegs(em2_context* ctx, const ScanPlan& plan, const uint64_t* sig, uint
 // See ScanPlan (common.cuh).  Candidate streams cost appends and prunes (each stream has to learn the row's
 // bound on its own), so a row block is cut into column segments only where it is needed to fill the machine.
 ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount, uint64_t k, uint32_t tileCols,
-                      uint32_t rowsPerCta, uint32_t ctasPerSm, uint32_t streamsPerSegment)
+                      uint32_t rowsPerCta, uint32_t ctasPerSm, uint32_t streamsPerSegment, uint32_t slotsOverride)
 {
     ScanPlan p;
     p.rowsPerCta = rowsPerCta;
     p.rowBlocks = uint32_t((rows + rowsPerCta - 1) / rowsPerCta);
-    p.cap = candidateCapacity(uint32_t(k));
-    const uint32_t slots = uint32_t(ctx->smCount) * ctasPerSm;
+    p.cap = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
+    const uint32_t slots = slotsOverride ? slotsOverride : uint32_t(ctx->smCount) * ctasPerSm;
     p.mainBlocks = p.rowBlocks / slots * slots;
     const uint32_t tail = p.rowBlocks - p.mainBlocks;
     uint32_t seg = 1;

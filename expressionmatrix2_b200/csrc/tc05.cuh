@@ -132,6 +132,68 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster, on the two SMs of one TPC, run ONE M=256 MMA -----------
+// Each CTA holds its 128 rows of A and D in its own TMEM and HALF of the B tile (N/2 rows) in its own shared
+// memory; the leader (cluster rank 0) issues the instruction.  In a 2-CTA cluster the rank sits in bit 24 of a
+// shared-memory address, so clearing it names the same location in the leader CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t clusterRank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void clusterSync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t leaderAddr(const void* p) { return smemAddr(p) & kPeerBitMask; }
+// arrive on the LEADER CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbarArriveLeader(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leaderAddr(bar)) : "memory");
+}
+// TMA tile load into THIS CTA's shared memory whose completion bytes are credited to the leader's barrier
+__device__ __forceinline__ void tmaLoad2dPair(void* smemDst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1)
+{
+    const uint64_t evictNormal = 0x1000000000000000ull;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smemAddr(smemDst)), "l"(map), "r"(leaderAddr(bar)), "r"(c0), "r"(c1), "l"(evictNormal)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> one arrival on the same barrier offset in BOTH CTAs
+__device__ __forceinline__ void commitPair(uint64_t* bar)
+{
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smemAddr(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mmaI8TsPair(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmemD),
+        "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmemAllocPair(uint32_t* slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmemDeallocPair(uint32_t base, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
 // Shared-memory matrix descriptor: K-major operand tile whose rows are 128 bytes (one swizzle atom) apart and
 // whose 8-row groups are 1024 bytes apart, 128-byte swizzle (the layout a TMA box of {128 bytes, rows} with
 // CU_TENSOR_MAP_SWIZZLE_128B produces).  Encoding per the PTX ISA matrix-descriptor table, version 1 (sm_100).

@@ -84,6 +84,59 @@ static __device__ __noinline__ uint32_t warpPrune(uint64_t* buf, uint32_t count,
     return h;                               // later ids are larger: ties at h can no longer enter
 }
 
+// Same contract, for regions of at most 32*EPL keys: the region is read ONCE into registers (EPL independent
+// loads per lane, one memory round trip), the k-th smallest mismatch count is found by bisection on registers
+// only, and the stable compaction writes straight from registers.  ~4x shorter than the version above, whose
+// every bisection step goes back to memory -- and prune latency is what stalls the MMA pipeline of the scan
+// on clustered data.
+template <int EPL>
+static __device__ __noinline__ uint32_t warpPruneRegs(uint64_t* buf, uint32_t count, uint32_t k, uint32_t tau)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t m[EPL], id[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+        const uint32_t i = e * 32 + lane;
+        const uint64_t key = i < count ? buf[i] : ~0ull;
+        m[e] = uint32_t(key >> 32);          // 0xffffffff for the slots beyond count: never selected
+        id[e] = uint32_t(key);
+    }
+    uint32_t lo = 0, hi = tau - 1;           // every stored mismatch count is < tau
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        uint32_t c = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) c += (m[e] <= mid);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) hi = mid;
+        else lo = mid + 1;
+    }
+    const uint32_t h = lo;
+    uint32_t less = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) less += (m[e] < h);
+    less = __reduce_add_sync(0xffffffffu, less);
+    const uint32_t r = k - less;             // ties at h that still fit
+    uint32_t out = 0, tiesBefore = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+        if (uint32_t(e) * 32 < count) {      // warp-uniform
+            const bool tie = m[e] == h;
+            const uint32_t tieMask = __ballot_sync(0xffffffffu, tie);
+            const bool keep = m[e] < h || (tie && tiesBefore + __popc(tieMask & lt) < r);
+            const uint32_t keepMask = __ballot_sync(0xffffffffu, keep);
+            if (keep) buf[out + __popc(keepMask & lt)] = (uint64_t(m[e]) << 32) | id[e];
+            out += __popc(keepMask);
+            tiesBefore += __popc(tieMask);
+        }
+    }
+    __syncwarp();
+    return h;
+}
+
+constexpr int kPruneRegsPerLane = 8;         // register prune for regions of up to 256 keys
+
 // Call with the warp converged.  Serves every lane whose region has less than kPruneSlack free slots.
 static __device__ __forceinline__ void warpPruneIfNeeded(RowState& st, uint32_t k, uint32_t cap)
 {
@@ -95,7 +148,9 @@ static __device__ __forceinline__ void warpPruneIfNeeded(RowState& st, uint32_t 
         const uint64_t b = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(st.buf), src);
         const uint32_t c = __shfl_sync(0xffffffffu, st.count, src);
         const uint32_t t = __shfl_sync(0xffffffffu, st.tau, src);
-        const uint32_t h = warpPrune(reinterpret_cast<uint64_t*>(b), c, k, t);
+        const uint32_t h = cap <= 32 * kPruneRegsPerLane
+                               ? warpPruneRegs<kPruneRegsPerLane>(reinterpret_cast<uint64_t*>(b), c, k, t)
+                               : warpPrune(reinterpret_cast<uint64_t*>(b), c, k, t);
         if (int(threadIdx.x & 31) == src) {
             st.count = k;
             st.tau = h;
