@@ -55,6 +55,8 @@ struct em2_context {
     uint32_t filterUncertainCap = 0;   // test knob: capacity of the uncertain list (0 = automatic)
     uint64_t exactMatrixBytes = 0;     // test knob: budget of the exact path's similarity matrix (0 = 8 GiB)
     int candCapExtra = 0;              // candidate regions hold (2 + candCapExtra) * k + 32 keys
+    int debugFlags = 0;                // bit 0: no bound sharing between MMA sub-streams; bit 1: memory prune
+    int mmaStreamed = 0;               // 1: force the streamed-operand MMA scan kernel also for L <= 1024
     int mmaCtaPair = 0;                // 1: the MMA scan runs on CTA pairs (cta_group::2, M = 256)
     int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM
     em2::DeviceBuffer scratch[S_COUNT];

@@ -85,6 +85,7 @@ struct MmaParams {
     uint32_t* candCount;
     unsigned long long* appendedTotal;
     uint16_t* dump;          // optional: all distances of the scanned rows (tests)
+    uint32_t flags;          // debug: bit 0 = no bound sharing between sub-streams
 };
 
 template <bool DUMP, bool PAIR>
@@ -275,8 +276,9 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * p.rows + (valid ? localRow : 0)) * p.cap;
             // The two sub-streams of a row exchange their bounds through shared memory (stale values are only
             // looser).  The slot is re-initialised per item; the barrier keeps a fast warp from reading the
-            // previous item's value.
-            tauShare[sub * kRowsPerItem + rowInItem] = st.tau;
+            // previous item's value.  The initial value must be harmless for ANY row: the partner warp may still
+            // be finishing the previous item (a different row) when it reads it -- so never the 0 of a padding row.
+            tauShare[sub * kRowsPerItem + rowInItem] = p.tau0;
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.lim);      // hamming < lim  <=>  dot > K - 2 lim
 
@@ -339,13 +341,13 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
                     }
                 } else {
                     const uint32_t other = tauShare[(sub ^ 1) * kRowsPerItem + rowInItem];
-                    if (other + 1 < st.lim) {       // a tie with the other stream's k-th best can still win on id
+                    if (other + 1 < st.lim && !(p.flags & 1)) {       // a tie with the other stream's k-th best can still win on id
                         st.lim = other + 1;
                         dotThr = int32_t(dotK) - 2 * int32_t(st.lim);
                     }
                     chunk(v0, idBase);
                     chunk(v1, idBase + 32);
-                    tauShare[sub * kRowsPerItem + rowInItem] = st.tau;
+                    if (valid) tauShare[sub * kRowsPerItem + rowInItem] = st.tau;
                 }
             }
             if (!DUMP && valid) {
@@ -363,6 +365,213 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
         __syncthreads();
         if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Any L (used for L > 1024, where the A operand no longer fits in tensor memory): both operands stream.
+// Tile = 128 rows x 256 columns, K looped in 128-byte chunks; per chunk the producer loads the row block's
+// A chunk (16 KB) and the column tile's B chunk (32 KB) by TMA into a 4-stage ring, the MMA thread issues four
+// M=128 N=256 K=32 instructions with both descriptors in shared memory, accumulators double buffered in TMEM
+// (2 x 256 columns).  The main loop of a tile is K/1024 times longer than in the kernel above, so the epilogue
+// (thread = row x one of two 128-column sub-streams, four 32-column chunks per tile) has time to spare.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSsTileN = 256;
+constexpr int kSsStages = 4;
+constexpr uint32_t kSsABytes = kRowsPerItem * kChunkBytes;      // 16 KB
+constexpr uint32_t kSsBBytes = kSsTileN * kChunkBytes;          // 32 KB
+constexpr uint32_t kSsStageBytes = kSsABytes + kSsBBytes;
+constexpr uint32_t kInstrDescSs = (kInstrDesc & ~(0x3Fu << 17)) | (uint32_t(kSsTileN >> 3) << 17);
+
+template <bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1)
+scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const MmaParams p)
+{
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(kSsStages) * kSsStageBytes);
+    uint64_t* accFull = bars + 0;    // [2]
+    uint64_t* accEmpty = bars + 2;   // [2]
+    uint64_t* full = bars + 4;       // [stages]
+    uint64_t* empty = full + kSsStages;
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(empty + kSsStages);
+    uint32_t* tauShare = reinterpret_cast<uint32_t*>(bars) + 64;    // [kSubStreams][kRowsPerItem], after 256 B of barriers
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbarInit(accFull + i, 1);
+            mbarInit(accEmpty + i, kEpiWarps * 32);
+        }
+        for (int i = 0; i < kSsStages; i++) {
+            mbarInit(full + i, 1);
+            mbarInit(empty + i, 1);
+        }
+        mbarInitFence();
+    }
+    if (warp == kEpiWarps) tmemAlloc(tmemSlot, 512);
+    fenceBefore();
+    __syncthreads();
+    fenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    const uint32_t items = p.items;
+
+    if (warp == kEpiWarps) {
+        // ===================== TMA producer (A chunk of the row block + B chunk of the column tile) =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
+                const int32_t rowA = int32_t(p.rowBegin + uint64_t(it.rowBlock) * kRowsPerItem);
+                const uint32_t tiles = uint32_t((it.colEnd - it.colBegin + kSsTileN - 1) / kSsTileN);
+                for (uint32_t t = 0; t < tiles; t++) {
+                    const int32_t col0 = int32_t(it.colBegin + uint64_t(t) * kSsTileN);
+                    for (uint32_t kc = 0; kc < p.panels; kc++) {
+                        mbarWait(empty + stage, phase ^ 1);
+                        mbarExpectTx(full + stage, kSsStageBytes);
+                        uint8_t* dst = ring + size_t(stage) * kSsStageBytes;
+                        tmaLoad2d(dst, &mapA, full + stage, int32_t(kc * kChunkBytes), rowA);
+                        tmaLoad2d(dst + kSsABytes, &mapB, full + stage, int32_t(kc * kChunkBytes), col0);
+                        if (++stage == kSsStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t tileIter = 0, stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
+                const uint32_t tiles = uint32_t((it.colEnd - it.colBegin + kSsTileN - 1) / kSsTileN);
+                for (uint32_t t = 0; t < tiles; t++, tileIter++) {
+                    const uint32_t buf = tileIter & 1;
+                    mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
+                    fenceAfter();
+                    const uint32_t tmemD = tmemBase + buf * kSsTileN;
+                    uint32_t accumulate = 0;
+                    for (uint32_t kc = 0; kc < p.panels; kc++) {
+                        mbarWait(full + stage, phase);
+                        fenceAfter();
+                        const uint32_t aAddr = smemAddr(ring + size_t(stage) * kSsStageBytes);
+                        const uint32_t bAddr = aAddr + kSsABytes;
+#pragma unroll
+                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++) {
+                            mmaI8Ss(tmemD, makeSmemDesc(aAddr + ks * kUmmaK), makeSmemDesc(bAddr + ks * kUmmaK), kInstrDescSs, accumulate);
+                            accumulate = 1;
+                        }
+                        commit(empty + stage);
+                        if (++stage == kSsStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    commit(accFull + buf);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: thread == (query row == TMEM lane, 128-column sub-stream) =====================
+        const uint32_t dotK = p.K;
+        const uint32_t rowInItem = threadIdx.x & (kRowsPerItem - 1);
+        const uint32_t sub = threadIdx.x / kRowsPerItem;
+        constexpr int kSubCols = kSsTileN / kSubStreams;
+        const uint32_t laneField = uint32_t((warp & 3) * 32) << 16;
+        uint32_t tileIter = 0;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
+            const uint32_t seg = it.segment;
+            const uint64_t localRow = uint64_t(it.rowBlock) * kRowsPerItem + rowInItem;
+            const bool valid = localRow < p.rows;
+            const uint64_t colBegin = it.colBegin;
+            const uint32_t colEnd = uint32_t(it.colEnd);
+            const uint32_t tiles = uint32_t((it.colEnd - colBegin + kSsTileN - 1) / kSsTileN);
+
+            RowState st;
+            st.rowId = valid ? uint32_t(p.rowBegin + localRow) : 0xffffffffu;
+            st.count = 0;
+            st.appended = 0;
+            st.tau = valid ? p.tau0 : 0;
+            st.lim = st.tau;
+            st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * p.rows + (valid ? localRow : 0)) * p.cap;
+            tauShare[sub * kRowsPerItem + rowInItem] = p.tau0;      // harmless for any row (see scanMmaKernel)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.lim);      // hamming < lim  <=>  dot > K - 2 lim
+
+            auto chunk = [&](const uint32_t (&v)[32], uint32_t id0) {
+                int32_t m[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    m[g] = int32_t(v[8 * g]);
+#pragma unroll
+                    for (int j = 1; j < 8; j++) m[g] = max(m[g], int32_t(v[8 * g + j]));
+                }
+                const int32_t mx = max(max(m[0], m[1]), max(m[2], m[3]));
+                if (mx > dotThr) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        if (m[g] > dotThr) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                if (int32_t(v[8 * g + j]) > dotThr)
+                                    consider(st, uint32_t(int32_t(dotK) - int32_t(v[8 * g + j])) >> 1, id0 + 8 * g + j, colEnd);
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, mx > dotThr)) {
+                    warpPruneIfNeeded(st, p.k, p.cap);
+                    dotThr = int32_t(dotK) - 2 * int32_t(st.lim);
+                }
+            };
+
+            for (uint32_t t = 0; t < tiles; t++, tileIter++) {
+                const uint32_t buf = tileIter & 1;
+                mbarWait(accFull + buf, (tileIter >> 1) & 1);
+                fenceAfter();
+                const uint32_t idBase = uint32_t(colBegin) + t * kSsTileN + sub * kSubCols;
+                const uint32_t taddr = tmemBase + buf * kSsTileN + sub * kSubCols + laneField;
+                if (!DUMP) {
+                    const uint32_t other = tauShare[(sub ^ 1) * kRowsPerItem + rowInItem];
+                    if (other + 1 < st.lim && !(p.flags & 1)) {
+                        st.lim = other + 1;
+                        dotThr = int32_t(dotK) - 2 * int32_t(st.lim);
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < kSubCols; c += 32) {
+                    uint32_t v[32];
+                    tmemLoad32(taddr + c, v);
+                    tmemLoadWait();
+                    if (c + 32 == kSubCols) {          // last chunk is in registers: hand the accumulator back
+                        fenceBefore();
+                        mbarArrive(accEmpty + buf);
+                    }
+                    if (DUMP) {
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const uint32_t id = idBase + c + j;
+                                if (id < colEnd) p.dump[localRow * p.cellCount + id] = uint16_t((int32_t(dotK) - int32_t(v[j])) >> 1);
+                            }
+                        }
+                    } else {
+                        chunk(v, idBase + c);
+                    }
+                }
+                if (!DUMP && valid) tauShare[sub * kRowsPerItem + rowInItem] = st.tau;
+            }
+            if (!DUMP && valid) {
+                p.candCount[uint64_t(seg * kSubStreams + sub) * p.rows + localRow] = st.count;
+                if (p.appendedTotal && st.appended) atomicAdd(p.appendedTotal, (unsigned long long)st.appended);
+            }
+        }
+    }
+    fenceBefore();
+    __syncthreads();
+    if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
 }
 
 // +-1 int8 expansion of the packed signatures: E[n][p] = bit p set ? +1 : -1, p < K; bits at and
@@ -399,8 +608,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     const uint64_t rows = rowEnd - rowBegin;
     const uint32_t W = uint32_t(wordCount(lshCount));
     const uint32_t K = uint32_t(roundUp(lshCount, kChunkBytes));
-    if (K > kMaxPanels * kChunkBytes)
-        return fail(ctx, EM2_ERR_INVALID, "EM2_VARIANT_MMA_I8 supports lshCount <= 1024 (use EM2_VARIANT_POPC)");
+    const bool streamed = K > kMaxPanels * kChunkBytes || ctx->mmaStreamed != 0;      // A no longer fits in tensor memory: scanMmaSsKernel
     if (cellCount > 0x7fffff00ull) return fail(ctx, EM2_ERR_INVALID, "cellCount too large for the MMA variant");
 
     // 1. encode
@@ -417,14 +625,15 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     MmaParams p{};
     const uint32_t panels = K / kChunkBytes;
     p.stages = kStages;
-    const bool pair = ctx->mmaCtaPair != 0;
-    ScanPlan plan = pair ? makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kPairRows, 1, kSubStreams,
+    const bool pair = ctx->mmaCtaPair != 0 && !streamed;
+    ScanPlan plan = streamed ? makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kSsTileN, kRowsPerItem, 1, kSubStreams) :
+                    pair ? makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kPairRows, 1, kSubStreams,
                                         uint32_t(ctx->smCount / 2))
                          : makeScanPlan(ctx, rows, cellCount, dump ? 1 : k, kTileN, kRowsPerItem, 1, kSubStreams);
     if (dump) {
         plan.mainBlocks = plan.rowBlocks;
         plan.segments = 1;
-        plan.segmentCols = roundUp(cellCount, kTileN);
+        plan.segmentCols = roundUp(cellCount, kSsTileN);
         plan.items = plan.rowBlocks;
     }
     void* cand = nullptr;
@@ -453,6 +662,28 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     p.candCount = static_cast<uint32_t*>(candCount);
     p.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
     p.dump = dump;
+    p.flags = uint32_t(ctx->debugFlags);
+
+    if (streamed) {
+        CUtensorMap mapA, mapB;
+        EM2_TRY(makeTensorMapU8(ctx, &mapA, enc, cellCount, K, K, kRowsPerItem));
+        EM2_TRY(makeTensorMapU8(ctx, &mapB, enc, cellCount, K, K, kSsTileN));
+        const size_t smem = 1024 + size_t(kSsStages) * kSsStageBytes + 256 + kShareBytes;
+        const unsigned grid = unsigned(std::min<uint32_t>(plan.items, uint32_t(ctx->smCount)));
+        if (dump) {
+            EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSsKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            scanMmaSsKernel<true><<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+        } else {
+            EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSsKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            scanMmaSsKernel<false><<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+        }
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+        if (dump) return EM2_OK;
+        ScanPlan merged = plan;
+        merged.segments = plan.segments * kSubStreams;
+        return launchFinalize(ctx, merged, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s);
+    }
 
     CUtensorMap mapB;
     EM2_TRY(makeTensorMapU8(ctx, &mapB, enc, cellCount, K, K, pair ? kTileN / 2 : kTileN));

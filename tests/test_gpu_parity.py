@@ -17,7 +17,8 @@ VARIANTS = [em2.VARIANT_POPC, em2.VARIANT_MMA_I8]
 
 
 def _variants_for(L):
-    return [v for v in VARIANTS if v != em2.VARIANT_MMA_I8 or L <= 1024]
+    """Both variants cover every L: above 1024 bits the MMA variant streams both operands (scanMmaSsKernel)."""
+    return list(VARIANTS)
 
 
 def _check_lists(got, want):
@@ -44,8 +45,6 @@ def test_golden_signatures_bit_exact(engine, name):
 def test_golden_neighbour_lists(engine, name, variant):
     g = load_golden(name)
     L = int(g["lsh_count"])
-    if variant not in _variants_for(L):
-        pytest.skip("the MMA variant covers lshCount <= 1024")
     for i in range(int(g["combos"])):
         k, thr = int(g[f"combo{i}_k"]), float(g[f"combo{i}_thr"])
         got = engine.find_similar_pairs(g["signatures"], L, k, thr, variant=variant)
@@ -87,7 +86,7 @@ def test_golden_hamming_bit_exact(engine, name):
         assert np.array_equal(block.cpu().numpy().view(np.uint16)[0].astype(np.uint32), g["row0_mismatch"])
 
 
-@pytest.mark.parametrize("L", [64, 200, 512, 1024])
+@pytest.mark.parametrize("L", [64, 200, 512, 1024, 1100, 2048, 4096])
 def test_mma_distances_equal_popc_distances(engine, oracle, L):
     """Every distance of a 300-row block from the tcgen05 arithmetic equals the reference popcount."""
     import torch
@@ -108,7 +107,8 @@ def test_mma_distances_equal_popc_distances(engine, oracle, L):
     (1100, 500, 0.03, 512, "iid"),
     (900, 333, 0.07, 200, "clustered"),     # L not a multiple of 64 or 128
     (700, 300, 0.05, 1, "iid"),             # one hyperplane
-    (640, 256, 0.05, 4096, "clustered"),    # L > 1024: shared-memory row panel
+    (640, 256, 0.05, 4096, "clustered"),    # L > 1024: shared-memory row panel (POPC), streamed operands (MMA)
+    (600, 256, 0.05, 1500, "iid"),          # L > 1024 and not a multiple of 128
 ])
 def test_signatures_and_lists_vs_oracle(engine, oracle, N, G, dens, L, mode):
     toc, genes, counts = synthetic.gen_expression_matrix(N, G, dens, seed=N + L, mode=mode, clusters=7)
@@ -339,3 +339,68 @@ def test_exact_path_rejects_non_integer_counts(engine):
     counts = np.array([1.5, 2, 3, 4], np.float32)
     with pytest.raises(em2.Em2Error):
         engine.exact_similar_pairs(toc, counts, 2, 1, 0.0, gene_ids=genes)
+
+
+# ---------------------------------------------------------------------------------------------------
+# scan variants of the MMA path: CTA pairs (cta_group::2) and streamed operands (L > 1024)
+# ---------------------------------------------------------------------------------------------------
+def test_mma_cta_pair_variant_matches(engine, oracle):
+    """The cta_group::2 form of the tcgen05 scan (two CTAs share one M=256 MMA and half of every B tile each)
+    gives the same distances and lists."""
+    import torch
+    engine.set_option("mma_cta_pair", 1)
+    try:
+        N, L = 3001, 1024
+        sig = synthetic.gen_signatures(N, L, seed=5, clusters=11)
+        d_sig = torch.from_numpy(sig.view(np.int64)).cuda()
+        out = torch.zeros((700, N), dtype=torch.int16, device="cuda")
+        engine.mismatch_block_device(d_sig, N, L, 1000, 1700, out, variant=em2.VARIANT_MMA_I8,
+                                     stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint16)
+        for r in (0, 127, 128, 255, 256, 699):
+            assert np.array_equal(got[r].astype(np.uint32), oracle.mismatch_row(sig, 1000 + r))
+        for k, thr in ((50, 0.2), (10, -1.0)):
+            _check_lists(engine.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_MMA_I8), oracle.topk(sig, L, k, thr)[:3])
+        # many row blocks: whole-row items plus a segmented tail
+        N = 40000
+        sig = synthetic.gen_signatures(N, 512, seed=6, clusters=50)
+        ids, sims, used = engine.find_similar_pairs(sig, 512, 20, 0.2, variant=em2.VARIANT_MMA_I8)
+        for r in (0, 255, 256, 19000, N - 1):
+            wi, ws, wu, _ = oracle.topk(sig, 512, 20, 0.2, r, r + 1)
+            _check_lists((ids[r:r + 1], sims[r:r + 1], used[r:r + 1]), (wi, ws, wu))
+    finally:
+        engine.set_option("mma_cta_pair", 0)
+
+
+def test_streamed_mma_scan_at_4096_bits(engine, oracle):
+    """L = 4096 through the streamed tcgen05 kernel at a size with whole-row items and a tail (24k cells)."""
+    N, L, k = 24000, 4096, 50
+    sig = synthetic.gen_signatures(N, L, seed=8, clusters=40)
+    ids, sims, used = engine.find_similar_pairs(sig, L, k, 0.2, variant=em2.VARIANT_MMA_I8)
+    pid, psim, pused = engine.find_similar_pairs(sig, L, k, 0.2, variant=em2.VARIANT_POPC)
+    assert np.array_equal(ids, pid) and np.array_equal(sims.view(np.uint32), psim.view(np.uint32)) and np.array_equal(used, pused)
+    for r in (0, 127, 128, 12345, N - 1):
+        wi, ws, wu, _ = oracle.topk(sig, L, k, 0.2, r, r + 1)
+        _check_lists((ids[r:r + 1], sims[r:r + 1], used[r:r + 1]), (wi, ws, wu))
+
+
+@pytest.mark.parametrize("N,L", [(30000, 512), (21000, 1024)])
+def test_mma_kernels_equal_popc_when_last_row_block_is_partial(engine, oracle, N, L):
+    """Regression: a persistent CTA goes from a full row block to the partial last one while its partner warp is
+    still finishing the previous rows; the bound a padding row publishes must not leak into them.  Every list of
+    every MMA kernel form (TMEM-resident A, streamed operands, CTA pairs) must equal the POPC variant's."""
+    sig = synthetic.gen_signatures(N, L, seed=1, clusters=100)
+    ref = engine.find_similar_pairs(sig, L, 50, 0.2, variant=em2.VARIANT_POPC)
+    for opt in (None, "mma_streamed", "mma_cta_pair"):
+        if opt:
+            engine.set_option(opt, 1)
+        try:
+            got = engine.find_similar_pairs(sig, L, 50, 0.2, variant=em2.VARIANT_MMA_I8)
+        finally:
+            if opt:
+                engine.set_option(opt, 0)
+        _check_lists(got, ref)
+    r = 11070
+    wi, ws, wu, _ = oracle.topk(sig, L, 50, 0.2, r, r + 1)
+    _check_lists((ref[0][r:r + 1], ref[1][r:r + 1], ref[2][r:r + 1]), (wi, ws, wu))
