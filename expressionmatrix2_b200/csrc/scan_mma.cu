@@ -542,6 +542,7 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
 #pragma unroll 1
                 for (int c = 0; c < kSubCols; c += 32) {
+                    // one chunk per round trip (two at a time measured slower: 168 registers and spills)
                     uint32_t v[32];
                     tmemLoad32(taddr + c, v);
                     tmemLoadWait();
@@ -608,7 +609,11 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     const uint64_t rows = rowEnd - rowBegin;
     const uint32_t W = uint32_t(wordCount(lshCount));
     const uint32_t K = uint32_t(roundUp(lshCount, kChunkBytes));
-    const bool streamed = K > kMaxPanels * kChunkBytes || ctx->mmaStreamed != 0;      // A no longer fits in tensor memory: scanMmaSsKernel
+    // Which tcgen05 kernel: above 1024 bits the A operand does not fit in tensor memory, so both operands stream
+    // (scanMmaSsKernel, N = 256 instructions).  Measured at 512..1024 bits the streamed kernel is also the faster one
+    // (3500 vs 2480 TOP/s on iid signatures at L = 1024: N = 128 instructions with A in TMEM top out at 2971), so it
+    // is the default from 512 bits; "mma_kernel" = 1 / 2 forces the TMEM-resident / the streamed form.
+    const bool streamed = K > kMaxPanels * kChunkBytes || ctx->mmaKernel == 2 || (ctx->mmaKernel == 0 && K >= 512);
     if (cellCount > 0x7fffff00ull) return fail(ctx, EM2_ERR_INVALID, "cellCount too large for the MMA variant");
 
     // 1. encode

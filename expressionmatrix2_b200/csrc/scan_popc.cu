@@ -481,11 +481,11 @@ int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCo
     const uint64_t rows = rowEnd - rowBegin;
     if (rows == 0) return EM2_OK;
     if (variant == EM2_VARIANT_AUTO) {
-        // ncu evidence (profiles/): from 384 bits up the tcgen05 variant runs 1.3-10x faster than the POPC
-        // variant, whose XU (POPC) pipe is saturated; below 384 bits the GEMM epilogue (one TMEM read and
-        // compare per pair) dominates and POPC wins.  Above 1024 bits the A operand no longer fits in TMEM and
+        // ncu evidence (profiles/): from 256 bits up the tcgen05 variant runs 2-12x faster than the POPC
+        // variant, whose XU (POPC) pipe is saturated (100k clustered cells: L=256 9.5 vs 19.0 ms, 384 9.3 vs 32.4,
+        // 1024 ~10 vs 64, 4096 24 vs 291); below that the GEMM epilogue (one TMEM read and compare per pair) dominates.  Above 1024 bits the A operand no longer fits in TMEM and
         // the MMA variant streams both operands (scanMmaSsKernel).
-        const bool mma = lshCount >= 384 && double(rows) * double(cellCount) >= 1e7;
+        const bool mma = lshCount >= 256 && double(rows) * double(cellCount) >= 1e7;
         variant = mma ? EM2_VARIANT_MMA_I8 : EM2_VARIANT_POPC;
     }
     ctx->stats.variant_used = variant;

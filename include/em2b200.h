@@ -109,7 +109,10 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
  * tensor-core filter + exact fix-up path), "popc_csa" (carry-save levels of the POPC scan, 0..2),
  * "filter_counts_signed" (1: the filter GEMM takes counts as s8 <= 127 instead of u8 <= 255),
  * "filter_uncertain_cap" (capacity of the filter's uncertain list; 0 = automatic), "exact_matrix_bytes"
- * (budget of the exact path's row-chunk similarity matrix; 0 = 8 GiB). */
+ * (budget of the exact path's row-chunk similarity matrix; 0 = 8 GiB), "mma_kernel" (tcgen05 scan kernel: 0 = automatic,
+ * 1 = A operand resident in tensor memory (L <= 1024), 2 = both operands streamed), "mma_cta_pair" (1: the TMEM-resident
+ * kernel runs on CTA pairs, cta_group::2), "cand_cap_extra" (candidate regions hold (2 + n) k + 32 keys),
+ * "debug_flags" (bit 0: no bound sharing between the MMA sub-streams). */
 int em2_set_option(em2_context* ctx, const char* name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ import expressionmatrix2_b200 as em2  # noqa: E402
 from expressionmatrix2_b200 import synthetic  # noqa: E402
 
 VARIANTS = [em2.VARIANT_POPC, em2.VARIANT_MMA_I8]
+MMA_KERNELS = [1, 2]      # em2_set_option("mma_kernel"): A operand resident in TMEM / both operands streamed
 
 
 def _variants_for(L):
@@ -88,18 +89,25 @@ def test_golden_hamming_bit_exact(engine, name):
 
 @pytest.mark.parametrize("L", [64, 200, 512, 1024, 1100, 2048, 4096])
 def test_mma_distances_equal_popc_distances(engine, oracle, L):
-    """Every distance of a 300-row block from the tcgen05 arithmetic equals the reference popcount."""
+    """Every distance of a 300-row block from the tcgen05 arithmetic (both kernel forms) equals the reference popcount."""
     import torch
     N = 3001
     sig = synthetic.gen_signatures(N, L, seed=L, clusters=11)
     d_sig = torch.from_numpy(sig.view(np.int64)).cuda()
-    out = torch.zeros((300, N), dtype=torch.int16, device="cuda")
-    engine.mismatch_block_device(d_sig, N, L, 1500, 1800, out, variant=em2.VARIANT_MMA_I8,
-                                 stream=torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    got = out.cpu().numpy().view(np.uint16)
-    for r in (0, 17, 299):
-        assert np.array_equal(got[r].astype(np.uint32), oracle.mismatch_row(sig, 1500 + r))
+    for kern in MMA_KERNELS:
+        if kern == 1 and L > 1024:
+            continue
+        engine.set_option("mma_kernel", kern)
+        try:
+            out = torch.zeros((300, N), dtype=torch.int16, device="cuda")
+            engine.mismatch_block_device(d_sig, N, L, 1500, 1800, out, variant=em2.VARIANT_MMA_I8,
+                                         stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        finally:
+            engine.set_option("mma_kernel", 0)
+        got = out.cpu().numpy().view(np.uint16)
+        for r in (0, 17, 299):
+            assert np.array_equal(got[r].astype(np.uint32), oracle.mismatch_row(sig, 1500 + r))
 
 
 @pytest.mark.parametrize("N,G,dens,L,mode", [
@@ -349,6 +357,7 @@ def test_mma_cta_pair_variant_matches(engine, oracle):
     gives the same distances and lists."""
     import torch
     engine.set_option("mma_cta_pair", 1)
+    engine.set_option("mma_kernel", 1)
     try:
         N, L = 3001, 1024
         sig = synthetic.gen_signatures(N, L, seed=5, clusters=11)
@@ -371,6 +380,7 @@ def test_mma_cta_pair_variant_matches(engine, oracle):
             _check_lists((ids[r:r + 1], sims[r:r + 1], used[r:r + 1]), (wi, ws, wu))
     finally:
         engine.set_option("mma_cta_pair", 0)
+        engine.set_option("mma_kernel", 0)
 
 
 def test_streamed_mma_scan_at_4096_bits(engine, oracle):
@@ -392,14 +402,14 @@ def test_mma_kernels_equal_popc_when_last_row_block_is_partial(engine, oracle, N
     every MMA kernel form (TMEM-resident A, streamed operands, CTA pairs) must equal the POPC variant's."""
     sig = synthetic.gen_signatures(N, L, seed=1, clusters=100)
     ref = engine.find_similar_pairs(sig, L, 50, 0.2, variant=em2.VARIANT_POPC)
-    for opt in (None, "mma_streamed", "mma_cta_pair"):
-        if opt:
-            engine.set_option(opt, 1)
+    for opts in ({"mma_kernel": 1}, {"mma_kernel": 2}, {"mma_kernel": 1, "mma_cta_pair": 1}):
+        for o, v in opts.items():
+            engine.set_option(o, v)
         try:
             got = engine.find_similar_pairs(sig, L, 50, 0.2, variant=em2.VARIANT_MMA_I8)
         finally:
-            if opt:
-                engine.set_option(opt, 0)
+            for o in opts:
+                engine.set_option(o, 0)
         _check_lists(got, ref)
     r = 11070
     wi, ws, wu, _ = oracle.topk(sig, L, 50, 0.2, r, r + 1)
