@@ -44,6 +44,8 @@ struct em2_context {
         S_COUNTERS,      // small uint64 counters
         S_TOC, S_COUNTS, S_SUM1, S_SUM2, S_U, S_SIG, S_LUT, S_PAIRS, S_USED,   // staging of the blocking API
         S_ENC,           // +-1 int8 encoded signatures (MMA variant)
+        S_ENCROWS,       // encoded signatures of the scanned rows in their grouped order (MMA variant)
+        S_ROWPERM,       // row grouping: sort keys, permutation, cub scratch
         S_DENSE,         // dense uint8 counts of the signature filter path
         S_UQ,            // quantised, transposed hyperplanes (two int8 digits) + per-column scale
         S_FLAGS,         // per-cell eligibility flags / fallback list / uncertain list
@@ -56,6 +58,7 @@ struct em2_context {
     uint64_t exactMatrixBytes = 0;     // test knob: budget of the exact path's similarity matrix (0 = 8 GiB)
     int candCapExtra = 0;              // candidate regions hold (2 + candCapExtra) * k + 32 keys
     int debugFlags = 0;                // bit 0: no bound sharing between MMA sub-streams; bit 1: memory prune
+    int rowGrouping = 0;               // MMA scan: 0 auto (group similar rows into the same warps), 1 off, 2 on
     int mmaKernel = 0;                 // MMA scan kernel: 0 auto, 1 A operand resident in TMEM (L <= 1024), 2 streamed operands
     int mmaCtaPair = 0;                // 1: the MMA scan runs on CTA pairs (cta_group::2, M = 256)
     int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM
@@ -182,9 +185,11 @@ __host__ __device__ inline ScanItem decodeScanItem(uint32_t item, uint32_t mainB
 // streamsPerSegment: candidate streams a kernel keeps per (row, segment) (the MMA variant's column sub-streams).
 ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount, uint64_t k, uint32_t tileCols,
                       uint32_t rowsPerCta, uint32_t ctasPerSm, uint32_t streamsPerSegment, uint32_t slotsOverride = 0);
+// rowPerm (optional): candidate regions are indexed by scan position q, the list of position q belongs to
+// row rowPerm[q] - rowBegin of the output.
 int launchFinalize(em2_context* ctx, const ScanPlan& plan, uint64_t rows, uint64_t k, const uint64_t* cand,
                    const uint32_t* candCount, const float* lut, em2_pair* pairs, uint32_t* usedCount,
-                   cudaStream_t s);
+                   cudaStream_t s, const uint32_t* rowPerm = nullptr, uint64_t rowBegin = 0);
 int launchScanMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                   uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
                   em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);

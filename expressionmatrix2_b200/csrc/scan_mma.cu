@@ -32,6 +32,8 @@
 #include "tc05.cuh"
 #include "topk.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -86,6 +88,8 @@ struct MmaParams {
     unsigned long long* appendedTotal;
     uint16_t* dump;          // optional: all distances of the scanned rows (tests)
     uint32_t flags;          // debug: bit 0 = no bound sharing between sub-streams
+    const uint8_t* encRows;  // encoded signatures of the scanned rows, indexed by scan position (TMEM-resident kernel)
+    const uint32_t* rowPerm; // scan position -> cell id of the row (nullptr: rowBegin + position)
 };
 
 template <bool DUMP, bool PAIR>
@@ -244,7 +248,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             // A operand: this thread's encoded row -> TMEM lane, columns [kTmemA, kTmemA + K/4).
             // The previous item's MMAs have all completed (its last accFull was waited on below).
             {
-                const uint4* src = reinterpret_cast<const uint4*>(enc + (p.rowBegin + (valid ? localRow : 0)) * uint64_t(p.K));
+                const uint4* src = reinterpret_cast<const uint4*>(p.encRows + (valid ? localRow : 0) * uint64_t(p.K));
                 for (uint32_t c = sub * 32; c < p.K / 4; c += 32 * kSubStreams) {   // sub-streams share the copy
                     uint32_t v[32];
 #pragma unroll
@@ -268,7 +272,7 @@ scanMmaKernel(const __grid_constant__ CUtensorMap mapB, const uint8_t* __restric
             }
 
             RowState st;
-            st.rowId = valid ? uint32_t(p.rowBegin + localRow) : 0xffffffffu;
+            st.rowId = !valid ? 0xffffffffu : p.rowPerm ? p.rowPerm[localRow] : uint32_t(p.rowBegin + localRow);
             st.count = 0;
             st.appended = 0;
             st.tau = valid ? p.tau0 : 0;
@@ -422,7 +426,7 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             uint32_t stage = 0, phase = 0;
             for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
                 const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
-                const int32_t rowA = int32_t(p.rowBegin + uint64_t(it.rowBlock) * kRowsPerItem);
+                const int32_t rowA = int32_t(uint64_t(it.rowBlock) * kRowsPerItem);      // mapA covers the scanned rows only
                 const uint32_t tiles = uint32_t((it.colEnd - it.colBegin + kSsTileN - 1) / kSsTileN);
                 for (uint32_t t = 0; t < tiles; t++) {
                     const int32_t col0 = int32_t(it.colBegin + uint64_t(t) * kSsTileN);
@@ -491,7 +495,7 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const uint32_t tiles = uint32_t((it.colEnd - colBegin + kSsTileN - 1) / kSsTileN);
 
             RowState st;
-            st.rowId = valid ? uint32_t(p.rowBegin + localRow) : 0xffffffffu;
+            st.rowId = !valid ? 0xffffffffu : p.rowPerm ? p.rowPerm[localRow] : uint32_t(p.rowBegin + localRow);
             st.count = 0;
             st.appended = 0;
             st.tau = valid ? p.tau0 : 0;
@@ -575,10 +579,60 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Row grouping.  A warp of the epilogue serves 32 query rows; when those rows are unrelated, almost every
+// 32-column chunk holds a passing column for SOME lane and the selection code runs with two or three lanes
+// active (ncu: ~90 % of the chunks, 10 of 32 threads per instruction on clustered data).  Rows that are
+// similar to each other pass on the SAME columns, so putting similar rows into the same warp makes most chunks
+// miss for the whole warp and the rest hit with most lanes active.  Only the ORDER IN WHICH ROWS ARE SCANNED
+// changes: columns stay in cell-id order (the tie-break of topk.cuh needs that), every row still sees every
+// column, results are identical.  Grouping = nearest of 256 pivot cells by Hamming distance on the first
+// <= 1024 bits, then a radix sort of (pivot, cell id).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPivots = 256;
+constexpr int kPivotWords = 16;
+
+__global__ void __launch_bounds__(256)
+pivotAssignKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCount, uint64_t rowBegin, uint64_t rows,
+                  unsigned long long* __restrict__ keys)
+{
+    __shared__ uint64_t piv[kPivots][kPivotWords];
+    const uint32_t wp = W < kPivotWords ? W : kPivotWords;
+    for (uint32_t i = threadIdx.x; i < kPivots * wp; i += blockDim.x) {
+        const uint32_t pv = i / wp, w = i % wp;
+        const uint64_t cell = uint64_t(pv) * cellCount / kPivots;
+        piv[pv][w] = sig[cell * W + w];
+    }
+    __syncthreads();
+    const uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (q >= rows) return;
+    uint64_t x[kPivotWords];
+#pragma unroll
+    for (int w = 0; w < kPivotWords; w++) x[w] = uint32_t(w) < wp ? sig[(rowBegin + q) * W + w] : 0;
+    uint32_t best = 0xffffffffu, bestPivot = 0;
+    for (int pv = 0; pv < kPivots; pv++) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int w = 0; w < kPivotWords; w++)
+            if (uint32_t(w) < wp) d += __popcll(x[w] ^ piv[pv][w]);
+        if (d < best) {
+            best = d;
+            bestPivot = pv;
+        }
+    }
+    keys[q] = (uint64_t(bestPivot) << 32) | uint32_t(rowBegin + q);
+}
+
+__global__ void keysToPermKernel(const unsigned long long* __restrict__ keys, uint64_t rows, uint32_t* __restrict__ perm)
+{
+    const uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (q < rows) perm[q] = uint32_t(keys[q]);
+}
+
 // +-1 int8 expansion of the packed signatures: E[n][p] = bit p set ? +1 : -1, p < K; bits at and
 // beyond lshCount (zero in the packed words, or beyond them) encode as -1 in every row.
 __global__ void encodeKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCount, uint32_t K,
-                             uint8_t* __restrict__ enc)
+                             uint8_t* __restrict__ enc, const uint32_t* __restrict__ index)
 {
     const uint32_t groupsPerRow = K / 16;      // 16 bits -> 16 bytes per thread
     const uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -587,7 +641,8 @@ __global__ void encodeKernel(const uint64_t* __restrict__ sig, uint32_t W, uint6
     const uint32_t g = uint32_t(idx - row * groupsPerRow);
     const uint32_t w = g >> 2;
     uint32_t bits = 0;
-    if (w < W) bits = uint32_t(sig[row * W + w] >> (48 - 16 * (g & 3))) & 0xFFFFu;   // MSB-first
+    const uint64_t srcRow = index ? uint64_t(index[row]) : row;      // output row `row` = signature of cell index[row]
+    if (w < W) bits = uint32_t(sig[srcRow * W + w] >> (48 - 16 * (g & 3))) & 0xFFFFu;   // MSB-first
     uint32_t out[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -621,9 +676,39 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     EM2_TRY(reserve(ctx, em2_context::S_ENC, cellCount * K, &enc));
     {
         const uint64_t threads = cellCount * (K / 16);
-        encodeKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(signatures, W, cellCount, K, static_cast<uint8_t*>(enc));
+        encodeKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(signatures, W, cellCount, K, static_cast<uint8_t*>(enc), nullptr);
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
+    }
+
+    // 1b. the scanned rows in grouped order (see pivotAssignKernel) and their encoded signatures by scan position
+    const bool grouped = !dump && (ctx->rowGrouping == 2 || (ctx->rowGrouping == 0 && rows >= 8192));
+    const uint8_t* encRows = static_cast<const uint8_t*>(enc) + rowBegin * uint64_t(K);
+    const uint32_t* rowPerm = nullptr;
+    if (grouped) {
+        size_t cubBytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, cubBytes, static_cast<const unsigned long long*>(nullptr),
+                                       static_cast<unsigned long long*>(nullptr), int(rows), 0, 40, s);
+        const size_t keyBytes = roundUp(rows * sizeof(unsigned long long), 256);
+        void* scratch = nullptr;
+        EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, 2 * keyBytes + roundUp(rows * 4, 256) + cubBytes, &scratch));
+        auto* keysIn = static_cast<unsigned long long*>(scratch);
+        auto* keysOut = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(scratch) + keyBytes);
+        auto* perm = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(scratch) + 2 * keyBytes);
+        void* cubTemp = static_cast<uint8_t*>(scratch) + 2 * keyBytes + roundUp(rows * 4, 256);
+        pivotAssignKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(signatures, W, cellCount, rowBegin, rows, keysIn);
+        EM2_CUDA(ctx, cudaGetLastError());
+        EM2_CUDA(ctx, cub::DeviceRadixSort::SortKeys(cubTemp, cubBytes, keysIn, keysOut, int(rows), 0, 40, s));
+        keysToPermKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(keysOut, rows, perm);
+        EM2_CUDA(ctx, cudaGetLastError());
+        void* er = nullptr;
+        EM2_TRY(reserve(ctx, em2_context::S_ENCROWS, rows * uint64_t(K), &er));
+        const uint64_t threads = rows * (K / 16);
+        encodeKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(signatures, W, rows, K, static_cast<uint8_t*>(er), perm);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 4;      // + the radix sort's own passes (library code, not counted)
+        encRows = static_cast<const uint8_t*>(er);
+        rowPerm = perm;
     }
 
     // 2. plan + scratch
@@ -668,10 +753,12 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     p.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
     p.dump = dump;
     p.flags = uint32_t(ctx->debugFlags);
+    p.encRows = encRows;
+    p.rowPerm = rowPerm;
 
     if (streamed) {
         CUtensorMap mapA, mapB;
-        EM2_TRY(makeTensorMapU8(ctx, &mapA, enc, cellCount, K, K, kRowsPerItem));
+        EM2_TRY(makeTensorMapU8(ctx, &mapA, encRows, rows, K, K, kRowsPerItem));
         EM2_TRY(makeTensorMapU8(ctx, &mapB, enc, cellCount, K, K, kSsTileN));
         const size_t smem = 1024 + size_t(kSsStages) * kSsStageBytes + 256 + kShareBytes;
         const unsigned grid = unsigned(std::min<uint32_t>(plan.items, uint32_t(ctx->smCount)));
@@ -687,7 +774,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         if (dump) return EM2_OK;
         ScanPlan merged = plan;
         merged.segments = plan.segments * kSubStreams;
-        return launchFinalize(ctx, merged, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s);
+        return launchFinalize(ctx, merged, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s, rowPerm, rowBegin);
     }
 
     CUtensorMap mapB;
@@ -734,7 +821,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     if (dump) return EM2_OK;
     ScanPlan merged = plan;                    // every (segment, sub-stream) buffer is one list to merge
     merged.segments = plan.segments * kSubStreams;
-    return launchFinalize(ctx, merged, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s);
+    return launchFinalize(ctx, merged, rows, k, p.cand, p.candCount, lut, pairs, usedCount, s, rowPerm, rowBegin);
 }
 
 }  // namespace

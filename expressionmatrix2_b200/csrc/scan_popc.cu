@@ -340,7 +340,7 @@ constexpr int kFinalWarps = 4;
 __global__ void __launch_bounds__(kFinalWarps * 32)
 finalizeKernel(uint64_t rows, uint32_t segments, uint32_t cap, uint32_t k, const uint64_t* __restrict__ cand,
                const uint32_t* __restrict__ candCount, const float* __restrict__ lut, em2_pair* __restrict__ pairs,
-               uint32_t* __restrict__ usedCount)
+               uint32_t* __restrict__ usedCount, const uint32_t* __restrict__ rowPerm, uint64_t rowBegin)
 {
     extern __shared__ __align__(16) uint64_t skeys[];      // kFinalWarps x (segments*cap)
     const int warp = threadIdx.x >> 5;
@@ -357,6 +357,7 @@ finalizeKernel(uint64_t rows, uint32_t segments, uint32_t cap, uint32_t k, const
     }
     __syncwarp();
     const uint32_t used = n < k ? n : k;
+    const uint64_t outRow = rowPerm ? uint64_t(rowPerm[row]) - rowBegin : row;
     for (uint32_t e = lane; e < n; e += 32) {
         const uint64_t key = keys[e];
         uint32_t rank = 0;
@@ -365,16 +366,16 @@ finalizeKernel(uint64_t rows, uint32_t segments, uint32_t cap, uint32_t k, const
             em2_pair p;
             p.cell = uint32_t(key);
             p.similarity = lut[uint32_t(key >> 32)];
-            pairs[row * k + rank] = p;
+            pairs[outRow * k + rank] = p;
         }
     }
     for (uint32_t i = used + lane; i < k; i += 32) {
         em2_pair z;
         z.cell = 0;
         z.similarity = 0.f;
-        pairs[row * k + i] = z;
+        pairs[outRow * k + i] = z;
     }
-    if (lane == 0) usedCount[row] = used;
+    if (lane == 0) usedCount[outRow] = used;
 }
 
 // Hamming distance of explicit pairs, one thread per pair.
@@ -458,13 +459,14 @@ ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount,
 }
 
 int launchFinalize(em2_context* ctx, const ScanPlan& plan, uint64_t rows, uint64_t k, const uint64_t* cand,
-                   const uint32_t* candCount, const float* lut, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s)
+                   const uint32_t* candCount, const float* lut, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s,
+                   const uint32_t* rowPerm, uint64_t rowBegin)
 {
     const size_t smem = size_t(kFinalWarps) * plan.segments * plan.cap * sizeof(uint64_t);
     if (smem > 200 * 1024) return fail(ctx, EM2_ERR_INVALID, "k too large for the finalize kernel");
     EM2_CUDA(ctx, cudaFuncSetAttribute(finalizeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     finalizeKernel<<<unsigned((rows + kFinalWarps - 1) / kFinalWarps), kFinalWarps * 32, smem, s>>>(
-        rows, plan.segments, plan.cap, uint32_t(k), cand, candCount, lut, pairs, usedCount);
+        rows, plan.segments, plan.cap, uint32_t(k), cand, candCount, lut, pairs, usedCount, rowPerm, rowBegin);
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
     return EM2_OK;
