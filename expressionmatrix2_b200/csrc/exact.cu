@@ -16,7 +16,8 @@
 // 4095; above that the reference rounds each product to float and agreement is to ~1e-7 relative).  The
 // epilogue then evaluates r with the reference's operation sequence (separate multiplies, subtract, sqrt,
 // divide, round-to-nearest doubles) and stores float(r) -- or a "rejected" marker when !(r > threshold) --
-// into a rows x N float matrix in HBM (a chunk of rows at a time); `exactSelectKernel` makes one pass over
+// into a rows x N float matrix in HBM (the whole matrix when it fits: then only tiles on or above the diagonal are
+// computed and mirrored; else a chunk of rows at a time); `exactSelectKernel` makes one pass over
 // each row to pick the k largest (float similarity desc, id asc), which is the file order after sort().
 //
 // GEMM kernel: persistent CTA per SM, warps 0-3 epilogue (thread = row cell = TMEM lane), warp 4 TMA producer,
@@ -115,6 +116,7 @@ struct ExactParams {
     uint64_t geneCount;
     uint32_t kChunks;
     uint32_t rowBlocks, colTiles, superCols, items;
+    uint32_t symmetric;          // 1: only tiles on or above the diagonal are computed; their results are stored twice
     uint32_t idesc;
     uint64_t ldOut;              // floats per row of the similarity matrix
     double threshold;
@@ -130,7 +132,7 @@ __device__ __forceinline__ bool itemToTile(const ExactParams& p, uint32_t item, 
     const uint32_t super = item / (kXSuper * kXSuper), within = item % (kXSuper * kXSuper);
     rb = (super / p.superCols) * kXSuper + within / kXSuper;
     ct = (super % p.superCols) * kXSuper + within % kXSuper;
-    return rb < p.rowBlocks && ct < p.colTiles;
+    return rb < p.rowBlocks && ct < p.colTiles && !(p.symmetric && ct < rb);
 }
 
 template <int DIGITS>
@@ -300,6 +302,15 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
                     if (valid) {
                         if (bBase + j4 + 3 < p.ldOut)
                             *reinterpret_cast<float4*>(outRow + q * 32 + j4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                        // r(a,b) == r(b,a): a tile above the diagonal also fills its mirror image.  For a fixed b the
+                        // 32 lanes of a warp write 32 consecutive floats of row b.
+                        if (p.symmetric && ct > rb) {
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const uint64_t b = bBase + j4 + jj;
+                                if (b < p.cellCount) p.out[b * p.ldOut + a] = r4[jj];
+                            }
+                        }
                     }
                 }
             }
@@ -437,9 +448,12 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
 
     // ---- row chunks: GEMM + epilogue into the similarity matrix, then selection --------------------------
     const uint64_t ldOut = roundUp(cellCount, kXTile);
-    const uint64_t budget = ctx->exactMatrixBytes ? ctx->exactMatrixBytes : (8ull << 30);
+    // If the whole N x N similarity matrix fits the budget, only the tiles on or above the diagonal are computed
+    // (half the MMAs) and mirrored; otherwise rows go in chunks and every chunk computes all of its tiles.
+    const uint64_t budget = ctx->exactMatrixBytes ? ctx->exactMatrixBytes : (48ull << 30);
     uint64_t chunkRows = std::max<uint64_t>(kXTile, budget / (ldOut * sizeof(float)) / kXTile * kXTile);
     chunkRows = std::min<uint64_t>(chunkRows, roundUp(cellCount, kXTile));
+    const bool symmetric = chunkRows >= cellCount;
     void* simMatrix = nullptr;
     EM2_TRY(reserve(ctx, em2_context::S_CAND, chunkRows * ldOut * sizeof(float), &simMatrix));
 
@@ -465,6 +479,7 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
         const uint32_t superRows = (p.rowBlocks + kXSuper - 1) / kXSuper;
         p.superCols = (p.colTiles + kXSuper - 1) / kXSuper;
         p.items = superRows * p.superCols * kXSuper * kXSuper;
+        p.symmetric = symmetric ? 1 : 0;
         p.idesc = instrDescI8(false, false, kXTile, kXTile);
         p.ldOut = ldOut;
         p.threshold = similarityThreshold;
