@@ -74,6 +74,8 @@ def lib():
     L.em2_find_similar_pairs.argtypes = [vp, vp, u64, u64, u64, u64, u64, dbl, i32, vp, vp]
     L.em2_lsh_similar_pairs.argtypes = [vp, u64, u64, vp, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_exact_similar_pairs.argtypes = [vp, u64, u64, vp, vp, u64, dbl, vp, vp]
+    L.em2_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, u64, vp, vp, vp]
+    L.em2_lsh_similar_pairs_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, u64, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_cell_sums_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
     L.em2_signatures_device.argtypes = [vp, u64, u64, vp, vp, vp, vp, vp, u64, u64, u64, vp, vp, vp]
     L.em2_scan_topk_device.argtypes = [vp, vp, u64, u64, u64, u64, u64, i64, vp, i32, vp, vp, vp]
@@ -230,6 +232,54 @@ class Engine:
         self._check(self._L.em2_find_similar_pairs(self._h, _ptr(signatures), n, lsh_count, row_begin, row_end, k,
                                                    similarity_threshold, variant, _ptr(out_pairs), _ptr(out_used)),
                     "em2_find_similar_pairs")
+
+    @staticmethod
+    def gene_local_ids(global_gene_count: int, gene_set) -> np.ndarray:
+        """GeneSet-<name>-LocalIds as the reference stores it: local id of every global gene, UINT32_MAX if absent."""
+        gene_set = np.ascontiguousarray(gene_set, np.uint32)
+        local = np.full(global_gene_count, 0xFFFFFFFF, np.uint32)
+        local[gene_set] = np.arange(len(gene_set), dtype=np.uint32)
+        return local
+
+    def subset(self, toc, counts, global_gene_count: int, gene_set, cell_set, gene_ids=None, want_sums: bool = False):
+        """ExpressionMatrixSubset on the device: returns (local_toc, local_pairs PAIR_DTYPE[nnz'][, sum1, sum2])."""
+        toc = np.ascontiguousarray(toc, np.uint64)
+        pairs = _as_pairs(counts, gene_ids)
+        cell_set = np.ascontiguousarray(cell_set, np.uint32)
+        local = self.gene_local_ids(global_gene_count, gene_set)
+        n = len(cell_set)
+        cap = int(sum(int(toc[c + 1] - toc[c]) for c in cell_set)) if n else 0
+        out_toc = np.zeros(n + 1, np.uint64)
+        out = np.zeros(max(cap, 1), PAIR_DTYPE)
+        nnz = C.c_uint64(0)
+        s1 = np.zeros(n, np.float64) if want_sums else None
+        s2 = np.zeros(n, np.float64) if want_sums else None
+        self._check(self._L.em2_subset(self._h, len(toc) - 1, _ptr(toc), _ptr(pairs), global_gene_count, _ptr(local), n,
+                                       _ptr(cell_set), _ptr(out_toc), _ptr(out), cap, C.addressof(nnz), _ptr(s1), _ptr(s2)),
+                    "em2_subset")
+        res = (out_toc, out[: int(nnz.value)].copy())
+        return res + (s1, s2) if want_sums else res
+
+    def lsh_similar_pairs_subset(self, toc, counts, global_gene_count: int, gene_set, cell_set, lsh_vectors, k: int,
+                                 similarity_threshold: float, gene_ids=None, variant: int = VARIANT_AUTO,
+                                 want_signatures: bool = False):
+        """findSimilarPairs4 for a gene set / cell set straight from the global counts (subset built on the device)."""
+        toc = np.ascontiguousarray(toc, np.uint64)
+        pairs = _as_pairs(counts, gene_ids)
+        cell_set = np.ascontiguousarray(cell_set, np.uint32)
+        local = self.gene_local_ids(global_gene_count, gene_set)
+        U = np.ascontiguousarray(lsh_vectors, np.float64)
+        G, Lc = U.shape
+        n = len(cell_set)
+        out = np.zeros((n, k), SIMPAIR_DTYPE)
+        used = np.zeros(n, np.uint32)
+        sig = np.empty((n, word_count(Lc)), np.uint64) if want_signatures else None
+        self._check(self._L.em2_lsh_similar_pairs_subset(self._h, len(toc) - 1, _ptr(toc), _ptr(pairs), global_gene_count,
+                                                         _ptr(local), G, n, _ptr(cell_set), _ptr(U), Lc, k,
+                                                         similarity_threshold, variant, _ptr(out), _ptr(used), _ptr(sig)),
+                    "em2_lsh_similar_pairs_subset")
+        res = (np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used)
+        return res + (sig,) if want_signatures else res
 
     def lsh_similar_pairs_into(self, toc, pairs, lsh_vectors, k: int, similarity_threshold: float, out_pairs, out_used,
                                variant: int = VARIANT_AUTO) -> None:

@@ -505,6 +505,142 @@ int em2_lsh_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCou
     return EM2_OK;
 }
 
+// Selected cells' rows -> device, then the subset kernels.  Leaves the local CSR in S_TOC / S_COUNTS.
+static int subsetOnDevice(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc, const em2_count* globalCounts,
+                          uint64_t globalGeneCount, const uint32_t* geneLocalId, uint64_t cellCount, const uint32_t* cellSet,
+                          uint64_t** dTocOut, em2_count** dCountsOut, uint64_t* nnzLocal)
+{
+    for (uint64_t i = 0; i < cellCount; i++) {
+        if (cellSet[i] >= globalCellCount) return fail(ctx, EM2_ERR_INVALID, "cell set entry outside the expression matrix");
+        if (i && cellSet[i] <= cellSet[i - 1]) return fail(ctx, EM2_ERR_INVALID, "Cell set is not sorted.");   // CZI_ASSERT, Subset.cpp:18
+    }
+    void* pin = nullptr;
+    EM2_TRY(reservePinned(ctx, 0, (cellCount + 1) * sizeof(uint64_t), &pin));
+    uint64_t* srcToc = static_cast<uint64_t*>(pin);
+    srcToc[0] = 0;
+    for (uint64_t i = 0; i < cellCount; i++) srcToc[i + 1] = srcToc[i] + (globalToc[cellSet[i] + 1] - globalToc[cellSet[i]]);
+    const uint64_t srcNnz = srcToc[cellCount];
+    void *dSrcToc, *dSrc, *dMap, *dToc, *dCounts;
+    EM2_TRY(reserve(ctx, em2_context::S_SRCTOC, (cellCount + 1) * sizeof(uint64_t), &dSrcToc));
+    EM2_TRY(reserve(ctx, em2_context::S_SRCCOUNTS, srcNnz * sizeof(em2_count), &dSrc));
+    EM2_TRY(reserve(ctx, em2_context::S_GENEMAP, globalGeneCount * sizeof(uint32_t), &dMap));
+    EM2_TRY(reserve(ctx, em2_context::S_TOC, (cellCount + 1) * sizeof(uint64_t), &dToc));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTS, srcNnz * sizeof(em2_count), &dCounts));
+    cudaStream_t s = ctx->stream;
+    EM2_CUDA(ctx, cudaEventRecord(ctx->ev[14], s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dSrcToc, srcToc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dMap, geneLocalId, globalGeneCount * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    // runs of consecutive cells are contiguous in the global file: one copy per run
+    for (uint64_t i = 0; i < cellCount;) {
+        uint64_t j = i;
+        while (j + 1 < cellCount && cellSet[j + 1] == cellSet[j] + 1) j++;
+        const uint64_t b = globalToc[cellSet[i]], e = globalToc[cellSet[j] + 1];
+        if (e > b)
+            EM2_CUDA(ctx, cudaMemcpyAsync(static_cast<em2_count*>(dSrc) + srcToc[i], globalCounts + b, (e - b) * sizeof(em2_count),
+                                          cudaMemcpyHostToDevice, s));
+        i = j + 1;
+    }
+    EM2_CUDA(ctx, cudaEventRecord(ctx->ev[15], s));
+    ctx->stats.h2d_bytes += (cellCount + 1) * 8 + globalGeneCount * 4 + srcNnz * 8;
+    EM2_TRY(launchSubset(ctx, cellCount, static_cast<uint64_t*>(dSrcToc), static_cast<em2_count*>(dSrc),
+                         static_cast<uint32_t*>(dMap), globalGeneCount, static_cast<uint64_t*>(dToc),
+                         static_cast<em2_count*>(dCounts), s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(nnzLocal, static_cast<uint64_t*>(dToc) + cellCount, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ctx->ev[14], ctx->ev[15]);
+    ctx->stats.h2d_ms += double(t);
+    *dTocOut = static_cast<uint64_t*>(dToc);
+    *dCountsOut = static_cast<em2_count*>(dCounts);
+    return EM2_OK;
+}
+
+int em2_subset(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc, const em2_count* globalCounts,
+               uint64_t globalGeneCount, const uint32_t* geneLocalId, uint64_t cellCount, const uint32_t* cellSet,
+               uint64_t* localToc, em2_count* localCounts, uint64_t localCapacity, uint64_t* localNnz, double* sum1,
+               double* sum2)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!globalToc || !geneLocalId || !localToc || !localNnz || (cellCount && !cellSet) || (!globalCounts && globalToc[globalCellCount]))
+        return fail(ctx, EM2_ERR_INVALID, "em2_subset: null pointer");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    uint64_t* dToc = nullptr;
+    em2_count* dCounts = nullptr;
+    uint64_t nnz = 0;
+    EM2_TRY(subsetOnDevice(ctx, globalCellCount, globalToc, globalCounts, globalGeneCount, geneLocalId, cellCount, cellSet,
+                           &dToc, &dCounts, &nnz));
+    *localNnz = nnz;
+    if (nnz > localCapacity) return fail(ctx, EM2_ERR_INVALID, "em2_subset: localCounts capacity is smaller than the subset");
+    cudaStream_t s = ctx->stream;
+    EM2_CUDA(ctx, cudaMemcpyAsync(localToc, dToc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (nnz && localCounts) EM2_CUDA(ctx, cudaMemcpyAsync(localCounts, dCounts, nnz * sizeof(em2_count), cudaMemcpyDeviceToHost, s));
+    ctx->stats.d2h_bytes += (cellCount + 1) * 8 + nnz * 8;
+    if (sum1 && cellCount) {
+        void *dSum1, *dSum2;
+        EM2_TRY(reserve(ctx, em2_context::S_SUM1, cellCount * sizeof(double), &dSum1));
+        EM2_TRY(reserve(ctx, em2_context::S_SUM2, cellCount * sizeof(double), &dSum2));
+        EM2_TRY(launchCellSums(ctx, cellCount, dToc, dCounts, static_cast<double*>(dSum1), static_cast<double*>(dSum2), s));
+        EM2_CUDA(ctx, cudaMemcpyAsync(sum1, dSum1, cellCount * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (sum2) EM2_CUDA(ctx, cudaMemcpyAsync(sum2, dSum2, cellCount * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
+int em2_lsh_similar_pairs_subset(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc,
+                                 const em2_count* globalCounts, uint64_t globalGeneCount, const uint32_t* geneLocalId,
+                                 uint64_t geneCount, uint64_t cellCount, const uint32_t* cellSet, const double* lshVectors,
+                                 uint64_t lshCount, uint64_t k, double similarityThreshold, int variant, em2_pair* pairs,
+                                 uint32_t* usedCount, uint64_t* signaturesOut)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!globalToc || !geneLocalId || !lshVectors || !pairs || !usedCount || (cellCount && !cellSet))
+        return fail(ctx, EM2_ERR_INVALID, "em2_lsh_similar_pairs_subset: null pointer");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    if (cellCount == 0) return EM2_OK;
+    StageTimer T(ctx);
+    cudaStream_t s = ctx->stream;
+    const uint64_t W = wordCount(lshCount);
+    void *dU, *dSum1, *dSum2, *dSig, *dCounters;
+    EM2_TRY(reserve(ctx, em2_context::S_U, geneCount * lshCount * sizeof(double), &dU));
+    EM2_TRY(reserve(ctx, em2_context::S_SUM1, cellCount * sizeof(double), &dSum1));
+    EM2_TRY(reserve(ctx, em2_context::S_SUM2, cellCount * sizeof(double), &dSum2));
+    EM2_TRY(reserve(ctx, em2_context::S_SIG, cellCount * W * sizeof(uint64_t), &dSig));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &dCounters));
+    EM2_CUDA(ctx, cudaMemsetAsync(dCounters, 0, 64, s));
+    // hyperplanes ride on the copy stream while the subset is built
+    EM2_CUDA(ctx, cudaMemcpyAsync(dU, lshVectors, geneCount * lshCount * sizeof(double), cudaMemcpyHostToDevice, ctx->copyStream));
+    EM2_CUDA(ctx, cudaEventRecord(ctx->ev[13], ctx->copyStream));
+    ctx->stats.h2d_bytes += geneCount * lshCount * 8;
+    uint64_t* dToc = nullptr;
+    em2_count* dCounts = nullptr;
+    uint64_t nnz = 0;
+    EM2_TRY(subsetOnDevice(ctx, globalCellCount, globalToc, globalCounts, globalGeneCount, geneLocalId, cellCount, cellSet,
+                           &dToc, &dCounts, &nnz));
+    EM2_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev[13], 0));
+    const int e0 = T.mark();
+    EM2_TRY(launchCellSums(ctx, cellCount, dToc, dCounts, static_cast<double*>(dSum1), static_cast<double*>(dSum2), s));
+    const int e1 = T.mark();
+    EM2_TRY(launchSignatures(ctx, cellCount, geneCount, dToc, dCounts, static_cast<double*>(dSum1), static_cast<double*>(dSum2),
+                             static_cast<double*>(dU), lshCount, lshCount, nnz, static_cast<uint64_t*>(dSig),
+                             static_cast<uint64_t*>(dCounters), s));
+    const int e2 = T.mark();
+    if (signaturesOut) {
+        EM2_CUDA(ctx, cudaMemcpyAsync(signaturesOut, dSig, cellCount * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += cellCount * W * 8;
+    }
+    EM2_TRY(scanToHost(ctx, T, static_cast<uint64_t*>(dSig), cellCount, lshCount, 0, cellCount, k, similarityThreshold, variant,
+                       pairs, usedCount));
+    ctx->stats.sums_ms += T.ms(e0, e1);
+    ctx->stats.signatures_ms += T.ms(e1, e2);
+    EM2_TRY(fetchCounters(ctx));
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
 int em2_exact_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                             const em2_count* counts, uint64_t k, double similarityThreshold, em2_pair* pairs,
                             uint32_t* usedCount)

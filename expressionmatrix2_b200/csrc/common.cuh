@@ -49,6 +49,7 @@ struct em2_context {
         S_DENSE,         // dense uint8 counts of the signature filter path
         S_UQ,            // quantised, transposed hyperplanes (two int8 digits) + per-column scale
         S_FLAGS,         // per-cell eligibility flags / fallback list / uncertain list
+        S_SRCTOC, S_SRCCOUNTS, S_GENEMAP,   // subset construction: gathered global rows, gene id map
         S_MISC,
         S_COUNT
     };
@@ -134,6 +135,9 @@ int launchSignaturesFp64(em2_context* ctx, uint64_t cellCount, uint64_t geneCoun
                          cudaStream_t s);
 int launchColumnStats(em2_context* ctx, uint64_t geneCount, const double* U, uint64_t ld, uint64_t lshCount,
                       uint64_t cols, double* sumU, double* scale, double* e1, double* e2, cudaStream_t s);
+// Device-side ExpressionMatrixSubset construction (subset.cu); all pointers are device pointers.
+int launchSubset(em2_context* ctx, uint64_t cellCount, const uint64_t* srcToc, const em2_count* src,
+                 const uint32_t* geneLocalId, uint64_t globalGeneCount, uint64_t* dstToc, em2_count* dst, cudaStream_t s);
 int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                    uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
                    int variant, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);

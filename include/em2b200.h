@@ -154,6 +154,27 @@ int em2_lsh_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCou
                           double similarityThreshold, int variant, em2_pair* pairs, uint32_t* usedCount,
                           uint64_t* signaturesOut /* may be NULL */);
 
+/* ExpressionMatrixSubset construction (src/ExpressionMatrixSubset.cpp:9-58) on the device: for every cell of the
+ * sorted cell set `cellSet` (global cell ids), the stored counts whose gene is in the gene set, in stored order,
+ * re-indexed to local gene ids; plus the per-cell sums.  geneLocalId: uint32[globalGeneCount], the local id of every
+ * global gene or UINT32_MAX when it is not in the set (GeneSet::getLocalGeneId, src/GeneSet.hpp:70-77 -- the
+ * contents of the GeneSet-<name>-LocalIds file).  localToc: uint64[cellCount+1]; localCounts: em2_count[localCapacity]
+ * (the selected cells' global nnz is always enough); *localNnz receives the number of counts kept; sum1/sum2 optional. */
+int em2_subset(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc, const em2_count* globalCounts,
+               uint64_t globalGeneCount, const uint32_t* geneLocalId, uint64_t cellCount, const uint32_t* cellSet,
+               uint64_t* localToc, em2_count* localCounts, uint64_t localCapacity, uint64_t* localNnz, double* sum1,
+               double* sum2);
+
+/* findSimilarPairs4 for a gene set / cell set straight from the GLOBAL expression counts: subset construction,
+ * sums, signatures and the scan all on the device -- the local CSR never exists on the host (the reference writes it
+ * to a temporary mmap file, src/ExpressionMatrixLsh.cpp:191-197).  geneCount = size of the gene set = rows of
+ * lshVectors.  Other arguments as in em2_subset and em2_lsh_similar_pairs. */
+int em2_lsh_similar_pairs_subset(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc,
+                                 const em2_count* globalCounts, uint64_t globalGeneCount, const uint32_t* geneLocalId,
+                                 uint64_t geneCount, uint64_t cellCount, const uint32_t* cellSet, const double* lshVectors,
+                                 uint64_t lshCount, uint64_t k, double similarityThreshold, int variant, em2_pair* pairs,
+                                 uint32_t* usedCount, uint64_t* signaturesOut /* may be NULL */);
+
 /* Exact path (findSimilarPairs0, src/ExpressionMatrixFindSimilarPairs.cpp:16-88 with
  * ExpressionMatrixSubset::computeCellSimilarity, src/ExpressionMatrixSubset.cpp:83-133):
  * Pearson correlation over all genes, deterministic top-k by (similarity desc, cellId asc) among

@@ -247,6 +247,61 @@ def exact_topk(gene_count, toc, gene_ids, counts, k: int, threshold: float, row_
     return ids, sims, used, r
 
 
+def subset(toc, gene_ids, counts, gene_count: int, gene_set, cell_set):
+    """ExpressionMatrixSubset construction (reference src/ExpressionMatrixSubset.cpp:9-42), restated: for every
+    cell of the sorted `cell_set`, the stored counts whose gene is in the sorted `gene_set`, in stored order,
+    with gene ids replaced by their index in `gene_set` (GeneSet::getLocalGeneId, src/GeneSet.hpp:70-77).
+    Returns (toc uint64[n+1], local_gene_ids uint32[nnz'], counts float32[nnz'])."""
+    toc = _c(toc, np.uint64)
+    gene_ids = _c(gene_ids, np.uint32)
+    counts = _c(counts, np.float32)
+    gene_set = _c(gene_set, np.uint32)
+    cell_set = _c(cell_set, np.uint32)
+    local = np.full(gene_count, 0xFFFFFFFF, np.uint32)
+    local[gene_set] = np.arange(len(gene_set), dtype=np.uint32)
+    out_toc = np.zeros(len(cell_set) + 1, np.uint64)
+    gs, cs = [], []
+    n = 0
+    for i, c in enumerate(cell_set):
+        b, e = int(toc[c]), int(toc[c + 1])
+        l = local[gene_ids[b:e]]
+        keep = l != 0xFFFFFFFF
+        gs.append(l[keep])
+        cs.append(counts[b:e][keep])
+        n += int(keep.sum())
+        out_toc[i + 1] = n
+    g = np.concatenate(gs) if gs else np.zeros(0, np.uint32)
+    c = np.concatenate(cs) if cs else np.zeros(0, np.float32)
+    return out_toc, g.astype(np.uint32), c.astype(np.float32)
+
+
+def ref_subset(toc, gene_ids, counts, gene_count: int, gene_set, cell_set):
+    """The reference's own ExpressionMatrixSubset constructor (oracle/_ref).  Returns (toc, genes, counts, sum1, sum2)."""
+    import tempfile
+    toc = _c(toc, np.uint64)
+    gene_ids = _c(gene_ids, np.uint32)
+    counts = _c(counts, np.float32)
+    gene_set = _c(gene_set, np.uint32)
+    cell_set = _c(cell_set, np.uint32)
+    n = len(cell_set)
+    out_toc = np.zeros(n + 1, np.uint64)
+    out_g = np.zeros(max(1, len(gene_ids)), np.uint32)
+    out_c = np.zeros(max(1, len(gene_ids)), np.float32)
+    s1 = np.zeros(n, np.float64)
+    s2 = np.zeros(n, np.float64)
+    nnz = C.c_uint64(0)
+    L = rlib()
+    L.em2ref_subset.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u64p, u32p, f32p, C.c_uint64, u32p, C.c_uint64, u32p,
+                                u64p, u32p, f32p, C.POINTER(C.c_uint64), f64p, f64p]
+    with tempfile.TemporaryDirectory(prefix="em2ref-") as d:
+        _check(L.em2ref_subset(d.encode(), len(toc) - 1, gene_count, _ptr(toc, u64p), _ptr(gene_ids, u32p),
+                               _ptr(counts, f32p), len(gene_set), _ptr(gene_set, u32p), n, _ptr(cell_set, u32p),
+                               _ptr(out_toc, u64p), _ptr(out_g, u32p), _ptr(out_c, f32p), C.byref(nnz),
+                               _ptr(s1, f64p), _ptr(s2, f64p)))
+    m = int(nnz.value)
+    return out_toc, out_g[:m].copy(), out_c[:m].copy(), s1, s2
+
+
 def murmur64a(data: bytes, seed: int = 231) -> int:
     buf = C.create_string_buffer(data, len(data))
     return int(olib().em2o_murmur64a(buf, len(data), seed))

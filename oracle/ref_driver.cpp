@@ -185,6 +185,54 @@ int em2ref_open_signatures(const char* dir, uint64_t cellCount, uint64_t lshCoun
     });
 }
 
+// The reference's own ExpressionMatrixSubset constructor (src/ExpressionMatrixSubset.cpp:9-42) on an arbitrary
+// gene set / cell set: returns the local CSR it builds and its per-cell sums.  outToc has cellSetSize + 1
+// entries; outGenes/outCounts must hold at least the global nnz; *outNnz receives the number of entries kept.
+int em2ref_subset(const char* dir, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc, const uint32_t* geneIds,
+                  const float* counts, uint64_t geneSetSize, const uint32_t* geneSet, uint64_t cellSetSize,
+                  const uint32_t* cellSet, uint64_t* outToc, uint32_t* outGenes, float* outCounts, uint64_t* outNnz,
+                  double* sum1, double* sum2)
+{
+    return guarded([&] {
+        (void)geneCount;
+        const std::string d = dir;
+        GeneSet gs;
+        gs.createNew(d + "/GeneSet-subset");
+        for (uint64_t i = 0; i < geneSetSize; i++) gs.addGene(geneSet[i]);
+        gs.forceSorted();
+        CellSet cs;
+        cs.createNew(d + "/CellSet-subset", cellSetSize);
+        for (uint64_t i = 0; i < cellSetSize; i++) cs[i] = cellSet[i];
+        ExpressionMatrixSubset::CellExpressionCounts global;
+        global.createNew(d + "/CellExpressionCounts-subset");
+        std::vector<std::pair<GeneId, float>> row;
+        for (uint64_t c = 0; c < cellCount; c++) {
+            row.clear();
+            for (uint64_t j = toc[c]; j < toc[c + 1]; j++) row.push_back(std::make_pair(geneIds[j], counts[j]));
+            global.appendVector(row.begin(), row.end());
+        }
+        {
+            ExpressionMatrixSubset subset(d + "/tmp-ExpressionMatrixSubset-subset", gs, cs, global);
+            uint64_t n = 0;
+            outToc[0] = 0;
+            for (uint64_t c = 0; c < cellSetSize; c++) {
+                for (const auto& p : subset.cellExpressionCounts[c]) {
+                    outGenes[n] = p.first;
+                    outCounts[n] = p.second;
+                    n++;
+                }
+                outToc[c + 1] = n;
+                if (sum1) sum1[c] = subset.sums[c].sum1;
+                if (sum2) sum2[c] = subset.sums[c].sum2;
+            }
+            *outNnz = n;
+        }   // the destructor removes the subset's temp files
+        global.remove();
+        gs.remove();
+        cs.remove();
+    });
+}
+
 int em2ref_close(void* handle)
 {
     return guarded([&] {

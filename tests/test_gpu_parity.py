@@ -414,3 +414,41 @@ def test_mma_kernels_equal_popc_when_last_row_block_is_partial(engine, oracle, N
     r = 11070
     wi, ws, wu, _ = oracle.topk(sig, L, 50, 0.2, r, r + 1)
     _check_lists((ref[0][r:r + 1], ref[1][r:r + 1], ref[2][r:r + 1]), (wi, ws, wu))
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-side ExpressionMatrixSubset construction
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,G,gn,cn", [(900, 400, 250, 600), (500, 300, 300, 500), (400, 257, 1, 399), (300, 200, 77, 1)])
+def test_subset_on_device_matches_oracle(engine, oracle, N, G, gn, cn):
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, 0.06, seed=N + gn, mode="clustered", clusters=5)
+    rng = np.random.default_rng(N)
+    gs = np.sort(rng.choice(G, gn, replace=False)).astype(np.uint32)
+    cs = np.sort(rng.choice(N, cn, replace=False)).astype(np.uint32)
+    wt, wg, wc = oracle.subset(toc, genes, counts, G, gs, cs)
+    lt, lp, s1, s2 = engine.subset(toc, counts, G, gs, cs, gene_ids=genes, want_sums=True)
+    assert np.array_equal(lt, wt)
+    assert np.array_equal(lp["gene"], wg) and np.array_equal(lp["count"].view(np.uint32), wc.view(np.uint32))
+    w1, w2 = oracle.cell_sums(wt, wc)
+    assert np.array_equal(s1, w1) and np.array_equal(s2, w2)
+    assert engine.stats()["kernel_launches"] >= 3
+
+
+def test_find_similar_pairs_from_global_counts_with_gene_and_cell_sets(engine, oracle):
+    """The fused call (subset + signatures + scan on the device) equals the oracle run on the oracle's subset."""
+    N, G, L, k, thr = 1500, 900, 512, 20, 0.2
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, 0.05, seed=77, mode="clustered", clusters=8)
+    rng = np.random.default_rng(5)
+    gs = np.sort(rng.choice(G, 600, replace=False)).astype(np.uint32)
+    cs = np.sort(rng.choice(N, 1100, replace=False)).astype(np.uint32)
+    U = em2.generate_lsh_vectors(len(gs), L, 231)
+    wt, wg, wc = oracle.subset(toc, genes, counts, G, gs, cs)
+    s1, _ = oracle.cell_sums(wt, wc)
+    want_sig, _ = oracle.signatures(wt, wg, wc, s1, U)
+    want = oracle.topk(want_sig, L, k, thr)[:3]
+    ids, sims, used, sig = engine.lsh_similar_pairs_subset(toc, counts, G, gs, cs, U, k, thr, gene_ids=genes,
+                                                           want_signatures=True)
+    assert np.array_equal(sig, want_sig)
+    _check_lists((ids, sims, used), want)
+    with pytest.raises(em2.Em2Error):
+        engine.subset(toc, counts, G, gs, cs[::-1].copy(), gene_ids=genes)      # unsorted cell set, like CZI_ASSERT

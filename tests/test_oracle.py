@@ -117,3 +117,23 @@ def test_against_reference_build(oracle):
             for x, y in zip(a, b):
                 assert np.array_equal(x, y)
     assert np.array_equal(np.sort(oracle.ref_keep_best_less([5, 3, 9, 1, 7, 2], 3)), [1, 2, 3])
+
+
+def test_subset_restatement_matches_reference_constructor():
+    """oracle.subset (numpy restatement of src/ExpressionMatrixSubset.cpp:9-42) against the reference's own
+    ExpressionMatrixSubset built from real GeneSet / CellSet objects (oracle/_ref), including the sums."""
+    import oracle
+    from expressionmatrix2_b200 import synthetic
+    if not oracle.have_ref():
+        pytest.skip("reference build (oracle/_ref) not present")
+    toc, genes, counts = synthetic.gen_expression_matrix(300, 200, 0.08, seed=3, mode="clustered", clusters=5)
+    rng = np.random.default_rng(0)
+    for gn, cn in ((120, 211), (200, 300), (1, 7), (37, 1)):
+        gs = np.sort(rng.choice(200, gn, replace=False)).astype(np.uint32)
+        cs = np.sort(rng.choice(300, cn, replace=False)).astype(np.uint32)
+        a = oracle.subset(toc, genes, counts, 200, gs, cs)
+        b = oracle.ref_subset(toc, genes, counts, 200, gs, cs)
+        for x, y in zip(a, b[:3]):
+            assert np.array_equal(x, y)
+        s1, s2 = oracle.cell_sums(a[0], a[2])
+        assert np.array_equal(s1, b[3]) and np.array_equal(s2, b[4])
