@@ -163,26 +163,42 @@ void ExpressionMatrix::findSimilarPairs4(std::ostream& out, const std::string& g
     const CellSet& cellSet = findCellSet(cellSetName);
     const CellId n = CellId(cellSet.size());
 
-    out << timestamp << "Creating expression matrix subset." << std::endl;
-    ExpressionMatrixSubset subset(directoryName + "/tmp-ExpressionMatrixSubset-" + similarPairsName, geneSet, cellSet,
-                                  cellExpressionCounts);
-
-    out << timestamp << "Computing cell LSH signatures on " << Gpu::instance().name() << "." << std::endl;
-    Lsh lsh(directoryName + "/tmp-Lsh-" + similarPairsName, subset, lshCount, seed);
-    lastSignatureMs = Gpu::instance().stats().signatures_ms;
-    out << "Computation of LSH cell signatures took " << 1e-3 * lastSignatureMs << " s on the device; "
-        << lsh.nearZeroProjections << " projections inside the rounding band." << std::endl;
+    // The whole job in one device call, straight from the global expression counts: the subset for this gene set
+    // and cell set (reference: a temporary mmap file, src/ExpressionMatrixLsh.cpp:191-197) is built in HBM, the
+    // signatures never leave the device, and the lists land in the mapped SimilarPairs file.
+    out << timestamp << "Generating LSH vectors." << std::endl;
+    std::vector<double> lshVectors(size_t(geneSet.size()) * lshCount);
+    if (em2_generate_lsh_vectors(geneSet.size(), lshCount, seed, lshVectors.data()) != EM2_OK)
+        throw std::runtime_error("em2_generate_lsh_vectors failed");
+    // GeneSet-<name>-LocalIds may be shorter than the global gene count (genes beyond the last member were never
+    // touched): pad with invalidGeneId
+    std::vector<GeneId> localIds(geneCount(), invalidGeneId);
+    std::copy(geneSet.localIds().begin(), geneSet.localIds().begin() + std::min<size_t>(geneSet.localIds().size(), localIds.size()),
+              localIds.begin());
 
     out << timestamp << "Initializing SimilarPairs object." << std::endl;
     SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
 
-    out << timestamp << "Begin computing similarities for all cell pairs." << std::endl;
-    lsh.findSimilarPairs(similarPairs, k, similarityThreshold, scanVariant);
-    lastScanMs = Gpu::instance().stats().scan_ms;
+    Gpu& gpu = Gpu::instance();
+    out << timestamp << "Expression matrix subset, LSH signatures and all cell pairs on " << gpu.name() << "." << std::endl;
+    static_assert(sizeof(std::pair<GeneId, float>) == sizeof(em2_count), "pair<GeneId,float> must be 8 bytes");
+    static_assert(sizeof(SimilarPairs::Pair) == sizeof(em2_pair), "pair<CellId,float> must be 8 bytes");
+    std::vector<uint32_t> used(n);
+    gpu.check(em2_lsh_similar_pairs_subset(gpu.context(), cellExpressionCounts.size(), cellExpressionCounts.tocBegin(),
+                                           reinterpret_cast<const em2_count*>(cellExpressionCounts.dataBegin()), geneCount(),
+                                           localIds.data(), geneSet.size(), n, cellSet.begin(), lshVectors.data(), lshCount, k,
+                                           similarityThreshold, scanVariant,
+                                           reinterpret_cast<em2_pair*>(similarPairs.begin(0)), used.data(), nullptr),
+              "em2_lsh_similar_pairs_subset");
+    similarPairs.setUsedCounts(used);
+    const em2_stats st = gpu.stats();
+    lastSignatureMs = st.signatures_ms;
+    lastScanMs = st.scan_ms;
+    out << "Computation of LSH cell signatures took " << 1e-3 * lastSignatureMs << " s on the device; "
+        << st.near_zero_projections << " projections inside the rounding band." << std::endl;
     out << "Time for all pairs: " << 1e-3 * lastScanMs << " s." << std::endl;
     if (n > 1) out << "Time per pair: " << 1e-3 * lastScanMs / (0.5 * double(n) * double(n - 1)) << " s." << std::endl;
     out << timestamp << "ExpressionMatrix::findSimilarPairs4 ends." << std::endl;
-    lsh.remove();
 }
 
 void ExpressionMatrix::findSimilarPairs4(const std::string& geneSetName, const std::string& cellSetName,

@@ -55,6 +55,8 @@ public:
     GeneId getLocalGeneId(GeneId global) const { return global < localIds_.size() ? localIds_[global] : invalidGeneId; }
     bool contains(GeneId global) const { return getLocalGeneId(global) != invalidGeneId; }
     const MemoryMapped::Vector<GeneId>& genes() const { return globalIds_; }
+    // local id of every global gene (invalidGeneId if absent): the GeneSet-<name>-LocalIds file
+    const MemoryMapped::Vector<GeneId>& localIds() const { return localIds_; }
     bool isIdentity() const { return size() == 0 || (globalIds_[0] == 0 && globalIds_[size() - 1] == size() - 1); }
     void close()
     {
