@@ -448,9 +448,23 @@ ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount,
         const uint32_t maxStreams = std::max<uint32_t>(1, uint32_t((160u << 10) / (size_t(p.cap) * 8 * 4)));
         const uint32_t maxSeg = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(32, maxStreams / streamsPerSegment),
                                                                                   cellCount / (4 * tileCols))));
-        seg = std::max<uint32_t>(1, std::min<uint32_t>(slots / tail, maxSeg));
-        // a tail that nearly fills a wave is better left whole
-        if (p.mainBlocks && tail * 10 >= slots * 9) seg = 1;
+        if (p.mainBlocks) {
+            seg = std::max<uint32_t>(1, std::min<uint32_t>(slots / tail, maxSeg));
+            if (tail * 10 >= slots * 9) seg = 1;      // a tail that nearly fills a wave is better left whole
+        } else {
+            // fewer row blocks than CTA slots (small jobs, or one rank's share of a multi-GPU job): the smallest
+            // number of segments whose items fill their waves to >= 90 %, else the best found
+            double bestEff = 0.;
+            for (uint32_t c = 1; c <= maxSeg; c++) {
+                const uint64_t items = uint64_t(tail) * c;
+                const double eff = double(items) / double((items + slots - 1) / slots * slots);
+                if (eff > bestEff + 1e-9) {
+                    bestEff = eff;
+                    seg = c;
+                }
+                if (eff >= 0.9) break;
+            }
+        }
     }
     p.segments = seg;
     p.segmentCols = roundUp((cellCount + seg - 1) / seg, tileCols);

@@ -68,6 +68,7 @@ __device__ __forceinline__ double2 ldU(const double* p)
 // beyond lshCount), ld even, base 16-byte aligned.  Cells are [rangeBegin, rangeBegin + rangeCells), or, when
 // `cellList` is given, the first *cellListCount entries of that list.  With `runIfCount` the whole launch is
 // a no-op unless *runIfCount > runIfCap (device-side predicate of the filter path's overflow rescue).
+template <bool PLAIN>      // PLAIN: one block per unit of a cell range, no list, no predicate (the common launch)
 __global__ void __launch_bounds__(kSigWarps * 32, 4)
 signatureKernel(uint64_t rangeBegin, uint64_t rangeCells, uint64_t geneCount, const uint64_t* __restrict__ toc,
                 const em2_count* __restrict__ counts, const double* __restrict__ sum1,
@@ -80,17 +81,17 @@ signatureKernel(uint64_t rangeBegin, uint64_t rangeCells, uint64_t geneCount, co
     __shared__ uint32_t sGene[kSigWarps][32];
     __shared__ double sCount[kSigWarps][32];
 
-    if (runIfCount != nullptr && *runIfCount <= runIfCap) return;
+    if (!PLAIN && runIfCount != nullptr && *runIfCount <= runIfCap) return;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint64_t nCells = cellList ? min(uint64_t(*cellListCount), rangeCells) : rangeCells;
-    const uint64_t cellBlocks = (nCells + kSigWarps - 1) / kSigWarps;
-    const uint64_t units = cellBlocks * slices;
-  for (uint64_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
-    const uint32_t slice = uint32_t(unit / cellBlocks);
-    const uint64_t idx = (unit % cellBlocks) * kSigWarps + warp;
+    const uint64_t nCells = (!PLAIN && cellList) ? min(uint64_t(*cellListCount), rangeCells) : rangeCells;
+    const uint32_t cellBlocks = uint32_t((nCells + kSigWarps - 1) / kSigWarps);
+    const uint32_t units = PLAIN ? blockIdx.x + 1 : cellBlocks * slices;
+  for (uint32_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const uint32_t slice = unit / cellBlocks;
+    const uint64_t idx = uint64_t(unit % cellBlocks) * kSigWarps + warp;
     if (idx >= nCells) continue;
-    const uint64_t cell = cellList ? uint64_t(cellList[idx]) : rangeBegin + idx;
+    const uint64_t cell = (!PLAIN && cellList) ? uint64_t(cellList[idx]) : rangeBegin + idx;
 
     const uint32_t colBase = slice * kSliceCols;
     const uint32_t c0 = colBase + 2 * lane;        // hyperplanes c0, c0+1
@@ -209,9 +210,14 @@ int launchSignaturesFp64(em2_context* ctx, uint64_t cellCount, uint64_t geneCoun
     // device-sized work (a list, or a predicate that is normally false): a persistent grid is enough
     if (cellList || runIfCount) blocks = std::min<uint64_t>(blocks, uint64_t(ctx->smCount) * 8);
     if (blocks > 0x7fffffffull) return fail(ctx, EM2_ERR_INVALID, "too many cells for one signature launch");
-    signatureKernel<<<unsigned(blocks), kSigWarps * 32, 0, s>>>(
-        rangeBegin, cells, geneCount, toc, counts, sum1, sum2, Uk, ldk, sumU, uint32_t(lshCount), uint32_t(W), slices,
-        signatures, reinterpret_cast<unsigned long long*>(nearZero), cellList, cellListCount, runIfCount, runIfCap);
+    if (cellList || runIfCount)
+        signatureKernel<false><<<unsigned(blocks), kSigWarps * 32, 0, s>>>(
+            rangeBegin, cells, geneCount, toc, counts, sum1, sum2, Uk, ldk, sumU, uint32_t(lshCount), uint32_t(W), slices,
+            signatures, reinterpret_cast<unsigned long long*>(nearZero), cellList, cellListCount, runIfCount, runIfCap);
+    else
+        signatureKernel<true><<<unsigned(blocks), kSigWarps * 32, 0, s>>>(
+            rangeBegin, cells, geneCount, toc, counts, sum1, sum2, Uk, ldk, sumU, uint32_t(lshCount), uint32_t(W), slices,
+            signatures, reinterpret_cast<unsigned long long*>(nearZero), nullptr, nullptr, nullptr, 0);
     ctx->stats.kernel_launches++;
     EM2_CUDA(ctx, cudaGetLastError());
     return EM2_OK;
