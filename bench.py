@@ -331,6 +331,13 @@ def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, wor
     roof["kernel"] = "scan_topk (encode + scanMmaKernel/scanPopc*Kernel + finalize)"
     roof["kernel_ms"] = scan_ms
     roof["traffic"] = None
+    try:       # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if variant_used == em2.VARIANT_MMA_I8 and world == 1 and N == 100_000 and L == 1024:
+            roof["traffic"] = tr["scanMmaSsKernel@c2"]["bytes"]
+            roof["traffic_source"] = tr["scanMmaSsKernel@c2"]["source"]
+    except Exception:
+        pass
     roof["note"] = ("achieved = algorithmic ops (one evaluation per UNORDERED pair, 2L bit-ops each); executed = what the "
                     "row-block design runs (every ordered pair): executed_frac is the kernel-quality figure, frac is capped "
                     "at half of it")

@@ -58,6 +58,7 @@ constexpr double kMaxSum1 = 1.6e7;    // keeps |sum c * qh| <= 127 * sum1 below 
 // kernel is organised around keeping that chain fed: a block owns 32 columns, all 8 warps stream 128-gene
 // tiles into a double-buffered shared-memory panel with cp.async, warp 0 runs the 32 chains from there.
 constexpr int kCsRows = 128;
+constexpr int kCsStages = 4;          // 4 x 32 KB panels in flight per block: the loads stay ahead of the add chain
 
 __device__ __forceinline__ void cpAsync8(void* smemDst, const void* gmemSrc)
 {
@@ -69,30 +70,29 @@ columnStatsKernel(uint64_t geneCount, const double* __restrict__ U, uint64_t ld,
                   double* __restrict__ sumU, double* __restrict__ scale, double* __restrict__ e1,
                   double* __restrict__ e2)
 {
-    extern __shared__ __align__(16) double panel[];      // [2][kCsRows][32]
+    extern __shared__ __align__(16) double panel[];      // [kCsStages][kCsRows][32]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * 32 + tx;
     const bool active = i < lshCount;
     const uint32_t tiles = uint32_t((geneCount + kCsRows - 1) / kCsRows);
     auto issue = [&](uint32_t t) {
-        double* dst = panel + size_t(t & 1) * kCsRows * 32;
-        if (active) {
+        if (t < tiles && active) {
+            double* dst = panel + size_t(t % kCsStages) * kCsRows * 32;
             for (int r = ty; r < kCsRows; r += 8) {
                 const uint64_t g = uint64_t(t) * kCsRows + r;
                 if (g < geneCount) cpAsync8(dst + r * 32 + tx, U + g * ld + i);
             }
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.commit_group;\n" ::: "memory");      // one group per tile slot, possibly empty
     };
     double s = 0., m = 0.;
-    if (tiles) issue(0);
+    for (uint32_t t = 0; t < kCsStages - 1; t++) issue(t);
     for (uint32_t t = 0; t < tiles; t++) {
-        if (t + 1 < tiles) issue(t + 1);
-        else asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        issue(t + kCsStages - 1);        // refills the panel consumed in the previous iteration
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kCsStages - 1) : "memory");
         __syncthreads();
         if (ty == 0 && active) {
-            const double* src = panel + size_t(t & 1) * kCsRows * 32 + tx;
+            const double* src = panel + size_t(t % kCsStages) * kCsRows * 32 + tx;
             const int rows = int(min(uint64_t(kCsRows), geneCount - uint64_t(t) * kCsRows));
             if (rows == kCsRows) {
 #pragma unroll 16
@@ -408,7 +408,7 @@ __global__ void recordFilterCounters(const uint32_t* uncertainCount, const uint3
 int launchColumnStats(em2_context* ctx, uint64_t geneCount, const double* U, uint64_t ld, uint64_t lshCount,
                       uint64_t cols, double* sumU, double* scale, double* e1, double* e2, cudaStream_t s)
 {
-    const size_t smem = 2 * size_t(kCsRows) * 32 * sizeof(double);
+    const size_t smem = size_t(kCsStages) * kCsRows * 32 * sizeof(double);
     EM2_CUDA(ctx, cudaFuncSetAttribute(columnStatsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     columnStatsKernel<<<unsigned((cols + 31) / 32), 256, smem, s>>>(geneCount, U, ld, uint32_t(lshCount), uint32_t(cols),
                                                                     sumU, scale, e1, e2);
