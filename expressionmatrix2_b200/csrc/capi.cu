@@ -182,6 +182,15 @@ int em2_create(int device, em2_context** out)
     ctx->smCount = ctx->prop.multiProcessorCount;
     cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    {
+        // high priority: its few, long-running blocks must be placed ahead of the pending blocks of the wide
+        // cell-side kernels it is meant to overlap with
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&ctx->auxStream, cudaStreamNonBlocking, hi);
+    }
+    cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evPrep, cudaEventDisableTiming);
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     if ((e = cudaGetLastError()) != cudaSuccess) {
         const int rc = cudaFail(nullptr, e, "stream/event creation", __FILE__, __LINE__);
@@ -207,6 +216,9 @@ void em2_destroy(em2_context* ctx)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->auxStream) cudaStreamDestroy(ctx->auxStream);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evPrep) cudaEventDestroy(ctx->evPrep);
     delete ctx;
 }
 

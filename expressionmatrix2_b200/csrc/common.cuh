@@ -32,6 +32,8 @@ struct em2_context {
     em2_stats stats{};
     cudaStream_t stream = nullptr;       // stream of the blocking calls
     cudaStream_t copyStream = nullptr;   // overlapped host<->device staging
+    cudaStream_t auxStream = nullptr;    // hyperplane-side preparation of the filter path, concurrent with the cell-side kernels
+    cudaEvent_t evFork = nullptr, evPrep = nullptr;
     cudaEvent_t ev[16] = {};
     cudaEvent_t pool[40] = {};           // per-chunk events of the pipelined host-buffer path (created on first use)
 
@@ -110,6 +112,7 @@ struct SignaturePlan {
     uint64_t gPad = 0, chunkMax = 0;
     uint32_t nBlocks = 0, uncertainCap = 0;
     void *uq = nullptr, *dense = nullptr, *lists = nullptr;
+    bool prepOnAux = false;           // the constants / quantised operand are produced on ctx->auxStream (wait evPrep)
     size_t offFlags = 0, offFallback = 0, offUncertain = 0;
 };
 int prepareSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const double* U, uint64_t ld,

@@ -432,17 +432,25 @@ int prepareSignaturesFiltered(em2_context* ctx, SignaturePlan& pl, uint64_t cell
     pl.scale = pl.sumU + Lpad;
     pl.e1 = pl.scale + Lpad;
     pl.e2 = pl.e1 + Lpad;
-    EM2_TRY(launchColumnStats(ctx, geneCount, pl.U, pl.ld, lshCount, Lpad, pl.sumU, pl.scale, pl.e1, pl.e2, s));
     const size_t uqBytes = size_t(pl.nBlocks) * kFN * pl.gPad;
     EM2_TRY(reserve(ctx, em2_context::S_UQ, uqBytes, &pl.uq));
-    EM2_CUDA(ctx, cudaMemsetAsync(pl.uq, 0, uqBytes, s));
+    // The column constants are G-long dependent FP64 add chains on 32 SMs (0.6 ms at 30k genes) and, like the
+    // quantisation, depend on the hyperplanes only: they run on a side stream while the main stream computes the
+    // per-cell sums and the dense counts; the GEMM launch waits for them (evPrep).
+    cudaStream_t a = ctx->auxStream;
+    EM2_CUDA(ctx, cudaEventRecord(ctx->evFork, s));
+    EM2_CUDA(ctx, cudaStreamWaitEvent(a, ctx->evFork, 0));
+    EM2_TRY(launchColumnStats(ctx, geneCount, pl.U, pl.ld, lshCount, Lpad, pl.sumU, pl.scale, pl.e1, pl.e2, a));
+    EM2_CUDA(ctx, cudaMemsetAsync(pl.uq, 0, uqBytes, a));
     {
         const dim3 grid(unsigned(pl.gPad / 128), unsigned((lshCount + 31) / 32));
-        quantizeKernel<<<grid, 256, 0, s>>>(geneCount, pl.U, pl.ld, uint32_t(lshCount), pl.scale, pl.gPad,
+        quantizeKernel<<<grid, 256, 0, a>>>(geneCount, pl.U, pl.ld, uint32_t(lshCount), pl.scale, pl.gPad,
                                             static_cast<int8_t*>(pl.uq));
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
     }
+    EM2_CUDA(ctx, cudaEventRecord(ctx->evPrep, a));
+    pl.prepOnAux = true;
 
     // scratch of the cell chunks: dense operand, flags, lists
     const uint64_t denseBudget = 6ull << 30;
@@ -519,6 +527,7 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
         EM2_TRY(makeTensorMapU8(ctx, &mapA, dense, chunkCells, gPad, gPad, kFM));
         const uint32_t items = p.mBlocks * p.nBlocks;
         const unsigned grid = std::min<uint32_t>(items, uint32_t(ctx->smCount));
+        if (pl.prepOnAux) EM2_CUDA(ctx, cudaStreamWaitEvent(s, ctx->evPrep, 0));
         sigFilterKernel<<<grid, kFThreads, smem, s>>>(mapA, mapB, p);
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
