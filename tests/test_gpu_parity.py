@@ -452,3 +452,25 @@ def test_find_similar_pairs_from_global_counts_with_gene_and_cell_sets(engine, o
     _check_lists((ids, sims, used), want)
     with pytest.raises(em2.Em2Error):
         engine.subset(toc, counts, G, gs, cs[::-1].copy(), gene_ids=genes)      # unsorted cell set, like CZI_ASSERT
+
+
+def test_one_million_cells_sampled_rows(engine, oracle):
+    """The headline size: 1M cells, 1024 bits, top-50.  Whole-row work items plus a segmented tail, row grouping,
+    2 GB of candidate regions; sampled rows (first/last of blocks, tail rows, random) must equal the oracle, and
+    the size-independent properties must hold."""
+    N, L, k, thr = 1_000_000, 1024, 50, 0.2
+    sig = synthetic.gen_signatures(N, L, seed=1000, clusters=500, centre_seed=77)
+    sig[N - 1] = sig[123456]                      # a planted duplicate across the whole id range
+    ids, sims, used = engine.find_similar_pairs(sig, L, k, thr)
+    assert engine.stats()["variant_used"] == em2.VARIANT_MMA_I8
+    rows = np.r_[0, 127, 128, 123456, 947199, 947200, N - 129, N - 1, np.random.default_rng(3).integers(0, N, 12)]
+    for r in rows:
+        wi, ws, wu, _ = oracle.topk(sig, L, k, thr, int(r), int(r) + 1)
+        _check_lists((ids[r:r + 1], sims[r:r + 1], used[r:r + 1]), (wi, ws, wu))
+    assert ids[123456, 0] == N - 1 and sims[123456, 0] == 1.0 and ids[N - 1, 0] == 123456
+    u = used.astype(np.int64)
+    valid = np.arange(k)[None, :] < u[:, None]
+    assert np.all(ids[~valid] == 0)
+    d = np.diff(sims.astype(np.float64), axis=1)
+    assert np.all(d[valid[:, 1:]] <= 0)           # similarities non-increasing along every list
+    assert not np.any((ids == np.arange(N, dtype=np.uint32)[:, None]) & valid)      # no self pairs
