@@ -474,3 +474,47 @@ def test_one_million_cells_sampled_rows(engine, oracle):
     d = np.diff(sims.astype(np.float64), axis=1)
     assert np.all(d[valid[:, 1:]] <= 0)           # similarities non-increasing along every list
     assert not np.any((ids == np.arange(N, dtype=np.uint32)[:, None]) & valid)      # no self pairs
+
+
+def test_lsh_against_exact_similarity_statistics_and_recall(engine, oracle):
+    """BASELINE config 5's purpose (dense validation of the LSH neighbours), at a size the exact path does in
+    milliseconds: per similarity bin the RMS error of the LSH estimate cos(pi m / L) against the exact Pearson r stays
+    within 1.25 x the theoretical sigma  pi sin(theta) sqrt(p (1-p) / L)  (reference analyzeLsh,
+    src/ExpressionMatrixLsh.cpp:1340-1364); and the LSH top-k is nearly as good, in exact similarity, as the exact top-k."""
+    N, G, L, k = 1000, 3000, 1024, 20          # k = N - 1 must stay within the API's 1024
+    toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, 150, seed=31, clusters=10)     # mates at r ~ 0.3
+    U = em2.generate_lsh_vectors(G, L, 231)
+    lid, lsim, lused, sig = engine.lsh_similar_pairs(toc, counts, U, N - 1, -1.0, gene_ids=genes, want_signatures=True)
+    eid, esim, eused = engine.exact_similar_pairs(toc, counts, G, N - 1, -1.0, gene_ids=genes)
+    assert np.all(lused == N - 1) and np.all(eused == N - 1)        # every pair, both paths
+    # exact and LSH similarity of every ordered pair, aligned by (row, neighbour id)
+    exact = np.zeros((N, N), np.float32)
+    lsh = np.zeros((N, N), np.float32)
+    rows = np.arange(N)[:, None]
+    exact[rows, eid] = esim
+    lsh[rows, lid] = lsim
+    mask = ~np.eye(N, dtype=bool)
+    err = (lsh - exact)[mask].astype(np.float64)
+    r = exact[mask].astype(np.float64)
+    bins = np.floor((r + 1.0) / 0.1).astype(int)
+    checked = 0
+    for b in np.unique(bins):
+        sel = bins == b
+        if sel.sum() < 2000:
+            continue
+        s = (b + 0.5) * 0.1 - 1.0
+        theta = np.arccos(s)
+        p = 1.0 - theta / np.pi
+        sigma = np.pi * np.sqrt(1.0 - s * s) * np.sqrt(p * (1.0 - p) / L)
+        rms = np.sqrt(np.mean(err[sel] ** 2))
+        assert rms <= 1.25 * sigma + 1e-3, (b, rms, sigma)
+        checked += 1
+    assert checked >= 2
+    # neighbour quality: the cells LSH picks as the 20 nearest are (in exact similarity) nearly as good as the exact
+    # 20 nearest -- the id sets themselves differ a lot inside a tight cluster, where all mates are about equally near
+    quality = np.mean([exact[c, lid[c, :k]].mean() for c in range(N)])
+    best = np.mean([esim[c, :k].mean() for c in range(N)])
+    assert quality >= 0.9 * best, (quality, best)
+    # and they are overwhelmingly inside the exact 3k nearest
+    hits = sum(len(np.intersect1d(eid[c, :3 * k], lid[c, :k])) for c in range(N))
+    assert hits / (N * k) > 0.5, hits / (N * k)
