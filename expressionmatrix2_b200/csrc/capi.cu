@@ -191,6 +191,12 @@ int em2_create(int device, em2_context** out)
     }
     cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evPrep, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->auxStream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->evFork2, cudaEventDisableTiming);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&ctx->evDense[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->evGemm[i], cudaEventDisableTiming);
+    }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     if ((e = cudaGetLastError()) != cudaSuccess) {
         const int rc = cudaFail(nullptr, e, "stream/event creation", __FILE__, __LINE__);
@@ -219,6 +225,12 @@ void em2_destroy(em2_context* ctx)
     if (ctx->auxStream) cudaStreamDestroy(ctx->auxStream);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evPrep) cudaEventDestroy(ctx->evPrep);
+    if (ctx->auxStream2) cudaStreamDestroy(ctx->auxStream2);
+    if (ctx->evFork2) cudaEventDestroy(ctx->evFork2);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->evDense[i]) cudaEventDestroy(ctx->evDense[i]);
+        if (ctx->evGemm[i]) cudaEventDestroy(ctx->evGemm[i]);
+    }
     delete ctx;
 }
 
@@ -245,6 +257,7 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     if (n == "signature_mode" && value >= 0 && value <= 2) ctx->signatureMode = int(value);
     else if (n == "popc_csa" && value >= 0 && value <= 2) ctx->popcCsa = int(value);
     else if (n == "filter_counts_signed" && value >= 0 && value <= 1) ctx->filterCountsSigned = int(value);
+    else if (n == "filter_parts" && value >= 0 && value <= 64) ctx->filterParts = int(value);
     else if (n == "cand_cap_extra" && value >= 0 && value <= 14) ctx->candCapExtra = int(value);
     else if (n == "debug_flags" && value >= 0 && value <= 255) ctx->debugFlags = int(value);
     else if (n == "row_grouping" && value >= 0 && value <= 2) ctx->rowGrouping = int(value);

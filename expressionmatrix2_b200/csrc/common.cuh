@@ -34,6 +34,10 @@ struct em2_context {
     cudaStream_t copyStream = nullptr;   // overlapped host<->device staging
     cudaStream_t auxStream = nullptr;    // hyperplane-side preparation of the filter path, concurrent with the cell-side kernels
     cudaEvent_t evFork = nullptr, evPrep = nullptr;
+    cudaStream_t auxStream2 = nullptr;   // dense expansion of the next chunk of cells, overlapping the current chunk's GEMM
+    cudaEvent_t evFork2 = nullptr, evDense[2] = {}, evGemm[2] = {};
+    bool slotUsed[2] = {false, false};
+    uint64_t filterChunkSeq = 0;
     cudaEvent_t ev[16] = {};
     cudaEvent_t pool[40] = {};           // per-chunk events of the pipelined host-buffer path (created on first use)
 
@@ -59,6 +63,7 @@ struct em2_context {
     int popcCsa = 1;         // carry-save levels of the POPC scan
     uint32_t filterUncertainCap = 0;   // test knob: capacity of the uncertain list (0 = automatic)
     uint64_t exactMatrixBytes = 0;     // test knob: budget of the exact path's similarity matrix (0 = 8 GiB)
+    int filterParts = 0;               // test knob: chunks per filter call (0 = automatic)
     int candCapExtra = 0;              // candidate regions hold (2 + candCapExtra) * k + 32 keys
     int debugFlags = 0;                // bit 0: no bound sharing between MMA sub-streams; bit 1: memory prune
     int rowGrouping = 0;               // MMA scan: 0 auto (group similar rows into the same warps), 1 off, 2 on
@@ -113,7 +118,7 @@ struct SignaturePlan {
     uint32_t nBlocks = 0, uncertainCap = 0;
     void *uq = nullptr, *dense = nullptr, *lists = nullptr;
     bool prepOnAux = false;           // the constants / quantised operand are produced on ctx->auxStream (wait evPrep)
-    size_t offFlags = 0, offFallback = 0, offUncertain = 0;
+    size_t offFlags = 0, offFallback = 0, offUncertain = 0, slotBytes = 0;   // lists: two slots of slotBytes
 };
 int prepareSignatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const double* U, uint64_t ld,
                       uint64_t lshCount, uint64_t nnzHint, SignaturePlan* plan, cudaStream_t s);

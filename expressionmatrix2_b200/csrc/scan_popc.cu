@@ -356,6 +356,31 @@ finalizeKernel(uint64_t rows, uint32_t segments, uint32_t cap, uint32_t k, const
         n += c;
     }
     __syncwarp();
+    if (n > 2 * k) {
+        // Many streams: first cut the pool down to the keys whose mismatch count is at most the k-th smallest one
+        // (bisection, 16 steps over <= n/32 keys per lane), then rank only those.
+        uint32_t lo = 0, hi = 0xffffu;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            uint32_t c = 0;
+            for (uint32_t e = lane; e < n; e += 32) c += (uint32_t(keys[e] >> 32) <= mid);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= k) hi = mid;
+            else lo = mid + 1;
+        }
+        uint32_t out = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t e = base + lane;
+            const uint64_t key = e < n ? keys[e] : ~0ull;
+            const bool keep = e < n && uint32_t(key >> 32) <= lo;
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) keys[out + __popc(mask & lt)] = key;      // out + rank <= e: never overtakes the reads
+            out += __popc(mask);
+        }
+        n = out;
+        __syncwarp();
+    }
     const uint32_t used = n < k ? n : k;
     const uint64_t outRow = rowPerm ? uint64_t(rowPerm[row]) - rowBegin : row;
     for (uint32_t e = lane; e < n; e += 32) {

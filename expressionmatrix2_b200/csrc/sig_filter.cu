@@ -170,7 +170,7 @@ quantizeKernel(uint64_t geneCount, const double* __restrict__ U, uint64_t ld, ui
 __global__ void __launch_bounds__(256)
 densifyKernel(uint64_t chunkBegin, uint32_t chunkCells, uint64_t geneCount, uint64_t gPad,
               const uint64_t* __restrict__ toc, const em2_count* __restrict__ counts,
-              const double* __restrict__ sum1, float maxCount, uint8_t* __restrict__ dense,
+              float maxCount, uint8_t* __restrict__ dense,
               uint8_t* __restrict__ flags, uint32_t* __restrict__ fallbackList, uint32_t* __restrict__ fallbackCount)
 {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -181,15 +181,20 @@ densifyKernel(uint64_t chunkBegin, uint32_t chunkCells, uint64_t geneCount, uint
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint64_t o = uint64_t(lane) * 16; o < gPad; o += 512) *reinterpret_cast<uint4*>(row + o) = z;
     __syncwarp();
-    bool ok = sum1[cell] < kMaxSum1;
+    bool ok = true;
+    double rowSum = 0.;      // the eligibility bound on the cell's sum, computed here so that this kernel does not
+                             // depend on the per-cell sums kernel (it runs ahead on its own stream)
     const uint64_t end = toc[cell + 1];
     for (uint64_t e = toc[cell] + lane; e < end; e += 32) {
         const em2_count p = counts[e];
         const float c = p.count;
         ok = ok && (c >= 0.f) && (c <= maxCount) && (c == truncf(c)) && (p.gene < geneCount);
+        rowSum += double(fminf(fmaxf(c, 0.f), 65536.f));
         if (p.gene < geneCount) row[p.gene] = uint8_t(min(255u, __float2uint_rz(fmaxf(c, 0.f))));
     }
-    ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rowSum += __shfl_xor_sync(0xffffffffu, rowSum, o);
+    ok = __all_sync(0xffffffffu, ok) && rowSum < kMaxSum1;
     if (lane == 0) {
         flags[w] = ok ? 1 : 0;
         if (!ok) fallbackList[atomicAdd(fallbackCount, 1u)] = uint32_t(cell);
@@ -452,18 +457,26 @@ int prepareSignaturesFiltered(em2_context* ctx, SignaturePlan& pl, uint64_t cell
     EM2_CUDA(ctx, cudaEventRecord(ctx->evPrep, a));
     pl.prepOnAux = true;
 
-    // scratch of the cell chunks: dense operand, flags, lists
-    const uint64_t denseBudget = 6ull << 30;
+    // scratch of the cell chunks: two slots (dense operand, flags, lists) so that the dense expansion of chunk
+    // c+1 (HBM-write bound, on a side stream) overlaps the GEMM of chunk c (tensor bound)
+    const uint64_t denseBudget = 3ull << 30;                 // per slot
+    const uint64_t hint = std::max<uint64_t>(cellCountHint, 1);
+    // Measured (100k cells x 30k genes): 1 / 2 / 4 / 8 chunks per call take 7.6 / 7.9 / 8.1 / 9.3 ms -- the GEMM loses
+    // more to wave quantisation and the extra small launches than the overlap of the next expansion wins, so a call
+    // is cut only where the 3 GB slot demands it; the two slots still overlap consecutive calls (the blocking API's
+    // PCIe chunks) and let the expansion start while the hyperplane-side preparation runs.
+    const uint64_t parts = ctx->filterParts ? uint64_t(ctx->filterParts) : 1;
     pl.chunkMax = std::max<uint64_t>(kFM, denseBudget / pl.gPad / kFM * kFM);
-    pl.chunkMax = std::min<uint64_t>(pl.chunkMax, roundUp(std::max<uint64_t>(cellCountHint, 1), kFM));
-    EM2_TRY(reserve(ctx, em2_context::S_DENSE, pl.chunkMax * pl.gPad, &pl.dense));
+    pl.chunkMax = std::min<uint64_t>(pl.chunkMax, roundUp((hint + parts - 1) / parts, kFM));
+    EM2_TRY(reserve(ctx, em2_context::S_DENSE, 2 * pl.chunkMax * pl.gPad, &pl.dense));
     pl.uncertainCap = ctx->filterUncertainCap ? ctx->filterUncertainCap :
         uint32_t(std::min<uint64_t>(std::max<uint64_t>(1u << 20, pl.chunkMax * lshCount / 32), 1u << 28));
-    // layout of S_FLAGS: [counters: 2 x u32 (+pad to 16)] [flags: chunkMax bytes] [fallback list: chunkMax u32] [uncertain: cap u64]
+    // layout of one slot of S_FLAGS: [counters: 2 x u32 (+pad to 16)] [flags: chunkMax bytes] [fallback list: chunkMax u32] [uncertain: cap u64]
     pl.offFlags = 16;
     pl.offFallback = roundUp(pl.offFlags + pl.chunkMax, 16);
     pl.offUncertain = roundUp(pl.offFallback + 4 * pl.chunkMax, 16);
-    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, pl.offUncertain + size_t(pl.uncertainCap) * 8, &pl.lists));
+    pl.slotBytes = roundUp(pl.offUncertain + size_t(pl.uncertainCap) * 8, 256);
+    EM2_TRY(reserve(ctx, em2_context::S_FLAGS, 2 * pl.slotBytes, &pl.lists));
     return EM2_OK;
 }
 
@@ -477,13 +490,7 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
     const uint32_t nBlocks = pl.nBlocks, uncertainCap = pl.uncertainCap;
     const double *U = pl.U, *Upadded = pl.Upadded, *sumU = pl.sumU, *scale = pl.scale, *e1 = pl.e1, *e2 = pl.e2;
     const uint64_t ld = pl.ld, ldPadded = pl.ldPadded;
-    void *uq = pl.uq, *dense = pl.dense;
-    uint8_t* base = static_cast<uint8_t*>(pl.lists);
-    uint32_t* uncertainCount = reinterpret_cast<uint32_t*>(base);
-    uint32_t* fallbackCount = uncertainCount + 1;
-    uint8_t* dFlags = base + pl.offFlags;
-    uint32_t* fallbackList = reinterpret_cast<uint32_t*>(base + pl.offFallback);
-    uint64_t* uncertain = reinterpret_cast<uint64_t*>(base + pl.offUncertain);
+    void* uq = pl.uq;
     const uint64_t cellCount = cellEnd;
 
     const bool unsignedCounts = ctx->filterCountsSigned == 0;
@@ -492,14 +499,32 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
     CUtensorMap mapB;
     EM2_TRY(makeTensorMapU8(ctx, &mapB, uq, uint64_t(nBlocks) * kFN, gPad, gPad, 128));
 
+    // the dense expansion runs ahead on its own stream; it only needs the CSR, which everything enqueued on `s` so far provides
+    cudaStream_t d = ctx->auxStream2;
+    EM2_CUDA(ctx, cudaEventRecord(ctx->evFork2, s));
+    EM2_CUDA(ctx, cudaStreamWaitEvent(d, ctx->evFork2, 0));
+
     for (uint64_t begin = cellBegin; begin < cellEnd; begin += chunkMax) {
         const uint32_t chunkCells = uint32_t(std::min<uint64_t>(chunkMax, cellEnd - begin));
-        EM2_CUDA(ctx, cudaMemsetAsync(base, 0, 16, s));
-        densifyKernel<<<(chunkCells + 7) / 8, 256, 0, s>>>(begin, chunkCells, geneCount, gPad, toc, counts, sum1,
-                                                           unsignedCounts ? 255.f : 127.f, static_cast<uint8_t*>(dense),
-                                                           dFlags, fallbackList, fallbackCount);
+        const int slot = int(ctx->filterChunkSeq++ & 1);
+        uint8_t* dense = static_cast<uint8_t*>(pl.dense) + size_t(slot) * chunkMax * gPad;
+        uint8_t* base = static_cast<uint8_t*>(pl.lists) + size_t(slot) * pl.slotBytes;
+        uint32_t* uncertainCount = reinterpret_cast<uint32_t*>(base);
+        uint32_t* fallbackCount = uncertainCount + 1;
+        uint8_t* dFlags = base + pl.offFlags;
+        uint32_t* fallbackList = reinterpret_cast<uint32_t*>(base + pl.offFallback);
+        uint64_t* uncertain = reinterpret_cast<uint64_t*>(base + pl.offUncertain);
+
+        // side stream: wait until the slot's previous user (GEMM + fix-ups) is done, then expand
+        if (ctx->slotUsed[slot]) EM2_CUDA(ctx, cudaStreamWaitEvent(d, ctx->evGemm[slot], 0));
+        EM2_CUDA(ctx, cudaMemsetAsync(base, 0, 16, d));
+        densifyKernel<<<(chunkCells + 7) / 8, 256, 0, d>>>(begin, chunkCells, geneCount, gPad, toc, counts,
+                                                           unsignedCounts ? 255.f : 127.f, dense, dFlags, fallbackList,
+                                                           fallbackCount);
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
+        EM2_CUDA(ctx, cudaEventRecord(ctx->evDense[slot], d));
+        EM2_CUDA(ctx, cudaStreamWaitEvent(s, ctx->evDense[slot], 0));
 
         FilterParams p{};
         p.chunkBegin = begin;
@@ -550,6 +575,8 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
                                              reinterpret_cast<unsigned long long*>(ctx->scratch[em2_context::S_COUNTERS].ptr));
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
+        EM2_CUDA(ctx, cudaEventRecord(ctx->evGemm[slot], s));
+        ctx->slotUsed[slot] = true;
     }
     return EM2_OK;
 }
