@@ -282,11 +282,13 @@ def _timed_steps(args, world, dev, local_rank, step, n_marks):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi samples every 100 ms; a multi-GPU step of this workload can be a few ms, so the sampler also covers the
+    # warm-up steps (same kernels, same clocks) -- otherwise a short timed region would end before its first sample
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -295,8 +297,14 @@ def _timed_steps(args, world, dev, local_rank, step, n_marks):
         step(ev[i])
     t_end.record()
     barrier()
-    clocks = sampler.stop()
     total_ms = t_begin.elapsed_time(t_end)
+    if total_ms < 300.0:          # keep the GPU busy with the same step until the sampler has something to report
+        t0 = time.time()
+        while time.time() - t0 < 0.35:
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps" + (" + identical extra steps (timed region shorter than the 100 ms sampling period)" if total_ms < 300.0 else "")
     stage = [float(np.mean([ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)])) for j in range(n_marks - 1)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
