@@ -408,7 +408,9 @@ def run_b200(args, w):
         Gpad = (G + 127) // 128 * 128
         peak, which = int8_peak(peaks, st["scan_ms"])
         roof = dict(bound="tensor", unit="TOP/s", achieved=pairs_total * 2 * G / (st["scan_ms"] * 1e-3) / 1e12,
-                    executed=float(N) * N * 2 * Gpad / (st["scan_ms"] * 1e-3) / 1e12, peak=peak,
+                    # the N x N float matrix fits (<= 48 GB) for N <= ~109k: only tiles on or above the diagonal are computed
+                    executed=(float(N) * N / 2 + 128.0 * N if 4.0 * N * N <= 48 * 2 ** 30 else float(N) * N) * 2 * Gpad
+                    / (st["scan_ms"] * 1e-3) / 1e12, peak=peak,
                     peak_source=INT8_PEAK_NOTE.format(src=peaks["source"]), kernel="exactGemmKernel + exactSelectKernel",
                     kernel_ms=st["scan_ms"], traffic=None)
         roof["frac"] = roof["achieved"] / peak

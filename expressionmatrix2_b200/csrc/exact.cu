@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace em2 {
 
@@ -116,10 +117,13 @@ struct ExactParams {
     uint64_t geneCount;
     uint32_t kChunks;
     uint32_t rowBlocks, colTiles, superCols, items;
-    uint32_t symmetric;          // 1: only tiles on or above the diagonal are computed; their results are stored twice
+    uint32_t colsPerTile;        // 256 with one digit plane (N = 256 instructions), 128 with two
+    uint32_t rowsPerItem;        // 128, or 256 when a CTA pair shares one M = 256 instruction
+    uint32_t symmetric;          // 1: only 128-column blocks on or above the diagonal are computed; results are stored twice
     uint32_t idesc;
     uint64_t ldOut;              // floats per row of the similarity matrix
     double threshold;
+    const uint2* tiles;          // work list, p.items entries of (row unit, column tile)
     const double* sum1;
     const double* var;
     const float* rinv;
@@ -127,21 +131,38 @@ struct ExactParams {
     float* out;
 };
 
+// The work list is built on the host: only the tiles that are needed (symmetric mode drops those below the diagonal),
+// in super-tile order.  Every entry is real work of equal size, so the persistent CTAs -- which take entries
+// worker, worker + workers, ... -- move from one super-tile to the next TOGETHER and stream its 24 operand panels
+// through L2 in step.  (Skipping unneeded entries of a dense enumeration on the device let the CTAs drift apart:
+// 54 % L2 hit rate, 135 GB of DRAM reads for 1 GB of operands, kernel DRAM-bound at half the tensor peak.)
+// rb counts row units of p.rowsPerItem rows (128, or 256 for a CTA pair); ct column tiles of p.colsPerTile columns.
 __device__ __forceinline__ bool itemToTile(const ExactParams& p, uint32_t item, uint32_t& rb, uint32_t& ct)
 {
-    const uint32_t super = item / (kXSuper * kXSuper), within = item % (kXSuper * kXSuper);
-    rb = (super / p.superCols) * kXSuper + within / kXSuper;
-    ct = (super % p.superCols) * kXSuper + within % kXSuper;
-    return rb < p.rowBlocks && ct < p.colTiles && !(p.symmetric && ct < rb);
+    const uint2 t = __ldg(p.tiles + item);
+    rb = t.x;
+    ct = t.y;
+    return true;
 }
 
-template <int DIGITS>
+template <int DIGITS, bool PAIR>
 __global__ void __launch_bounds__(kXThreads, 1)
 exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant__ CUtensorMap mapHi, const ExactParams p)
 {
-    constexpr int kStages = DIGITS == 1 ? 6 : 3;
-    constexpr uint32_t kStageBytes = 2 * DIGITS * kXPlaneBytes;       // A planes then B planes
-    constexpr int kAccBufs = DIGITS == 1 ? 2 : 1;                     // TMEM: 2 x 128 columns, or HH | X | LL
+    // one digit plane: 128 x 256 tiles (N = 256 instructions: a third less operand traffic per MAC than 128 x 128,
+    // which is what this kernel is short of -- ncu: DRAM 5 TB/s, tensor pipe 41 %), accumulators 2 x 256 TMEM columns;
+    // two planes: 128 x 128 tiles with the three accumulators HH | X | LL.
+    constexpr int kN = DIGITS == 1 ? 256 : 128;
+    constexpr uint32_t kBPlaneBytes = kN * kXChunk;
+    // PAIR (one digit only): two CTAs of a cluster share one M = 256 instruction; each streams its own 128 rows of A
+    // and HALF of the 256-column B tile, i.e. 32 KB per stage per SM for the same MMA work as 48 KB above.  The kernel
+    // is short of operand bandwidth, not of tensor throughput (a third of its loads miss L2 and, with ~200 KB in
+    // flight per SM, DRAM latency caps a 128 x 256 tile at ~50 % of the tensor peak).
+    static_assert(!PAIR || DIGITS == 1, "the CTA-pair form exists for one digit plane");
+    constexpr uint32_t kBLoadBytes = PAIR ? kBPlaneBytes / 2 : kBPlaneBytes;
+    constexpr int kStages = PAIR ? 6 : DIGITS == 1 ? 4 : 3;
+    constexpr uint32_t kStageBytes = DIGITS * (kXPlaneBytes + kBLoadBytes);       // A planes then B planes
+    constexpr int kAccBufs = DIGITS == 1 ? 2 : 1;
     extern __shared__ uint8_t smemRaw[];
     uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(kStages) * kStageBytes);
@@ -153,6 +174,9 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? clusterRank() : 0;
+    const uint32_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+    const uint32_t workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; i++) {
             mbarInit(full + i, 1);
@@ -160,13 +184,17 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
         }
         for (int i = 0; i < 2; i++) {
             mbarInit(accFull + i, 1);
-            mbarInit(accEmpty + i, 128);
+            mbarInit(accEmpty + i, PAIR ? 8 : 128);      // PAIR: one arrival per epilogue warp of either CTA
         }
         mbarInitFence();
     }
-    if (warp == 4) tmemAlloc(tmemSlot, 512);
+    if (warp == 4) {
+        if (PAIR) tmemAllocPair(tmemSlot, 512);
+        else tmemAlloc(tmemSlot, 512);
+    }
     fenceBefore();
-    __syncthreads();
+    if (PAIR) clusterSync();
+    else __syncthreads();
     fenceAfter();
     const uint32_t tmemBase = *tmemSlot;
 
@@ -174,21 +202,31 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             prefetchMap(&mapLo);
-            if (DIGITS == 2) prefetchMap(&mapHi);
+            if (DIGITS == 2 || !PAIR) prefetchMap(&mapHi);
             uint32_t stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+            for (uint32_t item = worker; item < p.items; item += workers) {
                 uint32_t rb, ct;
                 if (!itemToTile(p, item, rb, ct)) continue;
-                const int32_t rowA = int32_t(p.rowBegin + uint64_t(rb) * kXTile);
-                const int32_t rowB = int32_t(ct * kXTile);
+                const int32_t rowA = int32_t(p.rowBegin + uint64_t(rb) * p.rowsPerItem + rank * kXTile);
+                const int32_t rowB = int32_t(ct * kN + (PAIR ? rank * (kN / 2) : 0));
                 for (uint32_t kc = 0; kc < p.kChunks; kc++) {
                     mbarWait(empty + stage, phase ^ 1);
-                    mbarExpectTx(full + stage, kStageBytes);
                     uint8_t* dst = ring + size_t(stage) * kStageBytes;
                     const int32_t k0 = int32_t(kc * kXChunk);
+                    if (PAIR) {
+                        if (rank == 0) mbarExpectTx(full + stage, 2 * kStageBytes);     // both CTAs' bytes
+                        tmaLoad2dPair(dst, &mapLo, full + stage, k0, rowA);
+                        tmaLoad2dPair(dst + kXPlaneBytes, &mapLo, full + stage, k0, rowB);   // 128-row box: this CTA's half of B
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
+                    mbarExpectTx(full + stage, kStageBytes);
                     if (DIGITS == 1) {
                         tmaLoad2d(dst, &mapLo, full + stage, k0, rowA);
-                        tmaLoad2d(dst + kXPlaneBytes, &mapLo, full + stage, k0, rowB);
+                        tmaLoad2d(dst + kXPlaneBytes, &mapHi, full + stage, k0, rowB);      // mapHi: same plane, 256-row box
                     } else {
                         tmaLoad2d(dst, &mapHi, full + stage, k0, rowA);
                         tmaLoad2d(dst + kXPlaneBytes, &mapLo, full + stage, k0, rowA);
@@ -204,16 +242,16 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             uint32_t stage = 0, phase = 0, tileIter = 0;
-            for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+            for (uint32_t item = worker; item < p.items; item += workers) {
                 uint32_t rb, ct;
                 if (!itemToTile(p, item, rb, ct)) continue;
                 const uint32_t buf = tileIter % kAccBufs;
                 const uint32_t use = tileIter / kAccBufs;
                 mbarWait(accEmpty + buf, (use & 1) ^ 1);
                 fenceAfter();
-                const uint32_t tmemD = tmemBase + buf * kXTile;
+                const uint32_t tmemD = tmemBase + buf * kN;
                 uint32_t accumulate = 0;
                 for (uint32_t kc = 0; kc < p.kChunks; kc++) {
                     mbarWait(full + stage, phase);
@@ -221,7 +259,10 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
                     const uint32_t base = smemAddr(ring + size_t(stage) * kStageBytes);
 #pragma unroll
                     for (int ks = 0; ks < kXChunk / 32; ks++) {
-                        if (DIGITS == 1) {
+                        if (PAIR) {
+                            mmaI8SsPair(tmemD, makeSmemDesc(base + ks * 32), makeSmemDesc(base + kXPlaneBytes + ks * 32), p.idesc,
+                                        accumulate);
+                        } else if (DIGITS == 1) {
                             mmaI8Ss(tmemD, makeSmemDesc(base + ks * 32), makeSmemDesc(base + kXPlaneBytes + ks * 32), p.idesc,
                                     accumulate);
                         } else {
@@ -235,13 +276,15 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
                         }
                         accumulate = 1;
                     }
-                    commit(empty + stage);
+                    if (PAIR) commitPair(empty + stage);
+                    else commit(empty + stage);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                commit(accFull + buf);
+                if (PAIR) commitPair(accFull + buf);
+                else commit(accFull + buf);
                 tileIter++;
             }
         }
@@ -250,9 +293,10 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
         const uint32_t laneField = uint32_t(warp * 32) << 16;
         const double n = double(p.geneCount);
         uint32_t tileIter = 0;
-        for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
-            uint32_t rb, ct;
-            if (!itemToTile(p, item, rb, ct)) continue;
+        for (uint32_t item = worker; item < p.items; item += workers) {
+            uint32_t rbItem, ct;
+            if (!itemToTile(p, item, rbItem, ct)) continue;
+            const uint32_t rb = rbItem * (p.rowsPerItem / kXTile) + rank;       // this CTA's 128-row block
             const uint64_t localRow = uint64_t(rb) * kXTile + threadIdx.x;
             const bool valid = localRow < p.rows;
             const uint64_t a = p.rowBegin + (valid ? localRow : 0);
@@ -262,10 +306,15 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
             const uint32_t use = tileIter / kAccBufs;
             mbarWait(accFull + buf, use & 1);
             fenceAfter();
-            const uint32_t taddr = tmemBase + buf * kXTile + laneField;
-            float* outRow = p.out + localRow * p.ldOut + uint64_t(ct) * kXTile;
+            const uint32_t taddr = tmemBase + buf * kN + laneField;
+            float* outRow = p.out + localRow * p.ldOut + uint64_t(ct) * kN;
 #pragma unroll 1
-            for (int q = 0; q < kXTile / 32; q++) {
+            for (int q = 0; q < kN / 32; q++) {
+                // symmetric mode works per 128-column block: above the diagonal block -> store and mirror; the diagonal
+                // block itself -> store; below -> nothing (the mirror of another tile covers it)
+                const uint32_t colBlock = ct * (kN / kXTile) + uint32_t(q) / (kXTile / 32);
+                if (p.symmetric && colBlock < rb) continue;
+                const bool mirror = p.symmetric && colBlock > rb;
                 uint32_t ll[32], xx[32], hh[32];
                 if (DIGITS == 1) {
                     tmemLoad32(taddr + q * 32, ll);
@@ -275,7 +324,7 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
                     tmemLoad32(taddr + 2 * kXTile + q * 32, ll);
                 }
                 tmemLoadWait();
-                const uint64_t bBase = uint64_t(ct) * kXTile + q * 32;
+                const uint64_t bBase = uint64_t(ct) * kN + q * 32;
 #pragma unroll
                 for (int j4 = 0; j4 < 32; j4 += 4) {
                     float r4[4];
@@ -304,7 +353,7 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
                             *reinterpret_cast<float4*>(outRow + q * 32 + j4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
                         // r(a,b) == r(b,a): a tile above the diagonal also fills its mirror image.  For a fixed b the
                         // 32 lanes of a warp write 32 consecutive floats of row b.
-                        if (p.symmetric && ct > rb) {
+                        if (mirror) {
 #pragma unroll
                             for (int jj = 0; jj < 4; jj++) {
                                 const uint64_t b = bBase + j4 + jj;
@@ -315,13 +364,23 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
                 }
             }
             fenceBefore();
-            mbarArrive(accEmpty + buf);
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbarArriveLeader(accEmpty + buf);
+            } else {
+                mbarArrive(accEmpty + buf);
+            }
             tileIter++;
         }
     }
     fenceBefore();
-    __syncthreads();
-    if (warp == 4) tmemDealloc(tmemBase, 512);
+    if (PAIR) {
+        clusterSync();
+        if (warp == 4) tmemDeallocPair(tmemBase, 512);
+    } else {
+        __syncthreads();
+        if (warp == 4) tmemDealloc(tmemBase, 512);
+    }
 }
 
 // ---- selection -------------------------------------------------------------------------------------
@@ -447,7 +506,7 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
     EM2_CUDA(ctx, cudaGetLastError());
 
     // ---- row chunks: GEMM + epilogue into the similarity matrix, then selection --------------------------
-    const uint64_t ldOut = roundUp(cellCount, kXTile);
+    const uint64_t ldOut = roundUp(cellCount, 256);
     // If the whole N x N similarity matrix fits the budget, only the tiles on or above the diagonal are computed
     // (half the MMAs) and mirrored; otherwise rows go in chunks and every chunk computes all of its tiles.
     const uint64_t budget = ctx->exactMatrixBytes ? ctx->exactMatrixBytes : (48ull << 30);
@@ -459,9 +518,11 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
 
     CUtensorMap mapLo, mapHi;
     EM2_TRY(makeTensorMapU8(ctx, &mapLo, lo, cellCount, gPad, gPad, kXTile));
-    EM2_TRY(makeTensorMapU8(ctx, &mapHi, digits == 2 ? hi : lo, cellCount, gPad, gPad, kXTile));
-    const int stages = digits == 1 ? 6 : 3;
-    const size_t smemGemm = 1024 + size_t(stages) * 2 * digits * kXPlaneBytes + 256;
+    // one digit: the second map is the same plane with a 256-row box (the B operand of the N = 256 tiles)
+    EM2_TRY(makeTensorMapU8(ctx, &mapHi, digits == 2 ? hi : lo, cellCount, gPad, gPad, digits == 2 ? kXTile : 256));
+    const uint32_t colsPerTile = digits == 1 ? 256 : kXTile;
+    const int stages = digits == 1 ? 4 : 3;
+    const size_t smemGemm = 1024 + size_t(stages) * digits * (kXPlaneBytes + size_t(colsPerTile) * kXChunk) + 256;
     const uint32_t cap = uint32_t(2 * k + 64);
     const size_t smemSel = size_t(kSelWarps) * 2 * cap * sizeof(uint64_t);
     EM2_CUDA(ctx, cudaFuncSetAttribute(exactSelectKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemSel)));
@@ -474,13 +535,38 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
         p.rows = rows;
         p.geneCount = geneCount;
         p.kChunks = uint32_t(gPad / kXChunk);
-        p.rowBlocks = uint32_t((rows + kXTile - 1) / kXTile);
-        p.colTiles = uint32_t(ldOut / kXTile);
+        const bool pair = digits == 1 && ctx->exactCtaPair != 0;
+        p.rowsPerItem = pair ? 2 * kXTile : kXTile;
+        p.rowBlocks = uint32_t((rows + p.rowsPerItem - 1) / p.rowsPerItem);
+        p.colsPerTile = colsPerTile;
+        p.colTiles = uint32_t(ldOut / colsPerTile);
         const uint32_t superRows = (p.rowBlocks + kXSuper - 1) / kXSuper;
         p.superCols = (p.colTiles + kXSuper - 1) / kXSuper;
-        p.items = superRows * p.superCols * kXSuper * kXSuper;
         p.symmetric = symmetric ? 1 : 0;
-        p.idesc = instrDescI8(false, false, kXTile, kXTile);
+        {
+            // needed tiles in super-tile order (see itemToTile)
+            std::vector<uint2> list;
+            list.reserve(size_t(p.rowBlocks) * p.colTiles / (symmetric ? 2 : 1) + 1024);
+            const uint32_t colBlocksPerTile = colsPerTile / kXTile, rowBlocksPerItem = p.rowsPerItem / kXTile;
+            for (uint32_t sr = 0; sr < superRows; sr++)
+                for (uint32_t sc = 0; sc < p.superCols; sc++)
+                    for (uint32_t r = sr * kXSuper; r < std::min<uint32_t>((sr + 1) * kXSuper, p.rowBlocks); r++)
+                        for (uint32_t c = sc * kXSuper; c < std::min<uint32_t>((sc + 1) * kXSuper, p.colTiles); c++) {
+                            // symmetric: needed iff the tile's LAST 128-column block is on or above the FIRST 128-row block
+                            if (symmetric && (c + 1) * colBlocksPerTile - 1 < r * rowBlocksPerItem) continue;
+                            list.push_back(make_uint2(r, c));
+                        }
+            p.items = uint32_t(list.size());
+            void* dList = nullptr;
+            EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, list.size() * sizeof(uint2) + 16, &dList));
+            void* pin = nullptr;
+            if (begin > 0) EM2_CUDA(ctx, cudaStreamSynchronize(s));      // the previous chunk's list copy used the same staging
+            EM2_TRY(reservePinned(ctx, 0, list.size() * sizeof(uint2) + 16, &pin));
+            std::memcpy(pin, list.data(), list.size() * sizeof(uint2));
+            EM2_CUDA(ctx, cudaMemcpyAsync(dList, pin, list.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+            p.tiles = static_cast<const uint2*>(dList);
+        }
+        p.idesc = instrDescI8(false, false, p.rowsPerItem, colsPerTile);
         p.ldOut = ldOut;
         p.threshold = similarityThreshold;
         p.sum1 = sum1;
@@ -488,13 +574,35 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
         p.rinv = rinv;
         p.thresholdLow = float(similarityThreshold) - 1e-4f;
         p.out = static_cast<float*>(simMatrix);
-        const unsigned grid = unsigned(std::min<uint32_t>(p.items, uint32_t(ctx->smCount)));
-        if (digits == 1) {
-            EM2_CUDA(ctx, cudaFuncSetAttribute(exactGemmKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemGemm)));
-            exactGemmKernel<1><<<grid, kXThreads, smemGemm, s>>>(mapLo, mapHi, p);
+        if (pair) {
+            const size_t smemPair = 1024 + 6 * (kXPlaneBytes + size_t(colsPerTile / 2) * kXChunk) + 256;
+            EM2_CUDA(ctx, cudaFuncSetAttribute(exactGemmKernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemPair)));
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(kXThreads);
+            cfg.dynamicSmemBytes = smemPair;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cfg.gridDim = dim3(2 * unsigned(ctx->smCount / 2));
+            int clusters = 0;
+            EM2_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, exactGemmKernel<1, true>, &cfg));
+            if (clusters < 1) return fail(ctx, EM2_ERR_CUDA, "no CTA pair of the exact kernel fits on this device");
+            cfg.gridDim = dim3(2 * std::min<unsigned>(unsigned(clusters), unsigned(ctx->smCount / 2)));
+            EM2_CUDA(ctx, cudaLaunchKernelEx(&cfg, exactGemmKernel<1, true>, mapLo, mapHi, p));
         } else {
-            EM2_CUDA(ctx, cudaFuncSetAttribute(exactGemmKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemGemm)));
-            exactGemmKernel<2><<<grid, kXThreads, smemGemm, s>>>(mapLo, mapHi, p);
+            const unsigned grid = unsigned(std::min<uint32_t>(p.items, uint32_t(ctx->smCount)));
+            if (digits == 1) {
+                EM2_CUDA(ctx, cudaFuncSetAttribute(exactGemmKernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemGemm)));
+                exactGemmKernel<1, false><<<grid, kXThreads, smemGemm, s>>>(mapLo, mapHi, p);
+            } else {
+                EM2_CUDA(ctx, cudaFuncSetAttribute(exactGemmKernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemGemm)));
+                exactGemmKernel<2, false><<<grid, kXThreads, smemGemm, s>>>(mapLo, mapHi, p);
+            }
         }
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());

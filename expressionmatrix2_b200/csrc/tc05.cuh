@@ -184,6 +184,18 @@ __device__ __forceinline__ void mmaI8TsPair(uint32_t tmemD, uint32_t tmemA, uint
         "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate), "r"(z)
         : "memory");
 }
+__device__ __forceinline__ void mmaI8SsPair(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmemD),
+        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
 __device__ __forceinline__ void tmemAllocPair(uint32_t* slot, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(slot)), "r"(cols) : "memory");
