@@ -26,4 +26,4 @@ for r in range(4):
     eng.scan_topk_device(d_sig, N, L, 0, N, k, mm, lut, pairs, used, variant=variant, stream=s)
     b.record(); torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
-print(json.dumps(dict(real=True, N=N, variant=variant, epi=os.environ.get("EM2_MMA_EPI"), ms=min(ts[1:]))))
+print(json.dumps(dict(real=True, N=N, variant=variant, ms=min(ts[1:]))))

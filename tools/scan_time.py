@@ -26,5 +26,5 @@ for r in range(4):
     b.record(); torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 t = min(ts[1:])
-print(json.dumps(dict(N=N, L=L, variant=variant, csa=os.environ.get("EM2_POPC_CSA"), ms=t, ordered_pairs_per_s=N * N / (t * 1e-3),
+print(json.dumps(dict(N=N, L=L, variant=variant, ms=t, ordered_pairs_per_s=N * N / (t * 1e-3),
                       used_mean=float(used.float().mean()))))
