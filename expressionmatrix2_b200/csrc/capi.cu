@@ -257,6 +257,7 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     if (n == "signature_mode" && value >= 0 && value <= 2) ctx->signatureMode = int(value);
     else if (n == "popc_csa" && value >= 0 && value <= 2) ctx->popcCsa = int(value);
     else if (n == "filter_counts_signed" && value >= 0 && value <= 1) ctx->filterCountsSigned = int(value);
+    else if (n == "exact_general" && value >= 0 && value <= 1) ctx->exactGeneral = int(value);
     else if (n == "exact_cta_pair" && value >= 0 && value <= 1) ctx->exactCtaPair = int(value);
     else if (n == "filter_parts" && value >= 0 && value <= 64) ctx->filterParts = int(value);
     else if (n == "cand_cap_extra" && value >= 0 && value <= 14) ctx->candCapExtra = int(value);

@@ -13,7 +13,8 @@
 // two for counts <= 65535), tcgen05.mma kind::i8 (u8 x u8 -> s32) accumulates the digit Gram matrices
 // LL, HL+LH and HH in TMEM, and the epilogue recombines them as 65536 HH + 256 (HL+LH) + LL in double --
 // the same value the reference's merge loop produces while every product x_a*x_b is below 2^24 (counts <=
-// 4095; above that the reference rounds each product to float and agreement is to ~1e-7 relative).  The
+// 4095; above that the reference rounds each product to float and agreement is to ~1e-7 relative; counts that
+// are not integers in [0, 65535] take exactGeneralKernel below).  The
 // epilogue then evaluates r with the reference's operation sequence (separate multiplies, subtract, sqrt,
 // divide, round-to-nearest doubles) and stores float(r) -- or a "rejected" marker when !(r > threshold) --
 // into a rows x N float matrix in HBM (the whole matrix when it fits: then only tiles on or above the diagonal are
@@ -55,7 +56,8 @@ __global__ void exactScanKernel(uint64_t cellCount, uint64_t geneCount, const ui
     for (uint64_t e = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; e < nnz; e += uint64_t(gridDim.x) * blockDim.x) {
         const em2_count p = counts[e];
         const float c = p.count;
-        if (!(c >= 0.f) || c > 65535.f || c != truncf(c) || p.gene >= geneCount) bad = 1;
+        if (p.gene >= geneCount) bad |= 2;                                         // malformed input
+        else if (!(c >= 0.f) || c > 65535.f || c != truncf(c)) bad |= 1;           // not a small integer: general path
         else mx = max(mx, uint32_t(c));
     }
     double s2 = 0.;
@@ -72,7 +74,7 @@ __global__ void exactScanKernel(uint64_t cellCount, uint64_t geneCount, const ui
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMax(out + 0, (unsigned long long)mx);
-        if (bad) atomicOr(out + 1, 1ull);
+        if (bad) atomicOr(out + 1, (unsigned long long)bad);
         atomicMax(out + 2, (unsigned long long)__double_as_longlong(s2));   // non-negative doubles order like integers
         atomicMax(out + 3, (unsigned long long)nz);
     }
@@ -89,25 +91,27 @@ exactDensifyKernel(uint64_t cellCount, uint64_t geneCount, uint64_t gPad, const 
     const uint64_t cell = blockIdx.x * uint64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (cell >= cellCount) return;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint64_t o = uint64_t(lane) * 16; o < gPad; o += 512) {
-        *reinterpret_cast<uint4*>(lo + cell * gPad + o) = z;
-        if (hi) *reinterpret_cast<uint4*>(hi + cell * gPad + o) = z;
-    }
-    __syncwarp();
-    const uint64_t end = toc[cell + 1];
-    for (uint64_t e = toc[cell] + lane; e < end; e += 32) {
-        const em2_count p = counts[e];
-        const uint32_t c = uint32_t(p.count);
-        lo[cell * gPad + p.gene] = uint8_t(c & 255u);
-        if (hi) hi[cell * gPad + p.gene] = uint8_t(c >> 8);
+    if (lo) {        // lo == nullptr: only the variance term is wanted (general path)
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (uint64_t o = uint64_t(lane) * 16; o < gPad; o += 512) {
+            *reinterpret_cast<uint4*>(lo + cell * gPad + o) = z;
+            if (hi) *reinterpret_cast<uint4*>(hi + cell * gPad + o) = z;
+        }
+        __syncwarp();
+        const uint64_t end = toc[cell + 1];
+        for (uint64_t e = toc[cell] + lane; e < end; e += 32) {
+            const em2_count p = counts[e];
+            const uint32_t c = uint32_t(p.count);
+            lo[cell * gPad + p.gene] = uint8_t(c & 255u);
+            if (hi) hi[cell * gPad + p.gene] = uint8_t(c >> 8);
+        }
     }
     if (lane == 0) {
         const double n = double(geneCount), s1 = sum1[cell];
         const double v = __dsub_rn(__dmul_rn(n, sum2[cell]), __dmul_rn(s1, s1));
         var[cell] = v;
         // float reciprocal root for the epilogue's cheap pre-filter; NaN for degenerate cells (never rejects)
-        rinv[cell] = v > 0. ? rsqrtf(float(v)) : __int_as_float(0x7fc00000);
+        if (rinv) rinv[cell] = v > 0. ? rsqrtf(float(v)) : __int_as_float(0x7fc00000);
     }
 }
 
@@ -383,6 +387,65 @@ exactGemmKernel(const __grid_constant__ CUtensorMap mapLo, const __grid_constant
     }
 }
 
+// ---- general counts (non-integer, negative, or too large for the digit planes) ------------------------------
+// The reference's arithmetic directly: scalar product = sum over shared genes of float(x_a * x_b) accumulated in
+// double (src/ExpressionMatrixSubset.cpp:95-112), here with the partial sums of 32 lanes combined in double, so the
+// result can differ from the sequential sum in the last bits of the double (never more than ~1e-15 relative;
+// tests allow 1e-6 on the stored float).  A CTA keeps TWO query rows as dense float vectors in shared memory;
+// each of its 8 warps walks other cells' stored counts 32 at a time.  Every CTA streams the whole CSR through L2, so
+// the kernel is L2-bandwidth bound: 7.2 s at 50k cells x 20k genes (the tensor-core path: 35 ms; the reference: 8437 s)
+// -- the fallback for normalised data, not the fast path.
+constexpr int kGenWarps = 8;
+
+__global__ void __launch_bounds__(kGenWarps * 32)
+exactGeneralKernel(uint64_t cellCount, uint64_t geneCount, uint64_t gPad, uint64_t rowBegin, uint64_t rows,
+                   const uint64_t* __restrict__ toc, const em2_count* __restrict__ counts, const double* __restrict__ sum1,
+                   const double* __restrict__ var, double threshold, uint64_t ldOut, float* __restrict__ out)
+{
+    extern __shared__ __align__(16) float dense[];      // [2][gPad]
+    const uint64_t local0 = uint64_t(blockIdx.x) * 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t i = threadIdx.x; i < 2 * gPad; i += blockDim.x) dense[i] = 0.f;
+    __syncthreads();
+    for (int r = 0; r < 2; r++) {
+        const uint64_t lr = local0 + r;
+        if (lr >= rows) continue;
+        const uint64_t a = rowBegin + lr;
+        for (uint64_t e = toc[a] + threadIdx.x; e < toc[a + 1]; e += blockDim.x) dense[r * gPad + counts[e].gene] = counts[e].count;
+    }
+    __syncthreads();
+    const double n = double(geneCount);
+    const uint64_t a0 = rowBegin + local0, a1 = a0 + 1;
+    const bool has1 = local0 + 1 < rows;
+    const double s1a0 = sum1[a0], va0 = var[a0];
+    const double s1a1 = has1 ? sum1[a1] : 0., va1 = has1 ? var[a1] : 0.;
+    for (uint64_t b = warp; b < cellCount; b += kGenWarps) {
+        double acc0 = 0., acc1 = 0.;
+        const uint64_t end = toc[b + 1];
+        for (uint64_t e = toc[b] + lane; e < end; e += 32) {
+            const em2_count p = counts[e];
+            acc0 += double(__fmul_rn(dense[p.gene], p.count));               // float product, double sum
+            acc1 += double(__fmul_rn(dense[gPad + p.gene], p.count));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        }
+        if (lane < 2 && (lane == 0 || has1)) {
+            const double sp = lane == 0 ? acc0 : acc1, s1a = lane == 0 ? s1a0 : s1a1, va = lane == 0 ? va0 : va1;
+            const uint64_t a = lane == 0 ? a0 : a1;
+            float res = kRejected;
+            if (b != a) {
+                const double num = __dsub_rn(__dmul_rn(n, sp), __dmul_rn(s1a, sum1[b]));
+                const double r = __ddiv_rn(num, __dsqrt_rn(__dmul_rn(va, var[b])));
+                if (r > threshold) res = float(r);
+            }
+            out[(local0 + lane) * ldOut + b] = res;
+        }
+    }
+}
+
 // ---- selection -------------------------------------------------------------------------------------
 // key = (~orderable(similarity) << 32) | cellId : ascending key == (similarity desc, id asc)
 __device__ __forceinline__ uint32_t orderable(float f)
@@ -482,16 +545,50 @@ int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const 
     unsigned long long h[4];
     EM2_CUDA(ctx, cudaMemcpyAsync(h, misc, sizeof(h), cudaMemcpyDeviceToHost, s));
     EM2_CUDA(ctx, cudaStreamSynchronize(s));
-    if (h[1])
-        return fail(ctx, EM2_ERR_INVALID,
-                    "em2_exact_similar_pairs: the tensor-core exact path needs integer-valued counts in [0, 65535] "
-                    "(raw UMI counts) and gene ids below geneCount");
+    if (h[1] & 2) return fail(ctx, EM2_ERR_INVALID, "em2_exact_similar_pairs: a stored gene id is not below geneCount");
     const int digits = h[0] <= 255 ? 1 : 2;
     double maxSum2;
     std::memcpy(&maxSum2, &h[2], 8);
     const double llBound = digits == 1 ? maxSum2 : std::min(maxSum2, 65025. * double(h[3]));
-    if (llBound >= 2147483648. || maxSum2 / 128. >= 2147483648.)
-        return fail(ctx, EM2_ERR_INVALID, "em2_exact_similar_pairs: a cell's sum of squared counts overflows the s32 accumulators");
+    // Counts that are not integers in [0, 65535], or sums that would overflow the s32 accumulators, take the general
+    // FP64 kernel (exactGeneralKernel); "exact_general" = 1 forces it (tests).
+    const bool general = (h[1] & 1) || llBound >= 2147483648. || maxSum2 / 128. >= 2147483648. || ctx->exactGeneral != 0;
+    if (general) {
+        const uint64_t ldG = roundUp(cellCount, 256);
+        if (2 * gPad * sizeof(float) > 200 * 1024)
+            return fail(ctx, EM2_ERR_INVALID, "em2_exact_similar_pairs: non-integer counts with more than 25,600 genes are not supported");
+        void* varG = nullptr;
+        EM2_TRY(reserve(ctx, em2_context::S_FLAGS, cellCount * sizeof(double), &varG));
+        // per-cell variance term (the densify kernel's by-product in the tensor-core path)
+        exactDensifyKernel<<<unsigned((cellCount + 7) / 8), 256, 0, s>>>(cellCount, geneCount, 0, toc, counts, sum1, sum2, nullptr,
+                                                                        nullptr, static_cast<double*>(varG), nullptr);
+        ctx->stats.kernel_launches++;
+        EM2_CUDA(ctx, cudaGetLastError());
+        const uint64_t budgetG = ctx->exactMatrixBytes ? ctx->exactMatrixBytes : (48ull << 30);
+        uint64_t chunkG = std::max<uint64_t>(2, budgetG / (ldG * sizeof(float)) / 2 * 2);
+        chunkG = std::min<uint64_t>(chunkG, roundUp(cellCount, 2));
+        void* simG = nullptr;
+        EM2_TRY(reserve(ctx, em2_context::S_CAND, chunkG * ldG * sizeof(float), &simG));
+        const size_t smemG = 2 * gPad * sizeof(float);
+        EM2_CUDA(ctx, cudaFuncSetAttribute(exactGeneralKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemG)));
+        const uint32_t capG = uint32_t(2 * k + 64);
+        const size_t smemSelG = size_t(kSelWarps) * 2 * capG * sizeof(uint64_t);
+        EM2_CUDA(ctx, cudaFuncSetAttribute(exactSelectKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemSelG)));
+        for (uint64_t begin = 0; begin < cellCount; begin += chunkG) {
+            const uint64_t rows = std::min(chunkG, cellCount - begin);
+            exactGeneralKernel<<<unsigned((rows + 1) / 2), kGenWarps * 32, smemG, s>>>(
+                cellCount, geneCount, gPad, begin, rows, toc, counts, sum1, static_cast<const double*>(varG), similarityThreshold,
+                ldG, static_cast<float*>(simG));
+            ctx->stats.kernel_launches++;
+            EM2_CUDA(ctx, cudaGetLastError());
+            exactSelectKernel<<<unsigned((rows + kSelWarps - 1) / kSelWarps), kSelWarps * 32, smemSelG, s>>>(
+                rows, cellCount, ldG, static_cast<const float*>(simG), uint32_t(k), capG, pairs + begin * k, usedCount + begin);
+            ctx->stats.kernel_launches++;
+            EM2_CUDA(ctx, cudaGetLastError());
+        }
+        ctx->stats.variant_used = EM2_VARIANT_POPC;      // "not the tensor-core path"
+        return EM2_OK;
+    }
 
     // ---- dense digit planes ----------------------------------------------------------------------------
     void *lo = nullptr, *hi = nullptr, *var = nullptr;

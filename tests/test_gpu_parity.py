@@ -341,12 +341,31 @@ def test_exact_path_degenerate_cells(engine, oracle):
     _check_exact(engine, oracle, toc, genes, counts, 5, 3, -1.0)
 
 
-def test_exact_path_rejects_non_integer_counts(engine):
-    toc = np.array([0, 2, 4], np.uint64)
-    genes = np.array([0, 1, 0, 1], np.uint32)
-    counts = np.array([1.5, 2, 3, 4], np.float32)
-    with pytest.raises(em2.Em2Error):
-        engine.exact_similar_pairs(toc, counts, 2, 1, 0.0, gene_ids=genes)
+def test_exact_path_general_counts(engine, oracle):
+    """Counts that are not small integers (normalised expression values) take the FP64 kernel: the reference's float
+    product / double sum with the lanes' partial sums combined in double.  On integer data that is still bit-exact
+    (integer sums are exact in any order); on fractional data r agrees to ~1e-15 and the stored floats to 1 ULP."""
+    N, G, k, thr = 600, 400, 25, 0.05
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, 0.06, seed=12, mode="clustered", clusters=5)
+    engine.set_option("exact_general", 1)
+    try:
+        _check_exact(engine, oracle, toc, genes, counts, G, k, thr)            # integer data through the general kernel
+    finally:
+        engine.set_option("exact_general", 0)
+    frac = np.log1p(counts).astype(np.float32) * np.float32(1.7)                # fractional "normalised" counts
+    ids, sims, used = engine.exact_similar_pairs(toc, frac, G, k, thr, gene_ids=genes)
+    assert engine.stats()["variant_used"] == em2.VARIANT_POPC                  # i.e. not the tensor-core path
+    wids, wsims, wused, r = oracle.exact_topk(G, toc, genes, frac, k, thr)
+    assert np.array_equal(used, wused)
+    assert np.allclose(sims, wsims, rtol=0, atol=2e-7)
+    same = ids == wids
+    # ids may only differ where two neighbours' similarities are equal to within the last float bit
+    for c, j in zip(*np.nonzero(~same)):
+        assert abs(float(r[c, ids[c, j]]) - float(r[c, wids[c, j]])) <= 2e-7
+    assert same.mean() > 0.999
+    bad = np.array([0, 2, 4], np.uint64), np.array([0, 1, 0, 9], np.uint32), np.array([1.5, 2, 3, 4], np.float32)
+    with pytest.raises(em2.Em2Error):                                           # gene id 9 >= geneCount 2: malformed input
+        engine.exact_similar_pairs(bad[0], bad[2], 2, 1, 0.0, gene_ids=bad[1])
 
 
 # ---------------------------------------------------------------------------------------------------
