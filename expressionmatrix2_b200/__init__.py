@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libem2b200.so")
 
 VARIANT_AUTO, VARIANT_POPC, VARIANT_MMA_I8 = 0, 1, 2
 SIMPAIR_DTYPE = np.dtype([("cell", "<u4"), ("similarity", "<f4")])  # SimilarPairs::Pair
+EDGE_DTYPE = np.dtype([("vertex0", "<u4"), ("vertex1", "<u4"), ("similarity", "<f4")])  # em2_edge
 
 
 class Em2Error(RuntimeError):
@@ -74,6 +75,7 @@ def lib():
     L.em2_find_similar_pairs.argtypes = [vp, vp, u64, u64, u64, u64, u64, dbl, i32, vp, vp]
     L.em2_lsh_similar_pairs.argtypes = [vp, u64, u64, vp, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_exact_similar_pairs.argtypes = [vp, u64, u64, vp, vp, u64, dbl, vp, vp]
+    L.em2_cell_graph_edges.argtypes = [vp, u64, u64, vp, vp, vp, dbl, u64, vp, u64, vp]
     L.em2_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, u64, vp, vp, vp]
     L.em2_lsh_similar_pairs_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, u64, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_cell_sums_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
@@ -280,6 +282,22 @@ class Engine:
                     "em2_lsh_similar_pairs_subset")
         res = (np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used)
         return res + (sig,) if want_signatures else res
+
+    def cell_graph_edges(self, ids, sims, used, vertex_of, similarity_threshold: float, max_connectivity: int):
+        """Edge list of the reference's CellGraph constructor from a SimilarPairs payload (em2_cell_graph_edges).
+        Returns a structured array (vertex0, vertex1, similarity) in the reference's insertion order."""
+        n, k = ids.shape
+        pairs = np.zeros((n, k), SIMPAIR_DTYPE)
+        pairs["cell"] = ids
+        pairs["similarity"] = sims
+        used = np.ascontiguousarray(used, np.uint32)
+        vertex_of = np.ascontiguousarray(vertex_of, np.uint32)
+        cap = max(1, n * min(k, max_connectivity))
+        out = np.zeros(cap, EDGE_DTYPE)
+        count = C.c_uint64(0)
+        self._check(self._L.em2_cell_graph_edges(self._h, n, k, _ptr(pairs), _ptr(used), _ptr(vertex_of), similarity_threshold,
+                                                 max_connectivity, _ptr(out), cap, C.addressof(count)), "em2_cell_graph_edges")
+        return out[: int(count.value)].copy()
 
     def lsh_similar_pairs_into(self, toc, pairs, lsh_vectors, k: int, similarity_threshold: float, out_pairs, out_used,
                                variant: int = VARIANT_AUTO) -> None:

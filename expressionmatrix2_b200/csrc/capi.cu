@@ -668,6 +668,40 @@ int em2_lsh_similar_pairs_subset(em2_context* ctx, uint64_t globalCellCount, con
     return EM2_OK;
 }
 
+int em2_cell_graph_edges(em2_context* ctx, uint64_t cellCount, uint64_t k, const em2_pair* pairs, const uint32_t* usedCount,
+                         const uint32_t* vertexOf, double similarityThreshold, uint64_t maxConnectivity, em2_edge* edges,
+                         uint64_t capacity, uint64_t* edgeCount)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!edgeCount || (cellCount && (!pairs || !usedCount || !vertexOf)) || (capacity && !edges))
+        return fail(ctx, EM2_ERR_INVALID, "em2_cell_graph_edges: null pointer");
+    if (k == 0) return fail(ctx, EM2_ERR_INVALID, "em2_cell_graph_edges: k must be positive");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    *edgeCount = 0;
+    if (cellCount == 0) return EM2_OK;
+    cudaStream_t s = ctx->stream;
+    void *dPairs, *dUsed, *dVertex, *dEdges;
+    EM2_TRY(reserve(ctx, em2_context::S_PAIRS, cellCount * k * sizeof(em2_pair), &dPairs));
+    EM2_TRY(reserve(ctx, em2_context::S_USED, cellCount * sizeof(uint32_t), &dUsed));
+    EM2_TRY(reserve(ctx, em2_context::S_GENEMAP, cellCount * sizeof(uint32_t), &dVertex));
+    EM2_TRY(reserve(ctx, em2_context::S_SRCCOUNTS, std::max<uint64_t>(capacity, 1) * sizeof(em2_edge), &dEdges));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dPairs, pairs, cellCount * k * sizeof(em2_pair), cudaMemcpyHostToDevice, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dUsed, usedCount, cellCount * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dVertex, vertexOf, cellCount * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += cellCount * (k * 8 + 8);
+    EM2_TRY(launchCellGraphEdges(ctx, cellCount, k, static_cast<em2_pair*>(dPairs), static_cast<uint32_t*>(dUsed),
+                                 static_cast<uint32_t*>(dVertex), similarityThreshold, maxConnectivity,
+                                 static_cast<em2_edge*>(dEdges), capacity, edgeCount, s));
+    if (*edgeCount) {
+        EM2_CUDA(ctx, cudaMemcpyAsync(edges, dEdges, *edgeCount * sizeof(em2_edge), cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += *edgeCount * sizeof(em2_edge);
+    }
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
 int em2_exact_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                             const em2_count* counts, uint64_t k, double similarityThreshold, em2_pair* pairs,
                             uint32_t* usedCount)

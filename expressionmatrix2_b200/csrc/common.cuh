@@ -148,6 +148,10 @@ int launchColumnStats(em2_context* ctx, uint64_t geneCount, const double* U, uin
 // Device-side ExpressionMatrixSubset construction (subset.cu); all pointers are device pointers.
 int launchSubset(em2_context* ctx, uint64_t cellCount, const uint64_t* srcToc, const em2_count* src,
                  const uint32_t* geneLocalId, uint64_t globalGeneCount, uint64_t* dstToc, em2_count* dst, cudaStream_t s);
+// CellGraph edge list (cellgraph.cu); device pointers, *edgeCountHost is written after a stream synchronisation.
+int launchCellGraphEdges(em2_context* ctx, uint64_t cellCount, uint64_t k, const em2_pair* pairs, const uint32_t* usedCount,
+                         const uint32_t* vertexOf, double similarityThreshold, uint64_t maxConnectivity, em2_edge* edges,
+                         uint64_t capacity, uint64_t* edgeCountHost, cudaStream_t s);
 int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                    uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
                    int variant, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);

@@ -72,6 +72,14 @@ typedef struct em2_pair {
     float similarity;
 } em2_pair;
 
+/* One undirected edge of the cell similarity graph (CellGraphEdge, reference src/CellGraph.hpp): vertex indices
+ * (positions in the graph's cell set) and the similarity of the SimilarPairs entry that created it. */
+typedef struct em2_edge {
+    uint32_t vertex0; /* the cell whose row inserted the edge */
+    uint32_t vertex1;
+    float similarity;
+} em2_edge;
+
 /* Per-stage device timings (CUDA events) and counters of the last blocking call on a context.
  * Replaces the reference's chrono brackets (src/Lsh.cpp:160,209-222, src/ExpressionMatrixLsh.cpp:217,270-274). */
 typedef struct em2_stats {
@@ -174,6 +182,18 @@ int em2_lsh_similar_pairs_subset(em2_context* ctx, uint64_t globalCellCount, con
                                  uint64_t geneCount, uint64_t cellCount, const uint32_t* cellSet, const double* lshVectors,
                                  uint64_t lshCount, uint64_t k, double similarityThreshold, int variant, em2_pair* pairs,
                                  uint32_t* usedCount, uint64_t* signaturesOut /* may be NULL */);
+
+/* Edge list of CellGraph::CellGraph (src/CellGraph.cpp:60-107) from a SimilarPairs payload: for every cell that is a
+ * vertex, in cell order, its first `maxConnectivity` stored neighbours that are vertices and whose similarity is not
+ * below the threshold; an edge that both endpoints select is kept once, with the orientation and similarity of its
+ * first insertion; edges come out in the reference's insertion order.
+ *   pairs / usedCount: as written by em2_find_similar_pairs (rows sorted by decreasing similarity)
+ *   vertexOf: uint32[cellCount], vertex index of each SimilarPairs-local cell or UINT32_MAX if it is not in the
+ *             graph's cell set (vertex indices must increase with the cell index, as sorted cell sets give)
+ *   edges: em2_edge[capacity]; *edgeCount receives the number of edges (cellCount*maxConnectivity always suffices). */
+int em2_cell_graph_edges(em2_context* ctx, uint64_t cellCount, uint64_t k, const em2_pair* pairs, const uint32_t* usedCount,
+                         const uint32_t* vertexOf, double similarityThreshold, uint64_t maxConnectivity, em2_edge* edges,
+                         uint64_t capacity, uint64_t* edgeCount);
 
 /* Exact path (findSimilarPairs0, src/ExpressionMatrixFindSimilarPairs.cpp:16-88 with
  * ExpressionMatrixSubset::computeCellSimilarity, src/ExpressionMatrixSubset.cpp:83-133):

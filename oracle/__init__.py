@@ -302,6 +302,43 @@ def ref_subset(toc, gene_ids, counts, gene_count: int, gene_set, cell_set):
     return out_toc, out_g[:m].copy(), out_c[:m].copy(), s1, s2
 
 
+def cell_graph_edges(ids, sims, used, vertex_of, similarity_threshold: float, max_connectivity: int):
+    """The edge loop of CellGraph::CellGraph (reference src/CellGraph.cpp:60-107), restated literally over a
+    SimilarPairs payload: cells in order; per cell walk the row, `break` at the first similarity < threshold (float
+    compare, as the reference's `float similarity < similarityThreshold`), skip neighbours that are not vertices, stop
+    at max_connectivity kept neighbours; add the edge unless it exists.  vertex_of[c] = vertex index or 0xFFFFFFFF.
+    Returns (vertex0 uint32[E], vertex1 uint32[E], similarity float32[E]) in insertion order.
+    (The reference's CellGraph itself needs Boost.Graph and cannot be compiled here: restatement only.)"""
+    ids = np.asarray(ids)
+    sims = np.asarray(sims, np.float32)
+    thr = np.float32(similarity_threshold)
+    seen = set()
+    v0s, v1s, ss = [], [], []
+    for c in range(len(used)):
+        v0 = int(vertex_of[c])
+        if v0 == 0xFFFFFFFF:
+            continue
+        kept = []
+        for i in range(int(used[c])):
+            if sims[c, i] < thr:
+                break
+            v1 = int(vertex_of[int(ids[c, i])])
+            if v1 == 0xFFFFFFFF:
+                continue
+            kept.append((v1, sims[c, i]))
+            if len(kept) == max_connectivity:
+                break
+        for v1, sim in kept:
+            key = (min(v0, v1), max(v0, v1))
+            if key in seen:
+                continue
+            seen.add(key)
+            v0s.append(v0)
+            v1s.append(v1)
+            ss.append(sim)
+    return np.array(v0s, np.uint32), np.array(v1s, np.uint32), np.array(ss, np.float32)
+
+
 def murmur64a(data: bytes, seed: int = 231) -> int:
     buf = C.create_string_buffer(data, len(data))
     return int(olib().em2o_murmur64a(buf, len(data), seed))

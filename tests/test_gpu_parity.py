@@ -537,3 +537,37 @@ def test_lsh_against_exact_similarity_statistics_and_recall(engine, oracle):
     # and they are overwhelmingly inside the exact 3k nearest
     hits = sum(len(np.intersect1d(eid[c, :3 * k], lid[c, :k])) for c in range(N))
     assert hits / (N * k) > 0.5, hits / (N * k)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CellGraph edge construction
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("thr,max_conn,drop", [(0.2, 20, 0.0), (0.5, 5, 0.3), (-1.0, 50, 0.0), (0.9, 3, 0.5)])
+def test_cell_graph_edges_match_the_reference_loop(engine, oracle, thr, max_conn, drop):
+    """Same edge set, same per-edge similarity and orientation, same insertion order as the literal restatement of
+    CellGraph.cpp:60-107 (including cells that are not vertices and duplicate-heavy rows)."""
+    N, L, k = 3000, 256, 30
+    sig = synthetic.gen_signatures(N, L, seed=17, clusters=25)
+    sig[100:140] = sig[100]                                   # identical cells: many equal similarities
+    ids, sims, used = engine.find_similar_pairs(sig, L, k, 0.1)
+    rng = np.random.default_rng(4)
+    is_vertex = rng.random(N) >= drop
+    vertex_of = np.full(N, 0xFFFFFFFF, np.uint32)
+    vertex_of[is_vertex] = np.arange(int(is_vertex.sum()), dtype=np.uint32)
+    w0, w1, ws = oracle.cell_graph_edges(ids, sims, used, vertex_of, thr, max_conn)
+    e = engine.cell_graph_edges(ids, sims, used, vertex_of, thr, max_conn)
+    assert len(e) == len(w0)
+    assert np.array_equal(e["vertex0"], w0) and np.array_equal(e["vertex1"], w1)
+    assert np.array_equal(e["similarity"].view(np.uint32), ws.view(np.uint32))
+
+
+def test_cell_graph_edges_degenerate(engine, oracle):
+    ids = np.zeros((4, 3), np.uint32)
+    sims = np.zeros((4, 3), np.float32)
+    used = np.zeros(4, np.uint32)
+    vertex_of = np.arange(4, dtype=np.uint32)
+    assert len(engine.cell_graph_edges(ids, sims, used, vertex_of, 0.2, 10)) == 0          # no stored pairs
+    ids[0, 0], sims[0, 0], used[0] = 1, 0.5, 1
+    ids[1, 0], sims[1, 0], used[1] = 0, 0.5, 1
+    e = engine.cell_graph_edges(ids, sims, used, vertex_of, 0.2, 10)                       # one edge, listed by both ends
+    assert len(e) == 1 and (e["vertex0"][0], e["vertex1"][0]) == (0, 1)
