@@ -271,7 +271,7 @@ def _setup_dist():
     return world, rank, local_rank, dev
 
 
-def _timed_steps(args, world, dev, local_rank, step, n_marks):
+def _timed_steps(args, world, dev, local_rank, step, n_marks, launch_counter=None):
     """W warm-up steps, then exactly K steps bracketed by barrier + synchronize; CUDA events; max over ranks."""
     import torch
     import torch.distributed as dist
@@ -292,10 +292,12 @@ def _timed_steps(args, world, dev, local_rank, step, n_marks):
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = launch_counter() if launch_counter else 0
     t_begin.record()
     for i in range(args.steps):
         step(ev[i])
     t_end.record()
+    launches = (launch_counter() - launches0) if launch_counter else 0      # kernels of this library enqueued by the K timed steps
     barrier()
     total_ms = t_begin.elapsed_time(t_end)
     if total_ms < 300.0:          # keep the GPU busy with the same step until the sampler has something to report
@@ -309,7 +311,7 @@ def _timed_steps(args, world, dev, local_rank, step, n_marks):
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item()) / args.steps, stage, clocks, barrier
+    return float(t.item()) / args.steps, stage, clocks, barrier, launches
 
 
 def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total, scan_ms, local_rank):
@@ -491,9 +493,8 @@ def run_b200(args, w):
         j += 1
         mark(j)
 
-    launches0 = eng.stats()["kernel_launches"]
-    ms_per_step, stage, clocks, barrier = _timed_steps(args, world, dev, local_rank, step, len(stage_names) + 1)
-    launches = (eng.stats()["kernel_launches"] - launches0) * args.steps // (args.steps + args.warmup)
+    ms_per_step, stage, clocks, barrier, launches = _timed_steps(args, world, dev, local_rank, step, len(stage_names) + 1,
+                                                                 launch_counter=lambda: eng.stats()["kernel_launches"])
     stage_ms = dict(zip(stage_names, stage))
     value = pairs_total / (ms_per_step * 1e-3)
 
