@@ -528,6 +528,8 @@ def run_b200(args, w):
         h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
         e2e_stats = {k2: st[k2] for k2 in ("h2d_ms", "sums_ms", "signatures_ms", "scan_ms", "d2h_ms")}
         e2e_stats["note"] = "h2d overlaps sums/signatures (chunked copy stream)"
+        # the host-buffer call and the device-resident steps must have produced the same lists
+        e2e_stats["lists_equal_device_path"] = bool(torch.equal(h_pairs, d_pairs.cpu()) and torch.equal(h_used, d_used.cpu()))
     else:
         api = "device API + pinned host copies per rank"
         if kind == "lsh":

@@ -257,6 +257,7 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     if (n == "signature_mode" && value >= 0 && value <= 2) ctx->signatureMode = int(value);
     else if (n == "popc_csa" && value >= 0 && value <= 2) ctx->popcCsa = int(value);
     else if (n == "filter_counts_signed" && value >= 0 && value <= 1) ctx->filterCountsSigned = int(value);
+    else if (n == "h2d_chunk_bytes" && value >= 0) ctx->h2dChunkBytes = uint64_t(value);
     else if (n == "exact_general" && value >= 0 && value <= 1) ctx->exactGeneral = int(value);
     else if (n == "exact_cta_pair" && value >= 0 && value <= 1) ctx->exactCtaPair = int(value);
     else if (n == "filter_parts" && value >= 0 && value <= 64) ctx->filterParts = int(value);
@@ -350,7 +351,7 @@ static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCoun
     cudaEvent_t* ev = ctx->pool;     // [0] copy begin, [1] hyperplanes landed, [2] copy end, [3 + 4i ..] per chunk
 
     // chunk boundaries: whole cells, roughly equal payload
-    const uint64_t chunkBytes = 256ull << 20;
+    const uint64_t chunkBytes = ctx->h2dChunkBytes ? ctx->h2dChunkBytes : (256ull << 20);
     const int chunks = int(std::max<uint64_t>(1, std::min<uint64_t>(kMaxChunks, nnz * sizeof(em2_count) / chunkBytes)));
     uint64_t bound[kMaxChunks + 1];
     bound[0] = 0;

@@ -63,6 +63,7 @@ struct em2_context {
     int popcCsa = 1;         // carry-save levels of the POPC scan
     uint32_t filterUncertainCap = 0;   // test knob: capacity of the uncertain list (0 = automatic)
     uint64_t exactMatrixBytes = 0;     // test knob: budget of the exact path's similarity matrix (0 = 8 GiB)
+    uint64_t h2dChunkBytes = 0;        // test knob: CSR bytes per PCIe chunk of the blocking API (0 = 256 MiB)
     int exactGeneral = 0;              // 1: force the general FP64 kernel of the exact path (tests)
     int exactCtaPair = 0;              // 1: the one-digit exact GEMM runs on CTA pairs (cta_group::2, M = 256)
     int filterParts = 0;               // test knob: chunks per filter call (0 = automatic)

@@ -113,14 +113,18 @@ void em2_destroy(em2_context* ctx);
 const char* em2_last_error(const em2_context* ctx);
 int em2_device_name(em2_context* ctx, char* buffer, size_t bufferSize);
 int em2_get_stats(const em2_context* ctx, em2_stats* stats);
-/* Tuning / test knobs.  Names: "signature_mode" (0 = automatic, 1 = FP64 kernel only, 2 = force the
- * tensor-core filter + exact fix-up path), "popc_csa" (carry-save levels of the POPC scan, 0..2),
- * "filter_counts_signed" (1: the filter GEMM takes counts as s8 <= 127 instead of u8 <= 255),
- * "filter_uncertain_cap" (capacity of the filter's uncertain list; 0 = automatic), "exact_matrix_bytes"
- * (budget of the exact path's row-chunk similarity matrix; 0 = 8 GiB), "mma_kernel" (tcgen05 scan kernel: 0 = automatic,
- * 1 = A operand resident in tensor memory (L <= 1024), 2 = both operands streamed), "mma_cta_pair" (1: the TMEM-resident
- * kernel runs on CTA pairs, cta_group::2), "cand_cap_extra" (candidate regions hold (2 + n) k + 32 keys),
- * "debug_flags" (bit 0: no bound sharing between the MMA sub-streams). */
+/* Tuning / test knobs (value 0 restores the automatic behaviour everywhere).
+ *   "signature_mode"   1 = FP64 signature kernel only, 2 = force the tensor-core filter + exact fix-up path
+ *   "filter_counts_signed" 1 = the filter GEMM takes counts as s8 <= 127 instead of u8 <= 255
+ *   "filter_uncertain_cap" capacity of the filter's uncertain list;  "filter_parts" chunks of cells per filter call
+ *   "h2d_chunk_bytes"  CSR bytes per PCIe chunk of the blocking calls (default 256 MiB)
+ *   "mma_kernel"       tcgen05 scan kernel: 1 = A operand resident in tensor memory (L <= 1024), 2 = both operands streamed
+ *   "mma_cta_pair"     1 = the TMEM-resident scan kernel runs on CTA pairs (cta_group::2)
+ *   "row_grouping"     MMA scan: 1 = scan rows in cell order, 2 = always group similar rows into the same warps
+ *   "cand_cap_extra"   candidate regions hold (2 + n) k + 32 keys;  "popc_csa" carry-save levels of the POPC scan (0..2)
+ *   "exact_matrix_bytes" budget of the exact path's similarity matrix (default 48 GiB);  "exact_cta_pair" 1 = CTA-pair GEMM
+ *   "exact_general"    1 = force the exact path's general FP64 kernel
+ *   "debug_flags"      bit 0: no bound sharing between the MMA scan's sub-streams */
 int em2_set_option(em2_context* ctx, const char* name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------

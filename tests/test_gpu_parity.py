@@ -571,3 +571,26 @@ def test_cell_graph_edges_degenerate(engine, oracle):
     ids[1, 0], sims[1, 0], used[1] = 0, 0.5, 1
     e = engine.cell_graph_edges(ids, sims, used, vertex_of, 0.2, 10)                       # one edge, listed by both ends
     assert len(e) == 1 and (e["vertex0"][0], e["vertex1"][0]) == (0, 1)
+
+
+def test_blocking_call_with_many_pcie_chunks(engine, oracle):
+    """The host-buffer call copies the CSR in chunks on a second stream while sums/signatures of the previous chunk
+    run (one chunk per 256 MiB by default): force ~20 chunks on a small input, through both signature paths."""
+    N, G, L, k, thr = 5000, 1200, 512, 20, 0.2
+    toc, genes, counts = synthetic.gen_expression_matrix(N, G, 0.05, seed=21, mode="clustered", clusters=9)
+    U = em2.generate_lsh_vectors(G, L, 231)
+    s1, _ = oracle.cell_sums(toc, counts)
+    want_sig, _ = oracle.signatures(toc, genes, counts, s1, U)
+    want = oracle.topk(want_sig, L, k, thr)[:3]
+    engine.set_option("h2d_chunk_bytes", int(toc[-1]) * 8 // 20)
+    try:
+        for mode in (1, 2):
+            engine.set_option("signature_mode", mode)
+            ids, sims, used, sig = engine.lsh_similar_pairs(toc, counts, U, k, thr, gene_ids=genes, want_signatures=True)
+            assert np.array_equal(sig, want_sig)
+            _check_lists((ids, sims, used), want)
+            sig2, a1, a2 = engine.compute_signatures(toc, counts, U, gene_ids=genes, want_sums=True)
+            assert np.array_equal(sig2, want_sig) and np.array_equal(a1, s1)
+    finally:
+        engine.set_option("signature_mode", 0)
+        engine.set_option("h2d_chunk_bytes", 0)
