@@ -587,10 +587,10 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 // miss for the whole warp and the rest hit with most lanes active.  Only the ORDER IN WHICH ROWS ARE SCANNED
 // changes: columns stay in cell-id order (the tie-break of topk.cuh needs that), every row still sees every
 // column, results are identical.  Grouping = nearest of 256 pivot cells by Hamming distance on the first
-// <= 1024 bits, then a radix sort of (pivot, cell id).
+// <= 512 bits, then a radix sort of (pivot, cell id).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPivots = 256;
-constexpr int kPivotWords = 16;
+constexpr int kPivotWords = 8;        // 512 bits are plenty to tell clusters apart; halves the assignment pass
 
 __global__ void __launch_bounds__(256)
 pivotAssignKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCount, uint64_t rowBegin, uint64_t rows,
