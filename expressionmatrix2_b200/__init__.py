@@ -37,11 +37,11 @@ class Stats(C.Structure):
         ("near_zero_projections", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("candidates_appended", C.c_uint64), ("filter_cells", C.c_uint64),
         ("filter_uncertain", C.c_uint64), ("variant_used", C.c_int32),
-        ("reserved", C.c_int32),
+        ("scan_symmetric", C.c_int32),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 _u64p = C.POINTER(C.c_uint64)

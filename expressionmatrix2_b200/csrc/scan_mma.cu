@@ -580,6 +580,471 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Symmetric scan (whole-matrix jobs, K <= 1024): every unordered pair of cells is evaluated ONCE.
+//
+// Cells are taken in scan-position order (the grouped order when row grouping is on; rows AND columns) and cut
+// into super blocks of 256 positions.  The CTA that owns row block a (128 rows of super block A = a / 2) visits
+// the column tiles C = (A + d) mod S for the offsets d = 0 .. S/2: of every unordered pair of distinct super
+// blocks exactly one owner sees the pair's tile (for even S the offset S/2 is seen by both owners and treated as
+// two one-directional tiles, like the diagonal d = 0).  A tile's accumulators then feed BOTH directions:
+//   row direction     the thread's own row, exactly as in the kernels above (private bound, private candidate
+//                     region), except that candidates do not arrive in id order: the order-independent prune of
+//                     topk.cuh is used and every new bound is published to limEx[row position] (atomicMin);
+//   column direction  the same 32 accumulators are compared with the bounds of the tile's COLUMN cells
+//                     (limEx, staged per tile in shared memory as dot-product thresholds, with one loosest
+//                     threshold per 8 columns so that the common case is four extra compares per chunk);
+//                     survivors go to the THREAD's private log (a plain store: no atomics, nothing to wait for in
+//                     the hot loop -- an atomic slot per survivor cost a ~700-cycle round trip each and made the
+//                     sweep 3x slower on clustered data); a scatter kernel then files the logs into per-cell inboxes.
+//                     For the same reason candidate keys carry scan positions, not cell ids; ids are looked up where
+//                     they decide something (ties at a prune, the finalize kernel).
+// limEx starts from a sampling pre-pass (the k-th best of every cell against N/32 sample cells, a valid upper
+// bound of its final k-th best) and tightens as the cell's own row streams progress; a stale bound is only
+// looser.  The finalize kernel merges a cell's row streams and its inbox.  An inbox that overflows raises a
+// flag and the caller reruns the job with the one-directional kernel: exactness never depends on the bounds
+// being tight.
+//
+// Operand traffic: per tile the one-directional kernel re-reads the row block's A chunks from L2 (48 KB per
+// K-chunk and SM, ~19 TB/s at full tensor rate -- sustainable only because all CTAs stream the SAME B tile).
+// Here the B tiles of concurrently running CTAs differ (a sliding window of ~74 super blocks), so A is kept
+// RESIDENT IN SHARED MEMORY for the whole item (K x 128 B <= 128 KB) and only B streams: 32 KB per K-chunk.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSymMaxStages = 6;
+constexpr uint32_t kSymSmallBytes = 192 + 2 * kSsTileN * 2 + 2 * (kSsTileN / 8) * 2 + kEpiThreads * 2;
+
+struct SymParams {
+    uint64_t cellCount;            // N: rows == columns, in scan-position order
+    uint32_t K, panels, stages;
+    uint32_t mainBlocks, segments, items;
+    uint64_t segmentCols;          // in virtual columns: offset * 256
+    uint32_t superBlocks;          // S = ceil(N / 256)
+    uint32_t offsets;              // column tiles per row block: S / 2 + 1
+    uint32_t halfOffset;           // S even: the offset visited by both owners (no column direction); else 0
+    uint32_t dBegin;               // this launch sweeps the offsets [dBegin, dBegin + offsetsHere)
+    uint32_t offsetsHere;
+    uint32_t streamBase;           // first candidate stream of this launch
+    uint32_t k, cap;
+    uint64_t* cand;
+    uint32_t* candCount;
+    unsigned long long* appendedTotal;   // both directions
+    uint32_t* limEx;               // per position: accept iff mismatch count < limEx
+    ulonglong2* colLog;            // column-direction survivors, one append-only log per epilogue thread of the grid:
+    uint32_t* colLogCount;         //   {mismatch << 32 | row cell id, column position}; scattered to the inboxes afterwards
+    uint32_t colLogCap;
+    uint32_t* overflow;
+    const uint32_t* perm;          // position -> cell id (nullptr: identity)
+    uint32_t flags;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SymParams p)
+{
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* smA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smA + size_t(p.panels) * kSsABytes;
+    uint8_t* small = ring + size_t(p.stages) * kSsBBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(small);
+    uint64_t* accFull = bars + 0;    // [2]
+    uint64_t* accEmpty = bars + 2;   // [2]
+    uint64_t* aFull = bars + 4;      // the item's A operand has landed
+    uint64_t* aEmpty = bars + 5;     // every MMA of the item has read it
+    uint64_t* full = bars + 6;       // [stages]
+    uint64_t* empty = full + kSymMaxStages;
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(empty + kSymMaxStages);
+    int16_t* colThr = reinterpret_cast<int16_t*>(small + 192);          // [2][256] dot thresholds of the tile's columns
+    int16_t* grpThr = colThr + 2 * kSsTileN;                             // [2][32]  loosest threshold of each 8 columns
+    uint16_t* tauShare = reinterpret_cast<uint16_t*>(grpThr + 2 * (kSsTileN / 8));   // [kSubStreams][kRowsPerItem]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbarInit(accFull + i, 1);
+            mbarInit(accEmpty + i, kEpiWarps * 32);
+        }
+        mbarInit(aFull, 1);
+        mbarInit(aEmpty, 1);
+        for (int i = 0; i < kSymMaxStages; i++) {
+            mbarInit(full + i, 1);
+            mbarInit(empty + i, 1);
+        }
+        mbarInitFence();
+    }
+    if (warp == kEpiWarps) tmemAlloc(tmemSlot, 512);
+    fenceBefore();
+    __syncthreads();
+    fenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    const uint32_t items = p.items;
+    const uint64_t virtualCols = uint64_t(p.offsetsHere) * kSsTileN;
+
+    if (warp == kEpiWarps) {
+        // ===================== TMA producer: A once per item, B per tile =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, itemIter = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
+                const uint32_t super = it.rowBlock >> 1;
+                const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
+                const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+                mbarWait(aEmpty, (itemIter & 1) ^ 1);
+                mbarExpectTx(aFull, p.panels * kSsABytes);
+                for (uint32_t kc = 0; kc < p.panels; kc++)
+                    tmaLoad2d(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes), int32_t(it.rowBlock * kRowsPerItem));
+                for (uint32_t d = d0; d < d1; d++) {
+                    const int32_t col0 = int32_t(((super + d) % p.superBlocks) * kSsTileN);
+                    for (uint32_t kc = 0; kc < p.panels; kc++) {
+                        mbarWait(empty + stage, phase ^ 1);
+                        mbarExpectTx(full + stage, kSsBBytes);
+                        tmaLoad2d(ring + size_t(stage) * kSsBBytes, &mapB, full + stage, int32_t(kc * kChunkBytes), col0);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t tileIter = 0, stage = 0, phase = 0, itemIter = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
+                const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
+                const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+                mbarWait(aFull, itemIter & 1);
+                fenceAfter();
+                const uint32_t aBase = smemAddr(smA);
+                for (uint32_t d = d0; d < d1; d++, tileIter++) {
+                    const uint32_t buf = tileIter & 1;
+                    mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
+                    fenceAfter();
+                    const uint32_t tmemD = tmemBase + buf * kSsTileN;
+                    uint32_t accumulate = 0;
+                    for (uint32_t kc = 0; kc < p.panels; kc++) {
+                        mbarWait(full + stage, phase);
+                        fenceAfter();
+                        const uint32_t aAddr = aBase + kc * kSsABytes;
+                        const uint32_t bAddr = smemAddr(ring + size_t(stage) * kSsBBytes);
+#pragma unroll
+                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++) {
+                            mmaI8Ss(tmemD, makeSmemDesc(aAddr + ks * kUmmaK), makeSmemDesc(bAddr + ks * kUmmaK), kInstrDescSs, accumulate);
+                            accumulate = 1;
+                        }
+                        commit(empty + stage);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    commit(accFull + buf);
+                }
+                commit(aEmpty);      // fires when the item's last MMAs have read A: the producer may overwrite it
+            }
+        }
+    } else {
+        // ===================== epilogue: thread == (row == TMEM lane, 128-column sub-stream) =====================
+        const uint32_t dotK = p.K;
+        const uint32_t N = uint32_t(p.cellCount);
+        const uint32_t rowInItem = threadIdx.x & (kRowsPerItem - 1);
+        const uint32_t sub = threadIdx.x / kRowsPerItem;
+        constexpr int kSubCols = kSsTileN / kSubStreams;
+        const uint32_t laneField = uint32_t((warp & 3) * 32) << 16;
+        uint32_t tileIter = 0;
+        const uint32_t logSlot = blockIdx.x * kEpiThreads + threadIdx.x;
+        ulonglong2* const log = p.colLog + uint64_t(logSlot) * p.colLogCap;
+        const uint32_t logBegin = p.colLogCount[logSlot];       // an earlier launch of the same job may have written
+        uint32_t logCount = logBegin;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
+            const uint32_t seg = p.streamBase / kSubStreams + it.segment;
+            const uint32_t super = it.rowBlock >> 1;
+            const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
+            const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+            const uint32_t rowPos = it.rowBlock * kRowsPerItem + rowInItem;
+            const bool valid = rowPos < N;
+            const uint32_t rowCell = !valid ? 0xffffffffu : p.perm ? p.perm[rowPos] : rowPos;
+            uint32_t* limPtr = p.limEx + (valid ? rowPos : 0);
+
+            RowState st;
+            st.rowId = rowPos;            // self test is on positions
+            st.count = 0;
+            st.appended = 0;
+            st.tau = valid ? __ldcg(limPtr) : 0;
+            st.lim = st.tau;
+            st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * N + (valid ? rowPos : 0)) * p.cap;
+            tauShare[sub * kRowsPerItem + rowInItem] = 0xffffu;      // harmless for any row (see scanMmaKernel)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.lim);      // mismatch < lim  <=>  dot > K - 2 lim
+
+            for (uint32_t d = d0; d < d1; d++, tileIter++) {
+                const uint32_t buf = tileIter & 1;
+                const uint32_t colSuper = (super + d) % p.superBlocks;
+                const bool colDir = d != 0 && d != p.halfOffset;          // CTA-uniform
+                const int16_t* thr = colThr + buf * kSsTileN + sub * kSubCols;
+                const int16_t* grp = grpThr + buf * (kSsTileN / 8) + sub * (kSubCols / 8);
+                if (colDir) {
+                    // stage the bounds of this sub-stream's 128 columns (the same 128 threads use them)
+                    const uint32_t c = threadIdx.x;                       // == sub * 128 + rowInItem
+                    const uint32_t pos = colSuper * kSsTileN + c;
+                    const uint32_t lim = pos < N ? __ldcg(p.limEx + pos) : 0u;       // padding columns: nothing passes
+                    int32_t t = int32_t(dotK) - 2 * int32_t(lim);
+                    colThr[buf * kSsTileN + c] = int16_t(t);
+                    t = min(t, __shfl_xor_sync(0xffffffffu, t, 1));
+                    t = min(t, __shfl_xor_sync(0xffffffffu, t, 2));
+                    t = min(t, __shfl_xor_sync(0xffffffffu, t, 4));
+                    if ((lane & 7) == 0) grpThr[buf * (kSsTileN / 8) + (c >> 3)] = int16_t(t);
+                    asm volatile("bar.sync %0, %1;" ::"r"(2 + sub), "n"(kRowsPerItem) : "memory");
+                }
+                mbarWait(accFull + buf, (tileIter >> 1) & 1);
+                fenceAfter();
+                const uint32_t posBase = colSuper * kSsTileN + sub * kSubCols;
+                const uint32_t taddr = tmemBase + buf * kSsTileN + sub * kSubCols + laneField;
+                {
+                    const uint32_t other = tauShare[(sub ^ 1) * kRowsPerItem + rowInItem];
+                    if (other < st.lim && !(p.flags & 1)) {
+                        st.lim = other;
+                        dotThr = int32_t(dotK) - 2 * int32_t(st.lim);
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < kSubCols; c += 32) {
+                    uint32_t v[32];
+                    tmemLoad32(taddr + c, v);
+                    tmemLoadWait();
+                    if (c + 32 == kSubCols) {          // last chunk is in registers: hand the accumulator back
+                        fenceBefore();
+                        mbarArrive(accEmpty + buf);
+                    }
+                    int32_t m[4];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        m[g] = int32_t(v[8 * g]);
+#pragma unroll
+                        for (int j = 1; j < 8; j++) m[g] = max(m[g], int32_t(v[8 * g + j]));
+                    }
+                    const int32_t mx = max(max(m[0], m[1]), max(m[2], m[3]));
+                    // ---- row direction
+                    if (mx > dotThr) {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            if (m[g] > dotThr) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const int32_t dv = int32_t(v[8 * g + j]);
+                                    const uint32_t pos = posBase + c + 8 * g + j;
+                                    if (dv > dotThr && pos < N && pos != rowPos) {
+                                        const uint32_t ham = uint32_t(int32_t(dotK) - dv) >> 1;
+                                        st.buf[st.count++] = (uint64_t(ham) << 32) | pos;
+                                        st.appended++;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // ---- column direction
+                    if (colDir && valid) {
+                        const short4 gt = *reinterpret_cast<const short4*>(grp + (c >> 3));
+                        const int32_t gtv[4] = {gt.x, gt.y, gt.z, gt.w};
+                        if (m[0] > gtv[0] || m[1] > gtv[1] || m[2] > gtv[2] || m[3] > gtv[3]) {
+#pragma unroll
+                            for (int g = 0; g < 4; g++) {
+                                if (m[g] > gtv[g]) {
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) {
+                                        const int32_t dv = int32_t(v[8 * g + j]);
+                                        if (dv > int32_t(thr[c + 8 * g + j])) {
+                                            const uint32_t ham = uint32_t(int32_t(dotK) - dv) >> 1;
+                                            if (logCount < p.colLogCap)
+                                                log[logCount] = make_ulonglong2((uint64_t(ham) << 32) | rowCell, posBase + c + 8 * g + j);
+                                            logCount++;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, mx > dotThr)) {
+                        warpPruneIfNeededAnyOrder(st, p.k, p.cap, limPtr, p.perm);
+                        dotThr = int32_t(dotK) - 2 * int32_t(st.lim);
+                    }
+                }
+                if (valid) tauShare[sub * kRowsPerItem + rowInItem] = uint16_t(min(st.tau, 0xffffu));
+            }
+            if (valid) {
+                p.candCount[uint64_t(seg * kSubStreams + sub) * N + rowPos] = st.count;
+                if (p.appendedTotal && st.appended) atomicAdd(p.appendedTotal, (unsigned long long)st.appended);
+            }
+        }
+        if (logCount > p.colLogCap) {
+            *p.overflow = 1u;
+            logCount = p.colLogCap;
+        }
+        p.colLogCount[logSlot] = logCount;
+        if (p.appendedTotal && logCount > logBegin) atomicAdd(p.appendedTotal, (unsigned long long)(logCount - logBegin));
+    }
+    fenceBefore();
+    __syncthreads();
+    if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
+}
+
+// Sample rows of the encoded matrix (every stride-th scan position) as the column operand of the pre-pass, and for
+// every scan position its index in the sample (the pre-pass must not count a cell as its own neighbour).
+__global__ void sampleGatherKernel(const uint8_t* __restrict__ enc, uint32_t K, uint64_t cellCount, uint32_t stride,
+                                   uint32_t sampleCount, uint8_t* __restrict__ out, uint32_t* __restrict__ selfIndex)
+{
+    const uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    const uint32_t perRow = K / 16;
+    if (idx < uint64_t(sampleCount) * perRow) {
+        const uint64_t r = idx / perRow, o = idx % perRow;
+        reinterpret_cast<uint4*>(out + r * K)[o] = reinterpret_cast<const uint4*>(enc + r * stride * uint64_t(K))[o];
+    }
+    if (idx < cellCount) selfIndex[idx] = (idx % stride == 0 && idx / stride < sampleCount) ? uint32_t(idx / stride) : 0xffffffffu;
+}
+
+// Pre-pass result -> limEx: the k-th smallest mismatch count a cell has against the sample, plus one (exclusive
+// bound, ties still accepted); tau0 when the sample holds fewer than k admissible cells.  One warp per cell.
+__global__ void __launch_bounds__(128)
+sampleBoundKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k, const uint64_t* __restrict__ cand,
+                  const uint32_t* __restrict__ candCount, uint32_t tau0, uint32_t* __restrict__ limEx)
+{
+    const uint64_t row = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (row >= cellCount) return;
+    uint32_t n = 0;
+    for (uint32_t s = 0; s < streams; s++) n += candCount[uint64_t(s) * cellCount + row];
+    uint32_t bound = tau0;
+    if (n >= k && tau0 > 0) {
+        uint32_t lo = 0, hi = tau0 - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            uint32_t c = 0;
+            for (uint32_t s = 0; s < streams; s++) {
+                const uint32_t cs = candCount[uint64_t(s) * cellCount + row];
+                const uint64_t* src = cand + (uint64_t(s) * cellCount + row) * cap;
+                for (uint32_t i = lane; i < cs; i += 32) c += (uint32_t(src[i] >> 32) <= mid);
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= k) hi = mid;
+            else lo = mid + 1;
+        }
+        bound = lo + 1;
+    }
+    if (lane == 0) limEx[row] = bound;
+}
+
+// Files the column-direction logs into the per-cell inboxes (one warp per log).
+__global__ void __launch_bounds__(256)
+scatterLogKernel(uint32_t logs, uint32_t logCap, const ulonglong2* __restrict__ log, const uint32_t* __restrict__ logCount,
+                 uint64_t* __restrict__ inbox, uint32_t* __restrict__ inCount, uint32_t inCap, uint32_t* __restrict__ overflow)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= logs) return;
+    const uint32_t n = logCount[w];
+    const ulonglong2* src = log + uint64_t(w) * logCap;
+    for (uint32_t i = threadIdx.x & 31; i < n; i += 32) {
+        const ulonglong2 e = src[i];
+        const uint32_t pos = uint32_t(e.y);
+        const uint32_t slot = atomicAdd(inCount + pos, 1u);
+        if (slot < inCap) inbox[uint64_t(pos) * inCap + slot] = e.x;
+        else *overflow = 1u;
+    }
+}
+
+// Merge of a cell's row streams and inbox (symmetric scan).  Only keys below the cell's final bound can be among
+// its k best; they are compacted into shared memory and ranked like in finalizeKernel (scan_popc.cu).
+constexpr int kSymFinalWarps = 4;
+
+__global__ void __launch_bounds__(kSymFinalWarps * 32)
+finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k, const uint64_t* __restrict__ cand,
+                  const uint32_t* __restrict__ candCount, const uint64_t* __restrict__ inbox, const uint32_t* __restrict__ inCount,
+                  uint32_t inCap, const uint32_t* __restrict__ limEx, const float* __restrict__ lut, em2_pair* __restrict__ pairs,
+                  uint32_t* __restrict__ usedCount, const uint32_t* __restrict__ perm, uint32_t* __restrict__ overflow,
+                  uint32_t keysPerWarp)
+{
+    extern __shared__ __align__(16) uint64_t skeys[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t row = uint64_t(blockIdx.x) * kSymFinalWarps + warp;
+    if (row >= cellCount) return;
+    uint64_t* keys = skeys + size_t(warp) * keysPerWarp;
+    const uint32_t lim = limEx[row];
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t n = 0;
+    bool over = false;
+    auto gather = [&](const uint64_t* src, uint32_t c, bool positions) {
+        for (uint32_t base = 0; base < c; base += 32) {
+            const uint32_t i = base + lane;
+            uint64_t key = i < c ? src[i] : ~0ull;
+            const bool keep = i < c && uint32_t(key >> 32) < lim;
+            if (keep && positions && perm) key = (key & 0xffffffff00000000ull) | perm[uint32_t(key)];   // stream keys carry positions
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (n + __popc(mask) > keysPerWarp) {
+                over = true;
+                return;
+            }
+            if (keep) keys[n + __popc(mask & lt)] = key;
+            n += __popc(mask);
+        }
+    };
+    for (uint32_t s = 0; s < streams && !over; s++)
+        gather(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row], true);
+    if (!over) {
+        const uint32_t c = inCount[row];
+        if (c > inCap) over = true;
+        else gather(inbox + row * uint64_t(inCap), c, false);
+    }
+    if (over) {
+        if (lane == 0) *overflow = 1u;
+        return;
+    }
+    __syncwarp();
+    if (n > 2 * k) {
+        uint32_t lo = 0, hi = lim;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            uint32_t c = 0;
+            for (uint32_t e = lane; e < n; e += 32) c += (uint32_t(keys[e] >> 32) <= mid);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= k) hi = mid;
+            else lo = mid + 1;
+        }
+        uint32_t out = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t e = base + lane;
+            const uint64_t key = e < n ? keys[e] : ~0ull;
+            const bool keep = e < n && uint32_t(key >> 32) <= lo;
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) keys[out + __popc(mask & lt)] = key;
+            out += __popc(mask);
+        }
+        n = out;
+        __syncwarp();
+    }
+    const uint32_t used = n < k ? n : k;
+    const uint64_t outRow = perm ? uint64_t(perm[row]) : row;
+    for (uint32_t e = lane; e < n; e += 32) {
+        const uint64_t key = keys[e];
+        uint32_t rank = 0;
+        for (uint32_t f = 0; f < n; f++) rank += (keys[f] < key);      // keys are unique (ids are)
+        if (rank < k) {
+            em2_pair pr;
+            pr.cell = uint32_t(key);
+            pr.similarity = lut[uint32_t(key >> 32)];
+            pairs[outRow * k + rank] = pr;
+        }
+    }
+    for (uint32_t i = used + lane; i < k; i += 32) {
+        em2_pair z;
+        z.cell = 0;
+        z.similarity = 0.f;
+        pairs[outRow * k + i] = z;
+    }
+    if (lane == 0) usedCount[outRow] = used;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Row grouping.  A warp of the epilogue serves 32 query rows; when those rows are unrelated, almost every
 // 32-column chunk holds a passing column for SOME lane and the selection code runs with two or three lanes
 // active (ncu: ~90 % of the chunks, 10 of 32 threads per instruction on clustered data).  Rows that are
@@ -657,6 +1122,167 @@ __global__ void encodeKernel(const uint64_t* __restrict__ sig, uint32_t W, uint6
     *reinterpret_cast<uint4*>(enc + row * K + size_t(g) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+// Symmetric scan of the whole matrix; encP = encoded signatures in scan-position order (rows and columns),
+// perm = position -> cell id (nullptr: identity).  *overflowed = 1 means a candidate inbox (or the finalize
+// staging) ran out of room and NOTHING was written that the caller may use: rerun one-directionally.
+int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, uint64_t cellCount, uint32_t K, uint64_t k,
+                 uint32_t tau0, const float* lut, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s, int* overflowed)
+{
+    const uint64_t N = cellCount;
+    const uint32_t panels = K / kChunkBytes;
+    // ---- sampling pre-pass: every cell against M ~ N/32 sample cells with the one-directional kernel
+    const uint32_t M = uint32_t(std::min<uint64_t>(N, std::max<uint64_t>(256, roundUp(N / 32, kSsTileN))));
+    const uint32_t stride = uint32_t(N / M);
+    ScanPlan pre = makeScanPlan(ctx, N, M, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
+    const uint32_t superBlocks = uint32_t((N + kSsTileN - 1) / kSsTileN);
+    const uint32_t offsets = superBlocks / 2 + 1;
+    // Two launches: the offsets next to the diagonal first, for ALL row blocks.  In grouped order a cell's nearest
+    // neighbours sit in its own and the adjacent super blocks, so after this short launch every cell's published bound
+    // is already tight on clustered data (the sample bound is the tight one on unstructured data) -- before any CTA of
+    // the long second launch starts feeding the cell's inbox.
+    const uint32_t nearOffsets = std::min<uint32_t>(2, offsets);
+    ScanPlan nearPlan = makeScanPlan(ctx, N, uint64_t(nearOffsets) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
+    ScanPlan plan = nearPlan;
+    uint32_t streams = nearPlan.segments * kSubStreams;
+    if (offsets > nearOffsets) {
+        plan = makeScanPlan(ctx, N, uint64_t(offsets - nearOffsets) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
+        streams += plan.segments * kSubStreams;
+    }
+    const uint32_t maxSegments = std::max(pre.segments, streams / kSubStreams);
+    const uint32_t inCap = uint32_t(40 * k + 256);
+
+    void *cand = nullptr, *candCount = nullptr, *counters = nullptr, *sample = nullptr, *sym = nullptr, *inbox = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_CAND, size_t(maxSegments) * kSubStreams * N * plan.cap * sizeof(uint64_t), &cand));
+    EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(maxSegments) * kSubStreams * N * sizeof(uint32_t), &candCount));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
+    EM2_TRY(reserve(ctx, em2_context::S_SAMPLE, size_t(M) * K, &sample));
+    // [limEx N][inCount N][selfIndex N][overflow 1]
+    EM2_TRY(reserve(ctx, em2_context::S_SYM, (3 * N + 4) * sizeof(uint32_t), &sym));
+    EM2_TRY(reserve(ctx, em2_context::S_INBOX, N * size_t(inCap) * sizeof(uint64_t), &inbox));
+    // column-direction logs: one per epilogue thread of the grid, 8x the share a thread expects (~2k survivors per cell)
+    const uint32_t logs = uint32_t(ctx->smCount) * kEpiThreads;
+    const uint32_t logCap = uint32_t(roundUp(std::max<uint64_t>(2048, 16 * N * k / logs), 256));
+    void *colLog = nullptr, *colLogCount = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_COLLOG, size_t(logs) * logCap * sizeof(ulonglong2) + size_t(logs) * sizeof(uint32_t), &colLog));
+    colLogCount = static_cast<uint8_t*>(colLog) + size_t(logs) * logCap * sizeof(ulonglong2);
+    EM2_CUDA(ctx, cudaMemsetAsync(colLogCount, 0, size_t(logs) * sizeof(uint32_t), s));
+    uint32_t* limEx = static_cast<uint32_t*>(sym);
+    uint32_t* inCount = limEx + N;
+    uint32_t* selfIndex = inCount + N;
+    uint32_t* overflow = selfIndex + N;
+    EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, N * sizeof(uint32_t), s));
+    EM2_CUDA(ctx, cudaMemsetAsync(overflow, 0, sizeof(uint32_t), s));
+    {
+        const uint64_t threads = std::max<uint64_t>(uint64_t(M) * (K / 16), N);
+        sampleGatherKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(encP, K, N, stride, M, static_cast<uint8_t*>(sample), selfIndex);
+        EM2_CUDA(ctx, cudaGetLastError());
+    }
+    CUtensorMap mapA, mapB, mapS;
+    EM2_TRY(makeTensorMapU8(ctx, &mapA, encP, N, K, K, kRowsPerItem));
+    EM2_TRY(makeTensorMapU8(ctx, &mapB, encP, N, K, K, kSsTileN));
+    EM2_TRY(makeTensorMapU8(ctx, &mapS, sample, M, K, K, kSsTileN));
+    {
+        MmaParams q{};
+        q.cellCount = M;
+        q.rowBegin = 0;
+        q.rows = N;
+        q.K = K;
+        q.panels = panels;
+        q.mainBlocks = pre.mainBlocks;
+        q.segments = pre.segments;
+        q.items = pre.items;
+        q.segmentCols = pre.segmentCols;
+        q.k = uint32_t(k);
+        q.cap = pre.cap;
+        q.tau0 = tau0;
+        q.cand = static_cast<uint64_t*>(cand);
+        q.candCount = static_cast<uint32_t*>(candCount);
+        q.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
+        q.flags = uint32_t(ctx->debugFlags);
+        q.rowPerm = selfIndex;
+        if (pre.segments > 1)
+            EM2_CUDA(ctx, cudaMemsetAsync(candCount, 0, size_t(pre.segments) * kSubStreams * N * sizeof(uint32_t), s));
+        const size_t smem = 1024 + size_t(kSsStages) * kSsStageBytes + 256 + kShareBytes;
+        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSsKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        scanMmaSsKernel<false><<<unsigned(std::min<uint32_t>(pre.items, uint32_t(ctx->smCount))), kThreads, smem, s>>>(mapA, mapS, q);
+        EM2_CUDA(ctx, cudaGetLastError());
+        sampleBoundKernel<<<unsigned((N * 32 + 127) / 128), 128, 0, s>>>(N, pre.segments * kSubStreams, pre.cap, uint32_t(k), q.cand,
+                                                                         q.candCount, tau0, limEx);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 3;
+    }
+    // ---- the symmetric sweep
+    SymParams p{};
+    p.cellCount = N;
+    p.K = K;
+    p.panels = panels;
+    const size_t budget = 227 * 1024 - 1024 - kSymSmallBytes - size_t(panels) * kSsABytes;
+    p.stages = uint32_t(std::min<size_t>(kSymMaxStages, budget / kSsBBytes));
+    p.superBlocks = superBlocks;
+    p.offsets = offsets;
+    p.halfOffset = superBlocks % 2 == 0 ? superBlocks / 2 : 0;
+    p.k = uint32_t(k);
+    p.cap = plan.cap;
+    p.cand = static_cast<uint64_t*>(cand);
+    p.candCount = static_cast<uint32_t*>(candCount);
+    p.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
+    p.limEx = limEx;
+    p.colLog = static_cast<ulonglong2*>(colLog);
+    p.colLogCount = static_cast<uint32_t*>(colLogCount);
+    p.colLogCap = logCap;
+    p.overflow = overflow;
+    p.perm = perm;
+    p.flags = uint32_t(ctx->debugFlags);
+    if (nearPlan.segments > 1 || plan.segments > 1)      // streams a main row block never touches must read as empty
+        EM2_CUDA(ctx, cudaMemsetAsync(candCount, 0, size_t(streams) * N * sizeof(uint32_t), s));
+    {
+        const size_t smem = 1024 + size_t(panels) * kSsABytes + size_t(p.stages) * kSsBBytes + kSymSmallBytes;
+        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        auto sweep = [&](const ScanPlan& pl, uint32_t dBegin, uint32_t count, uint32_t streamBase) -> int {
+            p.mainBlocks = pl.mainBlocks;
+            p.segments = pl.segments;
+            p.items = pl.items;
+            p.segmentCols = pl.segmentCols;
+            p.dBegin = dBegin;
+            p.offsetsHere = count;
+            p.streamBase = streamBase;
+            scanMmaSymKernel<<<unsigned(std::min<uint32_t>(pl.items, uint32_t(ctx->smCount))), kThreads, smem, s>>>(mapA, mapB, p);
+            EM2_CUDA(ctx, cudaGetLastError());
+            ctx->stats.kernel_launches++;
+            return EM2_OK;
+        };
+        EM2_TRY(sweep(nearPlan, 0, nearOffsets, 0));
+        if (offsets > nearOffsets) EM2_TRY(sweep(plan, nearOffsets, offsets - nearOffsets, nearPlan.segments * kSubStreams));
+        scatterLogKernel<<<unsigned((uint64_t(logs) * 32 + 255) / 256), 256, 0, s>>>(logs, logCap, p.colLog, p.colLogCount,
+                                                                                     static_cast<uint64_t*>(inbox), inCount, inCap, overflow);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        // staging for the keys below a cell's final bound: about k per stream plus ties and the inbox's share; small, so
+        // that several CTAs fit on an SM (running out of it raises the overflow flag like a full inbox does)
+        const uint32_t keysPerWarp = uint32_t(roundUp(uint64_t(streams) * (k + 32) + 4 * k + 256, 256));
+        const size_t smemF = size_t(kSymFinalWarps) * keysPerWarp * sizeof(uint64_t);
+        if (smemF > 200 * 1024) return fail(ctx, EM2_ERR_INVALID, "k too large for the symmetric finalize kernel");
+        EM2_CUDA(ctx, cudaFuncSetAttribute(finalizeSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
+        finalizeSymKernel<<<unsigned((N + kSymFinalWarps - 1) / kSymFinalWarps), kSymFinalWarps * 32, smemF, s>>>(
+            N, streams, plan.cap, uint32_t(k), p.cand, p.candCount, static_cast<const uint64_t*>(inbox), inCount, inCap, limEx, lut, pairs,
+            usedCount, perm,
+            overflow, keysPerWarp);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    // the overflow flag decides whether the result stands
+    uint32_t* flagHost = nullptr;
+    {
+        void* pin = nullptr;
+        EM2_TRY(reservePinned(ctx, 2, 64, &pin));
+        flagHost = static_cast<uint32_t*>(pin);
+    }
+    EM2_CUDA(ctx, cudaMemcpyAsync(flagHost, overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    *overflowed = *flagHost ? 1 : 0;
+    return EM2_OK;
+}
+
 int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount, uint64_t rowBegin,
            uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut, em2_pair* pairs, uint32_t* usedCount,
            uint16_t* dump, cudaStream_t s)
@@ -711,6 +1337,22 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         rowPerm = perm;
     }
 
+    // 1c. whole-matrix jobs: every unordered pair once (scanMmaSymKernel); falls through to the one-directional
+    //     kernels if a candidate inbox overflowed (nothing of the symmetric attempt is kept)
+    const uint32_t tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
+    ctx->stats.scan_symmetric = 0;
+    {
+        const uint32_t capSym = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
+        const bool eligible = streamed && !dump && K <= kMaxPanels * kChunkBytes && rowBegin == 0 && rows == cellCount &&
+                              capSym <= 32 * kPruneRegsPerLane && cellCount >= 1024 && tau0 > 0;
+        if (eligible && (ctx->scanSymmetric == 2 || (ctx->scanSymmetric == 0 && cellCount >= 16384))) {
+            int overflowed = 0;
+            EM2_TRY(runSymmetric(ctx, encRows, rowPerm, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
+            ctx->stats.scan_symmetric = overflowed ? 2 : 1;
+            if (!overflowed) return EM2_OK;
+        }
+    }
+
     // 2. plan + scratch
     MmaParams p{};
     const uint32_t panels = K / kChunkBytes;
@@ -747,7 +1389,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     p.segmentCols = plan.segmentCols;
     p.k = uint32_t(k);
     p.cap = plan.cap;
-    p.tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
+    p.tau0 = tau0;
     p.cand = static_cast<uint64_t*>(cand);
     p.candCount = static_cast<uint32_t*>(candCount);
     p.appendedTotal = static_cast<unsigned long long*>(counters) + 1;

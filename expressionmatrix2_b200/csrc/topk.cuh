@@ -159,4 +159,109 @@ static __device__ __forceinline__ void warpPruneIfNeeded(RowState& st, uint32_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Order-independent forms, used by the symmetric scan (scan_mma.cu), whose streams do NOT visit candidates in
+// increasing id: a later candidate that ties with the k-th best mismatch count may carry a smaller id and win.
+// Bounds are therefore kept in EXCLUSIVE form over the mismatch count alone -- after a prune that found h as the
+// k-th smallest count, tau = h + 1 (a tie is still accepted) -- and the prune keeps the k smallest full keys
+// (mismatch, id), choosing among the ties at h by id with a second bisection.
+// ---------------------------------------------------------------------------------------------------------
+template <int EPL>
+static __device__ __noinline__ uint32_t warpPruneRegsAnyOrder(uint64_t* buf, uint32_t count, uint32_t k, uint32_t tau,
+                                                              const uint32_t* __restrict__ idOf)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t m[EPL], id[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+        const uint32_t i = e * 32 + lane;
+        const uint64_t key = i < count ? buf[i] : ~0ull;
+        m[e] = uint32_t(key >> 32);
+        id[e] = uint32_t(key);
+    }
+    uint32_t lo = 0, hi = tau - 1;           // every stored mismatch count is < tau
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        uint32_t c = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) c += (m[e] <= mid);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) hi = mid;
+        else lo = mid + 1;
+    }
+    const uint32_t h = lo;
+    uint32_t less = 0, ties = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+        less += (m[e] < h);
+        ties += (m[e] == h);
+    }
+    less = __reduce_add_sync(0xffffffffu, less);
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    const uint32_t r = k - less;             // ties at h that still fit: those with the r smallest ids
+    if (ties > r) {
+        // The low word of a key is a scan POSITION (the hot path appends without looking anything up); the tie-break
+        // is on cell ids, looked up here -- for the ties only, all loads in flight at once.
+        uint32_t pos[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+            pos[e] = id[e];
+            if (idOf && m[e] == h) id[e] = idOf[pos[e]];
+        }
+        uint32_t a = 0, b = 0xffffffffu;
+        while (a < b) {
+            const uint32_t mid = a + ((b - a) >> 1);
+            uint32_t c = 0;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) c += (m[e] == h && id[e] <= mid);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= r) b = mid;
+            else a = mid + 1;
+        }
+        const uint32_t idCut = a;             // ids are unique: exactly r ties have id <= idCut
+        // back to positions, with the losing ties marked
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+            if (m[e] == h && id[e] > idCut) m[e] = 0xffffffffu;
+            id[e] = pos[e];
+        }
+    }
+    uint32_t out = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+        if (uint32_t(e) * 32 < count) {      // warp-uniform
+            const bool keep = m[e] <= h;         // losing ties were marked above
+            const uint32_t keepMask = __ballot_sync(0xffffffffu, keep);
+            if (keep) buf[out + __popc(keepMask & lt)] = (uint64_t(m[e]) << 32) | id[e];
+            out += __popc(keepMask);
+        }
+    }
+    __syncwarp();
+    return h;
+}
+
+// Call with the warp converged; regions of at most 32 * kPruneRegsPerLane keys.  The owner's new bound is also
+// published (atomicMin) to *shared, the row's entry of a global bound array read by other CTAs.
+static __device__ __forceinline__ void warpPruneIfNeededAnyOrder(RowState& st, uint32_t k, uint32_t cap, uint32_t* shared,
+                                                                 const uint32_t* __restrict__ idOf)
+{
+    uint32_t need = __ballot_sync(0xffffffffu, st.count + kPruneSlack > cap);
+    if (need) __syncwarp();
+    while (need) {
+        const int src = __ffs(int(need)) - 1;
+        need &= need - 1;
+        const uint64_t b = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(st.buf), src);
+        const uint32_t c = __shfl_sync(0xffffffffu, st.count, src);
+        const uint32_t t = __shfl_sync(0xffffffffu, st.tau, src);
+        const uint32_t h = warpPruneRegsAnyOrder<kPruneRegsPerLane>(reinterpret_cast<uint64_t*>(b), c, k, t, idOf);
+        if (int(threadIdx.x & 31) == src) {
+            st.count = k;
+            st.tau = h + 1;
+            st.lim = st.lim < h + 1 ? st.lim : h + 1;
+            atomicMin(shared, h + 1);
+        }
+    }
+}
+
 }  // namespace em2

@@ -99,7 +99,7 @@ typedef struct em2_stats {
     uint64_t filter_cells;        /* cells whose signatures came from the tensor-core filter path */
     uint64_t filter_uncertain;    /* projections the filter could not decide (recomputed exactly in FP64) */
     int32_t variant_used;     /* em2_variant actually run                                */
-    int32_t reserved;
+    int32_t scan_symmetric;   /* 1 = the scan evaluated every unordered pair once; 2 = it tried, a candidate inbox overflowed, rerun one-directionally */
 } em2_stats;
 
 /* ------------------------------------------------------------------------------------------------
@@ -121,6 +121,7 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
  *   "mma_kernel"       tcgen05 scan kernel: 1 = A operand resident in tensor memory (L <= 1024), 2 = both operands streamed
  *   "mma_cta_pair"     1 = the TMEM-resident scan kernel runs on CTA pairs (cta_group::2)
  *   "row_grouping"     MMA scan: 1 = scan rows in cell order, 2 = always group similar rows into the same warps
+ *   "scan_symmetric"   whole-matrix MMA scans: 1 = one-directional kernels only, 2 = symmetric kernel whenever eligible
  *   "cand_cap_extra"   candidate regions hold (2 + n) k + 32 keys;  "popc_csa" carry-save levels of the POPC scan (0..2)
  *   "exact_matrix_bytes" budget of the exact path's similarity matrix (default 48 GiB);  "exact_cta_pair" 1 = CTA-pair GEMM
  *   "exact_general"    1 = force the exact path's general FP64 kernel

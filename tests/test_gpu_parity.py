@@ -594,3 +594,77 @@ def test_blocking_call_with_many_pcie_chunks(engine, oracle):
     finally:
         engine.set_option("signature_mode", 0)
         engine.set_option("h2d_chunk_bytes", 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# symmetric scan (every unordered pair evaluated once; row + column direction, inboxes, sampling pre-pass)
+# ---------------------------------------------------------------------------------------------------
+def _sym(engine, sig, L, k, thr, expect=1, **opts):
+    opts = dict(opts, scan_symmetric=2)
+    for o, v in opts.items():
+        engine.set_option(o, v)
+    try:
+        got = engine.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_MMA_I8)
+        assert engine.stats()["scan_symmetric"] == expect
+    finally:
+        for o in opts:
+            engine.set_option(o, 0)
+    return got
+
+
+@pytest.mark.parametrize("N,L,k,thr,clusters", [
+    (3072, 1024, 20, -1.0, 0),       # 12 super blocks (even: the half offset is visited from both sides)
+    (3300, 1024, 50, 0.2, 30),       # 13 super blocks (odd), partial last block
+    (2900, 512, 10, 0.5, 10),        # K = 512, partial last row block AND last super block
+    (1100, 600, 100, -1.0, 0),       # 5 super blocks, K padded 600 -> 640, wide lists
+    (9000, 1024, 50, 0.2, 50),       # several waves' worth of tiles per CTA
+])
+def test_symmetric_scan_equals_oracle(engine, oracle, N, L, k, thr, clusters):
+    """The symmetric kernel must return exactly the lists of the one-directional scan / the oracle: candidates
+    reach a cell from its own row streams and, through the inbox, from the rows of other CTAs."""
+    sig = synthetic.gen_signatures(N, L, seed=N, clusters=clusters) if clusters else synthetic.gen_signatures(N, L, seed=N)
+    want = oracle.topk(sig, L, k, thr)[:3]
+    _check_lists(_sym(engine, sig, L, k, thr), want)
+    _check_lists(_sym(engine, sig, L, k, thr, row_grouping=2), want)     # rows AND columns in grouped order
+    _check_lists(_sym(engine, sig, L, k, thr, row_grouping=1), want)
+
+
+def test_symmetric_scan_ties_resolve_by_cell_id(engine, oracle):
+    """Candidates do not arrive in id order (cyclic column order, grouped positions, inbox appends from many CTAs):
+    ties at the k-th place must still go to the smaller cell id.  Few distinct signatures = ties everywhere, but
+    not so many equal pairs that the inboxes overflow."""
+    rng = np.random.default_rng(5)
+    base = synthetic.gen_signatures(600, 512, seed=9)
+    sig = base[rng.integers(0, 600, 6000)]           # every signature ~10 times
+    for k, thr in ((5, -1.0), (12, 0.3), (40, -1.0)):
+        want = oracle.topk(sig, 512, k, thr)[:3]
+        _check_lists(_sym(engine, sig, 512, k, thr), want)
+        _check_lists(_sym(engine, sig, 512, k, thr, row_grouping=2), want)
+
+
+def test_symmetric_scan_inbox_overflow_falls_back(engine, oracle):
+    """4 distinct signatures among 5000 cells: over a thousand exact duplicates per cell, every bound collapses to 0
+    and the column-direction inboxes overflow.  The call must notice, rerun one-directionally and still be exact."""
+    rng = np.random.default_rng(3)
+    base = synthetic.gen_signatures(4, 512, seed=1)
+    sig = base[rng.integers(0, 4, 5000)]
+    got = _sym(engine, sig, 512, 3, -1.0, expect=2)
+    _check_lists(got, oracle.topk(sig, 512, 3, -1.0)[:3])
+
+
+def test_symmetric_scan_is_the_default_for_whole_matrix_jobs(engine, oracle):
+    """Auto policy at 40k cells: symmetric kernel; identical to the POPC variant on every row; row-range calls
+    (the multi-GPU decomposition) keep the one-directional kernels."""
+    N, L, k, thr = 40000, 1024, 50, 0.2
+    sig = synthetic.gen_signatures(N, L, seed=4, clusters=200)
+    got = engine.find_similar_pairs(sig, L, k, thr)
+    st = engine.stats()
+    assert st["variant_used"] == em2.VARIANT_MMA_I8 and st["scan_symmetric"] == 1
+    ref = engine.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_POPC)
+    _check_lists(got, ref)
+    for r in (0, 255, 256, 20000, N - 1):
+        wi, ws, wu, _ = oracle.topk(sig, L, k, thr, r, r + 1)
+        _check_lists((got[0][r:r + 1], got[1][r:r + 1], got[2][r:r + 1]), (wi, ws, wu))
+    part = engine.find_similar_pairs(sig, L, k, thr, row_begin=10000, row_end=30000)
+    assert engine.stats()["scan_symmetric"] == 0
+    _check_lists(part, (ref[0][10000:30000], ref[1][10000:30000], ref[2][10000:30000]))
