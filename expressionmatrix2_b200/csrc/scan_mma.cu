@@ -878,7 +878,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
         if (logCount > p.colLogCap) {
-            *p.overflow = 1u;
+            atomicOr(p.overflow, 1u);          // bit 0: a column-direction log
             logCount = p.colLogCap;
         }
         p.colLogCount[logSlot] = logCount;
@@ -948,12 +948,14 @@ scatterLogKernel(uint32_t logs, uint32_t logCap, const ulonglong2* __restrict__ 
         const uint32_t pos = uint32_t(e.y);
         const uint32_t slot = atomicAdd(inCount + pos, 1u);
         if (slot < inCap) inbox[uint64_t(pos) * inCap + slot] = e.x;
-        else *overflow = 1u;
+        else atomicOr(overflow, 2u);           // bit 1: an inbox
     }
 }
 
-// Merge of a cell's row streams and inbox (symmetric scan).  Only keys below the cell's final bound can be among
-// its k best; they are compacted into shared memory and ranked like in finalizeKernel (scan_popc.cu).
+// Merge of a cell's row streams and inbox (symmetric scan), one warp per cell.  Pass 1 stages only the mismatch
+// counts (16 bit) of the keys below the cell's final bound and bisects the k-th smallest, h; pass 2 re-reads the
+// regions and stages the keys with count <= h -- k plus the ties at h -- which are ranked like in finalizeKernel
+// (scan_popc.cu).  Stream keys carry scan positions (translated here), inbox keys cell ids.
 constexpr int kSymFinalWarps = 4;
 
 __global__ void __launch_bounds__(kSymFinalWarps * 32)
@@ -961,67 +963,80 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
                   const uint32_t* __restrict__ candCount, const uint64_t* __restrict__ inbox, const uint32_t* __restrict__ inCount,
                   uint32_t inCap, const uint32_t* __restrict__ limEx, const float* __restrict__ lut, em2_pair* __restrict__ pairs,
                   uint32_t* __restrict__ usedCount, const uint32_t* __restrict__ perm, uint32_t* __restrict__ overflow,
-                  uint32_t keysPerWarp)
+                  uint32_t hamsPerWarp, uint32_t keysPerWarp)
 {
-    extern __shared__ __align__(16) uint64_t skeys[];
+    extern __shared__ __align__(16) uint64_t skeys[];      // [warps][keysPerWarp] keys, then [warps][hamsPerWarp] uint16
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t row = uint64_t(blockIdx.x) * kSymFinalWarps + warp;
     if (row >= cellCount) return;
     uint64_t* keys = skeys + size_t(warp) * keysPerWarp;
+    uint16_t* hams = reinterpret_cast<uint16_t*>(skeys + size_t(kSymFinalWarps) * keysPerWarp) + size_t(warp) * hamsPerWarp;
     const uint32_t lim = limEx[row];
     const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t inboxCount = inCount[row];
+    if (inboxCount > inCap) {                 // (the scatter kernel has raised the flag already)
+        if (lane == 0) atomicOr(overflow, 2u);
+        return;
+    }
+    // ---- pass 1: mismatch counts below the bound
     uint32_t n = 0;
-    bool over = false;
-    auto gather = [&](const uint64_t* src, uint32_t c, bool positions) {
+    auto stageHams = [&](const uint64_t* src, uint32_t c) {
         for (uint32_t base = 0; base < c; base += 32) {
             const uint32_t i = base + lane;
-            uint64_t key = i < c ? src[i] : ~0ull;
-            const bool keep = i < c && uint32_t(key >> 32) < lim;
-            if (keep && positions && perm) key = (key & 0xffffffff00000000ull) | perm[uint32_t(key)];   // stream keys carry positions
+            const uint32_t m = i < c ? uint32_t(src[i] >> 32) : 0xffffffffu;
+            const bool keep = m < lim;
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            if (n + __popc(mask) > keysPerWarp) {
-                over = true;
-                return;
-            }
-            if (keep) keys[n + __popc(mask & lt)] = key;
+            if (keep) hams[n + __popc(mask & lt)] = uint16_t(m);       // n <= streams * cap + inCap == hamsPerWarp
             n += __popc(mask);
         }
     };
-    for (uint32_t s = 0; s < streams && !over; s++)
-        gather(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row], true);
-    if (!over) {
-        const uint32_t c = inCount[row];
-        if (c > inCap) over = true;
-        else gather(inbox + row * uint64_t(inCap), c, false);
-    }
-    if (over) {
-        if (lane == 0) *overflow = 1u;
-        return;
-    }
+    for (uint32_t s = 0; s < streams; s++)
+        stageHams(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row]);
+    stageHams(inbox + row * uint64_t(inCap), inboxCount);
     __syncwarp();
-    if (n > 2 * k) {
-        uint32_t lo = 0, hi = lim;
+    uint32_t h = lim;                         // fewer than k keys: all of them
+    if (n > k) {
+        uint32_t lo = 0, hi = lim - 1;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
             uint32_t c = 0;
-            for (uint32_t e = lane; e < n; e += 32) c += (uint32_t(keys[e] >> 32) <= mid);
+            for (uint32_t e = lane; e < n; e += 32) c += (hams[e] <= mid);
             c = __reduce_add_sync(0xffffffffu, c);
             if (c >= k) hi = mid;
             else lo = mid + 1;
         }
-        uint32_t out = 0;
-        for (uint32_t base = 0; base < n; base += 32) {
-            const uint32_t e = base + lane;
-            const uint64_t key = e < n ? keys[e] : ~0ull;
-            const bool keep = e < n && uint32_t(key >> 32) <= lo;
-            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            if (keep) keys[out + __popc(mask & lt)] = key;
-            out += __popc(mask);
-        }
-        n = out;
-        __syncwarp();
+        h = lo;
     }
+    // ---- pass 2: the keys with count <= h
+    n = 0;
+    bool over = false;
+    auto stageKeys = [&](const uint64_t* src, uint32_t c, bool positions) {
+        for (uint32_t base = 0; base < c && !over; base += 32) {
+            const uint32_t i = base + lane;
+            uint64_t key = i < c ? src[i] : ~0ull;
+            const uint32_t m = uint32_t(key >> 32);
+            const bool keep = i < c && m < lim && m <= h;
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (n + __popc(mask) > keysPerWarp) {
+                over = true;
+                break;
+            }
+            if (keep) {
+                if (positions && perm) key = (key & 0xffffffff00000000ull) | perm[uint32_t(key)];
+                keys[n + __popc(mask & lt)] = key;
+            }
+            n += __popc(mask);
+        }
+    };
+    for (uint32_t s = 0; s < streams; s++)
+        stageKeys(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row], true);
+    stageKeys(inbox + row * uint64_t(inCap), inboxCount, false);
+    if (over) {
+        if (lane == 0) atomicOr(overflow, 4u);      // bit 2: more ties at the k-th place than the staging holds
+        return;
+    }
+    __syncwarp();
     const uint32_t used = n < k ? n : k;
     const uint64_t outRow = perm ? uint64_t(perm[row]) : row;
     for (uint32_t e = lane; e < n; e += 32) {
@@ -1257,16 +1272,15 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
                                                                                      static_cast<uint64_t*>(inbox), inCount, inCap, overflow);
         EM2_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
-        // staging for the keys below a cell's final bound: about k per stream plus ties and the inbox's share; small, so
-        // that several CTAs fit on an SM (running out of it raises the overflow flag like a full inbox does)
-        const uint32_t keysPerWarp = uint32_t(roundUp(uint64_t(streams) * (k + 32) + 4 * k + 256, 256));
-        const size_t smemF = size_t(kSymFinalWarps) * keysPerWarp * sizeof(uint64_t);
+        // staging: 16-bit mismatch counts of everything below the bound, then the k best keys plus the ties at the k-th place
+        const uint32_t hamsPerWarp = uint32_t(roundUp(uint64_t(streams) * plan.cap + inCap, 64));
+        const uint32_t keysPerWarp = uint32_t(roundUp(2 * k + 256, 64));
+        const size_t smemF = size_t(kSymFinalWarps) * (size_t(keysPerWarp) * sizeof(uint64_t) + size_t(hamsPerWarp) * sizeof(uint16_t));
         if (smemF > 200 * 1024) return fail(ctx, EM2_ERR_INVALID, "k too large for the symmetric finalize kernel");
         EM2_CUDA(ctx, cudaFuncSetAttribute(finalizeSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         finalizeSymKernel<<<unsigned((N + kSymFinalWarps - 1) / kSymFinalWarps), kSymFinalWarps * 32, smemF, s>>>(
             N, streams, plan.cap, uint32_t(k), p.cand, p.candCount, static_cast<const uint64_t*>(inbox), inCount, inCap, limEx, lut, pairs,
-            usedCount, perm,
-            overflow, keysPerWarp);
+            usedCount, perm, overflow, hamsPerWarp, keysPerWarp);
         EM2_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
     }
@@ -1279,7 +1293,7 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     }
     EM2_CUDA(ctx, cudaMemcpyAsync(flagHost, overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     EM2_CUDA(ctx, cudaStreamSynchronize(s));
-    *overflowed = *flagHost ? 1 : 0;
+    *overflowed = int(*flagHost);
     return EM2_OK;
 }
 
@@ -1348,7 +1362,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         if (eligible && (ctx->scanSymmetric == 2 || (ctx->scanSymmetric == 0 && cellCount >= 16384))) {
             int overflowed = 0;
             EM2_TRY(runSymmetric(ctx, encRows, rowPerm, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
-            ctx->stats.scan_symmetric = overflowed ? 2 : 1;
+            ctx->stats.scan_symmetric = overflowed ? 2 + 16 * overflowed : 1;      // 2 + 16 * (which capacity ran out)
             if (!overflowed) return EM2_OK;
         }
     }

@@ -166,9 +166,11 @@ static __device__ __forceinline__ void warpPruneIfNeeded(RowState& st, uint32_t 
 // k-th smallest count, tau = h + 1 (a tie is still accepted) -- and the prune keeps the k smallest full keys
 // (mismatch, id), choosing among the ties at h by id with a second bisection.
 // ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kTieSurplus = 16;
+
 template <int EPL>
 static __device__ __noinline__ uint32_t warpPruneRegsAnyOrder(uint64_t* buf, uint32_t count, uint32_t k, uint32_t tau,
-                                                              const uint32_t* __restrict__ idOf)
+                                                              const uint32_t* __restrict__ idOf, uint32_t* newCount)
 {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t m[EPL], id[EPL];
@@ -199,7 +201,9 @@ static __device__ __noinline__ uint32_t warpPruneRegsAnyOrder(uint64_t* buf, uin
     less = __reduce_add_sync(0xffffffffu, less);
     ties = __reduce_add_sync(0xffffffffu, ties);
     const uint32_t r = k - less;             // ties at h that still fit: those with the r smallest ids
-    if (ties > r) {
+    // A few surplus ties are simply kept (the region then holds a little more than k keys); only when they would eat
+    // into the room for new candidates are the r smallest ids among them selected.
+    if (ties > r + (k < kTieSurplus ? k : kTieSurplus)) {      // kept keys <= 2k: a slack of appends always fits
         // The low word of a key is a scan POSITION (the hot path appends without looking anything up); the tie-break
         // is on cell ids, looked up here -- for the ties only, all loads in flight at once.
         uint32_t pos[EPL];
@@ -238,6 +242,7 @@ static __device__ __noinline__ uint32_t warpPruneRegsAnyOrder(uint64_t* buf, uin
         }
     }
     __syncwarp();
+    *newCount = out;
     return h;
 }
 
@@ -254,9 +259,10 @@ static __device__ __forceinline__ void warpPruneIfNeededAnyOrder(RowState& st, u
         const uint64_t b = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(st.buf), src);
         const uint32_t c = __shfl_sync(0xffffffffu, st.count, src);
         const uint32_t t = __shfl_sync(0xffffffffu, st.tau, src);
-        const uint32_t h = warpPruneRegsAnyOrder<kPruneRegsPerLane>(reinterpret_cast<uint64_t*>(b), c, k, t, idOf);
+        uint32_t kept;
+        const uint32_t h = warpPruneRegsAnyOrder<kPruneRegsPerLane>(reinterpret_cast<uint64_t*>(b), c, k, t, idOf, &kept);
         if (int(threadIdx.x & 31) == src) {
-            st.count = k;
+            st.count = kept;          // k, or up to k + kTieSurplus when ties at h were kept
             st.tau = h + 1;
             st.lim = st.lim < h + 1 ? st.lim : h + 1;
             atomicMin(shared, h + 1);

@@ -99,7 +99,7 @@ typedef struct em2_stats {
     uint64_t filter_cells;        /* cells whose signatures came from the tensor-core filter path */
     uint64_t filter_uncertain;    /* projections the filter could not decide (recomputed exactly in FP64) */
     int32_t variant_used;     /* em2_variant actually run                                */
-    int32_t scan_symmetric;   /* 1 = the scan evaluated every unordered pair once; 2 = it tried, a candidate inbox overflowed, rerun one-directionally */
+    int32_t scan_symmetric;   /* 1 = the scan evaluated every unordered pair once; 2 + 16 f = it tried, a capacity ran out (f: 1 log, 2 inbox, 4 merge staging), rerun one-directionally */
 } em2_stats;
 
 /* ------------------------------------------------------------------------------------------------
