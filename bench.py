@@ -314,9 +314,12 @@ def _timed_steps(args, world, dev, local_rank, step, n_marks, launch_counter=Non
     return float(t.item()) / args.steps, stage, clocks, barrier, launches
 
 
-def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total, scan_ms, local_rank):
+def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total, scan_ms, local_rank,
+                   symmetric=False):
     scan_s = scan_ms * 1e-3
     ordered = rows * N                      # pair evaluations this GPU executed per launch
+    if symmetric:                           # every unordered pair once (256-cell super blocks, diagonal blocks in full)
+        ordered = N * (N + 512) / 2 + N * max(256, N // 32)      # + the sampling pre-pass
     alg_pairs = pairs_total / world         # algorithmic units per GPU per launch
     if variant_used == em2.VARIANT_MMA_I8:
         peak, which = int8_peak(peaks, scan_ms)
@@ -374,6 +377,8 @@ def run_b200(args, w):
     part = Partition(N, world, rank)
     rows = part.rows
     eng = em2.Engine(local_rank)
+    if args.symmetric:
+        eng.set_option("scan_symmetric", 2)
     stream = torch.cuda.current_stream().cuda_stream
     peaks = load_peaks()
     pairs_total = N * (N - 1) / 2
@@ -560,8 +565,14 @@ def run_b200(args, w):
 
     # ---- rooflines ---------------------------------------------------------------------------------
     variant_used = eng.stats()["variant_used"] or (em2.VARIANT_POPC if variant != em2.VARIANT_MMA_I8 else variant)
+    sym_used = int(eng.stats()["scan_symmetric"])
     roof = _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total,
-                          stage_ms["scan_topk"], local_rank)
+                          stage_ms["scan_topk"], local_rank, symmetric=(sym_used == 1))
+    if sym_used == 1:
+        roof["kernel"] = "scan_topk (encode + sampling pre-pass + scanMmaSymKernel + scatter + merge)"
+        roof["traffic"] = None
+        roof["note"] = ("symmetric scan: achieved = algorithmic ops (one evaluation per unordered pair, 2L bit-ops); executed adds "
+                        "the diagonal blocks' duplicates and the N/32-column sampling pre-pass")
     sig_roof = None
     if kind == "lsh":
         sig_s = stage_ms["signatures"] * 1e-3
@@ -587,7 +598,7 @@ def run_b200(args, w):
         line.update(value=value, ms_per_step=ms_per_step,
                     dtype=("s8 tcgen05 / u64 popc (scan), u8 x s8 tcgen05 filter + f64 fix-up (signatures)" if kind == "lsh"
                            else "s8 tcgen05 / u64 popc (scan)"),
-                    config=dict(cfg, variant={1: "popc", 2: "mma_i8"}.get(variant_used, "popc"),
+                    config=dict(cfg, variant={1: "popc", 2: "mma_i8"}.get(variant_used, "popc"), scan_symmetric=sym_used,
                                 parallelism=f"cell-row blocks x{world}" + (", 1 NCCL all-gather of signatures" if world > 1 else ""),
                                 l2=("inputs (CSR + hyperplanes, >1.4 GB) exceed the 126 MB L2; no flush needed" if kind == "lsh" else
                                     "encoded signatures (N x L bytes) exceed the 126 MB L2 for N*L > 1.3e8; candidate buffers are rewritten every step"),
@@ -623,6 +634,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "mma"])
     ap.add_argument("--lsh", type=int, default=0, help="override the workload's LSH bit count (config 4 sweep)")
+    ap.add_argument("--symmetric", action="store_true",
+                    help="whole-matrix scans evaluate every unordered pair once (em2_set_option scan_symmetric = 2; N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -60,7 +60,8 @@ struct em2_context {
         S_SAMPLE,        // symmetric scan: encoded signatures of the pre-pass sample
         S_SYM,           // symmetric scan: per-cell bounds, inbox counts, sample index, overflow flag
         S_INBOX,         // symmetric scan: column-direction candidates, uint64[N][inCap]
-        S_COLLOG,        // symmetric scan: per-thread logs of column-direction survivors
+        S_COLLOG,        // symmetric scan: chunked log of column-direction survivors
+        S_COLLOGFILL,    // symmetric scan: entries per log chunk + the chunk allocator
         S_COUNT
     };
     int signatureMode = 0;   // 0 auto, 1 FP64 kernel only, 2 force the tensor-core filter path
@@ -75,7 +76,7 @@ struct em2_context {
     int debugFlags = 0;                // bit 0: no bound sharing between MMA sub-streams; bit 1: memory prune
     int rowGrouping = 0;               // MMA scan: 0 auto (group similar rows into the same warps), 1 off, 2 on
     int mmaKernel = 0;                 // MMA scan kernel: 0 auto, 1 A operand resident in TMEM (L <= 1024), 2 streamed operands
-    int scanSymmetric = 0;             // whole-matrix MMA scans: 0 auto (every unordered pair once), 1 off, 2 on whenever eligible
+    int scanSymmetric = 0;             // whole-matrix MMA scans: 2 = symmetric kernel (every unordered pair once) whenever eligible; 0/1 = off
     int mmaCtaPair = 0;                // 1: the MMA scan runs on CTA pairs (cta_group::2, M = 256)
     int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM
     em2::DeviceBuffer scratch[S_COUNT];

@@ -652,19 +652,36 @@ def test_symmetric_scan_inbox_overflow_falls_back(engine, oracle):
     _check_lists(got, oracle.topk(sig, 512, 3, -1.0)[:3])
 
 
-def test_symmetric_scan_is_the_default_for_whole_matrix_jobs(engine, oracle):
-    """Auto policy at 40k cells: symmetric kernel; identical to the POPC variant on every row; row-range calls
-    (the multi-GPU decomposition) keep the one-directional kernels."""
+def test_symmetric_scan_at_40k_cells_and_row_range_calls(engine, oracle):
+    """40k clustered cells (segmented tail, several waves): the symmetric kernel's lists equal the POPC variant's on
+    every row and the oracle's on sampled rows; without the option, and for row-range calls (the multi-GPU
+    decomposition), the one-directional kernels run."""
     N, L, k, thr = 40000, 1024, 50, 0.2
     sig = synthetic.gen_signatures(N, L, seed=4, clusters=200)
-    got = engine.find_similar_pairs(sig, L, k, thr)
-    st = engine.stats()
-    assert st["variant_used"] == em2.VARIANT_MMA_I8 and st["scan_symmetric"] == 1
+    got = _sym(engine, sig, L, k, thr)
     ref = engine.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_POPC)
     _check_lists(got, ref)
     for r in (0, 255, 256, 20000, N - 1):
         wi, ws, wu, _ = oracle.topk(sig, L, k, thr, r, r + 1)
         _check_lists((got[0][r:r + 1], got[1][r:r + 1], got[2][r:r + 1]), (wi, ws, wu))
-    part = engine.find_similar_pairs(sig, L, k, thr, row_begin=10000, row_end=30000)
-    assert engine.stats()["scan_symmetric"] == 0
+    _check_lists(engine.find_similar_pairs(sig, L, k, thr), ref)
+    st = engine.stats()
+    assert st["variant_used"] == em2.VARIANT_MMA_I8 and st["scan_symmetric"] == 0
+    engine.set_option("scan_symmetric", 2)
+    try:
+        part = engine.find_similar_pairs(sig, L, k, thr, row_begin=10000, row_end=30000)
+        assert engine.stats()["scan_symmetric"] == 0
+    finally:
+        engine.set_option("scan_symmetric", 0)
     _check_lists(part, (ref[0][10000:30000], ref[1][10000:30000], ref[2][10000:30000]))
+
+
+def test_symmetric_scan_without_threshold_and_wide_lists(engine, oracle):
+    """No similarity threshold (every pair is a candidate until the bounds tighten) and k = 100: the heaviest
+    candidate traffic the log pool and the inboxes are sized for, on 30k unstructured cells."""
+    N, L = 30000, 1024
+    sig = synthetic.gen_signatures(N, L, seed=21)
+    for k, thr in ((100, -1.0), (50, -1.0)):
+        got = _sym(engine, sig, L, k, thr)
+        ref = engine.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_POPC)
+        _check_lists(got, ref)

@@ -33,7 +33,9 @@ for name, opt in (("one_directional", 1), ("symmetric", 2)):
         b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     sym = eng.stats()["scan_symmetric"]
+    eng.set_option("debug_flags", 8)
     eng.find_similar_pairs(sig, L, k, thr, variant=2)
+    eng.set_option("debug_flags", 0)
     out[name] = dict(ms=min(ts[1:]), appended=eng.stats()["candidates_appended"], sym=sym)
     res[name] = (pairs.cpu().numpy().copy(), used.cpu().numpy().copy())
 out["equal"] = len(res) < 2 or bool(np.array_equal(res["one_directional"][0], res["symmetric"][0]) and
