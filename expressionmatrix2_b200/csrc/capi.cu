@@ -265,6 +265,7 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     else if (n == "debug_flags" && value >= 0 && value <= 255) ctx->debugFlags = int(value);
     else if (n == "row_grouping" && value >= 0 && value <= 2) ctx->rowGrouping = int(value);
     else if (n == "scan_symmetric" && value >= 0 && value <= 2) ctx->scanSymmetric = int(value);
+    else if (n == "dense_warp_kernel" && value >= 0 && value <= 1) ctx->denseWarpKernel = int(value);
     else if (n == "mma_kernel" && value >= 0 && value <= 2) ctx->mmaKernel = int(value);
     else if (n == "mma_cta_pair" && value >= 0 && value <= 1) ctx->mmaCtaPair = int(value);
     else if (n == "exact_matrix_bytes" && value >= 0) ctx->exactMatrixBytes = uint64_t(value);

@@ -201,6 +201,66 @@ densifyKernel(uint64_t chunkBegin, uint32_t chunkCells, uint64_t geneCount, uint
     }
 }
 
+// Same result, one CTA per cell with the row built in SHARED memory: the scatter of ~5 % non-zero bytes lands in
+// shared memory instead of read-modify-writing 32-byte sectors of a freshly zeroed row in L2, and the row leaves
+// the SM once, as coalesced 16-byte stores (the copy loop re-zeroes the buffer for the next cell).  Measured on
+// config 2 (100k cells x 30k genes): 1.70 -> see DESIGN.md 4.1; the warp-per-cell kernel above stays for gene
+// counts whose row does not fit (gPad > kDenseSmemMax).
+constexpr uint32_t kDenseSmemMax = 96 * 1024;
+
+__global__ void __launch_bounds__(256)
+densifySmemKernel(uint64_t chunkBegin, uint32_t chunkCells, uint64_t geneCount, uint64_t gPad,
+                  const uint64_t* __restrict__ toc, const em2_count* __restrict__ counts,
+                  float maxCount, uint8_t* __restrict__ dense,
+                  uint8_t* __restrict__ flags, uint32_t* __restrict__ fallbackList, uint32_t* __restrict__ fallbackCount)
+{
+    extern __shared__ __align__(16) uint8_t srow[];       // gPad bytes
+    __shared__ double warpSum[8];
+    __shared__ int warpOk[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t o = uint64_t(threadIdx.x) * 16; o < gPad; o += 256 * 16) *reinterpret_cast<uint4*>(srow + o) = z;
+    __syncthreads();
+    for (uint32_t w = blockIdx.x; w < chunkCells; w += gridDim.x) {
+        const uint64_t cell = chunkBegin + w;
+        bool ok = true;
+        double rowSum = 0.;
+        const uint64_t end = toc[cell + 1];
+        for (uint64_t e = toc[cell] + threadIdx.x; e < end; e += 256) {
+            const em2_count p = counts[e];
+            const float c = p.count;
+            ok = ok && (c >= 0.f) && (c <= maxCount) && (c == truncf(c)) && (p.gene < geneCount);
+            rowSum += double(fminf(fmaxf(c, 0.f), 65536.f));
+            if (p.gene < geneCount) srow[p.gene] = uint8_t(min(255u, __float2uint_rz(fmaxf(c, 0.f))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rowSum += __shfl_xor_sync(0xffffffffu, rowSum, o);
+        ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) {
+            warpSum[warp] = rowSum;
+            warpOk[warp] = ok ? 1 : 0;
+        }
+        __syncthreads();
+        uint8_t* row = dense + uint64_t(w) * gPad;
+        for (uint64_t o = uint64_t(threadIdx.x) * 16; o < gPad; o += 256 * 16) {
+            *reinterpret_cast<uint4*>(row + o) = *reinterpret_cast<const uint4*>(srow + o);
+            *reinterpret_cast<uint4*>(srow + o) = z;
+        }
+        if (threadIdx.x == 0) {
+            double sum = 0.;
+            bool all = true;
+            for (int i = 0; i < 8; i++) {      // fixed order: the sum only feeds the eligibility test
+                sum += warpSum[i];
+                all = all && warpOk[i];
+            }
+            all = all && sum < kMaxSum1;
+            flags[w] = all ? 1 : 0;
+            if (!all) fallbackList[atomicAdd(fallbackCount, 1u)] = uint32_t(cell);
+        }
+        __syncthreads();
+    }
+}
+
 struct FilterParams {
     uint64_t chunkBegin;
     uint32_t chunkCells;
@@ -518,9 +578,17 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
         // side stream: wait until the slot's previous user (GEMM + fix-ups) is done, then expand
         if (ctx->slotUsed[slot]) EM2_CUDA(ctx, cudaStreamWaitEvent(d, ctx->evGemm[slot], 0));
         EM2_CUDA(ctx, cudaMemsetAsync(base, 0, 16, d));
-        densifyKernel<<<(chunkCells + 7) / 8, 256, 0, d>>>(begin, chunkCells, geneCount, gPad, toc, counts,
-                                                           unsignedCounts ? 255.f : 127.f, dense, dFlags, fallbackList,
-                                                           fallbackCount);
+        if (gPad <= kDenseSmemMax && ctx->denseWarpKernel == 0) {
+            EM2_CUDA(ctx, cudaFuncSetAttribute(densifySmemKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gPad)));
+            const unsigned ctasPerSm = unsigned(std::max<uint64_t>(1, std::min<uint64_t>(8, (200 * 1024) / (gPad + 1024))));
+            densifySmemKernel<<<std::min<unsigned>(chunkCells, unsigned(ctx->smCount) * ctasPerSm), 256, gPad, d>>>(
+                begin, chunkCells, geneCount, gPad, toc, counts, unsignedCounts ? 255.f : 127.f, dense, dFlags, fallbackList,
+                fallbackCount);
+        } else {
+            densifyKernel<<<(chunkCells + 7) / 8, 256, 0, d>>>(begin, chunkCells, geneCount, gPad, toc, counts,
+                                                               unsignedCounts ? 255.f : 127.f, dense, dFlags, fallbackList,
+                                                               fallbackCount);
+        }
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
         EM2_CUDA(ctx, cudaEventRecord(ctx->evDense[slot], d));

@@ -116,6 +116,7 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
 /* Tuning / test knobs (value 0 restores the automatic behaviour everywhere).
  *   "signature_mode"   1 = FP64 signature kernel only, 2 = force the tensor-core filter + exact fix-up path
  *   "filter_counts_signed" 1 = the filter GEMM takes counts as s8 <= 127 instead of u8 <= 255
+ *   "dense_warp_kernel" 1 = the filter's dense expansion uses the warp-per-cell kernel instead of the shared-memory one
  *   "filter_uncertain_cap" capacity of the filter's uncertain list;  "filter_parts" chunks of cells per filter call
  *   "h2d_chunk_bytes"  CSR bytes per PCIe chunk of the blocking calls (default 256 MiB)
  *   "mma_kernel"       tcgen05 scan kernel: 1 = A operand resident in tensor memory (L <= 1024), 2 = both operands streamed

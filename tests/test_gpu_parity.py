@@ -264,6 +264,9 @@ def test_filter_ineligible_cells_and_overflow(engine, oracle):
     sig = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes),
                      filter_uncertain_cap=1)
     assert np.array_equal(sig, want)
+    # both dense-expansion kernels (row built in shared memory / warp per cell) flag the same cells
+    sig = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes), dense_warp_kernel=1)
+    assert np.array_equal(sig, want) and engine.stats()["filter_cells"] == st["filter_cells"]
 
 
 def test_filter_equals_fp64_at_scale(engine, oracle):
