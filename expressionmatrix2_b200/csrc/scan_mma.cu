@@ -1389,7 +1389,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     const uint32_t tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
     ctx->stats.scan_symmetric = 0;
     {
-        const uint32_t capSym = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
+        const uint32_t capSym = scanCandidateCapacity(uint32_t(k), uint32_t(ctx->candCapExtra));
         const bool eligible = streamed && !dump && K <= kMaxPanels * kChunkBytes && rowBegin == 0 && rows == cellCount &&
                               capSym <= 32 * kPruneRegsPerLane && cellCount >= 1024 && tau0 > 0;
         // Opt-in ("scan_symmetric" = 2): measured 1.7x faster than the one-directional kernel when few candidates pass the

@@ -463,7 +463,7 @@ ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount,
     ScanPlan p;
     p.rowsPerCta = rowsPerCta;
     p.rowBlocks = uint32_t((rows + rowsPerCta - 1) / rowsPerCta);
-    p.cap = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
+    p.cap = scanCandidateCapacity(uint32_t(k), uint32_t(ctx->candCapExtra));
     const uint32_t slots = slotsOverride ? slotsOverride : uint32_t(ctx->smCount) * ctasPerSm;
     p.mainBlocks = p.rowBlocks / slots * slots;
     const uint32_t tail = p.rowBlocks - p.mainBlocks;

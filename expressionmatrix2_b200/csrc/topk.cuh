@@ -34,6 +34,18 @@ struct RowState {
 
 // capacity of a candidate region for a given k
 __host__ __device__ inline uint32_t candidateCapacity(uint32_t k) { return 2 * k + kPruneSlack; }
+// The capacity the scans use: as large as the register prune allows (256 keys), up to 4k + slack -- a prune costs
+// the same for 132 or 232 keys, so fewer, larger prunes are cheaper (config 2: 8.33 -> 8.01 ms; beyond 256 keys the
+// memory-walking prune takes over and the scan is slower, 9.6 ms).  extra > 0 (option "cand_cap_extra") forces
+// (2 + extra) k + slack.
+__host__ __device__ inline uint32_t scanCandidateCapacity(uint32_t k, uint32_t extra)
+{
+    const uint32_t base = candidateCapacity(k);
+    if (extra) return base + k * extra;
+    if (base > 256) return base;
+    const uint32_t wide = 4 * k + kPruneSlack < 256 ? 4 * k + kPruneSlack : 256;
+    return wide > base ? wide : base;
+}
 
 // Plain append; the caller guarantees at most kPruneSlack appends between two warpPruneIfNeeded() calls.
 static __device__ __forceinline__ void consider(RowState& st, uint32_t ham, uint32_t id, uint32_t colEnd)
