@@ -33,6 +33,7 @@
 #include "topk.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdlib>
@@ -584,7 +585,8 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 //
 // Cells are taken in scan-position order (the grouped order when row grouping is on; rows AND columns) and cut
 // into super blocks of 256 positions.  The CTA that owns row block a (128 rows of super block A = a / 2) visits
-// the column tiles C = (A + d) mod S for the offsets d = 0 .. S/2: of every unordered pair of distinct super
+// the column tiles C = (A - d) mod S for the offsets d = 0 .. S/2 (backwards: row blocks are processed in increasing
+// order, so the column cells of most tiles have already had their own sweep and carry their final, tight bounds): of every unordered pair of distinct super
 // blocks exactly one owner sees the pair's tile (for even S the offset S/2 is seen by both owners and treated as
 // two one-directional tiles, like the diagonal d = 0).  A tile's accumulators then feed BOTH directions:
 //   row direction     the thread's own row, exactly as in the kernels above (private bound, private candidate
@@ -709,7 +711,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 for (uint32_t kc = 0; kc < p.panels; kc++)
                     tmaLoad2d(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes), int32_t(it.rowBlock * kRowsPerItem));
                 for (uint32_t d = d0; d < d1; d++) {
-                    const int32_t col0 = int32_t(((super + d) % p.superBlocks) * kSsTileN);
+                    const int32_t col0 = int32_t(((super + p.superBlocks - d) % p.superBlocks) * kSsTileN);
                     for (uint32_t kc = 0; kc < p.panels; kc++) {
                         mbarWait(empty + stage, phase ^ 1);
                         mbarExpectTx(full + stage, kSsBBytes);
@@ -798,7 +800,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
             for (uint32_t d = d0; d < d1; d++, tileIter++) {
                 const uint32_t buf = tileIter & 1;
-                const uint32_t colSuper = (super + d) % p.superBlocks;
+                const uint32_t colSuper = (super + p.superBlocks - d) % p.superBlocks;
                 const bool colDir = d != 0 && d != p.halfOffset;          // CTA-uniform
                 const int16_t* thr = colThr + buf * kSsTileN + sub * kSubCols;
                 const int16_t* grp = grpThr + buf * (kSsTileN / 8) + sub * (kSubCols / 8);
@@ -951,37 +953,40 @@ sampleBoundKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
     if (lane == 0) limEx[row] = bound;
 }
 
-// Files the column-direction log into the per-cell inboxes (one warp per chunk).
+// Files the column-direction log into per-cell inboxes of exactly the needed length (count -> exclusive scan -> fill,
+// one warp per log chunk): FILL = false counts the entries per column cell, FILL = true writes them at
+// inOffset[cell] + (a running cursor per cell).
+template <bool FILL>
 __global__ void __launch_bounds__(256)
 scatterLogKernel(const uint32_t* __restrict__ chunkNext, uint32_t chunkCap, const ulonglong2* __restrict__ log,
-                 const uint32_t* __restrict__ chunkFill, uint64_t* __restrict__ inbox, uint32_t* __restrict__ inCount, uint32_t inCap,
-                 uint32_t* __restrict__ overflow, unsigned long long* __restrict__ appendedTotal)
+                 const uint32_t* __restrict__ chunkFill, uint32_t* __restrict__ inCount, const uint32_t* __restrict__ inOffset,
+                 uint64_t* __restrict__ inbox, unsigned long long* __restrict__ appendedTotal)
 {
     const uint32_t chunks = min(*chunkNext, chunkCap);
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < chunks; w += (gridDim.x * blockDim.x) >> 5) {
         const uint32_t n = chunkFill[w];
-        if (lane == 0 && n) atomicAdd(appendedTotal, (unsigned long long)n);      // statistics: survivors of the column direction
+        if (!FILL && lane == 0 && n) atomicAdd(appendedTotal, (unsigned long long)n);      // statistics
         for (uint32_t i = lane; i < n; i += 32) {
             const ulonglong2 e = log[uint64_t(w) * kLogChunk + i];
             const uint32_t pos = uint32_t(e.y);
             const uint32_t slot = atomicAdd(inCount + pos, 1u);
-            if (slot < inCap) inbox[uint64_t(pos) * inCap + slot] = e.x;
-            else atomicOr(overflow, 2u);           // bit 1: an inbox
+            if (FILL) inbox[uint64_t(inOffset[pos]) + slot] = e.x;
         }
     }
 }
 
-// Merge of a cell's row streams and inbox (symmetric scan), one warp per cell.  Pass 1 stages only the mismatch
-// counts (16 bit) of the keys below the cell's final bound and bisects the k-th smallest, h; pass 2 re-reads the
-// regions and stages the keys with count <= h -- k plus the ties at h -- which are ranked like in finalizeKernel
+// Merge of a cell's row streams and inbox (symmetric scan), one warp per cell.  Pass 1 finds h, the k-th smallest
+// mismatch count among the keys below the cell's final bound: their 16-bit counts are staged in shared memory for the
+// bisection when they fit, else (a cell with an unusually long inbox) every bisection step re-reads the regions.
+// Pass 2 stages the keys with count <= h -- k plus the ties at h -- which are ranked like in finalizeKernel
 // (scan_popc.cu).  Stream keys carry scan positions (translated here), inbox keys cell ids.
 constexpr int kSymFinalWarps = 4;
 
 __global__ void __launch_bounds__(kSymFinalWarps * 32)
 finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k, const uint64_t* __restrict__ cand,
-                  const uint32_t* __restrict__ candCount, const uint64_t* __restrict__ inbox, const uint32_t* __restrict__ inCount,
-                  uint32_t inCap, const uint32_t* __restrict__ limEx, const float* __restrict__ lut, em2_pair* __restrict__ pairs,
+                  const uint32_t* __restrict__ candCount, const uint64_t* __restrict__ inbox, const uint32_t* __restrict__ inOffset,
+                  const uint32_t* __restrict__ limEx, const float* __restrict__ lut, em2_pair* __restrict__ pairs,
                   uint32_t* __restrict__ usedCount, const uint32_t* __restrict__ perm, uint32_t* __restrict__ overflow,
                   uint32_t hamsPerWarp, uint32_t keysPerWarp)
 {
@@ -994,12 +999,12 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
     uint16_t* hams = reinterpret_cast<uint16_t*>(skeys + size_t(kSymFinalWarps) * keysPerWarp) + size_t(warp) * hamsPerWarp;
     const uint32_t lim = limEx[row];
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t inboxCount = inCount[row];
-    if (inboxCount > inCap) {                 // (the scatter kernel has raised the flag already)
-        if (lane == 0) atomicOr(overflow, 2u);
-        return;
-    }
-    // ---- pass 1: mismatch counts below the bound
+    const uint64_t* in = inbox + inOffset[row];
+    const uint32_t inboxCount = inOffset[row + 1] - inOffset[row];
+    uint32_t total = inboxCount;
+    for (uint32_t s = 0; s < streams; s++) total += candCount[uint64_t(s) * cellCount + row];
+    const bool staged = total <= hamsPerWarp;
+    // ---- pass 1
     uint32_t n = 0;
     auto stageHams = [&](const uint64_t* src, uint32_t c) {
         for (uint32_t base = 0; base < c; base += 32) {
@@ -1007,23 +1012,34 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
             const uint32_t m = i < c ? uint32_t(src[i] >> 32) : 0xffffffffu;
             const bool keep = m < lim;
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            if (keep) hams[n + __popc(mask & lt)] = uint16_t(m);       // n <= streams * cap + inCap == hamsPerWarp
+            if (keep && staged) hams[n + __popc(mask & lt)] = uint16_t(m);
             n += __popc(mask);
         }
     };
     for (uint32_t s = 0; s < streams; s++)
         stageHams(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row]);
-    stageHams(inbox + row * uint64_t(inCap), inboxCount);
+    stageHams(in, inboxCount);
     __syncwarp();
-    uint32_t h = lim;                         // fewer than k keys: all of them
+    auto countAtMost = [&](uint32_t mid) {
+        uint32_t c = 0;
+        if (staged) {
+            for (uint32_t e = lane; e < n; e += 32) c += (hams[e] <= mid);
+        } else {
+            for (uint32_t s = 0; s < streams; s++) {
+                const uint64_t* src = cand + (uint64_t(s) * cellCount + row) * cap;
+                const uint32_t cs = candCount[uint64_t(s) * cellCount + row];
+                for (uint32_t i = lane; i < cs; i += 32) c += (uint32_t(src[i] >> 32) <= mid);
+            }
+            for (uint32_t i = lane; i < inboxCount; i += 32) c += (uint32_t(in[i] >> 32) <= mid);
+        }
+        return __reduce_add_sync(0xffffffffu, c);
+    };
+    uint32_t h = lim;                         // fewer than k keys below the bound: all of them
     if (n > k) {
         uint32_t lo = 0, hi = lim - 1;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            uint32_t c = 0;
-            for (uint32_t e = lane; e < n; e += 32) c += (hams[e] <= mid);
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (c >= k) hi = mid;
+            if (countAtMost(mid) >= k) hi = mid;
             else lo = mid + 1;
         }
         h = lo;
@@ -1051,7 +1067,7 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
     };
     for (uint32_t s = 0; s < streams; s++)
         stageKeys(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row], true);
-    stageKeys(inbox + row * uint64_t(inCap), inboxCount, false);
+    stageKeys(in, inboxCount, false);
     if (over) {
         if (lane == 0) atomicOr(overflow, 4u);      // bit 2: more ties at the k-th place than the staging holds
         return;
@@ -1180,21 +1196,25 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     ScanPlan plan = nearPlan;
     if (offsets > nearOffsets)
         plan = makeScanPlan(ctx, N, uint64_t(offsets - nearOffsets) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
+    // small regions here: a cell's bound is published when its region is pruned, and the column direction of other CTAs
+    // lives on fresh bounds (with the one-directional kernels' 4k + 32 keys: 90 M instead of 70 M survivors at config 2)
+    nearPlan.cap = plan.cap = pre.cap = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
     // stream pair 0 of a row is shared by the diagonal launch and segment 0 of the second launch (which continues it)
     const uint32_t streams = std::max(nearPlan.segments, plan.segments) * kSubStreams;
     const uint32_t maxSegments = std::max(pre.segments, streams / kSubStreams);
-    const uint32_t inCap = uint32_t(40 * k + 256);
 
     void *cand = nullptr, *candCount = nullptr, *counters = nullptr, *sample = nullptr, *sym = nullptr, *inbox = nullptr;
     EM2_TRY(reserve(ctx, em2_context::S_CAND, size_t(maxSegments) * kSubStreams * N * plan.cap * sizeof(uint64_t), &cand));
     EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(maxSegments) * kSubStreams * N * sizeof(uint32_t), &candCount));
     EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
     EM2_TRY(reserve(ctx, em2_context::S_SAMPLE, size_t(M) * K, &sample));
-    // [limEx N][inCount N][selfIndex N][overflow 1]
-    EM2_TRY(reserve(ctx, em2_context::S_SYM, (3 * N + 4) * sizeof(uint32_t), &sym));
-    EM2_TRY(reserve(ctx, em2_context::S_INBOX, N * size_t(inCap) * sizeof(uint64_t), &inbox));
-    // column-direction log pool: 12 k entries per cell (measured: 1.5-4 k per cell on clustered data)
-    const uint32_t chunkCap = uint32_t(std::min<uint64_t>(0x7fffffffu, (12 * N * k + kLogChunk - 1) / kLogChunk + 2 * uint64_t(ctx->smCount) * kEpiThreads));
+    // [limEx N][inCount N][selfIndex N][inOffset N + 1][overflow 1]
+    EM2_TRY(reserve(ctx, em2_context::S_SYM, (4 * N + 8) * sizeof(uint32_t), &sym));
+    // column-direction log pool: 24 k entries per cell (measured: 1.5-12 k per cell on clustered data); the inboxes are
+    // cut from a buffer of the same number of keys (count -> scan -> fill)
+    const uint64_t poolEntries = std::min<uint64_t>(0xf0000000ull, 24 * N * k + 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk);
+    const uint32_t chunkCap = uint32_t(poolEntries / kLogChunk);
+    EM2_TRY(reserve(ctx, em2_context::S_INBOX, size_t(chunkCap) * kLogChunk * sizeof(uint64_t), &inbox));
     void *colLog = nullptr, *chunkFill = nullptr;
     EM2_TRY(reserve(ctx, em2_context::S_COLLOG, (size_t(chunkCap) + 1) * kLogChunk * sizeof(ulonglong2), &colLog));   // + spill chunk
     EM2_TRY(reserve(ctx, em2_context::S_COLLOGFILL, (size_t(chunkCap) + 4) * sizeof(uint32_t), &chunkFill));
@@ -1214,7 +1234,8 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     uint32_t* limEx = static_cast<uint32_t*>(sym);
     uint32_t* inCount = limEx + N;
     uint32_t* selfIndex = inCount + N;
-    uint32_t* overflow = selfIndex + N;
+    uint32_t* inOffset = selfIndex + N;
+    uint32_t* overflow = inOffset + N + 1;
     EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, N * sizeof(uint32_t), s));
     EM2_CUDA(ctx, cudaMemsetAsync(overflow, 0, sizeof(uint32_t), s));
     {
@@ -1301,18 +1322,32 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
         report("diagonal launch");
         if (offsets > nearOffsets) EM2_TRY(sweep(plan, nearOffsets, offsets - nearOffsets, 1));
         report("main sweep");
-        scatterLogKernel<<<unsigned(ctx->smCount) * 8, 256, 0, s>>>(chunkNext, chunkCap, p.colLog, p.chunkFill, static_cast<uint64_t*>(inbox),
-                                                                   inCount, inCap, overflow, p.appendedTotal);
+        // inboxes: count the log entries per column cell, exclusive scan, fill
+        scatterLogKernel<false><<<unsigned(ctx->smCount) * 8, 256, 0, s>>>(chunkNext, chunkCap, p.colLog, p.chunkFill, inCount, nullptr,
+                                                                          nullptr, p.appendedTotal);
         EM2_CUDA(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches++;
-        // staging: 16-bit mismatch counts of everything below the bound, then the k best keys plus the ties at the k-th place
-        const uint32_t hamsPerWarp = uint32_t(roundUp(uint64_t(streams) * plan.cap + inCap, 64));
+        {
+            size_t cubBytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, cubBytes, inCount, inOffset, int(N + 1), s);
+            void* cubTemp = nullptr;
+            EM2_TRY(reserve(ctx, em2_context::S_MISC, cubBytes, &cubTemp));
+            // inCount[N] is selfIndex[0]: only the first N + 1 outputs' prefix property matters, inOffset[N] = total
+            EM2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cubTemp, cubBytes, inCount, inOffset, int(N + 1), s));
+        }
+        EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, N * sizeof(uint32_t), s));
+        scatterLogKernel<true><<<unsigned(ctx->smCount) * 8, 256, 0, s>>>(chunkNext, chunkCap, p.colLog, p.chunkFill, inCount, inOffset,
+                                                                         static_cast<uint64_t*>(inbox), p.appendedTotal);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 2;      // + the scan's own kernels (library code, not counted)
+        // staging: 16-bit mismatch counts of everything below the bound (cells with longer lists bisect in place), then
+        // the k best keys plus the ties at the k-th place
+        const uint32_t hamsPerWarp = uint32_t(roundUp(uint64_t(streams) * plan.cap + 40 * k + 256, 64));
         const uint32_t keysPerWarp = uint32_t(roundUp(2 * k + 256, 64));
         const size_t smemF = size_t(kSymFinalWarps) * (size_t(keysPerWarp) * sizeof(uint64_t) + size_t(hamsPerWarp) * sizeof(uint16_t));
         if (smemF > 200 * 1024) return fail(ctx, EM2_ERR_INVALID, "k too large for the symmetric finalize kernel");
         EM2_CUDA(ctx, cudaFuncSetAttribute(finalizeSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
         finalizeSymKernel<<<unsigned((N + kSymFinalWarps - 1) / kSymFinalWarps), kSymFinalWarps * 32, smemF, s>>>(
-            N, streams, plan.cap, uint32_t(k), p.cand, p.candCount, static_cast<const uint64_t*>(inbox), inCount, inCap, limEx, lut, pairs,
+            N, streams, plan.cap, uint32_t(k), p.cand, p.candCount, static_cast<const uint64_t*>(inbox), inOffset, limEx, lut, pairs,
             usedCount, perm, overflow, hamsPerWarp, keysPerWarp);
         EM2_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;

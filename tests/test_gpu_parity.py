@@ -688,3 +688,14 @@ def test_symmetric_scan_without_threshold_and_wide_lists(engine, oracle):
         got = _sym(engine, sig, L, k, thr)
         ref = engine.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_POPC)
         _check_lists(got, ref)
+
+
+def test_symmetric_scan_on_a_fresh_context(oracle):
+    """A new context has no scratch buffers grown by earlier calls: every region the symmetric path touches
+    (pre-pass candidate regions included) must be sized by the call itself."""
+    N, L, k, thr = 20000, 1024, 50, 0.2
+    sig = synthetic.gen_signatures(N, L, seed=8, clusters=40)
+    with em2.Engine(0) as fresh:
+        got = _sym(fresh, sig, L, k, thr)
+        ref = fresh.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_POPC)
+    _check_lists(got, ref)
