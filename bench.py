@@ -379,6 +379,8 @@ def run_b200(args, w):
     eng = em2.Engine(local_rank)
     if args.symmetric:
         eng.set_option("scan_symmetric", 2)
+    if args.one_directional:
+        eng.set_option("scan_symmetric", 1)
     stream = torch.cuda.current_stream().cuda_stream
     peaks = load_peaks()
     pairs_total = N * (N - 1) / 2
@@ -636,6 +638,7 @@ def main():
     ap.add_argument("--lsh", type=int, default=0, help="override the workload's LSH bit count (config 4 sweep)")
     ap.add_argument("--symmetric", action="store_true",
                     help="whole-matrix scans evaluate every unordered pair once (em2_set_option scan_symmetric = 2; N = 1 only)")
+    ap.add_argument("--one-directional", action="store_true", help="never use the symmetric scan (scan_symmetric = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -76,7 +76,7 @@ struct em2_context {
     int debugFlags = 0;                // bit 0: no bound sharing between MMA sub-streams; bit 1: memory prune
     int rowGrouping = 0;               // MMA scan: 0 auto (group similar rows into the same warps), 1 off, 2 on
     int mmaKernel = 0;                 // MMA scan kernel: 0 auto, 1 A operand resident in TMEM (L <= 1024), 2 streamed operands
-    int scanSymmetric = 0;             // whole-matrix MMA scans: 2 = symmetric kernel (every unordered pair once) whenever eligible; 0/1 = off
+    int scanSymmetric = 0;             // whole-matrix MMA scans, symmetric kernel (every unordered pair once): 0 auto (400k..2M cells), 1 off, 2 whenever eligible
     int mmaCtaPair = 0;                // 1: the MMA scan runs on CTA pairs (cta_group::2, M = 256)
     int denseWarpKernel = 0;           // 1: dense expansion of the filter path with the warp-per-cell kernel (tests / comparison)
     int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM

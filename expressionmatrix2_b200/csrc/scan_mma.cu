@@ -613,6 +613,7 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kSymMaxStages = 6;
 constexpr uint32_t kLogChunk = 64;
+constexpr uint32_t kPaceWindow = 256;      // tiles a CTA may run ahead of the slowest one (64 MB of distinct B tiles)
 constexpr uint32_t kSymSmallBytes = 192 + 2 * kSsTileN * 2 + 2 * (kSsTileN / 8) * 2 + kEpiThreads * 2;
 
 struct SymParams {
@@ -636,6 +637,7 @@ struct SymParams {
     uint32_t* chunkNext;           //   chunkFill[c] = valid entries of chunk c; scattered to the inboxes afterwards
     uint32_t chunkCap;
     uint32_t* overflow;
+    uint32_t* progress;            // [grid] pacing of whole-sweep items (nullptr: none)
     const uint32_t* perm;          // position -> cell id (nullptr: identity)
     uint32_t flags;
 };
@@ -699,18 +701,39 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     if (warp == kEpiWarps) {
         // ===================== TMA producer: A once per item, B per tile =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, itemIter = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
-                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
-                const uint32_t super = it.rowBlock >> 1;
-                const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
-                const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+        // Lane 0 issues the loads; the whole warp takes part in the PACING of whole-sweep items: every CTA publishes how
+        // far it is (in tiles) and none runs more than kPaceWindow tiles ahead of the slowest.  The B tiles of
+        // neighbouring row blocks are the same blocks one step apart, so in step they are read from DRAM once and from
+        // L2 147 times; without pacing a CTA that falls behind starts missing L2, gets slower still, and the sweep
+        // settles DRAM-bound (1 M cells: 3.25 TB read from DRAM, L2 hit rate 33 %, tensor pipe 47 %).
+        uint32_t stage = 0, phase = 0, itemIter = 0;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+            const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
+            const uint32_t super = it.rowBlock >> 1;
+            const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
+            const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+            const bool paced = p.progress != nullptr && item < p.mainBlocks;
+            if (lane == 0) {
+                if (p.progress && !paced) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
                 mbarWait(aEmpty, (itemIter & 1) ^ 1);
                 mbarExpectTx(aFull, p.panels * kSsABytes);
                 for (uint32_t kc = 0; kc < p.panels; kc++)
                     tmaLoad2d(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes), int32_t(it.rowBlock * kRowsPerItem));
-                for (uint32_t d = d0; d < d1; d++) {
+            }
+            for (uint32_t d = d0; d < d1; d++) {
+                if (paced && ((d - d0) & 7u) == 0) {
+                    const uint32_t vt = itemIter * p.offsetsHere + (d - d0);
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = vt;
+                    for (int spin = 0; spin < 4000; spin++) {           // bounded: pacing is an optimisation, never a dependency
+                        uint32_t slowest = 0xffffffffu;
+                        for (uint32_t c = lane; c < gridDim.x; c += 32)
+                            slowest = min(slowest, *reinterpret_cast<volatile const uint32_t*>(p.progress + c));
+                        slowest = __reduce_min_sync(0xffffffffu, slowest);
+                        if (slowest >= vt || slowest + kPaceWindow >= vt) break;
+                        __nanosleep(500);
+                    }
+                }
+                if (lane == 0) {
                     const int32_t col0 = int32_t(((super + p.superBlocks - d) % p.superBlocks) * kSsTileN);
                     for (uint32_t kc = 0; kc < p.panels; kc++) {
                         mbarWait(empty + stage, phase ^ 1);
@@ -722,8 +745,10 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         }
                     }
                 }
+                __syncwarp();
             }
         }
+        if (lane == 0 && p.progress) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
     } else if (warp == kEpiWarps + 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
@@ -1208,8 +1233,8 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(maxSegments) * kSubStreams * N * sizeof(uint32_t), &candCount));
     EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
     EM2_TRY(reserve(ctx, em2_context::S_SAMPLE, size_t(M) * K, &sample));
-    // [limEx N][inCount N][selfIndex N][inOffset N + 1][overflow 1]
-    EM2_TRY(reserve(ctx, em2_context::S_SYM, (4 * N + 8) * sizeof(uint32_t), &sym));
+    // [limEx N][inCount N][selfIndex N][inOffset N + 1][overflow 1][pad][progress 1024]
+    EM2_TRY(reserve(ctx, em2_context::S_SYM, (4 * N + 8 + 1024) * sizeof(uint32_t), &sym));
     // column-direction log pool: 24 k entries per cell (measured: 1.5-12 k per cell on clustered data); the inboxes are
     // cut from a buffer of the same number of keys (count -> scan -> fill)
     const uint64_t poolEntries = std::min<uint64_t>(0xf0000000ull, 24 * N * k + 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk);
@@ -1236,6 +1261,7 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     uint32_t* selfIndex = inCount + N;
     uint32_t* inOffset = selfIndex + N;
     uint32_t* overflow = inOffset + N + 1;
+    uint32_t* progress = overflow + 4;
     EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, N * sizeof(uint32_t), s));
     EM2_CUDA(ctx, cudaMemsetAsync(overflow, 0, sizeof(uint32_t), s));
     {
@@ -1313,6 +1339,10 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
             p.dBegin = dBegin;
             p.offsetsHere = count;
             p.resume = resume;
+            // only sweeps long enough for the CTAs to drift apart by more blocks than L2 holds (~490): paced at 200k cells
+            // (390 tiles per item) the sweep was 1.5x SLOWER, at 1 M cells (1953 tiles) 1.2x faster
+            p.progress = (count >= 768 && !(ctx->debugFlags & 16)) ? progress : nullptr;
+            if (p.progress) EM2_CUDA(ctx, cudaMemsetAsync(progress, 0, 1024 * sizeof(uint32_t), s));
             scanMmaSymKernel<<<unsigned(std::min<uint32_t>(pl.items, uint32_t(ctx->smCount))), kThreads, smem, s>>>(mapA, mapB, p);
             EM2_CUDA(ctx, cudaGetLastError());
             ctx->stats.kernel_launches++;
@@ -1427,10 +1457,12 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         const uint32_t capSym = scanCandidateCapacity(uint32_t(k), uint32_t(ctx->candCapExtra));
         const bool eligible = streamed && !dump && K <= kMaxPanels * kChunkBytes && rowBegin == 0 && rows == cellCount &&
                               capSym <= 32 * kPruneRegsPerLane && cellCount >= 1024 && tau0 > 0;
-        // Opt-in ("scan_symmetric" = 2): measured 1.7x faster than the one-directional kernel when few candidates pass the
-        // bounds (similarity threshold doing most of the filtering) but only 0.9-1.05x on clustered data, where the
-        // selection epilogue, not the MMA pipe, is what the sweep waits for.
-        if (eligible && ctx->scanSymmetric == 2) {
+        // "scan_symmetric" = 2 asks for the symmetric kernel whenever it is eligible.  AUTO takes it for 400k..2M cells:
+        // there the one-directional sweep sits at the power cap and the paced symmetric sweep is 1.3x faster (1 M clustered
+        // cells: 570 vs 756 ms); around 100k densely clustered cells it is 5-15 % slower -- the selection epilogue, not
+        // the MMA pipe, is what the sweep waits for -- and above 2 M cells its logs outgrow the memory.
+        const bool automatic = ctx->scanSymmetric == 0 && cellCount >= 400000 && cellCount <= 2000000;
+        if (eligible && (ctx->scanSymmetric == 2 || automatic)) {
             int overflowed = 0;
             EM2_TRY(runSymmetric(ctx, encRows, rowPerm, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
             ctx->stats.scan_symmetric = overflowed ? 2 + 16 * overflowed : 1;      // 2 + 16 * (which capacity ran out)

@@ -122,8 +122,9 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
  *   "mma_kernel"       tcgen05 scan kernel: 1 = A operand resident in tensor memory (L <= 1024), 2 = both operands streamed
  *   "mma_cta_pair"     1 = the TMEM-resident scan kernel runs on CTA pairs (cta_group::2)
  *   "row_grouping"     MMA scan: 1 = scan rows in cell order, 2 = always group similar rows into the same warps
- *   "scan_symmetric"   2 = whole-matrix MMA scans (L <= 1024, k <= 112) evaluate every unordered pair once (symmetric kernel);
- *                      faster when the similarity threshold rejects most pairs, about equal on densely clustered data
+ *   "scan_symmetric"   whole-matrix MMA scans (L <= 1024, k <= 112) that evaluate every unordered pair once: 0 = automatic
+ *                      (400k..2M cells), 1 = never, 2 = whenever eligible (faster when the similarity threshold rejects
+ *                      most pairs and on large jobs, 5-15 % slower on ~100k densely clustered cells)
  *   "cand_cap_extra"   candidate regions hold (2 + n) k + 32 keys;  "popc_csa" carry-save levels of the POPC scan (0..2)
  *   "exact_matrix_bytes" budget of the exact path's similarity matrix (default 48 GiB);  "exact_cta_pair" 1 = CTA-pair GEMM
  *   "exact_general"    1 = force the exact path's general FP64 kernel

@@ -484,7 +484,8 @@ def test_one_million_cells_sampled_rows(engine, oracle):
     sig = synthetic.gen_signatures(N, L, seed=1000, clusters=500, centre_seed=77)
     sig[N - 1] = sig[123456]                      # a planted duplicate across the whole id range
     ids, sims, used = engine.find_similar_pairs(sig, L, k, thr)
-    assert engine.stats()["variant_used"] == em2.VARIANT_MMA_I8
+    st = engine.stats()
+    assert st["variant_used"] == em2.VARIANT_MMA_I8 and st["scan_symmetric"] == 1     # AUTO: paced symmetric sweep at this size
     rows = np.r_[0, 127, 128, 123456, 947199, 947200, N - 129, N - 1, np.random.default_rng(3).integers(0, N, 12)]
     for r in rows:
         wi, ws, wu, _ = oracle.topk(sig, L, k, thr, int(r), int(r) + 1)
@@ -496,6 +497,14 @@ def test_one_million_cells_sampled_rows(engine, oracle):
     d = np.diff(sims.astype(np.float64), axis=1)
     assert np.all(d[valid[:, 1:]] <= 0)           # similarities non-increasing along every list
     assert not np.any((ids == np.arange(N, dtype=np.uint32)[:, None]) & valid)      # no self pairs
+    # the one-directional kernels must give the same 50 M list entries
+    engine.set_option("scan_symmetric", 1)
+    try:
+        ids1, sims1, used1 = engine.find_similar_pairs(sig, L, k, thr)
+        assert engine.stats()["scan_symmetric"] == 0
+    finally:
+        engine.set_option("scan_symmetric", 0)
+    _check_lists((ids, sims, used), (ids1, sims1, used1))
 
 
 def test_lsh_against_exact_similarity_statistics_and_recall(engine, oracle):
