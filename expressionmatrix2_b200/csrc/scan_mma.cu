@@ -1069,7 +1069,37 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
         }
         h = lo;
     }
-    // ---- pass 2: the keys with count <= h
+    // ---- pass 2: the keys with count <= h.  Normally all ties at h are staged and the ranking below picks the
+    // smallest ids; a cell with more ties than the staging holds (hundreds of identical cells) first finds the id of
+    // the last tie that still fits by bisection over the regions themselves.
+    uint32_t idCut = 0xffffffffu;
+    if (n > k) {
+        const uint32_t less = h ? countAtMost(h - 1) : 0;
+        const uint32_t ties = countAtMost(h) - less;
+        if (less + ties > keysPerWarp) {
+            const uint32_t r = k - less;              // ties that still fit (>= 1 by the choice of h)
+            auto tiesUpTo = [&](uint32_t id) {
+                uint32_t c = 0;
+                for (uint32_t s = 0; s < streams; s++) {
+                    const uint64_t* src = cand + (uint64_t(s) * cellCount + row) * cap;
+                    const uint32_t cs = candCount[uint64_t(s) * cellCount + row];
+                    for (uint32_t i = lane; i < cs; i += 32) {
+                        const uint64_t key = src[i];
+                        if (uint32_t(key >> 32) == h) c += ((perm ? perm[uint32_t(key)] : uint32_t(key)) <= id);
+                    }
+                }
+                for (uint32_t i = lane; i < inboxCount; i += 32) c += (uint32_t(in[i] >> 32) == h && uint32_t(in[i]) <= id);
+                return __reduce_add_sync(0xffffffffu, c);
+            };
+            uint32_t a = 0, b = 0xffffffffu;
+            while (a < b) {
+                const uint32_t mid = a + ((b - a) >> 1);
+                if (tiesUpTo(mid) >= r) b = mid;
+                else a = mid + 1;
+            }
+            idCut = a;                                // ids are unique: exactly r ties have id <= idCut
+        }
+    }
     n = 0;
     bool over = false;
     auto stageKeys = [&](const uint64_t* src, uint32_t c, bool positions) {
@@ -1077,16 +1107,15 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
             const uint32_t i = base + lane;
             uint64_t key = i < c ? src[i] : ~0ull;
             const uint32_t m = uint32_t(key >> 32);
-            const bool keep = i < c && m < lim && m <= h;
+            bool keep = i < c && m < lim && m <= h;
+            if (keep && positions && perm) key = (key & 0xffffffff00000000ull) | perm[uint32_t(key)];
+            if (keep && m == h && uint32_t(key) > idCut) keep = false;
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
             if (n + __popc(mask) > keysPerWarp) {
                 over = true;
                 break;
             }
-            if (keep) {
-                if (positions && perm) key = (key & 0xffffffff00000000ull) | perm[uint32_t(key)];
-                keys[n + __popc(mask & lt)] = key;
-            }
+            if (keep) keys[n + __popc(mask & lt)] = key;
             n += __popc(mask);
         }
     };
@@ -1094,7 +1123,7 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
         stageKeys(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row], true);
     stageKeys(in, inboxCount, false);
     if (over) {
-        if (lane == 0) atomicOr(overflow, 4u);      // bit 2: more ties at the k-th place than the staging holds
+        if (lane == 0) atomicOr(overflow, 4u);      // bit 2: cannot happen (k <= keysPerWarp); kept as a guard
         return;
     }
     __syncwarp();

@@ -654,14 +654,28 @@ def test_symmetric_scan_ties_resolve_by_cell_id(engine, oracle):
         _check_lists(_sym(engine, sig, 512, k, thr, row_grouping=2), want)
 
 
-def test_symmetric_scan_inbox_overflow_falls_back(engine, oracle):
-    """4 distinct signatures among 5000 cells: over a thousand exact duplicates per cell, every bound collapses to 0
-    and the column-direction inboxes overflow.  The call must notice, rerun one-directionally and still be exact."""
+def test_symmetric_scan_with_thousands_of_identical_cells(engine, oracle):
+    """4 distinct signatures among 5000 cells: over a thousand exact duplicates per cell -- every bound collapses to 0,
+    half of a cell's duplicates arrive through its inbox, and the merge has far more ties at the k-th place than its
+    staging holds: it must pick the smallest cell ids among them (bisection over the regions), not fall back."""
     rng = np.random.default_rng(3)
     base = synthetic.gen_signatures(4, 512, seed=1)
     sig = base[rng.integers(0, 4, 5000)]
+    for k in (3, 60):
+        got = _sym(engine, sig, 512, k, -1.0, expect=1)
+        _check_lists(got, oracle.topk(sig, 512, k, -1.0)[:3])
+        got = _sym(engine, sig, 512, k, -1.0, expect=1, row_grouping=2)
+        _check_lists(got, oracle.topk(sig, 512, k, -1.0)[:3])
+
+
+def test_symmetric_scan_falls_back_when_the_log_pool_runs_dry(engine, oracle):
+    """20000 identical cells: ~10000 column-direction survivors per cell against a pool of 24 k = 72 per cell.  The call
+    must notice, rerun with the one-directional kernels and still return the exact lists."""
+    sig = np.repeat(synthetic.gen_signatures(1, 512, seed=2), 20000, axis=0)
     got = _sym(engine, sig, 512, 3, -1.0, expect=2)
-    _check_lists(got, oracle.topk(sig, 512, 3, -1.0)[:3])
+    want = oracle.topk(sig, 512, 3, -1.0, 0, 4)
+    _check_lists((got[0][:4], got[1][:4], got[2][:4]), want[:3])
+    assert np.array_equal(got[0][1000], [0, 1, 2]) and np.array_equal(got[0][0], [1, 2, 3])
 
 
 def test_symmetric_scan_at_40k_cells_and_row_range_calls(engine, oracle):
