@@ -1490,7 +1490,17 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         // there the one-directional sweep sits at the power cap and the paced symmetric sweep is 1.3x faster (1 M clustered
         // cells: 570 vs 756 ms); around 100k densely clustered cells it is 5-15 % slower -- the selection epilogue, not
         // the MMA pipe, is what the sweep waits for -- and above 2 M cells its logs outgrow the memory.
-        const bool automatic = ctx->scanSymmetric == 0 && cellCount >= 400000 && cellCount <= 2000000;
+        bool automatic = ctx->scanSymmetric == 0 && cellCount >= 400000 && cellCount <= 2000000;
+        if (automatic) {
+            // its scratch (log pool 16 B + inbox 8 B per entry, 24 k entries per cell; candidate regions; sample) must fit
+            // beside what is already allocated -- otherwise stay with the one-directional kernels instead of failing
+            const size_t want = size_t(cellCount) * (24 * k * 24 + 8 * (2 * k + 32) * 8 + 64) + (size_t(1) << 30);
+            size_t have = ctx->scratch[em2_context::S_COLLOG].bytes + ctx->scratch[em2_context::S_INBOX].bytes +
+                          ctx->scratch[em2_context::S_CAND].bytes;
+            size_t freeBytes = 0, totalBytes = 0;
+            if (cudaMemGetInfo(&freeBytes, &totalBytes) != cudaSuccess) freeBytes = 0;
+            automatic = want <= have + freeBytes / 10 * 9;
+        }
         if (eligible && (ctx->scanSymmetric == 2 || automatic)) {
             int overflowed = 0;
             EM2_TRY(runSymmetric(ctx, encRows, rowPerm, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
