@@ -585,25 +585,27 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 //
 // Cells are taken in scan-position order (the grouped order when row grouping is on; rows AND columns) and cut
 // into super blocks of 256 positions.  The CTA that owns row block a (128 rows of super block A = a / 2) visits
-// the column tiles C = (A - d) mod S for the offsets d = 0 .. S/2 (backwards: row blocks are processed in increasing
-// order, so the column cells of most tiles have already had their own sweep and carry their final, tight bounds): of every unordered pair of distinct super
-// blocks exactly one owner sees the pair's tile (for even S the offset S/2 is seen by both owners and treated as
-// two one-directional tiles, like the diagonal d = 0).  A tile's accumulators then feed BOTH directions:
+// the column tiles C = (A - d) mod S for the offsets d = 0 .. S/2 -- backwards: row blocks are processed in
+// increasing order, so the column cells of most tiles have already had their own sweep and carry their final,
+// tight bounds.  Of every unordered pair of distinct super blocks exactly one owner sees the pair's tile (for even
+// S the offset S/2 is seen by both owners and treated as two one-directional tiles, like the diagonal d = 0;
+// tests/test_symmetric_schedule.py restates the rule).  A tile's accumulators then feed BOTH directions:
 //   row direction     the thread's own row, exactly as in the kernels above (private bound, private candidate
 //                     region), except that candidates do not arrive in id order: the order-independent prune of
 //                     topk.cuh is used and every new bound is published to limEx[row position] (atomicMin);
 //   column direction  the same 32 accumulators are compared with the bounds of the tile's COLUMN cells
 //                     (limEx, staged per tile in shared memory as dot-product thresholds, with one loosest
 //                     threshold per 8 columns so that the common case is four extra compares per chunk);
-//                     survivors go to the THREAD's private log (a plain store: no atomics, nothing to wait for in
-//                     the hot loop -- an atomic slot per survivor cost a ~700-cycle round trip each and made the
-//                     sweep 3x slower on clustered data); a scatter kernel then files the logs into per-cell inboxes.
+//                     survivors go to a log, a pool of 64-entry chunks of which a thread owns one at a time (a plain
+//                     store per survivor, one atomic per 64: an atomic slot per survivor cost a ~700-cycle round
+//                     trip each and made the sweep 3x slower on clustered data); afterwards the log is filed into
+//                     per-cell inboxes of exactly the needed length (count -> scan -> fill).
 //                     For the same reason candidate keys carry scan positions, not cell ids; ids are looked up where
 //                     they decide something (ties at a prune, the finalize kernel).
 // limEx starts from a sampling pre-pass (the k-th best of every cell against N/32 sample cells, a valid upper
 // bound of its final k-th best) and tightens as the cell's own row streams progress; a stale bound is only
-// looser.  The finalize kernel merges a cell's row streams and its inbox.  An inbox that overflows raises a
-// flag and the caller reruns the job with the one-directional kernel: exactness never depends on the bounds
+// looser.  The finalize kernel merges a cell's row streams and its inbox.  If the log pool runs dry a flag is
+// raised and the caller reruns the job with the one-directional kernels: exactness never depends on the bounds
 // being tight.
 //
 // Operand traffic: per tile the one-directional kernel re-reads the row block's A chunks from L2 (48 KB per
@@ -1228,8 +1230,8 @@ __global__ void encodeKernel(const uint64_t* __restrict__ sig, uint32_t W, uint6
 }
 
 // Symmetric scan of the whole matrix; encP = encoded signatures in scan-position order (rows and columns),
-// perm = position -> cell id (nullptr: identity).  *overflowed = 1 means a candidate inbox (or the finalize
-// staging) ran out of room and NOTHING was written that the caller may use: rerun one-directionally.
+// perm = position -> cell id (nullptr: identity).  *overflowed != 0 means the log pool ran dry (bit 0) and NOTHING
+// that was written may be used: rerun one-directionally.
 int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, uint64_t cellCount, uint32_t K, uint64_t k,
                  uint32_t tau0, const float* lut, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s, int* overflowed)
 {
