@@ -24,6 +24,7 @@ LIB_PATH = os.path.join(_HERE, "libem2b200.so")
 VARIANT_AUTO, VARIANT_POPC, VARIANT_MMA_I8 = 0, 1, 2
 SIMPAIR_DTYPE = np.dtype([("cell", "<u4"), ("similarity", "<f4")])  # SimilarPairs::Pair
 EDGE_DTYPE = np.dtype([("vertex0", "<u4"), ("vertex1", "<u4"), ("similarity", "<f4")])  # em2_edge
+SIGNATURE_EDGE_DTYPE = np.dtype([("vertex0", "<u4"), ("vertex1", "<u4")])  # em2_signature_edge
 
 
 class Em2Error(RuntimeError):
@@ -76,6 +77,7 @@ def lib():
     L.em2_lsh_similar_pairs.argtypes = [vp, u64, u64, vp, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_exact_similar_pairs.argtypes = [vp, u64, u64, vp, vp, u64, dbl, vp, vp]
     L.em2_cell_graph_edges.argtypes = [vp, u64, u64, vp, vp, vp, dbl, u64, vp, u64, vp]
+    L.em2_signature_graph.argtypes = [vp, vp, u64, u64, u64, vp, vp, u64, vp, vp, u64, vp]
     L.em2_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, u64, vp, vp, vp]
     L.em2_lsh_similar_pairs_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, u64, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_cell_sums_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
@@ -298,6 +300,23 @@ class Engine:
         self._check(self._L.em2_cell_graph_edges(self._h, n, k, _ptr(pairs), _ptr(used), _ptr(vertex_of), similarity_threshold,
                                                  max_connectivity, _ptr(out), cap, C.addressof(count)), "em2_cell_graph_edges")
         return out[: int(count.value)].copy()
+
+    def signature_graph(self, signatures, lsh_count: int, min_cell_count: int, edge_capacity: int | None = None):
+        """Vertices and edges of the reference's SignatureGraph (em2_signature_graph).
+        Returns (cell_order uint32[kept], vertex_offsets uint64[V+1], edges SIGNATURE_EDGE_DTYPE[E]): the cells of
+        vertex v are cell_order[vertex_offsets[v]:vertex_offsets[v+1]] (ascending), vertices are in the lexicographic
+        order of their signatures, edges in the reference's insertion order."""
+        sig = np.ascontiguousarray(signatures, np.uint64)
+        n = sig.shape[0]
+        order = np.zeros(max(n, 1), np.uint32)
+        offsets = np.zeros(n + 1, np.uint64)
+        vcount, ecount = C.c_uint64(0), C.c_uint64(0)
+        cap = edge_capacity if edge_capacity is not None else max(1, min(n * lsh_count, 1 << 26))
+        edges = np.zeros(cap, SIGNATURE_EDGE_DTYPE)
+        self._check(self._L.em2_signature_graph(self._h, _ptr(sig), n, lsh_count, min_cell_count, _ptr(order), _ptr(offsets), n,
+                                                C.addressof(vcount), _ptr(edges), cap, C.addressof(ecount)), "em2_signature_graph")
+        v = int(vcount.value)
+        return order[: int(offsets[v])].copy(), offsets[: v + 1].copy(), edges[: int(ecount.value)].copy()
 
     def lsh_similar_pairs_into(self, toc, pairs, lsh_vectors, k: int, similarity_threshold: float, out_pairs, out_used,
                                variant: int = VARIANT_AUTO) -> None:

@@ -705,6 +705,44 @@ int em2_cell_graph_edges(em2_context* ctx, uint64_t cellCount, uint64_t k, const
     return EM2_OK;
 }
 
+int em2_signature_graph(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                        uint64_t minCellCount, uint32_t* cellOrder, uint64_t* vertexOffsets, uint64_t vertexCapacity,
+                        uint64_t* vertexCount, em2_signature_edge* edges, uint64_t edgeCapacity, uint64_t* edgeCount)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!vertexCount || !edgeCount || !vertexOffsets || (cellCount && (!signatures || !cellOrder)) || (edgeCapacity && !edges))
+        return fail(ctx, EM2_ERR_INVALID, "em2_signature_graph: null pointer");
+    if (lshCount == 0 || lshCount > 65535) return fail(ctx, EM2_ERR_INVALID, "em2_signature_graph: lshCount must be in [1, 65535]");
+    resetStats(ctx);
+    const double t0 = nowMs();
+    *vertexCount = 0;
+    *edgeCount = 0;
+    vertexOffsets[0] = 0;
+    if (cellCount == 0) return EM2_OK;
+    cudaStream_t s = ctx->stream;
+    const uint64_t W = wordCount(lshCount);
+    const uint64_t vCap = std::min<uint64_t>(vertexCapacity, cellCount);
+    void *dSig, *dOrder, *dOffsets, *dEdges;
+    EM2_TRY(reserve(ctx, em2_context::S_SIG, cellCount * W * sizeof(uint64_t), &dSig));
+    EM2_TRY(reserve(ctx, em2_context::S_USED, cellCount * sizeof(uint32_t), &dOrder));
+    EM2_TRY(reserve(ctx, em2_context::S_SUM1, (cellCount + 1) * sizeof(uint64_t), &dOffsets));
+    EM2_TRY(reserve(ctx, em2_context::S_SRCCOUNTS, std::max<uint64_t>(edgeCapacity, 1) * sizeof(em2_signature_edge), &dEdges));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dSig, signatures, cellCount * W * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += cellCount * W * sizeof(uint64_t);
+    uint64_t kept = 0;
+    EM2_TRY(launchSignatureGraph(ctx, static_cast<uint64_t*>(dSig), cellCount, lshCount, minCellCount, static_cast<uint32_t*>(dOrder),
+                                 static_cast<uint64_t*>(dOffsets), vCap, vertexCount, &kept, static_cast<em2_signature_edge*>(dEdges),
+                                 edgeCapacity, edgeCount, s));
+    if (kept) EM2_CUDA(ctx, cudaMemcpyAsync(cellOrder, dOrder, kept * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(vertexOffsets, dOffsets, (*vertexCount + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (*edgeCount)
+        EM2_CUDA(ctx, cudaMemcpyAsync(edges, dEdges, *edgeCount * sizeof(em2_signature_edge), cudaMemcpyDeviceToHost, s));
+    ctx->stats.d2h_bytes += kept * 4 + (*vertexCount + 1) * 8 + *edgeCount * sizeof(em2_signature_edge);
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
 int em2_exact_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                             const em2_count* counts, uint64_t k, double similarityThreshold, em2_pair* pairs,
                             uint32_t* usedCount)

@@ -160,6 +160,11 @@ int launchSubset(em2_context* ctx, uint64_t cellCount, const uint64_t* srcToc, c
 int launchCellGraphEdges(em2_context* ctx, uint64_t cellCount, uint64_t k, const em2_pair* pairs, const uint32_t* usedCount,
                          const uint32_t* vertexOf, double similarityThreshold, uint64_t maxConnectivity, em2_edge* edges,
                          uint64_t capacity, uint64_t* edgeCountHost, cudaStream_t s);
+// SignatureGraph vertices and edges (siggraph.cu); sig and the outputs are device pointers, the counts host pointers.
+int launchSignatureGraph(em2_context* ctx, const uint64_t* sig, uint64_t cellCount, uint64_t lshCount, uint64_t minCellCount,
+                         uint32_t* cellOrder, uint64_t* vertexOffsets, uint64_t vertexCapacity, uint64_t* vertexCountHost,
+                         uint64_t* keptCellsHost, em2_signature_edge* edges, uint64_t edgeCapacity, uint64_t* edgeCountHost,
+                         cudaStream_t s);
 int launchScanTopK(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                    uint64_t rowBegin, uint64_t rowEnd, uint64_t k, int64_t mismatchMax, const float* lut,
                    int variant, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);

@@ -203,6 +203,27 @@ int em2_cell_graph_edges(em2_context* ctx, uint64_t cellCount, uint64_t k, const
                          const uint32_t* vertexOf, double similarityThreshold, uint64_t maxConnectivity, em2_edge* edges,
                          uint64_t capacity, uint64_t* edgeCount);
 
+/* ------------------------------------------------------------------------------------------------
+ * SignatureGraph construction.  Replaces the std::map grouping of
+ * ExpressionMatrix::createSignatureGraph (src/ExpressionMatrixSignatureGraph.cpp:69-125) and
+ * SignatureGraph::createEdges (src/SignatureGraph.cpp:23-48).  Cells (ids local to the cell set the Lsh object
+ * was built for) with identical signatures form one vertex; vertices are numbered in the lexicographic order of
+ * the signature words (std::map<BitSetPointer,...> order, src/BitSet.hpp:157-160); signatures with fewer than
+ * minCellCount cells get no vertex.  cellOrder lists the cells of vertex v at
+ * [vertexOffsets[v], vertexOffsets[v+1]) in ascending id (vertex.localCellIds); the vertex's signature is that of
+ * any of them.  edges: for every vertex, for every zero bit of its signature in bit order, the vertex whose
+ * signature has that bit set, if there is one -- the reference's add_edge order.
+ * All buffers are host buffers; vertexOffsets holds vertexCapacity + 1 entries.  If a capacity is too small the
+ * call fails with EM2_ERR_INVALID after writing the required counts to *vertexCount / *edgeCount.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct em2_signature_edge {
+    uint32_t vertex0;   /* the end whose signature has the bit clear */
+    uint32_t vertex1;
+} em2_signature_edge;
+int em2_signature_graph(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                        uint64_t minCellCount, uint32_t* cellOrder, uint64_t* vertexOffsets, uint64_t vertexCapacity,
+                        uint64_t* vertexCount, em2_signature_edge* edges, uint64_t edgeCapacity, uint64_t* edgeCount);
+
 /* Exact path (findSimilarPairs0, src/ExpressionMatrixFindSimilarPairs.cpp:16-88 with
  * ExpressionMatrixSubset::computeCellSimilarity, src/ExpressionMatrixSubset.cpp:83-133):
  * Pearson correlation over all genes, deterministic top-k by (similarity desc, cellId asc) among

@@ -339,6 +339,58 @@ def cell_graph_edges(ids, sims, used, vertex_of, similarity_threshold: float, ma
     return np.array(v0s, np.uint32), np.array(v1s, np.uint32), np.array(ss, np.float32)
 
 
+def signature_graph(signatures, lsh_count: int, min_cell_count: int):
+    """Vertices and edges of the reference's SignatureGraph, restated in numpy/Python:
+    ExpressionMatrix::createSignatureGraph (src/ExpressionMatrixSignatureGraph.cpp:69-75, 111-125): cells with the same
+    signature -> one vertex, std::map order = lexicographic over the 64-bit words (src/BitSet.hpp:157-160), cells in
+    ascending id, signatures with fewer than min_cell_count cells dropped; SignatureGraph::createEdges
+    (src/SignatureGraph.cpp:23-48): per vertex, per ZERO bit in bit order (bit 0 = MSB of word 0, BitSet.hpp:57-63),
+    an edge to the vertex whose signature has that bit set.
+    Returns (cell_order uint32, vertex_offsets uint64[V+1], edges int64[E, 2])."""
+    sig = np.ascontiguousarray(signatures, np.uint64)
+    n, W = sig.shape
+    groups = {}
+    for c in range(n):
+        groups.setdefault(tuple(int(x) for x in sig[c]), []).append(c)
+    keys = sorted(k for k, cells in groups.items() if len(cells) >= min_cell_count)      # tuple order == word order
+    index = {k: v for v, k in enumerate(keys)}
+    order, offsets = [], [0]
+    for k in keys:
+        order.extend(groups[k])
+        offsets.append(len(order))
+    edges = []
+    for v0, k in enumerate(keys):
+        for bit in range(lsh_count):
+            w, mask = bit >> 6, 1 << (63 - (bit & 63))
+            if k[w] & mask:
+                continue
+            k1 = k[:w] + (k[w] | mask,) + k[w + 1:]
+            v1 = index.get(k1)
+            if v1 is not None:
+                edges.append((v0, v1))
+    return (np.array(order, np.uint32), np.array(offsets, np.uint64),
+            np.array(edges, np.int64).reshape(-1, 2))
+
+
+def ref_signature_graph(signatures, lsh_count: int, min_cell_count: int):
+    """The same through the reference's own BitSet classes (oracle/_ref, ref_driver.cpp em2ref_signature_graph)."""
+    sig = np.ascontiguousarray(signatures, np.uint64)
+    n = sig.shape[0]
+    L = rlib()
+    u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    L.em2ref_signature_graph.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint64, u32p, u64p, u64p, u32p, u32p, C.c_uint64, u64p]
+    L.em2ref_signature_graph.restype = C.c_int
+    order = np.zeros(max(n, 1), np.uint32)
+    offsets = np.zeros(n + 1, np.uint64)
+    cap = max(1, n * lsh_count)
+    e0, e1 = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    vc, ec = C.c_uint64(0), C.c_uint64(0)
+    _check(L.em2ref_signature_graph(_ptr(sig, u64p), n, lsh_count, min_cell_count, _ptr(order, u32p), _ptr(offsets, u64p),
+                                    C.byref(vc), _ptr(e0, u32p), _ptr(e1, u32p), cap, C.byref(ec)))
+    v, e = int(vc.value), int(ec.value)
+    return order[: int(offsets[v])].copy(), offsets[: v + 1].copy(), np.stack([e0[:e], e1[:e]], axis=1).astype(np.int64)
+
+
 def murmur64a(data: bytes, seed: int = 231) -> int:
     buf = C.create_string_buffer(data, len(data))
     return int(olib().em2o_murmur64a(buf, len(data), seed))

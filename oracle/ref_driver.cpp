@@ -515,4 +515,53 @@ int em2ref_normal_stream(uint32_t seed, uint64_t n, double* out)
 
 uint64_t em2ref_murmur64a(const void* p, int len, uint64_t seed) { return MurmurHash64A(p, len, seed); }
 
+// SignatureGraph vertices and edges.  SignatureGraph itself needs Boost.Graph (absent here), so the two loops of
+// ExpressionMatrix::createSignatureGraph (ExpressionMatrixSignatureGraph.cpp:69-75, 111-125) and
+// SignatureGraph::createEdges (SignatureGraph.cpp:23-48) are restated -- over the reference's OWN BitSetPointer /
+// BitSet (BitSet.hpp): the std::map order is its operator<, the bit tests are its get() / set().
+// Vertices are numbered in map order (boost add_vertex on a vecS graph hands out 0, 1, 2, ...).
+int em2ref_signature_graph(const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount, uint64_t minCellCount,
+                           uint32_t* cellOrder, uint64_t* vertexOffsets, uint64_t* vertexCount, uint32_t* edgeV0,
+                           uint32_t* edgeV1, uint64_t edgeCapacity, uint64_t* edgeCount)
+{
+    return guarded([&] {
+        const uint64_t W = (lshCount - 1) / 64 + 1;
+        std::map<BitSetPointer, vector<CellId>> signatureMap;
+        for (CellId cellId = 0; cellId < cellCount; cellId++)
+            signatureMap[BitSetPointer(const_cast<uint64_t*>(signatures) + uint64_t(cellId) * W, W)].push_back(cellId);
+        std::map<BitSetPointer, uint32_t> vertexMap;
+        vector<BitSetPointer> vertexSignature;
+        uint64_t cells = 0;
+        vertexOffsets[0] = 0;
+        for (const auto& p : signatureMap) {
+            if (p.second.size() < minCellCount) continue;
+            vertexMap.insert(std::make_pair(p.first, uint32_t(vertexSignature.size())));
+            vertexSignature.push_back(p.first);
+            for (const CellId c : p.second) cellOrder[cells++] = c;
+            vertexOffsets[vertexSignature.size()] = cells;
+        }
+        *vertexCount = vertexSignature.size();
+        uint64_t edges = 0;
+        BitSet signature1(lshCount);
+        for (uint32_t v0 = 0; v0 < vertexSignature.size(); v0++) {
+            const BitSetPointer signature0 = vertexSignature[v0];
+            for (size_t bit = 0; bit != lshCount; bit++) {
+                if (signature0.get(bit) == 0) {
+                    std::copy(signature0.begin, signature0.end, signature1.begin);
+                    signature1.set(bit);
+                    const auto it1 = vertexMap.find(signature1);
+                    if (it1 != vertexMap.end()) {
+                        if (edges < edgeCapacity) {
+                            edgeV0[edges] = v0;
+                            edgeV1[edges] = it1->second;
+                        }
+                        edges++;
+                    }
+                }
+            }
+        }
+        *edgeCount = edges;
+    });
+}
+
 }  // extern "C"

@@ -722,3 +722,31 @@ def test_symmetric_scan_on_a_fresh_context(oracle):
         got = _sym(fresh, sig, L, k, thr)
         ref = fresh.find_similar_pairs(sig, L, k, thr, variant=em2.VARIANT_POPC)
     _check_lists(got, ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# SignatureGraph construction
+# ---------------------------------------------------------------------------------------------------
+def _check_signature_graph(engine, oracle, sig, L, min_cells):
+    order, offsets, edges = engine.signature_graph(sig, L, min_cells)
+    worder, woffsets, wedges = oracle.signature_graph(sig, L, min_cells)
+    assert np.array_equal(offsets, woffsets)
+    assert np.array_equal(order, worder)
+    assert np.array_equal(np.stack([edges["vertex0"], edges["vertex1"]], axis=1).astype(np.int64).reshape(-1, 2), wedges)
+
+
+def test_signature_graph_matches_the_reference_loops(engine, oracle):
+    """Vertices in std::map order with their cells in ascending id, the minimum-size cut, and the Hamming-1 edges
+    in (vertex, bit) order must equal the restated reference loops -- one word, several words, degenerate inputs."""
+    from test_oracle import _signature_graph_cases
+    for sig, L, min_cells in _signature_graph_cases():
+        _check_signature_graph(engine, oracle, sig, L, min_cells)
+
+
+def test_signature_graph_at_scale(engine, oracle):
+    """200k cells with 16-bit signatures (the regime SignatureGraph is meant for: most of the 65536 signatures
+    populated), and a capacity that is too small must be reported, not overrun."""
+    sig = synthetic.gen_signatures(200_000, 16, seed=4, clusters=50, flip_fraction=0.2)
+    _check_signature_graph(engine, oracle, sig, 16, 2)
+    with pytest.raises(em2.Em2Error):
+        engine.signature_graph(sig, 16, 2, edge_capacity=10)

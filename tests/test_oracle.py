@@ -137,3 +137,36 @@ def test_subset_restatement_matches_reference_constructor():
             assert np.array_equal(x, y)
         s1, s2 = oracle.cell_sums(a[0], a[2])
         assert np.array_equal(s1, b[3]) and np.array_equal(s2, b[4])
+
+
+def _signature_graph_cases():
+    from expressionmatrix2_b200 import synthetic
+    rng = np.random.default_rng(11)
+    base = synthetic.gen_signatures(40, 12, seed=3)
+    yield base[rng.integers(0, 40, 600)], 12, 1                 # 12-bit signatures: many shared, dense Hamming-1 links
+    yield base[rng.integers(0, 40, 600)], 12, 10                # sparse vertices after the minimum-size cut
+    yield synthetic.gen_signatures(500, 9, seed=5), 9, 1        # 512 possible signatures, 500 cells
+    wide = synthetic.gen_signatures(30, 130, seed=7)            # three words, bits across word boundaries
+    cells = wide[rng.integers(0, 30, 300)].copy()
+    flip = cells[:60].copy()
+    for i in range(60):                                         # planted Hamming-1 neighbours in every word
+        b = int(rng.integers(0, 130))
+        flip[i, b >> 6] ^= np.uint64(1) << np.uint64(63 - (b & 63))
+    yield np.concatenate([cells, flip]), 130, 1
+    yield np.zeros((5, 1), np.uint64), 1, 1                     # one signature, one vertex, no edge
+    yield np.array([[0], [1 << 63], [0]], np.uint64), 1, 1      # both 1-bit signatures: one edge
+
+
+def test_signature_graph_restatement_matches_reference_bitsets():
+    """oracle.signature_graph (numpy/Python) against the same loops run over the reference's own BitSetPointer /
+    BitSet (map order, get, set; oracle/_ref): vertices, their cells and the edge list in insertion order."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("reference build (oracle/_ref) not present")
+    for sig, L, min_cells in _signature_graph_cases():
+        a = oracle.signature_graph(sig, L, min_cells)
+        b = oracle.ref_signature_graph(sig, L, min_cells)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    order, offsets, edges = oracle.signature_graph(np.array([[0], [1 << 63], [0]], np.uint64), 1, 1)
+    assert order.tolist() == [0, 2, 1] and offsets.tolist() == [0, 2, 3] and edges.tolist() == [[0, 1]]
