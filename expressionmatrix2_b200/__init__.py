@@ -78,6 +78,7 @@ def lib():
     L.em2_exact_similar_pairs.argtypes = [vp, u64, u64, vp, vp, u64, dbl, vp, vp]
     L.em2_cell_graph_edges.argtypes = [vp, u64, u64, vp, vp, vp, dbl, u64, vp, u64, vp]
     L.em2_signature_graph.argtypes = [vp, vp, u64, u64, u64, vp, vp, u64, vp, vp, u64, vp]
+    L.em2_find_similar_pairs7.argtypes = [vp, vp, u64, u64, u64, dbl, vp, u64, C.c_uint32, u64, vp, vp]
     L.em2_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, u64, vp, vp, vp]
     L.em2_lsh_similar_pairs_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, u64, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
     L.em2_cell_sums_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
@@ -300,6 +301,19 @@ class Engine:
         self._check(self._L.em2_cell_graph_edges(self._h, n, k, _ptr(pairs), _ptr(used), _ptr(vertex_of), similarity_threshold,
                                                  max_connectivity, _ptr(out), cap, C.addressof(count)), "em2_cell_graph_edges")
         return out[: int(count.value)].copy()
+
+    def find_similar_pairs7(self, signatures, lsh_count: int, k: int, similarity_threshold: float, slice_lengths, max_check: int,
+                            log2_bucket_count: int):
+        """Bucketed LSH search with the semantics of the reference's findSimilarPairs7 (em2_find_similar_pairs7).
+        Returns (ids uint32 [N,k], sims float32 [N,k], used uint32 [N])."""
+        sig = np.ascontiguousarray(signatures, np.uint64)
+        n = sig.shape[0]
+        sl = np.ascontiguousarray(slice_lengths, np.int32)
+        out = np.zeros((n, k), SIMPAIR_DTYPE)
+        used = np.zeros(n, np.uint32)
+        self._check(self._L.em2_find_similar_pairs7(self._h, _ptr(sig), n, lsh_count, k, similarity_threshold, _ptr(sl), len(sl),
+                                                    max_check, log2_bucket_count, _ptr(out), _ptr(used)), "em2_find_similar_pairs7")
+        return np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used
 
     def signature_graph(self, signatures, lsh_count: int, min_cell_count: int, edge_capacity: int | None = None):
         """Vertices and edges of the reference's SignatureGraph (em2_signature_graph).

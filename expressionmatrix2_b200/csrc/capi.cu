@@ -705,6 +705,59 @@ int em2_cell_graph_edges(em2_context* ctx, uint64_t cellCount, uint64_t k, const
     return EM2_OK;
 }
 
+int em2_find_similar_pairs7(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount, uint64_t k,
+                            double similarityThreshold, const int32_t* lshSliceLengths, uint64_t sliceLengthCount,
+                            uint32_t maxCheck, uint64_t log2BucketCount, em2_pair* pairs, uint32_t* usedCount)
+{
+    EM2_TRY(guardDevice(ctx));
+    if (!lshSliceLengths || (cellCount && (!signatures || !pairs || !usedCount)))
+        return fail(ctx, EM2_ERR_INVALID, "em2_find_similar_pairs7: null pointer");
+    if (lshCount == 0 || lshCount > 65535) return fail(ctx, EM2_ERR_INVALID, "lshCount must be in [1, 65535]");
+    if (k == 0 || k > 1024) return fail(ctx, EM2_ERR_INVALID, "k must be in [1, 1024]");
+    if (maxCheck == 0) return fail(ctx, EM2_ERR_INVALID, "maxCheck must be positive");
+    if (log2BucketCount == 0 || log2BucketCount > 32) return fail(ctx, EM2_ERR_INVALID, "log2BucketCount must be in [1, 32]");
+    if (cellCount > 0xfffffff0ull) return fail(ctx, EM2_ERR_INVALID, "cellCount exceeds the 32-bit CellId range");
+    for (uint64_t i = 0; i < sliceLengthCount; i++) {
+        // the reference's own checks (src/ExpressionMatrixLsh.cpp:552-564)
+        if (i && lshSliceLengths[i] >= lshSliceLengths[i - 1]) return fail(ctx, EM2_ERR_INVALID, "The slice lengths are not in decreasing order.");
+        if (lshSliceLengths[i] > 64) return fail(ctx, EM2_ERR_INVALID, "Each slice length can be at most 64 bits.");
+        if (lshSliceLengths[i] < 1) return fail(ctx, EM2_ERR_INVALID, "Each slice length must be positive.");
+    }
+    resetStats(ctx);
+    const double t0 = nowMs();
+    if (cellCount == 0) return EM2_OK;
+    // Lsh::computeMismatchCountThresholdFromSimilarityThreshold (src/Lsh.hpp:86-95): (first m with table[m] < threshold) - 1
+    std::vector<double> table(lshCount + 1);
+    em2_similarity_table(lshCount, table.data());
+    uint64_t first = lshCount + 1;
+    for (uint64_t m = 0; m <= lshCount; m++)
+        if (table[m] < similarityThreshold) {
+            first = m;
+            break;
+        }
+    if (first > lshCount) return fail(ctx, EM2_ERR_INVALID, "similarityThreshold is below every similarity (the reference asserts here)");
+    const uint32_t mismatchThreshold = first == 0 ? 0xffffffffu : uint32_t(first - 1);
+    cudaStream_t s = ctx->stream;
+    const uint64_t W = wordCount(lshCount);
+    void *dSig, *dPairs, *dUsed;
+    EM2_TRY(reserve(ctx, em2_context::S_SIG, cellCount * W * sizeof(uint64_t), &dSig));
+    EM2_TRY(reserve(ctx, em2_context::S_PAIRS, cellCount * k * sizeof(em2_pair), &dPairs));
+    EM2_TRY(reserve(ctx, em2_context::S_USED, cellCount * sizeof(uint32_t), &dUsed));
+    float* dLut = nullptr;
+    EM2_TRY(uploadLut(ctx, lshCount, &dLut));
+    EM2_CUDA(ctx, cudaMemcpyAsync(dSig, signatures, cellCount * W * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    ctx->stats.h2d_bytes += cellCount * W * sizeof(uint64_t);
+    EM2_TRY(launchBucketedSearch(ctx, static_cast<uint64_t*>(dSig), cellCount, lshCount, k, mismatchThreshold, dLut, lshSliceLengths,
+                                 sliceLengthCount, maxCheck, uint32_t(log2BucketCount), static_cast<em2_pair*>(dPairs),
+                                 static_cast<uint32_t*>(dUsed), s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(pairs, dPairs, cellCount * k * sizeof(em2_pair), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaMemcpyAsync(usedCount, dUsed, cellCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    EM2_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.d2h_bytes += cellCount * k * sizeof(em2_pair) + cellCount * sizeof(uint32_t);
+    ctx->stats.total_ms = nowMs() - t0;
+    return EM2_OK;
+}
+
 int em2_signature_graph(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                         uint64_t minCellCount, uint32_t* cellOrder, uint64_t* vertexOffsets, uint64_t vertexCapacity,
                         uint64_t* vertexCount, em2_signature_edge* edges, uint64_t edgeCapacity, uint64_t* edgeCount)

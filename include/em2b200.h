@@ -224,6 +224,20 @@ int em2_signature_graph(em2_context* ctx, const uint64_t* signatures, uint64_t c
                         uint64_t minCellCount, uint32_t* cellOrder, uint64_t* vertexOffsets, uint64_t vertexCapacity,
                         uint64_t* vertexCount, em2_signature_edge* edges, uint64_t edgeCapacity, uint64_t* edgeCount);
 
+/* ------------------------------------------------------------------------------------------------
+ * Bucketed LSH search.  Replaces ExpressionMatrix::findSimilarPairs7 and its bucket
+ * assignment (src/ExpressionMatrixLsh.cpp:507-687, 707-827) on signatures that already exist (an Lsh-<name>
+ * object): for every slice length (strictly decreasing, each 1..64 bits) and every slice of that length a cell
+ * falls into the bucket of its slice value (hashed with MurmurHash64A seed 231 when the slice has at least
+ * log2BucketCount bits); per cell the buckets are walked in that order, every cell not looked at before is a
+ * candidate, at most maxCheck candidates are examined, candidates with a mismatch count below the reference's
+ * threshold (Lsh::computeMismatchCountThresholdFromSimilarityThreshold, strict) compete for the k list places by
+ * (mismatch, cellId).  Output layout as em2_find_similar_pairs.  log2BucketCount in [1, 32].
+ * ---------------------------------------------------------------------------------------------- */
+int em2_find_similar_pairs7(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount, uint64_t k,
+                            double similarityThreshold, const int32_t* lshSliceLengths, uint64_t sliceLengthCount,
+                            uint32_t maxCheck, uint64_t log2BucketCount, em2_pair* pairs, uint32_t* usedCount);
+
 /* Exact path (findSimilarPairs0, src/ExpressionMatrixFindSimilarPairs.cpp:16-88 with
  * ExpressionMatrixSubset::computeCellSimilarity, src/ExpressionMatrixSubset.cpp:83-133):
  * Pearson correlation over all genes, deterministic top-k by (similarity desc, cellId asc) among

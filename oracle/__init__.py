@@ -523,6 +523,22 @@ class Reference:
         _check(rlib().em2ref_get_similarity_table(self._h, _ptr(out, f64p)))
         return out
 
+    def find_similar_pairs7(self, k: int, similarity_threshold: float, slice_lengths, max_check: int, log2_bucket_count: int):
+        """ExpressionMatrix::findSimilarPairs7 (bucketed LSH; src/ExpressionMatrixLsh.cpp:507-827) restated over this
+        reference Lsh object (ref_driver.cpp em2ref_find_similar_pairs7).  Returns (ids, sims float32, used)."""
+        L = rlib()
+        i32p = C.POINTER(C.c_int32)
+        L.em2ref_find_similar_pairs7.argtypes = [C.c_void_p, C.c_uint64, C.c_double, i32p, C.c_uint64, C.c_uint32, C.c_uint64,
+                                                 u32p, f32p, u32p]
+        L.em2ref_find_similar_pairs7.restype = C.c_int
+        sl = np.ascontiguousarray(slice_lengths, np.int32)
+        ids = np.zeros((self.cell_count, k), np.uint32)
+        sims = np.zeros((self.cell_count, k), np.float32)
+        used = np.zeros(self.cell_count, np.uint32)
+        _check(L.em2ref_find_similar_pairs7(self._h, k, similarity_threshold, _ptr(sl, i32p), len(sl), max_check, log2_bucket_count,
+                                            _ptr(ids, u32p), _ptr(sims, f32p), _ptr(used, u32p)))
+        return ids, sims, used
+
     def mismatch_counts(self, c0, c1) -> np.ndarray:
         c0 = _c(c0, np.uint32)
         c1 = _c(c1, np.uint32)

@@ -515,6 +515,104 @@ int em2ref_normal_stream(uint32_t seed, uint64_t n, double* out)
 
 uint64_t em2ref_murmur64a(const void* p, int len, uint64_t seed) { return MurmurHash64A(p, len, seed); }
 
+// ExpressionMatrix::findSimilarPairs7 (ExpressionMatrixLsh.cpp:507-687) and its bucket assignment
+// (findSimilarPairs7AssignCellsToBuckets, :707-827).  ExpressionMatrix itself cannot be compiled here (HTTP server,
+// HDF5, Boost.Graph ...), so the two member functions are restated statement by statement over the reference's OWN
+// Lsh object (getSignature, computeMismatchCount, getSimilarity, computeMismatchCountThresholdFromSimilarityThreshold),
+// BitSet (getBits, the cellMap), MurmurHash64A and keepBest; what SimilarPairs::addUnsymmetricNoCheck would store
+// (cellId1, float(similarity), in this order) is returned row by row.
+int em2ref_find_similar_pairs7(void* handle, uint64_t k, double similarityThreshold, const int32_t* sliceLengths,
+                               uint64_t sliceLengthCount, uint32_t maxCheck, uint64_t log2BucketCount, uint32_t* outIds,
+                               float* outSims, uint32_t* outUsed)
+{
+    return guarded([&] {
+        Handle& h = *static_cast<Handle*>(handle);
+        Lsh& lsh = *h.lsh;
+        const CellId cellCount = lsh.cellCount();
+        const size_t lshBitCount = lsh.lshCount();
+        const vector<int> lshSliceLengths(sliceLengths, sliceLengths + sliceLengthCount);
+        for (size_t i = 1; i < sliceLengthCount; i++)
+            if (lshSliceLengths[i] >= lshSliceLengths[i - 1]) throw runtime_error("The slice lengths are not in decreasing order.");
+        for (size_t i = 0; i < sliceLengthCount; i++)
+            if (lshSliceLengths[i] > 64) throw runtime_error("Each slice length can be at most 64 bits.");
+
+        // ---- findSimilarPairs7AssignCellsToBuckets
+        vector<vector<vector<vector<CellId>>>> table4(sliceLengthCount);
+        vector<vector<vector<size_t>>> sliceBits3(sliceLengthCount);
+        const uint64_t bucketCount = (1ULL << log2BucketCount);
+        const uint64_t bucketMask = bucketCount - 1ULL;
+        for (size_t sliceLengthId = 0; sliceLengthId < sliceLengthCount; sliceLengthId++) {
+            const size_t sliceLength = lshSliceLengths[sliceLengthId];
+            const size_t sliceCount = lshBitCount / sliceLength;
+            table4[sliceLengthId].resize(sliceCount);
+            sliceBits3[sliceLengthId].resize(sliceCount);
+            const uint64_t tableSize = std::min(uint64_t(1ULL << sliceLength), bucketCount);
+            for (size_t sliceId = 0; sliceId < sliceCount; sliceId++) {
+                table4[sliceLengthId][sliceId].resize(tableSize);
+                auto& sliceBits1 = sliceBits3[sliceLengthId][sliceId];
+                sliceBits1.resize(sliceLength);
+                size_t bitPosition = sliceId * sliceLength;
+                for (size_t bitId = 0; bitId < sliceLength; bitId++, ++bitPosition) sliceBits1[bitId] = bitPosition;
+            }
+        }
+        for (CellId cellId = 0; cellId < cellCount; cellId++) {
+            const BitSetPointer signature = lsh.getSignature(cellId);
+            for (size_t sliceLengthId = 0; sliceLengthId < sliceLengthCount; sliceLengthId++) {
+                const size_t sliceLength = lshSliceLengths[sliceLengthId];
+                const size_t sliceCount = lshBitCount / sliceLength;
+                for (size_t sliceId = 0; sliceId < sliceCount; sliceId++) {
+                    const uint64_t signatureSlice = signature.getBits(sliceBits3[sliceLengthId][sliceId]);
+                    const uint64_t bucketId = (sliceLength < log2BucketCount) ? signatureSlice
+                                                                              : (MurmurHash64A(&signatureSlice, 8, 231) & bucketMask);
+                    table4[sliceLengthId][sliceId].at(bucketId).push_back(cellId);
+                }
+            }
+        }
+
+        // ---- the search loop
+        BitSet cellMap(cellCount);
+        vector<CellId> candidateNeighbors;
+        vector<pair<uint32_t, CellId>> neighbors;
+        const size_t mismatchCountThreshold = lsh.computeMismatchCountThresholdFromSimilarityThreshold(similarityThreshold);
+        for (CellId cellId0 = 0; cellId0 < cellCount; cellId0++) {
+            const BitSetPointer signature = lsh.getSignature(cellId0);
+            for (size_t sliceLengthId = 0; sliceLengthId < sliceLengthCount; sliceLengthId++) {
+                const size_t sliceLength = lshSliceLengths[sliceLengthId];
+                const size_t sliceCount = lshBitCount / sliceLength;
+                for (size_t sliceId = 0; sliceId < sliceCount; sliceId++) {
+                    const uint64_t signatureSlice = signature.getBits(sliceBits3[sliceLengthId][sliceId]);
+                    const uint64_t bucketId = (sliceLength < log2BucketCount) ? signatureSlice
+                                                                              : (MurmurHash64A(&signatureSlice, 8, 231) & bucketMask);
+                    const auto& table1 = table4[sliceLengthId][sliceId].at(bucketId);
+                    for (const CellId cellId1 : table1) {
+                        if (cellId1 == cellId0) continue;
+                        if (cellMap.get(cellId1)) continue;
+                        cellMap.set(cellId1);
+                        candidateNeighbors.push_back(cellId1);
+                        const uint32_t mismatchCount = uint32_t(lsh.computeMismatchCount(cellId0, cellId1));
+                        if (mismatchCount < mismatchCountThreshold) neighbors.push_back(make_pair(mismatchCount, cellId1));
+                        if (candidateNeighbors.size() == maxCheck) break;
+                    }
+                    if (candidateNeighbors.size() == maxCheck) break;
+                }
+                if (candidateNeighbors.size() == maxCheck) break;
+            }
+            keepBest(neighbors, k, std::less<pair<uint32_t, CellId>>());
+            sort(neighbors.begin(), neighbors.end());
+            uint32_t used = 0;
+            for (const auto& neighbor : neighbors) {
+                outIds[uint64_t(cellId0) * k + used] = neighbor.second;
+                outSims[uint64_t(cellId0) * k + used] = float(lsh.getSimilarity(neighbor.first));
+                used++;
+            }
+            outUsed[cellId0] = used;
+            for (const CellId cellId1 : candidateNeighbors) cellMap.clear(cellId1);
+            candidateNeighbors.clear();
+            neighbors.clear();
+        }
+    });
+}
+
 // SignatureGraph vertices and edges.  SignatureGraph itself needs Boost.Graph (absent here), so the two loops of
 // ExpressionMatrix::createSignatureGraph (ExpressionMatrixSignatureGraph.cpp:69-75, 111-125) and
 // SignatureGraph::createEdges (SignatureGraph.cpp:23-48) are restated -- over the reference's OWN BitSetPointer /

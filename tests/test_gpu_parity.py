@@ -750,3 +750,37 @@ def test_signature_graph_at_scale(engine, oracle):
     _check_signature_graph(engine, oracle, sig, 16, 2)
     with pytest.raises(em2.Em2Error):
         engine.signature_graph(sig, 16, 2, edge_capacity=10)
+
+
+# ---------------------------------------------------------------------------------------------------
+# bucketed LSH search, findSimilarPairs7 semantics
+# ---------------------------------------------------------------------------------------------------
+def _bucketed_cases():
+    rng = np.random.default_rng(17)
+    yield synthetic.gen_signatures(3000, 256, seed=2, clusters=30), 256, 20, 0.3, [16, 12, 8], 200, 10
+    yield synthetic.gen_signatures(3000, 256, seed=2, clusters=30), 256, 5, 0.3, [16, 12, 8], 7, 10      # cut inside a bucket
+    yield synthetic.gen_signatures(2500, 200, seed=3, clusters=20), 200, 30, 0.2, [63, 33, 5], 300, 12   # slices across words
+    base = synthetic.gen_signatures(40, 128, seed=1)
+    yield base[rng.integers(0, 40, 3000)], 128, 50, 0.5, [32, 9], 1000, 12                                # huge buckets, ties
+    yield synthetic.gen_signatures(8000, 512, seed=4, clusters=100), 512, 50, 0.2, [20, 16], 500, 16
+    yield synthetic.gen_signatures(700, 64, seed=5), 64, 10, 0.9, [8], 50, 3                              # nothing similar enough
+
+
+def test_bucketed_search_equals_the_reference_loops(engine, oracle):
+    """Tables, candidate order, the maxCheck cut-off, the strict mismatch threshold and the (mismatch, id) selection of
+    findSimilarPairs7, restated over the reference's own Lsh / BitSet / MurmurHash64A / keepBest (oracle/_ref), must be
+    reproduced list by list."""
+    if not oracle.have_ref():
+        pytest.skip("reference build (oracle/_ref) not present")
+    for sig, L, k, thr, slices, max_check, log2b in _bucketed_cases():
+        with oracle.Reference.from_signatures(sig, L) as ref:
+            want = ref.find_similar_pairs7(k, thr, slices, max_check, log2b)
+        got = engine.find_similar_pairs7(sig, L, k, thr, slices, max_check, log2b)
+        _check_lists(got, want)
+
+
+def test_bucketed_search_argument_checks(engine):
+    sig = synthetic.gen_signatures(100, 64, seed=1)
+    for slices, log2b in (([8, 8], 10), ([65], 10), ([8], 0), ([8], 33)):
+        with pytest.raises(em2.Em2Error):
+            engine.find_similar_pairs7(sig, 64, 5, 0.2, slices, 10, log2b)
