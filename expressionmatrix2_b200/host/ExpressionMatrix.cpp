@@ -219,6 +219,29 @@ void ExpressionMatrix::computeLshSignatures(const std::string& geneSetName, cons
     lastSignatureMs = Gpu::instance().stats().signatures_ms;
 }
 
+void ExpressionMatrix::findSimilarPairs7(const std::string& geneSetName, const std::string& cellSetName,
+                                         const std::string& lshName, const std::string& similarPairsName, size_t k,
+                                         double similarityThreshold, const std::vector<int>& lshSliceLengths, CellId maxCheck,
+                                         size_t log2BucketCount)
+{
+    std::cout << timestamp << "ExpressionMatrix::findSimilarPairs7 begins." << std::endl;
+    findGeneSet(geneSetName);                                   // must exist and be non-empty (reference :523-531)
+    const CellSet& cellSet = findCellSet(cellSetName);
+    Lsh lsh(directoryName + "/Lsh-" + lshName);
+    if (lsh.cellCount() != CellId(cellSet.size()))
+        throw std::runtime_error("LSH object " + lshName + " has a number of cells inconsistent with cell set " + cellSetName);
+    std::cout << "Number of LSH signature bits is " << lsh.lshCount() << std::endl;
+    for (size_t i = 1; i < lshSliceLengths.size(); i++)
+        if (lshSliceLengths[i] >= lshSliceLengths[i - 1]) throw std::runtime_error("The slice lengths are not in decreasing order.");
+    for (size_t i = 0; i < lshSliceLengths.size(); i++)
+        if (lshSliceLengths[i] > 64) throw std::runtime_error("Each slice length can be at most 64 bits.");
+    SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
+    std::cout << "Mismatch count threshold is " << lsh.computeMismatchCountThresholdFromSimilarityThreshold(similarityThreshold)
+              << std::endl;
+    lsh.findSimilarPairs7(similarPairs, k, similarityThreshold, lshSliceLengths, maxCheck, log2BucketCount);
+    std::cout << timestamp << "ExpressionMatrix::findSimilarPairs7 ends." << std::endl;
+}
+
 void ExpressionMatrix::findSimilarPairs0(std::ostream& out, const std::string& geneSetName,
                                          const std::string& cellSetName, const std::string& similarPairsName,
                                          size_t k, double similarityThreshold)

@@ -53,6 +53,11 @@ public:
     // Persistent signatures (reference src/ExpressionMatrixLsh.cpp:1150-1192): files Lsh-<lshName>-*.
     void computeLshSignatures(const std::string& geneSetName, const std::string& cellSetName,
                               const std::string& lshName, size_t lshCount, unsigned int seed);
+    // Bucketed LSH search on an existing Lsh-<lshName> object (reference src/ExpressionMatrixLsh.cpp:507-687; the
+    // gene set only names the SimilarPairs object, as there).
+    void findSimilarPairs7(const std::string& geneSetName, const std::string& cellSetName, const std::string& lshName,
+                           const std::string& similarPairsName, size_t k, double similarityThreshold,
+                           const std::vector<int>& lshSliceLengths, CellId maxCheck, size_t log2BucketCount);
     // Exact similar pairs (reference src/ExpressionMatrixFindSimilarPairs.cpp:16-99).
     void findSimilarPairs0(const std::string& geneSetName, const std::string& cellSetName,
                            const std::string& similarPairsName, size_t k, double similarityThreshold);

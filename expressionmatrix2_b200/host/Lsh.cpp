@@ -92,6 +92,22 @@ void Lsh::writeSignatureStatistics(std::ostream& csv)
     }
 }
 
+void Lsh::findSimilarPairs7(SimilarPairs& similarPairs, size_t k, double similarityThreshold,
+                            const std::vector<int>& lshSliceLengths, CellId maxCheck, size_t log2BucketCount)
+{
+    if (similarPairs.cellCount() != cellCount()) throw std::runtime_error("SimilarPairs and Lsh disagree on the cell count.");
+    if (similarPairs.k() != k) throw std::runtime_error("SimilarPairs was created with a different k.");
+    const size_t n = cellCount();
+    std::vector<uint32_t> used(n);
+    std::vector<int32_t> slices(lshSliceLengths.begin(), lshSliceLengths.end());
+    Gpu& gpu = Gpu::instance();
+    gpu.check(em2_find_similar_pairs7(gpu.context(), signatures.begin(), n, lshCount(), k, similarityThreshold, slices.data(),
+                                      slices.size(), maxCheck, log2BucketCount,
+                                      reinterpret_cast<em2_pair*>(similarPairs.begin(0)), used.data()),
+              "em2_find_similar_pairs7");
+    similarPairs.setUsedCounts(used);
+}
+
 void Lsh::findSimilarPairs(SimilarPairs& similarPairs, size_t k, double similarityThreshold, int variant)
 {
     if (similarPairs.cellCount() != cellCount()) throw std::runtime_error("SimilarPairs and Lsh disagree on the cell count.");

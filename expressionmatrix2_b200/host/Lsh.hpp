@@ -59,6 +59,10 @@ public:
     // All-pairs Hamming scan + per-cell top-k on the GPU, written straight into the mapped SimilarPairs
     // rows (already in SimilarPairs::sort() order).  variant: em2_variant.
     void findSimilarPairs(SimilarPairs&, size_t k, double similarityThreshold, int variant = 0);
+    // Bucketed search with the candidate order and lists of the reference's findSimilarPairs7
+    // (reference src/ExpressionMatrixLsh.cpp:507-827), on the GPU.
+    void findSimilarPairs7(SimilarPairs&, size_t k, double similarityThreshold, const std::vector<int>& lshSliceLengths,
+                           CellId maxCheck, size_t log2BucketCount);
 
     // Number of projections that fell inside the epsilon band around zero (reported, expected 0).
     uint64_t nearZeroProjections = 0;

@@ -91,6 +91,11 @@ PYBIND11_MODULE(ExpressionMatrix2, module)
                  ExpressionMatrix::findSimilarPairs4,
              arg("geneSetName") = "AllGenes", arg("cellSetName") = "AllCells", arg("similarPairsName"), arg("k") = 100,
              arg("similarityThreshold") = 0.2, arg("lshCount") = 1024, arg("seed") = 231)
+        .def("findSimilarPairs7", &ExpressionMatrix::findSimilarPairs7,
+             "LSH-based computation of similar cell pairs without looping over all possible pairs of cells "
+             "(candidate order and lists of the reference's findSimilarPairs7).",
+             arg("geneSetName") = "AllGenes", arg("cellSetName") = "AllCells", arg("lshName"), arg("similarPairsName"),
+             arg("k") = 100, arg("similarityThreshold") = 0.2, arg("lshSliceLengths"), arg("maxCheck"), arg("log2BucketCount"))
         .def("computeLshSignatures", &ExpressionMatrix::computeLshSignatures, arg("geneSetName") = "AllGenes",
              arg("cellSetName") = "AllCells", arg("lshName"), arg("lshCount") = 1024, arg("seed") = 231)
         .def_readwrite("scanVariant", &ExpressionMatrix::scanVariant)

@@ -28,7 +28,7 @@ def _make_matrix(M, path, N=200, G=90, seed=3):
 
 def test_module_has_reference_api(M):
     e = M.ExpressionMatrix
-    for name in ("findSimilarPairs4", "findSimilarPairs0", "computeLshSignatures", "geneCount", "cellCount"):
+    for name in ("findSimilarPairs4", "findSimilarPairs0", "findSimilarPairs7", "computeLshSignatures", "geneCount", "cellCount"):
         assert hasattr(e, name)
     doc = e.findSimilarPairs4.__doc__
     for token in ("geneSetName: str = 'AllGenes'", "cellSetName: str = 'AllCells'", "similarPairsName: str",
@@ -147,3 +147,25 @@ def test_subsets_and_persistent_signatures(M, oracle, tmp_path):
     ids, sims, used = e.getSimilarPairs("Sub")
     wi, ws, wu, _ = oracle.topk(want, L, 9, 0.1)
     assert np.array_equal(used, wu) and np.array_equal(ids, wi) and np.array_equal(sims, ws)
+
+
+@pytest.mark.gpu
+def test_find_similar_pairs7_on_persistent_signatures(M, oracle, tmp_path):
+    """computeLshSignatures -> findSimilarPairs7 with the reference's argument names: the stored lists must equal the
+    reference loops run over the reference's own Lsh object on the same signatures."""
+    if not oracle.have_ref():
+        pytest.skip("reference build (oracle/_ref) not present")
+    N, G, L, k, thr = 1200, 500, 256, 15, 0.3
+    e, _ = _make_matrix(M, tmp_path / "data", N=N, G=G, seed=11)
+    e.computeLshSignatures(lshName="S", lshCount=L, seed=231)
+    e.findSimilarPairs7(lshName="S", similarPairsName="Bucketed", k=k, similarityThreshold=thr, lshSliceLengths=[14, 10, 6],
+                        maxCheck=150, log2BucketCount=9)
+    ids, sims, used = e.getSimilarPairs("Bucketed")
+    sig = e.getLshSignatures("S")
+    with oracle.Reference.from_signatures(sig, L) as ref:
+        wi, ws, wu = ref.find_similar_pairs7(k, thr, [14, 10, 6], 150, 9)
+    assert np.array_equal(used, wu) and np.array_equal(ids, wi)
+    assert np.array_equal(sims.view(np.uint32), ws.view(np.uint32))
+    with pytest.raises(RuntimeError):
+        e.findSimilarPairs7(lshName="S", similarPairsName="Bad", k=k, similarityThreshold=thr, lshSliceLengths=[6, 10],
+                            maxCheck=150, log2BucketCount=9)
