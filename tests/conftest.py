@@ -24,6 +24,15 @@ def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
 
 
+def golden_bucketed_cases():
+    """(signatures, L, k, thr, slices, max_check, log2b, ids, sims, used) of tests/golden/next_bucketed.npz: lists the
+    reference's own classes produce for findSimilarPairs7 (tests/golden/make_golden_next_rows.py)."""
+    g = load_golden("next_bucketed")
+    for i in range(int(g["cases"])):
+        yield (g["signatures"], int(g["lsh_count"]), int(g[f"c{i}_k"]), float(g[f"c{i}_thr"]), g[f"c{i}_slices"].tolist(),
+               int(g[f"c{i}_max_check"]), int(g[f"c{i}_log2b"]), g[f"c{i}_ids"], g[f"c{i}_sims"], g[f"c{i}_used"])
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import oracle as O

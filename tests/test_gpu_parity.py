@@ -6,7 +6,7 @@ deterministic oracle (ids, order, usedCount), similarity floats 0 ULP."""
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden
+from conftest import golden_bucketed_cases, golden_cases, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -784,3 +784,14 @@ def test_bucketed_search_argument_checks(engine):
     for slices, log2b in (([8, 8], 10), ([65], 10), ([8], 0), ([8], 33)):
         with pytest.raises(em2.Em2Error):
             engine.find_similar_pairs7(sig, 64, 5, 0.2, slices, 10, log2b)
+
+
+def test_golden_bucketed_search_and_signature_graph(engine):
+    """The same two rows against committed golden vectors (tests/golden/next_*.npz, produced by the reference's own
+    classes): no reference build needed on the GPU box."""
+    for sig, L, k, thr, slices, max_check, log2b, ids, sims, used in golden_bucketed_cases():
+        _check_lists(engine.find_similar_pairs7(sig, L, k, thr, slices, max_check, log2b), (ids, sims, used))
+    g = load_golden("next_siggraph")
+    order, offsets, edges = engine.signature_graph(g["signatures"], int(g["lsh_count"]), int(g["min_cell_count"]))
+    assert np.array_equal(order, g["cell_order"]) and np.array_equal(offsets, g["vertex_offsets"])
+    assert np.array_equal(np.stack([edges["vertex0"], edges["vertex1"]], axis=1).astype(np.int64).reshape(-1, 2), g["edges"])

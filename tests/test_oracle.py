@@ -3,7 +3,7 @@ reference's own sources, and against the reference build itself when oracle/_ref
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden
+from conftest import golden_bucketed_cases, golden_cases, load_golden
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -170,3 +170,21 @@ def test_signature_graph_restatement_matches_reference_bitsets():
             assert np.array_equal(x, y)
     order, offsets, edges = oracle.signature_graph(np.array([[0], [1 << 63], [0]], np.uint64), 1, 1)
     assert order.tolist() == [0, 2, 1] and offsets.tolist() == [0, 2, 3] and edges.tolist() == [[0, 1]]
+
+
+def test_golden_vectors_of_the_next_rows_are_reproduced():
+    """tests/golden/next_*.npz (made by the reference's own classes): the numpy restatement of the SignatureGraph loops
+    reproduces the stored graph, and -- where oracle/_ref is present -- so do the reference-class drivers themselves."""
+    import oracle
+    g = load_golden("next_siggraph")
+    order, offsets, edges = oracle.signature_graph(g["signatures"], int(g["lsh_count"]), int(g["min_cell_count"]))
+    assert np.array_equal(order, g["cell_order"]) and np.array_equal(offsets, g["vertex_offsets"])
+    assert np.array_equal(edges, g["edges"])
+    cases = list(golden_bucketed_cases())
+    assert len(cases) == 2
+    if not oracle.have_ref():
+        pytest.skip("reference build (oracle/_ref) not present")
+    for sig, L, k, thr, slices, max_check, log2b, ids, sims, used in cases:
+        with oracle.Reference.from_signatures(sig, L) as ref:
+            wi, ws, wu = ref.find_similar_pairs7(k, thr, slices, max_check, log2b)
+        assert np.array_equal(wu, used) and np.array_equal(wi, ids) and np.array_equal(ws.view(np.uint32), sims.view(np.uint32))
