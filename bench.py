@@ -3,8 +3,10 @@
 
 A step = one pass of the hot path over the synthetic batch: per-cell sums -> LSH signatures ->
 (all-gather when N>1) -> all-pairs Hamming scan with fused top-k -> SimilarPairs payload.
-Workload (default "c2" = BASELINE.json configs[1]): 100k cells x 30k genes, 5% density, L=1024, k=50,
-similarityThreshold 0.2, synthetic clustered counts, hyperplanes from seed 231.
+Workload (default "m1" = the configuration BASELINE.json's metric is quoted on): 1,000,000 cells x 30k genes, 5% density
+(1500 stored counts per cell, 12 GB of CSR), L=1024, k=50, similarityThreshold 0.2, synthetic clustered counts (512
+clusters; benchdata.py, generated on the device per rank), hyperplanes from seed 231.  `--workload c2` is
+BASELINE.json configs[1] (100k cells), c1/c3/c4/c5 the other configs.
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -32,11 +34,15 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: cells, genes, nnz/cell, L, k, threshold
+    "m1": dict(cells=1_000_000, genes=30_000, nnz_per_cell=1500, lsh=1024, k=50, thr=0.2, clusters=512, hashed=True,
+               note="the metric's configuration: 1M cells x 30k genes, 5% density, full counts -> lists pipeline"),
+    "m1s": dict(cells=60_000, genes=30_000, nnz_per_cell=1500, lsh=1024, k=50, thr=0.2, clusters=32, hashed=True,
+                note="reduced m1 for quick checks (NOT a bench line)"),
     "c1": dict(cells=10_000, genes=20_000, nnz_per_cell=1000, lsh=1024, k=50, thr=0.2,
                note="BASELINE configs[0]: 10k x 20k, 5% density"),
     "c2": dict(cells=100_000, genes=30_000, nnz_per_cell=1500, lsh=1024, k=50, thr=0.2,
                note="BASELINE configs[1]: 100k x 30k, 5% density"),
-    "c3": dict(cells=1_300_000, genes=28_000, nnz_per_cell=2000, lsh=1024, k=50, thr=0.2, per_rank_generation=True,
+    "c3": dict(cells=1_300_000, genes=28_000, nnz_per_cell=2000, lsh=1024, k=50, thr=0.2, clusters=64, hashed=True,
                note="BASELINE configs[2]: 1.3M x 28k (10x mouse-brain shape, ~2.0k nnz/cell assumed), meant for 8 GPUs"),
     "c4": dict(kind="sig", cells=1_000_000, genes=0, lsh=1024, k=50, thr=0.2, clusters=500,
                note="BASELINE configs[3]: 1M cells, signatures-only synthetic (500 planted clusters, 12% bit flips); "
@@ -59,12 +65,35 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
-def int8_peak(peaks, kernel_ms):
-    """int8 tensor peak = 2x the measured dense bf16 figure: the burst number for a kernel timed alone, the
-    sustained (power-capped) one for a kernel that runs for more than ~100 ms at a time (B200_PROFILING.md)."""
-    if kernel_ms > 100.0:
-        return 2.0 * peaks["bf16_tflops_sustained"], "sustained"
-    return 2.0 * peaks["bf16_tflops"], "burst"
+_INT8 = {}
+
+
+def int8_peak(peaks, kernel_ms, device_index=0):
+    """Tensor-pipe roofline denominator of the int8 scan, MEASURED: tools/mma_peak.cu (back-to-back
+    tcgen05.mma.kind::i8 M=128 N=256 K=32, A in tensor memory -- the highest int8 issue rate the pipe gives) run live on
+    this GPU; else the committed run of the same tool (profiles/r2_mma_peak.json); else 2 x the bf16 figure of
+    MEASURED_PEAKS.json.  Burst figure for a kernel timed alone, sustained (power-capped clocks) for one that runs
+    for more than ~100 ms at a time (B200_PROFILING.md)."""
+    which = "sustained" if kernel_ms > 100.0 else "burst"
+    if not _INT8:
+        exe = os.path.join(ROOT, "expressionmatrix2_b200", "build", "mma_peak")
+        try:
+            out = subprocess.check_output([exe], env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(device_index)), timeout=120).decode()
+            _INT8.update(json.loads(out), source="tools/mma_peak.cu run live on this GPU by bench.py")
+        except Exception:
+            try:
+                _INT8.update(json.load(open(os.path.join(ROOT, "profiles", "r2_mma_peak.json"))),
+                             source="profiles/r2_mma_peak.json (tools/mma_peak.cu, committed run)")
+            except Exception:
+                _INT8.update(source="fallback")
+    key = "i8_ts_n256_tops_sustained" if which == "sustained" else "i8_ts_n256_tops"
+    if _INT8.get(key):
+        note = (f"{key} = {_INT8[key]} TOP/s, {_INT8['source']}; same run: operands in shared memory N=256 "
+                f"{_INT8.get('i8_ss_n256_tops')} (the scan kernels' instruction shape), sustained "
+                f"{_INT8.get('i8_ss_n256_tops_sustained')}; bf16 {_INT8.get('bf16_ss_n256_tflops')}")
+        return float(_INT8[key]), which, note
+    bf = peaks["bf16_tflops_sustained"] if which == "sustained" else peaks["bf16_tflops"]
+    return 2.0 * bf, which, f"2 x bf16 TF/s of MEASURED_PEAKS.json ({peaks['source']}, {which}): tools/mma_peak could not run"
 
 
 class ClockSampler:
@@ -122,41 +151,55 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def make_workload(w, seed=12345):
-    from expressionmatrix2_b200 import synthetic
-    import expressionmatrix2_b200 as em2
-    toc, genes, counts = synthetic.gen_expression_matrix_fast(w["cells"], w["genes"], w["nnz_per_cell"], seed=seed)
-    U = em2.generate_lsh_vectors(w["genes"], w["lsh"], 231)
-    return toc, genes, counts, U
+def _synthetic_module():
+    """expressionmatrix2_b200/synthetic.py loaded by path: the numpy generators of the small workloads without
+    importing the product package (the reference arm must not touch it)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_em2_synthetic", os.path.join(ROOT, "expressionmatrix2_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def host_counts(w, cell_begin, cell_end, seed=12345):
+    """(toc, gene_ids, counts) of cells [cell_begin, cell_end) of the workload, on the host."""
+    if w.get("hashed"):
+        import benchdata as bd
+        g, c = bd.counts_to_numpy(bd.gen_counts(cell_begin, cell_end, w["genes"], w["nnz_per_cell"], seed=seed,
+                                                clusters=w["clusters"]))
+        return bd.toc_of(cell_end - cell_begin, w["nnz_per_cell"]), g, c
+    toc, genes, counts = _synthetic_module().gen_expression_matrix_fast(w["cells"], w["genes"], w["nnz_per_cell"], seed=seed)
+    b, e = int(toc[cell_begin]), int(toc[cell_end])
+    return (toc[cell_begin:cell_end + 1] - toc[cell_begin]).astype(np.uint64), genes[b:e], counts[b:e]
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation (oracle/_ref), bounded sample per step
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(w, toc, genes, counts, signatures, sig_cells=1024, loop_rows=2048, lsh=None):
+def cpu_sample(w, head, signatures, loop_rows, lsh=None):
     """Times the reference's two instrumented regions on a bounded sample of the workload:
-    Lsh::computeCellLshSignatures on the first `sig_cells` cells (its own timer, Lsh.cpp:160,209) and the
-    findSimilarPairs4 pair loop (ExpressionMatrixLsh.cpp:217,270) for the last `loop_rows` cells against
-    all earlier cells.  Returns the extrapolated whole-job figures.  toc=None: signatures-only workload
-    (config 4), only the pair loop is timed."""
+    Lsh::computeCellLshSignatures on the cells of `head` = (toc, genes, counts) of the first cells (its own timer,
+    Lsh.cpp:160,209) and the findSimilarPairs4 pair loop (ExpressionMatrixLsh.cpp:217,270) for the last `loop_rows`
+    cells against all earlier cells.  Returns the extrapolated whole-job figures.  head=None: signatures-only
+    workload (config 4), only the pair loop is timed."""
     import oracle
     N, L, k, thr = w["cells"], lsh or w["lsh"], w["k"], w["thr"]
     kind = "reference" if oracle.have_ref() else "port"
-    sig_cells = min(sig_cells, N)
-    loop_rows = min(loop_rows if N < 500_000 else 1024, N)
+    loop_rows = min(loop_rows, N)
     t0 = time.time()
-    t_sig, ref_sig = 0.0, None
-    if toc is not None:
-        e = int(toc[sig_cells])
+    t_sig, ref_sig, sig_cells = 0.0, None, 0
+    if head is not None:
+        toc, genes, counts = head
+        sig_cells = len(toc) - 1
         if kind == "reference":
-            with oracle.Reference.from_csr(toc[: sig_cells + 1], genes[:e], counts[:e], w["genes"], L, 231) as R:
+            with oracle.Reference.from_csr(toc, genes, counts, w["genes"], L, 231) as R:
                 t_sig = R.signature_seconds
                 ref_sig = R.signatures()
         else:
             U = oracle.generate_lsh_vectors(w["genes"], L, 231)
-            s1, _ = oracle.cell_sums(toc[: sig_cells + 1], counts[:e])
+            s1, _ = oracle.cell_sums(toc, counts)
             t1 = time.time()
-            ref_sig, _ = oracle.signatures(toc[: sig_cells + 1], genes[:e], counts[:e], s1, U)
+            ref_sig, _ = oracle.signatures(toc, genes, counts, s1, U)
             t_sig = time.time() - t1
     if kind == "reference":
         with oracle.Reference.from_signatures(signatures, L) as R:
@@ -165,40 +208,45 @@ def cpu_sample(w, toc, genes, counts, signatures, sig_cells=1024, loop_rows=2048
     else:
         t_loop, pairs, _ = oracle.pair_loop(signatures, L, thr, N - loop_rows, N)
     total_pairs = N * (N - 1) / 2
-    sig_s_per_cell = t_sig / sig_cells
+    sig_s_per_cell = t_sig / max(sig_cells, 1)
     ns_per_pair = 1e9 * t_loop / max(pairs, 1)
     full_seconds = sig_s_per_cell * N + ns_per_pair * 1e-9 * total_pairs
-    what = (f"signatures of the first {sig_cells} cells + " if toc is not None else "")
+    what = (f"signatures of the first {sig_cells} cells + " if head is not None else "")
     out = dict(value=total_pairs / full_seconds, unit="cell-pairs/s", cores=1, kind=kind,
                sample=what + f"findSimilarPairs4 pair loop for the last {loop_rows} cells x all earlier cells "
                              f"({pairs} pairs), extrapolated to the whole job",
                ns_per_pair=ns_per_pair, signature_s_per_cell=sig_s_per_cell, extrapolated_job_seconds=full_seconds,
                sample_seconds=time.time() - t0)
     if ref_sig is not None:
-        out["sample_signatures_match_gpu"] = bool(np.array_equal(ref_sig, signatures[:sig_cells]))
+        out["_ref_sig"] = ref_sig
     return out
+
+
+def sample_sizes(N, per_step=False):
+    """Bounded CPU samples (about 15 s for the cpu_baseline leg, about 2 s per step of the reference arm):
+    (cells whose signatures the reference computes, rows of the pair loop)."""
+    budget = 1.0e8 if per_step else 1.0e9           # pair evaluations at ~13 ns each
+    rows = int(max(16, min(2048, budget // max(N, 1))))
+    return (128 if per_step else 1024), rows
 
 
 def run_reference(args, w):
     """The reference's own CPU code (oracle/_ref; the C port when the reference build is absent) on a bounded sample
-    of the same workload per step, one core (the reference is single threaded)."""
+    of the same workload per step, one core (the reference is single threaded).  Imports nothing of the product:
+    counts from the bench generators, hyperplanes from the reference's own Lsh constructor, and -- for the pair
+    loop, which needs the signatures of ALL cells -- synthetic signatures with the workload's cluster structure."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
-    from expressionmatrix2_b200 import synthetic
+    import benchdata as bd
     oracle.build()
     kind = w.get("kind", "lsh")
     N, L = w["cells"], args.lsh or w["lsh"]
-    try:
-        import torch
-        have_gpu = torch.cuda.is_available()
-    except Exception:
-        have_gpu = False
     samples = []
     if kind == "exact":
         G = w["genes"]
-        toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, w["nnz_per_cell"], seed=12345)
+        toc, genes, counts = host_counts(w, 0, N)
         s1, s2 = oracle.cell_sums(toc, counts)
         for i in range(args.warmup + args.steps):
             t0 = time.time()
@@ -211,22 +259,15 @@ def run_reference(args, w):
         sig_note = "n/a (exact path)"
         metric = "cell-pairs/sec (exact Pearson, top-50)"
     else:
-        toc = genes = counts = None
-        if kind == "lsh":
-            toc, genes, counts, U = make_workload(w)
-        # the pair loop needs the signatures of every cell: the GPU path supplies them when a GPU is present
-        # (they are checked bit-exact against the reference on the sampled cells); synthetic ones otherwise.
-        if kind == "lsh" and have_gpu:
-            import expressionmatrix2_b200 as em2
-            with em2.Engine(0) as eng:
-                signatures = eng.compute_signatures(toc, counts, U, gene_ids=genes)
-            sig_note = "signatures of all cells from the GPU path (bit-exact vs the reference on the sampled cells)"
-        else:
-            signatures = synthetic.gen_signatures(N, L, seed=1000, clusters=w.get("clusters", 64), centre_seed=77)
-            sig_note = "synthetic signatures" + ("" if kind == "sig" else " (no GPU visible)")
+        sig_cells, loop_rows = sample_sizes(N, per_step=True)
+        head = host_counts(w, 0, min(sig_cells, N)) if kind == "lsh" else None
+        signatures = bd.gen_signatures(0, N, L, clusters=w.get("clusters", 64)).numpy().view(np.uint64)
+        sig_note = ("pair loop on synthetic signatures with the workload's cluster structure (benchdata.gen_signatures); "
+                    "signature timing on the workload's own counts")
         for i in range(args.warmup + args.steps):
             t0 = time.time()
-            sm = cpu_sample(w, toc, genes, counts, signatures, lsh=L)
+            sm = cpu_sample(w, head, signatures, loop_rows, lsh=L)
+            sm.pop("_ref_sig", None)
             sm["wall_ms"] = 1e3 * (time.time() - t0)
             if i >= args.warmup:
                 samples.append(sm)
@@ -251,11 +292,6 @@ def run_reference(args, w):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-INT8_PEAK_NOTE = ("2 x bf16 TF/s of MEASURED_PEAKS.json ({src}); tools/mma_peak.cu measured 4216 TOP/s (kind::i8, A in "
-                  "TMEM, N=256), 3407 (operands in shared memory, N=256) and 2971 (A in TMEM, N=128 -- the scan's shape) "
-                  "issue-rate peaks on this pool")
-
-
 def _setup_dist():
     import torch
     import torch.distributed as dist
@@ -322,10 +358,10 @@ def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, wor
         ordered = N * (N + 512) / 2 + N * max(256, N // 32)      # + the sampling pre-pass
     alg_pairs = pairs_total / world         # algorithmic units per GPU per launch
     if variant_used == em2.VARIANT_MMA_I8:
-        peak, which = int8_peak(peaks, scan_ms)
+        peak, which, note = int8_peak(peaks, scan_ms, local_rank)
         K = (L + 127) // 128 * 128
         roof = dict(bound="tensor", unit="TOP/s", achieved=alg_pairs * 2 * L / scan_s / 1e12, peak=peak,
-                    peak_source=INT8_PEAK_NOTE.format(src=peaks["source"] + ", " + which),
+                    peak_source=note,
                     executed=ordered * 2 * K / scan_s / 1e12)
     else:
         mb = os.path.join(ROOT, "expressionmatrix2_b200", "build", "microbench")
@@ -343,14 +379,7 @@ def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, wor
     roof["executed_frac"] = roof["executed"] / roof["peak"]
     roof["kernel"] = "scan_topk (encode + scanMmaKernel/scanPopc*Kernel + finalize)"
     roof["kernel_ms"] = scan_ms
-    roof["traffic"] = None
-    try:       # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this workload
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if variant_used == em2.VARIANT_MMA_I8 and world == 1 and N == 100_000 and L == 1024:
-            roof["traffic"] = tr["scanMmaSsKernel@c2"]["bytes"]
-            roof["traffic_source"] = tr["scanMmaSsKernel@c2"]["source"]
-    except Exception:
-        pass
+    roof["traffic"] = None      # filled by the caller from profiles/r2_traffic.json (ncu --set full captures)
     roof["note"] = ("achieved = algorithmic ops (one evaluation per UNORDERED pair, 2L bit-ops each); executed = what the "
                     "row-block design runs (every ordered pair): executed_frac is the kernel-quality figure, frac is capped "
                     "at half of it")
@@ -415,12 +444,12 @@ def run_b200(args, w):
         e2e_t = float(np.mean(ms))
         dev_ms = st["sums_ms"] + st["scan_ms"]
         Gpad = (G + 127) // 128 * 128
-        peak, which = int8_peak(peaks, st["scan_ms"])
+        peak, which, peak_note = int8_peak(peaks, st["scan_ms"], local_rank)
         roof = dict(bound="tensor", unit="TOP/s", achieved=pairs_total * 2 * G / (st["scan_ms"] * 1e-3) / 1e12,
                     # the N x N float matrix fits (<= 48 GB) for N <= ~109k: only tiles on or above the diagonal are computed
                     executed=(float(N) * N / 2 + 128.0 * N if 4.0 * N * N <= 48 * 2 ** 30 else float(N) * N) * 2 * Gpad
                     / (st["scan_ms"] * 1e-3) / 1e12, peak=peak,
-                    peak_source=INT8_PEAK_NOTE.format(src=peaks["source"]), kernel="exactGemmKernel + exactSelectKernel",
+                    peak_source=peak_note, kernel="exactGemmKernel + exactSelectKernel",
                     kernel_ms=st["scan_ms"], traffic=None)
         roof["frac"] = roof["achieved"] / peak
         roof["executed_frac"] = roof["executed"] / peak
@@ -449,34 +478,43 @@ def run_b200(args, w):
         return
 
     # ---------------- LSH workloads: "lsh" (counts -> lists) and "sig" (signatures-only scan, config 4) -----------
+    import benchdata as bd
+    hashed = bool(w.get("hashed"))
     d_lut = torch.from_numpy(em2.similarity_table(L).astype(np.float32)).to(dev)
     d_pairs = torch.zeros((rows, k, 2), dtype=torch.int32, device=dev)
     d_used = torch.zeros(rows, dtype=torch.int32, device=dev)
     d_sig_local = torch.zeros((part.shard, W), dtype=torch.int64, device=dev)
     mm = em2.mismatch_max(L, thr)
     if kind == "lsh":
-        if w.get("per_rank_generation"):
-            # each rank synthesises only its own cells (the 1.3M-cell CSR is 21 GB)
-            ltoc, lgenes, lcounts = synthetic.gen_expression_matrix_fast(rows, G, w["nnz_per_cell"], seed=12345 + rank)
-            toc = genes = counts = None
+        m = w["nnz_per_cell"]
+        if hashed:
+            # every rank synthesises its own cells on its GPU (the 1M-cell CSR is 12 GB); benchdata is counter based, so
+            # any other rank / the host can reproduce any range of cells
+            d_counts = torch.empty(rows * m, dtype=torch.int64, device=dev)
+            step_cells = 20_000
+            for b0 in range(part.row_begin, part.row_end, step_cells):
+                e0 = min(part.row_end, b0 + step_cells)
+                d_counts[(b0 - part.row_begin) * m:(e0 - part.row_begin) * m] = bd.gen_counts(
+                    b0, e0, G, m, clusters=w["clusters"], device=dev)
+            d_toc = torch.arange(rows + 1, dtype=torch.int64, device=dev) * m
+            nnz_local = rows * m
         else:
-            toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, w["nnz_per_cell"], seed=12345)
+            toc, genes, counts = synthetic.gen_expression_matrix_fast(N, G, m, seed=12345)
             ltoc, lgenes, lcounts = part.slice_csr(toc, genes, counts)
+            lpairs = em2.to_pairs(lgenes, lcounts)
+            nnz_local = int(ltoc[-1])
+            d_toc = torch.from_numpy(ltoc.view(np.int64)).to(dev)
+            d_counts = torch.from_numpy(lpairs.view(np.int64)).to(dev)
         U = em2.generate_lsh_vectors(G, L, 231)
-        lpairs = em2.to_pairs(lgenes, lcounts)
-        nnz_local = int(ltoc[-1])
-        d_toc = torch.from_numpy(ltoc.view(np.int64)).to(dev)
-        d_counts = torch.from_numpy(lpairs.view(np.int64)).to(dev)
         d_U = torch.from_numpy(U).to(dev)
         d_sum1 = torch.empty(rows, dtype=torch.float64, device=dev)
         d_sum2 = torch.empty(rows, dtype=torch.float64, device=dev)
         d_nz = torch.zeros(8, dtype=torch.int64, device=dev)
         stage_names = ["sums", "signatures", "allgather", "scan_topk"]
     else:
-        sig_host = synthetic.gen_signatures(rows, L, seed=1000 + rank, clusters=w.get("clusters", 500), centre_seed=77)
-        p_sig = torch.from_numpy(sig_host.view(np.int64)).pin_memory()
-        d_sig_local[:rows].copy_(p_sig)
+        d_sig_local[:rows] = bd.gen_signatures(part.row_begin, part.row_end, L, clusters=w.get("clusters", 500), device=dev)
         stage_names = ["allgather", "scan_topk"]
+    torch.cuda.empty_cache()
 
     def step(events=None):
         def mark(i):
@@ -504,77 +542,87 @@ def run_b200(args, w):
                                                                  launch_counter=lambda: eng.stats()["kernel_launches"])
     stage_ms = dict(zip(stage_names, stage))
     value = pairs_total / (ms_per_step * 1e-3)
-
-    # ---- e2e: host buffers -> host lists ----------------------------------------------------------
-    h_pairs = torch.empty((rows, k, 2), dtype=torch.int32).pin_memory()
-    h_used = torch.empty(rows, dtype=torch.int32).pin_memory()
-    o_pairs = h_pairs.numpy().view(em2.SIMPAIR_DTYPE).reshape(rows, k)
-    o_used = h_used.numpy().view(np.uint32)
-    e2e_stats = {}
-    if world == 1:
-        # the reference-facing blocking C-ABI call; host buffers in pinned memory (inputs AND outputs)
-        if kind == "lsh":
-            p_toc = torch.from_numpy(ltoc.view(np.int64)).pin_memory()
-            p_counts = torch.from_numpy(lpairs.view(np.int64)).pin_memory()
-            p_U = torch.from_numpy(U).pin_memory()
-            n_toc, n_counts, n_U = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE), p_U.numpy()
-            call = lambda: eng.lsh_similar_pairs_into(n_toc, n_counts, n_U, k, thr, o_pairs, o_used, variant=variant)
-            api = "em2_lsh_similar_pairs (C-ABI, host buffers)"
-        else:
-            n_sig = p_sig.numpy().view(np.uint64)
-            call = lambda: eng.find_similar_pairs_into(n_sig, L, k, thr, o_pairs, o_used, variant=variant)
-            api = "em2_find_similar_pairs (C-ABI, host buffers)"
-        e2e_ms, st = [], None
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            call()
-            if i >= args.warmup:
-                e2e_ms.append(1e3 * (time.perf_counter() - t0))
-            st = eng.stats()
-        e2e_t = float(np.mean(e2e_ms))
-        h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
-        e2e_stats = {k2: st[k2] for k2 in ("h2d_ms", "sums_ms", "signatures_ms", "scan_ms", "d2h_ms")}
-        e2e_stats["note"] = "h2d overlaps sums/signatures (chunked copy stream)"
-        # the host-buffer call and the device-resident steps must have produced the same lists
-        e2e_stats["lists_equal_device_path"] = bool(torch.equal(h_pairs, d_pairs.cpu()) and torch.equal(h_used, d_used.cpu()))
-    else:
-        api = "device API + pinned host copies per rank"
-        if kind == "lsh":
-            p_toc = torch.from_numpy(ltoc.view(np.int64)).pin_memory()
-            p_counts = torch.from_numpy(lpairs.view(np.int64)).pin_memory()
-            p_U = torch.from_numpy(U).pin_memory()
-        e2e_ms = []
-        for i in range(args.warmup + args.steps):
-            barrier()
-            t0 = time.perf_counter()
-            if kind == "lsh":
-                d_toc.copy_(p_toc, non_blocking=True)
-                d_counts.copy_(p_counts, non_blocking=True)
-                d_U.copy_(p_U, non_blocking=True)
-            else:
-                d_sig_local[:rows].copy_(p_sig, non_blocking=True)
-            step()
-            h_pairs.copy_(d_pairs, non_blocking=True)
-            h_used.copy_(d_used, non_blocking=True)
-            barrier()
-            if i >= args.warmup:
-                e2e_ms.append(1e3 * (time.perf_counter() - t0))
-        tt = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t = float(tt.item())
-        h2d = (p_toc.numel() * 8 + p_counts.numel() * 8 + p_U.numel() * 8) if kind == "lsh" else p_sig.numel() * 8
-        d2h = h_pairs.numel() * 4 + h_used.numel() * 4
-
-    # ---- rooflines ---------------------------------------------------------------------------------
     variant_used = eng.stats()["variant_used"] or (em2.VARIANT_POPC if variant != em2.VARIANT_MMA_I8 else variant)
     sym_used = int(eng.stats()["scan_symmetric"])
+
+    # ---- e2e: host buffers -> host lists ----------------------------------------------------------
+    e2e_t, h2d, d2h, api, e2e_stats = float('nan'), 0, 0, 'skipped (--no-e2e)', {}
+    if not args.no_e2e:
+        h_pairs = torch.empty((rows, k, 2), dtype=torch.int32).pin_memory()
+        h_used = torch.empty(rows, dtype=torch.int32).pin_memory()
+        o_pairs = h_pairs.numpy().view(em2.SIMPAIR_DTYPE).reshape(rows, k)
+        o_used = h_used.numpy().view(np.uint32)
+        if kind == "lsh":
+            p_toc = d_toc.cpu().pin_memory()
+            p_counts = torch.empty(d_counts.shape, dtype=torch.int64).pin_memory()
+            p_counts.copy_(d_counts)
+            p_U = torch.from_numpy(U).pin_memory()
+        else:
+            p_sig = torch.empty((rows, W), dtype=torch.int64).pin_memory()
+            p_sig.copy_(d_sig_local[:rows])
+        if world == 1:
+            # the reference-facing blocking C-ABI call; host buffers in pinned memory (inputs AND outputs)
+            if kind == "lsh":
+                n_toc, n_counts, n_U = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE), p_U.numpy()
+                call = lambda: eng.lsh_similar_pairs_into(n_toc, n_counts, n_U, k, thr, o_pairs, o_used, variant=variant)
+                api = "em2_lsh_similar_pairs (C-ABI, host buffers)"
+            else:
+                n_sig = p_sig.numpy().view(np.uint64)
+                call = lambda: eng.find_similar_pairs_into(n_sig, L, k, thr, o_pairs, o_used, variant=variant)
+                api = "em2_find_similar_pairs (C-ABI, host buffers)"
+            e2e_ms, st = [], None
+            for i in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                call()
+                if i >= args.warmup:
+                    e2e_ms.append(1e3 * (time.perf_counter() - t0))
+                st = eng.stats()
+            e2e_t = float(np.mean(e2e_ms))
+            h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
+            e2e_stats = {k2: st[k2] for k2 in ("h2d_ms", "sums_ms", "signatures_ms", "scan_ms", "d2h_ms")}
+            e2e_stats["note"] = "h2d overlaps sums/signatures (chunked copy stream)"
+            # the host-buffer call and the device-resident steps must have produced the same lists
+            e2e_stats["lists_equal_device_path"] = bool(torch.equal(h_pairs, d_pairs.cpu()) and torch.equal(h_used, d_used.cpu()))
+        else:
+            api = "device API + pinned host copies per rank"
+            e2e_ms = []
+            for i in range(args.warmup + args.steps):
+                barrier()
+                t0 = time.perf_counter()
+                if kind == "lsh":
+                    d_toc.copy_(p_toc, non_blocking=True)
+                    d_counts.copy_(p_counts, non_blocking=True)
+                    d_U.copy_(p_U, non_blocking=True)
+                else:
+                    d_sig_local[:rows].copy_(p_sig, non_blocking=True)
+                step()
+                h_pairs.copy_(d_pairs, non_blocking=True)
+                h_used.copy_(d_used, non_blocking=True)
+                barrier()
+                if i >= args.warmup:
+                    e2e_ms.append(1e3 * (time.perf_counter() - t0))
+            tt = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_t = float(tt.item())
+            h2d = (p_toc.numel() * 8 + p_counts.numel() * 8 + p_U.numel() * 8) if kind == "lsh" else p_sig.numel() * 8
+            d2h = h_pairs.numel() * 4 + h_used.numel() * 4
+
+    # ---- rooflines ---------------------------------------------------------------------------------
     roof = _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total,
                           stage_ms["scan_topk"], local_rank, symmetric=(sym_used == 1))
     if sym_used == 1:
         roof["kernel"] = "scan_topk (encode + sampling pre-pass + scanMmaSymKernel + scatter + merge)"
-        roof["traffic"] = None
         roof["note"] = ("symmetric scan: achieved = algorithmic ops (one evaluation per unordered pair, 2L bit-ops); executed adds "
                         "the diagonal blocks' duplicates and the N/32-column sampling pre-pass")
+    try:       # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        ent = tr.get(f"{args.workload}@L{L}@n{world}@sym{1 if sym_used == 1 else 0}")
+        if ent:
+            roof["traffic"] = ent["bytes"]
+            roof["traffic_kernel"] = ent["kernel"]
+            roof["traffic_source"] = ent["source"]
+    except Exception:
+        pass
     sig_roof = None
     if kind == "lsh":
         sig_s = stage_ms["signatures"] * 1e-3
@@ -590,10 +638,11 @@ def run_b200(args, w):
         if filtered:
             Gpad, Lp = (G + 127) // 128 * 128, (L + 127) // 128 * 128
             ex = 2.0 * rows * Gpad * 3 * Lp
-            sig_roof.update(bound="tensor", executed_int8_tops=ex / sig_s / 1e12, peak=2.0 * peaks["bf16_tflops"],
-                            executed_frac=ex / sig_s / 1e12 / (2.0 * peaks["bf16_tflops"]),
-                            note="executed = dense G x 3L int8 MACs per cell over the whole stage time; the GEMM kernel "
-                                 "alone is ~70% of the stage (profiles/), i.e. ~0.95 of peak")
+            pk, _, pk_note = int8_peak(peaks, stage_ms["signatures"], local_rank)
+            sig_roof.update(bound="tensor", executed_int8_tops=ex / sig_s / 1e12, peak=pk, peak_source=pk_note,
+                            executed_frac=ex / sig_s / 1e12 / pk,
+                            note="executed = dense G x 3L int8 MACs per cell over the whole stage time (dense expansion, "
+                                 "column statistics and fix-up included)")
 
     if rank == 0:
         used_mean = float(d_used.float().mean().item())
@@ -607,8 +656,8 @@ def run_b200(args, w):
                                 ordered_evaluations_per_s=N * float(N) / (ms_per_step * 1e-3),
                                 mean_neighbours_stored=used_mean),
                     stage_ms=stage_ms, roofline=roof,
-                    e2e=dict(value=pairs_total / (e2e_t * 1e-3), unit="cell-pairs/s", ms=e2e_t,
-                             h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, stage_ms=e2e_stats, api=api),
+                    e2e=None if args.no_e2e else dict(value=pairs_total / (e2e_t * 1e-3), unit="cell-pairs/s", ms=e2e_t,
+                                                      h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, stage_ms=e2e_stats, api=api),
                     gpu_launches=int(launches), clocks=clocks)
         if sig_roof:
             line["signature_roofline"] = sig_roof
@@ -616,10 +665,12 @@ def run_b200(args, w):
             import oracle
             oracle.build()
             sig_np = d_sig_local[:rows].cpu().numpy().view(np.uint64)
-            if kind == "lsh":
-                cb = cpu_sample(w, toc, genes, counts, sig_np, lsh=L)
-            else:
-                cb = cpu_sample(w, None, None, None, sig_np, lsh=L)
+            sig_cells, loop_rows = sample_sizes(N)
+            head = host_counts(w, 0, min(sig_cells, N)) if kind == "lsh" else None
+            cb = cpu_sample(w, head, sig_np, loop_rows, lsh=L)
+            ref_sig = cb.pop("_ref_sig", None)
+            if ref_sig is not None:      # the reference's signatures of the sampled cells against the GPU's
+                cb["sample_signatures_match_gpu"] = bool(np.array_equal(ref_sig, sig_np[:len(ref_sig)]))
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     eng.close()
@@ -633,13 +684,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="m1", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "mma"])
     ap.add_argument("--lsh", type=int, default=0, help="override the workload's LSH bit count (config 4 sweep)")
     ap.add_argument("--symmetric", action="store_true",
                     help="whole-matrix scans evaluate every unordered pair once (em2_set_option scan_symmetric = 2; N = 1 only)")
     ap.add_argument("--one-directional", action="store_true", help="never use the symmetric scan (scan_symmetric = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     w = WORKLOADS[args.workload]

@@ -61,5 +61,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TOOLS = os.path.join(HERE, "..", "tools")
+
+
+def build_tools(force: bool = False) -> None:
+    """Pipe-rate microbenchmarks (tools/*.cu) -> build/<name>; bench.py runs them for the roofline denominators."""
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for name in ("mma_peak", "microbench"):
+        src = os.path.join(TOOLS, name + ".cu")
+        out = os.path.join(HERE, "build", name)
+        if not os.path.exists(src):
+            continue
+        if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+            continue
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
+                               "-o", out, src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -88,9 +88,33 @@ template <int KIND> double run(uint32_t idesc, int nTile, int kPer, int useTmemA
     return 2.0 * 128 * nTile * kPer * double(iters) * sms / (best * 1e-3) / 1e12;
 }
 
-int main()
+// Back-to-back launches for `seconds`; the rate over the second half (the GPU has reached its power-capped clocks by then).
+template <int KIND> double sustained(uint32_t idesc, int nTile, int kPer, int useTmemA, int sms, uint32_t* out, double seconds)
+{
+    const int iters = 20000;
+    const size_t smem = 100 * 1024;
+    cudaFuncSetAttribute(peak<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const double perLaunch = 2.0 * 128 * nTile * kPer * double(iters) * sms;
+    // one launch is ~1 ms: warm for the first half, time the second half
+    const int launches = int(seconds * 1000.0);
+    for (int i = 0; i < launches / 2; i++) peak<KIND><<<sms, 128, smem>>>(idesc, iters, nTile, useTmemA, out);
+    cudaEventRecord(a);
+    for (int i = 0; i < launches / 2; i++) peak<KIND><<<sms, 128, smem>>>(idesc, iters, nTile, useTmemA, out);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    if (cudaGetLastError() != cudaSuccess) return 0;
+    return perLaunch * (launches / 2) / (ms * 1e-3) / 1e12;
+}
+
+int main(int argc, char** argv)
 {
     cudaDeviceProp p;
+    const bool quick = argc > 1 && argv[1][0] == 'q';      // "quick": burst figures only
     cudaGetDeviceProperties(&p, 0);
     uint32_t* out;
     cudaMalloc(&out, 4096);
@@ -105,6 +129,11 @@ int main()
     printf("\"i8_ts_n256_tops\": %.1f, ", run<0>(idescI8(256), 256, 32, 1, sms, out));
     printf("\"f8_ss_n256_tflops\": %.1f, ", run<1>(idescF8(256), 256, 32, 0, sms, out));
     printf("\"bf16_ss_n256_tflops\": %.1f", run<2>(idescBf(256), 256, 16, 0, sms, out));
+    if (!quick) {
+        printf(", \"i8_ss_n256_tops_sustained\": %.1f", sustained<0>(idescI8(256), 256, 32, 0, sms, out, 3.0));
+        printf(", \"i8_ts_n256_tops_sustained\": %.1f", sustained<0>(idescI8(256), 256, 32, 1, sms, out, 3.0));
+        printf(", \"bf16_ss_n256_tflops_sustained\": %.1f", sustained<2>(idescBf(256), 256, 16, 0, sms, out, 3.0));
+    }
     printf("}\n");
     return 0;
 }
