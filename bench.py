@@ -354,8 +354,11 @@ def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, wor
                    symmetric=False):
     scan_s = scan_ms * 1e-3
     ordered = rows * N                      # pair evaluations this GPU executed per launch
-    if symmetric:                           # every unordered pair once (256-cell super blocks, diagonal blocks in full)
-        ordered = N * (N + 512) / 2 + N * max(256, N // 32)      # + the sampling pre-pass
+    if symmetric:      # every unordered pair once: near window (2w + 1 tiles of 256 columns, both owners) + offsets w+1 .. S/2
+        S = (N + 255) // 256
+        wn = max(16, (N // 32 + 511) // 512)
+        wn = min(wn, (S - 1) // 2)
+        ordered = rows * 256.0 * (2 * wn + 1 + max(0, S // 2 - wn))
     alg_pairs = pairs_total / world         # algorithmic units per GPU per launch
     if variant_used == em2.VARIANT_MMA_I8:
         peak, which, note = int8_peak(peaks, scan_ms, local_rank)
@@ -403,9 +406,18 @@ def run_b200(args, w):
     N, G, k, thr = w["cells"], w["genes"], w["k"], w["thr"]
     L = args.lsh or w["lsh"]
     W = em2.word_count(L)
-    part = Partition(N, world, rank)
+    part = Partition(N, world, rank)          # same rule as em2_dist_partition
+    assert (part.row_begin, part.row_end, part.shard) == em2.dist_partition(N, world, rank)
     rows = part.rows
     eng = em2.Engine(local_rank)
+    cpu_group = None
+    if world > 1:
+        # torch.distributed is the plumbing: it carries the library's communicator id to the ranks; the collectives of
+        # the data path (signature all-gather, candidate exchange) run inside libem2b200 on its own NCCL communicator
+        ident = [em2.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        eng.comm_init(ident[0], rank, world)
+        cpu_group = dist.new_group(backend="gloo")      # host-side waits that must not put a spinning kernel on the GPUs
     if args.symmetric:
         eng.set_option("scan_symmetric", 2)
     if args.one_directional:
@@ -510,11 +522,14 @@ def run_b200(args, w):
         d_sum1 = torch.empty(rows, dtype=torch.float64, device=dev)
         d_sum2 = torch.empty(rows, dtype=torch.float64, device=dev)
         d_nz = torch.zeros(8, dtype=torch.int64, device=dev)
-        stage_names = ["sums", "signatures", "allgather", "scan_topk"]
     else:
         d_sig_local[:rows] = bd.gen_signatures(part.row_begin, part.row_end, L, clusters=w.get("clusters", 500), device=dev)
-        stage_names = ["allgather", "scan_topk"]
     torch.cuda.empty_cache()
+
+    if kind == "lsh":
+        stage_names = ["sums", "signatures", "scan_topk"]
+    else:
+        stage_names = ["scan_topk"]
 
     def step(events=None):
         def mark(i):
@@ -530,11 +545,10 @@ def run_b200(args, w):
                                   nnz=nnz_local)
             j += 1
             mark(j)
-        full = all_gather_signatures(d_sig_local, part) if world > 1 else d_sig_local
-        j += 1
-        mark(j)
-        eng.scan_topk_device(full, N, L, part.row_begin, part.row_end, k, mm, d_lut, d_pairs, d_used,
-                             variant=variant, stream=stream)
+        if world > 1:      # collective: signature all-gather (+ the symmetric scan's exchange) on NCCL inside the library
+            eng.scan_topk_dist_device(d_sig_local, N, L, k, mm, d_lut, d_pairs, d_used, variant=variant, stream=stream)
+        else:
+            eng.scan_topk_device(d_sig_local, N, L, 0, N, k, mm, d_lut, d_pairs, d_used, variant=variant, stream=stream)
         j += 1
         mark(j)
 
@@ -542,78 +556,103 @@ def run_b200(args, w):
                                                                  launch_counter=lambda: eng.stats()["kernel_launches"])
     stage_ms = dict(zip(stage_names, stage))
     value = pairs_total / (ms_per_step * 1e-3)
+    if world > 1:      # one more step, bracketed by the library's own events: the collectives inside scan_topk
+        torch.cuda.synchronize()
+        s0 = eng.stats()
+        step()
+        torch.cuda.synchronize()
+        s1 = eng.stats()
+        stage_ms["allgather_inside_scan_topk"] = s1["allgather_ms"] - s0["allgather_ms"]
+        stage_ms["exchange_inside_scan_topk"] = s1["exchange_ms"] - s0["exchange_ms"]
+        stage_ms["exchange_bytes_sent_rank0"] = int(s1["exchange_bytes"] - s0["exchange_bytes"])
     variant_used = eng.stats()["variant_used"] or (em2.VARIANT_POPC if variant != em2.VARIANT_MMA_I8 else variant)
     sym_used = int(eng.stats()["scan_symmetric"])
+    used_mean = float(d_used.float().mean().item()) if rows else 0.0
 
     # ---- e2e: host buffers -> host lists ----------------------------------------------------------
+    # One blocking library call on HOST buffers, as the reference's host layer makes it: em2_lsh_similar_pairs on one
+    # GPU, em2_multi_lsh_similar_pairs over all N GPUs (rank 0 drives them from one process, exactly like the C++
+    # ExpressionMatrix::findSimilarPairs4 of host/; the other ranks have released their GPUs and wait on the host).
     e2e_t, h2d, d2h, api, e2e_stats = float('nan'), 0, 0, 'skipped (--no-e2e)', {}
+    sig_all_host = None
     if not args.no_e2e:
-        h_pairs = torch.empty((rows, k, 2), dtype=torch.int32).pin_memory()
-        h_used = torch.empty(rows, dtype=torch.int32).pin_memory()
-        o_pairs = h_pairs.numpy().view(em2.SIMPAIR_DTYPE).reshape(rows, k)
-        o_used = h_used.numpy().view(np.uint32)
+        own_pairs = d_pairs.cpu()
+        own_used = d_used.cpu()
+        sig_all_host = d_sig_local[:rows].cpu().numpy().view(np.uint64) if world == 1 else None
         if kind == "lsh":
-            p_toc = d_toc.cpu().pin_memory()
-            p_counts = torch.empty(d_counts.shape, dtype=torch.int64).pin_memory()
-            p_counts.copy_(d_counts)
-            p_U = torch.from_numpy(U).pin_memory()
-        else:
-            p_sig = torch.empty((rows, W), dtype=torch.int64).pin_memory()
-            p_sig.copy_(d_sig_local[:rows])
-        if world == 1:
-            # the reference-facing blocking C-ABI call; host buffers in pinned memory (inputs AND outputs)
+            n_toc = (np.arange(N + 1, dtype=np.uint64) * np.uint64(m)) if hashed else toc
+            if rank == 0:
+                p_counts = torch.empty(int(n_toc[-1]), dtype=torch.int64).pin_memory()
+                if hashed:
+                    if world == 1:
+                        p_counts.copy_(d_counts)
+                    else:      # rank 0 needs the whole job's counts on the host: regenerate the other ranks' cells here
+                        for b0 in range(0, N, 20_000):
+                            e0 = min(N, b0 + 20_000)
+                            p_counts[b0 * m:e0 * m].copy_(bd.gen_counts(b0, e0, G, m, clusters=w["clusters"], device=dev))
+                else:
+                    p_counts.copy_(torch.from_numpy(em2.to_pairs(genes, counts).view(np.int64)))
+                p_toc = torch.from_numpy(n_toc.view(np.int64)).pin_memory()
+                p_U = torch.from_numpy(U).pin_memory()
+        elif rank == 0:
+            p_sig = torch.empty((N, W), dtype=torch.int64).pin_memory()
+            for b0 in range(0, N, 100_000):
+                e0 = min(N, b0 + 100_000)
+                p_sig[b0:e0].copy_(bd.gen_signatures(b0, e0, L, clusters=w.get("clusters", 500), device=dev))
+        # release the device-resident leg's memory on every rank before the library allocates its own
+        eng.close()
+        del d_pairs, d_used, d_sig_local
+        if kind == "lsh":
+            del d_counts, d_toc, d_U, d_sum1, d_sum2
+        torch.cuda.empty_cache()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            h_pairs = torch.empty((N, k, 2), dtype=torch.int32).pin_memory()
+            h_used = torch.empty(N, dtype=torch.int32).pin_memory()
+            o_pairs = h_pairs.numpy().view(em2.SIMPAIR_DTYPE).reshape(N, k)
+            o_used = h_used.numpy().view(np.uint32)
+            runner = em2.Engine(local_rank) if world == 1 else em2.MultiEngine(devices=list(range(world)))
+            if args.symmetric:
+                runner.set_option("scan_symmetric", 2)
+            if args.one_directional:
+                runner.set_option("scan_symmetric", 1)
             if kind == "lsh":
-                n_toc, n_counts, n_U = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE), p_U.numpy()
-                call = lambda: eng.lsh_similar_pairs_into(n_toc, n_counts, n_U, k, thr, o_pairs, o_used, variant=variant)
-                api = "em2_lsh_similar_pairs (C-ABI, host buffers)"
+                a_toc, a_counts, a_U = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE), p_U.numpy()
+                call = lambda: runner.lsh_similar_pairs_into(a_toc, a_counts, a_U, k, thr, o_pairs, o_used, variant=variant)
+                api = ("em2_lsh_similar_pairs" if world == 1 else f"em2_multi_lsh_similar_pairs over {world} GPUs") + " (C-ABI, host buffers)"
             else:
-                n_sig = p_sig.numpy().view(np.uint64)
-                call = lambda: eng.find_similar_pairs_into(n_sig, L, k, thr, o_pairs, o_used, variant=variant)
-                api = "em2_find_similar_pairs (C-ABI, host buffers)"
+                a_sig = p_sig.numpy().view(np.uint64)
+                call = lambda: runner.find_similar_pairs_into(a_sig, L, k, thr, o_pairs, o_used, variant=variant)
+                api = ("em2_find_similar_pairs" if world == 1 else f"em2_multi_find_similar_pairs over {world} GPUs") + " (C-ABI, host buffers)"
             e2e_ms, st = [], None
             for i in range(args.warmup + args.steps):
                 t0 = time.perf_counter()
                 call()
                 if i >= args.warmup:
                     e2e_ms.append(1e3 * (time.perf_counter() - t0))
-                st = eng.stats()
+                st = runner.stats()
             e2e_t = float(np.mean(e2e_ms))
             h2d, d2h = int(st["h2d_bytes"]), int(st["d2h_bytes"])
-            e2e_stats = {k2: st[k2] for k2 in ("h2d_ms", "sums_ms", "signatures_ms", "scan_ms", "d2h_ms")}
-            e2e_stats["note"] = "h2d overlaps sums/signatures (chunked copy stream)"
-            # the host-buffer call and the device-resident steps must have produced the same lists
-            e2e_stats["lists_equal_device_path"] = bool(torch.equal(h_pairs, d_pairs.cpu()) and torch.equal(h_used, d_used.cpu()))
-        else:
-            api = "device API + pinned host copies per rank"
-            e2e_ms = []
-            for i in range(args.warmup + args.steps):
-                barrier()
-                t0 = time.perf_counter()
-                if kind == "lsh":
-                    d_toc.copy_(p_toc, non_blocking=True)
-                    d_counts.copy_(p_counts, non_blocking=True)
-                    d_U.copy_(p_U, non_blocking=True)
-                else:
-                    d_sig_local[:rows].copy_(p_sig, non_blocking=True)
-                step()
-                h_pairs.copy_(d_pairs, non_blocking=True)
-                h_used.copy_(d_used, non_blocking=True)
-                barrier()
-                if i >= args.warmup:
-                    e2e_ms.append(1e3 * (time.perf_counter() - t0))
-            tt = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_t = float(tt.item())
-            h2d = (p_toc.numel() * 8 + p_counts.numel() * 8 + p_U.numel() * 8) if kind == "lsh" else p_sig.numel() * 8
-            d2h = h_pairs.numel() * 4 + h_used.numel() * 4
+            e2e_stats = {k2: st[k2] for k2 in ("h2d_ms", "sums_ms", "signatures_ms", "scan_ms", "d2h_ms", "allgather_ms", "exchange_ms")}
+            e2e_stats["note"] = ("per-stage times are device-side maxima over the GPUs; h2d overlaps sums/signatures (chunked copy "
+                                 "stream); inputs and outputs are pinned host buffers")
+            e2e_stats["scan_symmetric"] = int(st["scan_symmetric"])
+            # the host-buffer call and the device-resident steps must have produced the same lists (rank 0's rows)
+            e2e_stats["lists_equal_device_path"] = bool(
+                torch.equal(h_pairs[part.row_begin:part.row_end], own_pairs) and torch.equal(h_used[part.row_begin:part.row_end], own_used))
+            runner.close()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     # ---- rooflines ---------------------------------------------------------------------------------
     roof = _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, world, pairs_total,
                           stage_ms["scan_topk"], local_rank, symmetric=(sym_used == 1))
     if sym_used == 1:
-        roof["kernel"] = "scan_topk (encode + sampling pre-pass + scanMmaSymKernel + scatter + merge)"
+        roof["kernel"] = "scan_topk (grouping + encode + scanMmaSymKernel near window and far sweep + scatter + merge)"
         roof["note"] = ("symmetric scan: achieved = algorithmic ops (one evaluation per unordered pair, 2L bit-ops); executed adds "
-                        "the diagonal blocks' duplicates and the N/32-column sampling pre-pass")
+                        "the near window, whose tiles both owners evaluate")
     try:       # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this workload
         tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         ent = tr.get(f"{args.workload}@L{L}@n{world}@sym{1 if sym_used == 1 else 0}")
@@ -645,12 +684,13 @@ def run_b200(args, w):
                                  "column statistics and fix-up included)")
 
     if rank == 0:
-        used_mean = float(d_used.float().mean().item())
         line.update(value=value, ms_per_step=ms_per_step,
                     dtype=("s8 tcgen05 / u64 popc (scan), u8 x s8 tcgen05 filter + f64 fix-up (signatures)" if kind == "lsh"
                            else "s8 tcgen05 / u64 popc (scan)"),
                     config=dict(cfg, variant={1: "popc", 2: "mma_i8"}.get(variant_used, "popc"), scan_symmetric=sym_used,
-                                parallelism=f"cell-row blocks x{world}" + (", 1 NCCL all-gather of signatures" if world > 1 else ""),
+                                parallelism=f"cell-row blocks x{world}" + ((", NCCL inside libem2b200: 1 all-gather of signatures" +
+                                             (" + 1 all-gather of bounds + 1 all-to-all of column-direction candidates (symmetric scan)"
+                                              if sym_used == 1 else "")) if world > 1 else ""),
                                 l2=("inputs (CSR + hyperplanes, >1.4 GB) exceed the 126 MB L2; no flush needed" if kind == "lsh" else
                                     "encoded signatures (N x L bytes) exceed the 126 MB L2 for N*L > 1.3e8; candidate buffers are rewritten every step"),
                                 ordered_evaluations_per_s=N * float(N) / (ms_per_step * 1e-3),
@@ -664,7 +704,7 @@ def run_b200(args, w):
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
-            sig_np = d_sig_local[:rows].cpu().numpy().view(np.uint64)
+            sig_np = sig_all_host if sig_all_host is not None else d_sig_local[:rows].cpu().numpy().view(np.uint64)
             sig_cells, loop_rows = sample_sizes(N)
             head = host_counts(w, 0, min(sig_cells, N)) if kind == "lsh" else None
             cb = cpu_sample(w, head, sig_np, loop_rows, lsh=L)

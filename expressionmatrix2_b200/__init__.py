@@ -39,6 +39,8 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_uint64), ("candidates_appended", C.c_uint64), ("filter_cells", C.c_uint64),
         ("filter_uncertain", C.c_uint64), ("variant_used", C.c_int32),
         ("scan_symmetric", C.c_int32),
+        ("bounced_bytes", C.c_uint64), ("allgather_ms", C.c_double), ("exchange_ms", C.c_double),
+        ("exchange_bytes", C.c_uint64), ("world_size", C.c_int32), ("rank", C.c_int32),
     ]
 
     def as_dict(self):
@@ -86,7 +88,24 @@ def lib():
     L.em2_scan_topk_device.argtypes = [vp, vp, u64, u64, u64, u64, u64, i64, vp, i32, vp, vp, vp]
     L.em2_mismatch_counts_device.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp]
     L.em2_mismatch_block_device.argtypes = [vp, vp, u64, u64, u64, u64, i32, vp, vp]
-    if L.em2_abi_version() != 1:
+    L.em2_multi_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.em2_multi_destroy.argtypes = [vp]
+    L.em2_multi_destroy.restype = None
+    L.em2_multi_last_error.argtypes = [vp]
+    L.em2_multi_last_error.restype = C.c_char_p
+    L.em2_multi_device_count.argtypes = [vp]
+    L.em2_multi_context.argtypes = [vp, i32]
+    L.em2_multi_context.restype = vp
+    L.em2_multi_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.em2_multi_get_stats.argtypes = [vp, i32, C.POINTER(Stats)]
+    L.em2_multi_find_similar_pairs.argtypes = [vp, vp, u64, u64, u64, dbl, i32, vp, vp]
+    L.em2_multi_lsh_similar_pairs.argtypes = [vp, u64, u64, vp, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
+    L.em2_multi_lsh_similar_pairs_subset.argtypes = [vp, u64, vp, vp, u64, vp, u64, u64, vp, vp, u64, u64, dbl, i32, vp, vp, vp]
+    L.em2_comm_unique_id.argtypes = [vp]
+    L.em2_comm_init.argtypes = [vp, vp, i32, i32]
+    L.em2_dist_partition.argtypes = [u64, i32, i32, _u64p, _u64p, _u64p]
+    L.em2_scan_topk_dist_device.argtypes = [vp, vp, u64, u64, u64, i64, vp, i32, vp, vp, vp]
+    if L.em2_abi_version() != 2:
         raise Em2Error("libem2b200.so ABI version mismatch")
     _lib = L
     return L
@@ -118,6 +137,26 @@ def similarity_table(lsh_count: int) -> np.ndarray:
 
 def mismatch_max(lsh_count: int, similarity_threshold: float) -> int:
     return int(lib().em2_mismatch_max(lsh_count, similarity_threshold))
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """A fresh communicator id (rank 0 makes it, the host program broadcasts the bytes; em2_comm_unique_id)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib().em2_comm_unique_id(buf)
+    if rc:
+        raise Em2Error(f"em2_comm_unique_id failed ({rc}): " + lib().em2_last_error(None).decode())
+    return buf.raw
+
+
+def dist_partition(cell_count: int, world_size: int, rank: int):
+    """(row_begin, row_end, shard_rows) of a rank's row block (em2_dist_partition)."""
+    b, e, sh = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    if lib().em2_dist_partition(cell_count, world_size, rank, C.byref(b), C.byref(e), C.byref(sh)):
+        raise Em2Error("em2_dist_partition: invalid argument")
+    return int(b.value), int(e.value), int(sh.value)
 
 
 def _ptr(x):
@@ -184,6 +223,17 @@ class Engine:
         s = Stats()
         self._check(self._L.em2_get_stats(self._h, C.byref(s)), "em2_get_stats")
         return s.as_dict()
+
+    # ---- multi-GPU, one process per GPU ------------------------------------------------------------
+    def comm_init(self, comm_id: bytes | None, rank: int, world_size: int) -> None:
+        """Joins the communicator of `comm_id` (em2_comm_init); every rank of the job must call it."""
+        self._check(self._L.em2_comm_init(self._h, comm_id, rank, world_size), "em2_comm_init")
+
+    def scan_topk_dist_device(self, d_sig_local, n, lsh_count, k, mismatch_max_, d_lut, d_pairs, d_used,
+                              variant: int = VARIANT_AUTO, stream=None):
+        """COLLECTIVE (em2_scan_topk_dist_device): this rank's signatures in, the lists of its rows out (device)."""
+        self._check(self._L.em2_scan_topk_dist_device(self._h, _ptr(d_sig_local), n, lsh_count, k, mismatch_max_, _ptr(d_lut),
+                                                      variant, _ptr(d_pairs), _ptr(d_used), stream), "em2_scan_topk_dist_device")
 
     # ---- blocking calls on host buffers -----------------------------------------------------------
     def compute_signatures(self, toc, counts, lsh_vectors, gene_ids=None, want_sums: bool = False):
@@ -387,3 +437,106 @@ class Engine:
                               stream=None):
         self._check(self._L.em2_mismatch_block_device(self._h, _ptr(d_sig), n, lsh_count, row_begin, row_end,
                                                       variant, _ptr(d_out), stream), "em2_mismatch_block_device")
+
+
+class MultiEngine:
+    """All GPUs of the box behind one blocking call (em2_multi): what the C++ ExpressionMatrix host layer uses."""
+
+    def __init__(self, devices=None, device_count: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        arr = None
+        if devices is not None:
+            device_count = len(devices)
+            arr = (C.c_int * device_count)(*devices)
+        rc = self._L.em2_multi_create(arr, device_count, C.byref(h))
+        if rc:
+            raise Em2Error(f"em2_multi_create failed ({rc}): " + self._L.em2_multi_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.em2_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise Em2Error(f"{what} failed ({rc}): " + self._L.em2_multi_last_error(self._h).decode())
+
+    @property
+    def device_count(self) -> int:
+        return int(self._L.em2_multi_device_count(self._h))
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self._L.em2_multi_set_option(self._h, name.encode(), value), "em2_multi_set_option")
+
+    def stats(self, index: int = -1) -> dict:
+        s = Stats()
+        self._check(self._L.em2_multi_get_stats(self._h, index, C.byref(s)), "em2_multi_get_stats")
+        return s.as_dict()
+
+    def find_similar_pairs_into(self, signatures, lsh_count: int, k: int, similarity_threshold: float, out_pairs, out_used,
+                                variant: int = VARIANT_AUTO) -> None:
+        self._check(self._L.em2_multi_find_similar_pairs(self._h, _ptr(signatures), signatures.shape[0], lsh_count, k,
+                                                         similarity_threshold, variant, _ptr(out_pairs), _ptr(out_used)),
+                    "em2_multi_find_similar_pairs")
+
+    def find_similar_pairs(self, signatures, lsh_count: int, k: int, similarity_threshold: float, variant: int = VARIANT_AUTO):
+        sig = np.ascontiguousarray(signatures, np.uint64)
+        out = np.zeros((sig.shape[0], k), SIMPAIR_DTYPE)
+        used = np.zeros(sig.shape[0], np.uint32)
+        self.find_similar_pairs_into(sig, lsh_count, k, similarity_threshold, out, used, variant)
+        return np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used
+
+    def lsh_similar_pairs_into(self, toc, pairs, lsh_vectors, k: int, similarity_threshold: float, out_pairs, out_used,
+                               variant: int = VARIANT_AUTO, out_signatures=None) -> None:
+        n = len(toc) - 1
+        G, Lc = lsh_vectors.shape
+        self._check(self._L.em2_multi_lsh_similar_pairs(self._h, n, G, _ptr(toc), _ptr(pairs), _ptr(lsh_vectors), Lc, k,
+                                                        similarity_threshold, variant, _ptr(out_pairs), _ptr(out_used),
+                                                        _ptr(out_signatures)), "em2_multi_lsh_similar_pairs")
+
+    def lsh_similar_pairs(self, toc, counts, lsh_vectors, k: int, similarity_threshold: float, gene_ids=None,
+                          variant: int = VARIANT_AUTO, want_signatures: bool = False):
+        toc = np.ascontiguousarray(toc, np.uint64)
+        pairs = _as_pairs(counts, gene_ids)
+        U = np.ascontiguousarray(lsh_vectors, np.float64)
+        n = len(toc) - 1
+        out = np.zeros((n, k), SIMPAIR_DTYPE)
+        used = np.zeros(n, np.uint32)
+        sig = np.empty((n, word_count(U.shape[1])), np.uint64) if want_signatures else None
+        self.lsh_similar_pairs_into(toc, pairs, U, k, similarity_threshold, out, used, variant, sig)
+        res = (np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used)
+        return res + (sig,) if want_signatures else res
+
+    def lsh_similar_pairs_subset(self, toc, counts, global_gene_count: int, gene_set, cell_set, lsh_vectors, k: int,
+                                 similarity_threshold: float, gene_ids=None, variant: int = VARIANT_AUTO,
+                                 want_signatures: bool = False):
+        toc = np.ascontiguousarray(toc, np.uint64)
+        pairs = _as_pairs(counts, gene_ids)
+        cell_set = np.ascontiguousarray(cell_set, np.uint32)
+        local = Engine.gene_local_ids(global_gene_count, gene_set)
+        U = np.ascontiguousarray(lsh_vectors, np.float64)
+        G, Lc = U.shape
+        n = len(cell_set)
+        out = np.zeros((n, k), SIMPAIR_DTYPE)
+        used = np.zeros(n, np.uint32)
+        sig = np.empty((n, word_count(Lc)), np.uint64) if want_signatures else None
+        self._check(self._L.em2_multi_lsh_similar_pairs_subset(self._h, len(toc) - 1, _ptr(toc), _ptr(pairs), global_gene_count,
+                                                               _ptr(local), G, n, _ptr(cell_set), _ptr(U), Lc, k,
+                                                               similarity_threshold, variant, _ptr(out), _ptr(used), _ptr(sig)),
+                    "em2_multi_lsh_similar_pairs_subset")
+        res = (np.ascontiguousarray(out["cell"]), np.ascontiguousarray(out["similarity"]), used)
+        return res + (sig,) if want_signatures else res

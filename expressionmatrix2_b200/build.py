@@ -14,12 +14,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libem2b200.so")
-SOURCES = ["capi.cu", "signatures.cu", "sig_filter.cu", "scan_popc.cu", "scan_mma.cu", "exact.cu", "subset.cu", "cellgraph.cu", "siggraph.cu", "bucketed.cu", "hostgen.cpp"]
+SOURCES = ["capi.cu", "signatures.cu", "sig_filter.cu", "scan_popc.cu", "scan_mma.cu", "exact.cu", "subset.cu", "cellgraph.cu", "siggraph.cu", "bucketed.cu", "multi.cu", "hostgen.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-pthread", "-Xptxas=-v",
-    "-ccbin", "/usr/bin/g++",
+    "-ccbin", "/usr/bin/g++", "-I/usr/include",
 ]
 
 
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread", "-ccbin", "/usr/bin/g++"])
+    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread", "-ldl", "-ccbin", "/usr/bin/g++"])
     return LIB
 
 

@@ -89,25 +89,6 @@ int makeTensorMapU8(em2_context* ctx, CUtensorMap* map, const void* base, uint64
     return EM2_OK;
 }
 
-namespace {
-
-struct StageTimer {
-    em2_context* ctx;
-    int next = 0;
-    explicit StageTimer(em2_context* c) : ctx(c) {}
-    int mark()   // records an event on the context stream, returns its index
-    {
-        cudaEventRecord(ctx->ev[next], ctx->stream);
-        return next++;
-    }
-    double ms(int a, int b)
-    {
-        float t = 0.f;
-        cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
-        return double(t);
-    }
-};
-
 double nowMs()
 {
     return 1e-6 * double(std::chrono::duration_cast<std::chrono::nanoseconds>(
@@ -127,6 +108,85 @@ void resetStats(em2_context* ctx)
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
 }
 
+// Host -> device copy of a caller's buffer.  Pinned (or registered) memory goes straight to the copy engine.  Pageable
+// memory -- the usual case: the C++ host layer hands over mmap regions of MemoryMapped::Vector files, whose pages
+// cannot be pinned reliably ("Ownership") -- is staged through two library-owned pinned bounce buffers:
+// the host thread copies piece i + 1 into one buffer while the copy engine moves piece i out of the other, so the
+// transfer is asynchronous to the compute stream either way.
+int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0) return EM2_OK;
+    cudaPointerAttributes attr{};
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, src);
+    if (pe != cudaSuccess) cudaGetLastError();
+    const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    if (pinned || ctx->noBounce) {
+        EM2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+        return EM2_OK;
+    }
+    constexpr size_t kPiece = size_t(16) << 20;
+    if (!ctx->bounce[0]) {
+        for (int i = 0; i < 2; i++) {
+            EM2_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], kPiece));
+            EM2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bounceFree[i], cudaEventDisableTiming));
+        }
+    }
+    for (size_t off = 0, i = ctx->bounceNext; off < bytes; off += kPiece, i ^= 1, ctx->bounceNext = int(i)) {
+        const size_t n = std::min(kPiece, bytes - off);
+        EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[i]));      // the copy that last read this buffer is done
+        std::memcpy(ctx->bounce[i], static_cast<const char*>(src) + off, n);
+        EM2_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(dst) + off, ctx->bounce[i], n, cudaMemcpyHostToDevice, s));
+        EM2_CUDA(ctx, cudaEventRecord(ctx->bounceFree[i], s));
+        ctx->stats.bounced_bytes += n;
+    }
+    return EM2_OK;
+}
+
+// Device -> host, same idea: results usually land in the mapped SimilarPairs-<name>-Pairs file.
+int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0) return EM2_OK;
+    cudaPointerAttributes attr{};
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, dst);
+    if (pe != cudaSuccess) cudaGetLastError();
+    const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    if (pinned || ctx->noBounce) {
+        EM2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+        return EM2_OK;
+    }
+    constexpr size_t kPiece = size_t(16) << 20;
+    if (!ctx->bounce[0]) {
+        for (int i = 0; i < 2; i++) {
+            EM2_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], kPiece));
+            EM2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bounceFree[i], cudaEventDisableTiming));
+        }
+    }
+    // piece i + 1 crosses PCIe while the host thread copies piece i out of its bounce buffer
+    size_t pendingOff[2] = {0, 0}, pendingBytes[2] = {0, 0};
+    int i = ctx->bounceNext;
+    EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[0]));
+    EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[1]));
+    for (size_t off = 0; off < bytes; off += kPiece, i ^= 1) {
+        const size_t n = std::min(kPiece, bytes - off);
+        if (pendingBytes[i]) {
+            EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[i]));
+            std::memcpy(static_cast<char*>(dst) + pendingOff[i], ctx->bounce[i], pendingBytes[i]);
+        }
+        EM2_CUDA(ctx, cudaMemcpyAsync(ctx->bounce[i], static_cast<const char*>(src) + off, n, cudaMemcpyDeviceToHost, s));
+        EM2_CUDA(ctx, cudaEventRecord(ctx->bounceFree[i], s));
+        pendingOff[i] = off;
+        pendingBytes[i] = n;
+        ctx->stats.bounced_bytes += n;
+    }
+    for (int j = 0; j < 2; j++, i ^= 1)
+        if (pendingBytes[i]) {
+            EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[i]));
+            std::memcpy(static_cast<char*>(dst) + pendingOff[i], ctx->bounce[i], pendingBytes[i]);
+        }
+    ctx->bounceNext = i;
+    return EM2_OK;
+}
+
 int uploadLut(em2_context* ctx, uint64_t lshCount, float** dLut)
 {
     std::vector<double> t(lshCount + 1);
@@ -143,7 +203,6 @@ int uploadLut(em2_context* ctx, uint64_t lshCount, float** dLut)
     return EM2_OK;
 }
 
-}  // namespace
 }  // namespace em2
 
 using namespace em2;
@@ -212,6 +271,11 @@ void em2_destroy(em2_context* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    commDestroy(ctx);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
+        if (ctx->bounceFree[i]) cudaEventDestroy(ctx->bounceFree[i]);
+    }
     for (auto& b : ctx->scratch)
         if (b.ptr) cudaFree(b.ptr);
     for (auto& b : ctx->pinned)
@@ -246,6 +310,9 @@ int em2_device_name(em2_context* ctx, char* buffer, size_t bufferSize)
 int em2_get_stats(const em2_context* ctx, em2_stats* stats)
 {
     if (!ctx || !stats) return EM2_ERR_INVALID;
+    // a device-resident collective call leaves its all-gather bracketed by two events; fold the time in once it is known
+    if (ctx->distTimed && cudaEventQuery(ctx->ev[13]) == cudaSuccess) distCollectTimes(const_cast<em2_context*>(ctx));
+    else cudaGetLastError();
     *stats = ctx->stats;
     return EM2_OK;
 }
@@ -269,6 +336,8 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     else if (n == "mma_kernel" && value >= 0 && value <= 2) ctx->mmaKernel = int(value);
     else if (n == "mma_cta_pair" && value >= 0 && value <= 1) ctx->mmaCtaPair = int(value);
     else if (n == "exact_matrix_bytes" && value >= 0) ctx->exactMatrixBytes = uint64_t(value);
+    else if (n == "sym_near_half_width" && value >= 0 && value <= 100000) ctx->symNearHalfWidth = int(value);
+    else if (n == "no_bounce" && value >= 0 && value <= 1) ctx->noBounce = int(value);
     else if (n == "filter_uncertain_cap" && value >= 0 && value <= (1 << 28)) ctx->filterUncertainCap = uint32_t(value);
     else return fail(ctx, EM2_ERR_INVALID, "em2_set_option: unknown option or value out of range: " + n);
     return EM2_OK;
@@ -325,27 +394,36 @@ int em2_mismatch_block_device(em2_context* ctx, const uint64_t* signatures, uint
                                static_cast<cudaStream_t>(stream));
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------------
 // blocking host-buffer calls
 // ------------------------------------------------------------------------------------------------
 // Counts -> signatures with host inputs.  The CSR payload dominates the transfer (1.2 GB at 100k cells), so it
 // is cut into a few chunks of whole cells: the copy stream moves chunk i+1 over PCIe while the compute stream
 // builds the sums and signatures of chunk i.  Hyperplanes go first (their preparation overlaps chunk 0).
-static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCount, uint64_t geneCount,
-                              const uint64_t* toc, const em2_count* counts, const double* U, uint64_t lshCount,
-                              uint64_t** dSigOut, double** dSum1Out, double** dSum2Out)
+// toc may be a slice of a longer table (one GPU's row block of a multi-GPU job): its entries index `counts` -- the
+// base of the WHOLE payload -- and only [toc[0], toc[cellCount]) is copied.  sigTotalRows / sigRowOffset: the
+// signatures are written at row sigRowOffset of a buffer of sigTotalRows rows (the all-gather buffer of a multi-GPU job).
+int em2::signaturesOnDevice(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc, const em2_count* counts,
+                       const double* U, uint64_t lshCount, uint64_t** dSigOut, double** dSum1Out, double** dSum2Out,
+                       uint64_t sigTotalRows, uint64_t sigRowOffset, const double* dUready)
 {
-    (void)T;
-    const uint64_t nnz = toc[cellCount];
+    const uint64_t base = toc[0];
+    const uint64_t nnz = toc[cellCount] - base;
     const uint64_t W = wordCount(lshCount);
-    void *dToc, *dCounts, *dU, *dSum1, *dSum2, *dSig, *dCounters;
+    if (sigTotalRows == 0) sigTotalRows = cellCount;
+    void *dToc, *dCountsRaw, *dU, *dSum1, *dSum2, *dSigAll, *dCounters;
     EM2_TRY(reserve(ctx, em2_context::S_TOC, (cellCount + 1) * sizeof(uint64_t), &dToc));
-    EM2_TRY(reserve(ctx, em2_context::S_COUNTS, nnz * sizeof(em2_count), &dCounts));
+    EM2_TRY(reserve(ctx, em2_context::S_COUNTS, nnz * sizeof(em2_count), &dCountsRaw));
     EM2_TRY(reserve(ctx, em2_context::S_U, geneCount * lshCount * sizeof(double), &dU));
     EM2_TRY(reserve(ctx, em2_context::S_SUM1, cellCount * sizeof(double), &dSum1));
     EM2_TRY(reserve(ctx, em2_context::S_SUM2, cellCount * sizeof(double), &dSum2));
-    EM2_TRY(reserve(ctx, em2_context::S_SIG, cellCount * W * sizeof(uint64_t), &dSig));
+    EM2_TRY(reserve(ctx, em2_context::S_SIG, sigTotalRows * W * sizeof(uint64_t), &dSigAll));
     EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &dCounters));
+    // the kernels index the payload with the table's own (absolute) entries
+    em2_count* dCounts = static_cast<em2_count*>(dCountsRaw) - base;
+    void* dSig = static_cast<uint64_t*>(dSigAll) + sigRowOffset * W;
     cudaStream_t s = ctx->stream, c = ctx->copyStream;
     constexpr int kMaxChunks = 8;
     if (!ctx->pool[0])
@@ -358,7 +436,7 @@ static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCoun
     uint64_t bound[kMaxChunks + 1];
     bound[0] = 0;
     for (int i = 1; i < chunks; i++) {
-        const uint64_t target = nnz / chunks * i;
+        const uint64_t target = base + nnz / chunks * i;
         bound[i] = uint64_t(std::lower_bound(toc, toc + cellCount + 1, target) - toc);
         bound[i] = std::min(std::max(bound[i], bound[i - 1]), cellCount);
     }
@@ -366,10 +444,15 @@ static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCoun
 
     EM2_CUDA(ctx, cudaMemsetAsync(dCounters, 0, 64, s));
     EM2_CUDA(ctx, cudaEventRecord(ev[0], c));
-    EM2_CUDA(ctx, cudaMemcpyAsync(dToc, toc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c));
-    EM2_CUDA(ctx, cudaMemcpyAsync(dU, U, geneCount * lshCount * sizeof(double), cudaMemcpyHostToDevice, c));
+    EM2_TRY(stageH2D(ctx, dToc, toc, (cellCount + 1) * sizeof(uint64_t), c));
+    if (dUready) {
+        dU = const_cast<double*>(dUready);      // the hyperplanes are on the device already (multi-GPU: sharded copy + all-gather)
+    } else {
+        EM2_TRY(stageH2D(ctx, dU, U, geneCount * lshCount * sizeof(double), c));
+        ctx->stats.h2d_bytes += geneCount * lshCount * 8;
+    }
     EM2_CUDA(ctx, cudaEventRecord(ev[1], c));
-    ctx->stats.h2d_bytes += (cellCount + 1) * 8 + nnz * 8 + geneCount * lshCount * 8;
+    ctx->stats.h2d_bytes += (cellCount + 1) * 8 + nnz * 8;
 
     EM2_CUDA(ctx, cudaStreamWaitEvent(s, ev[1], 0));
     SignaturePlan plan;
@@ -380,16 +463,14 @@ static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCoun
         const uint64_t b = bound[i], e = bound[i + 1];
         cudaEvent_t* ce = ev + 5 + 4 * i;      // landed, sums begin, signatures begin, end
         const uint64_t n0 = toc[b], n1 = toc[e];
-        if (n1 > n0)
-            EM2_CUDA(ctx, cudaMemcpyAsync(static_cast<em2_count*>(dCounts) + n0, counts + n0, (n1 - n0) * sizeof(em2_count),
-                                          cudaMemcpyHostToDevice, c));
+        if (n1 > n0) EM2_TRY(stageH2D(ctx, dCounts + n0, counts + n0, (n1 - n0) * sizeof(em2_count), c));
         EM2_CUDA(ctx, cudaEventRecord(ce[0], c));
         EM2_CUDA(ctx, cudaStreamWaitEvent(s, ce[0], 0));
         EM2_CUDA(ctx, cudaEventRecord(ce[1], s));
-        EM2_TRY(launchCellSums(ctx, e - b, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+        EM2_TRY(launchCellSums(ctx, e - b, static_cast<uint64_t*>(dToc), dCounts,
                                static_cast<double*>(dSum1), static_cast<double*>(dSum2), s, b));
         EM2_CUDA(ctx, cudaEventRecord(ce[2], s));
-        EM2_TRY(launchSignaturesRange(ctx, plan, static_cast<uint64_t*>(dToc), static_cast<em2_count*>(dCounts),
+        EM2_TRY(launchSignaturesRange(ctx, plan, static_cast<uint64_t*>(dToc), dCounts,
                                       static_cast<double*>(dSum1), static_cast<double*>(dSum2), b, e,
                                       static_cast<uint64_t*>(dSig), static_cast<uint64_t*>(dCounters), s));
         EM2_CUDA(ctx, cudaEventRecord(ce[3], s));
@@ -415,7 +496,11 @@ static int signaturesOnDevice(em2_context* ctx, StageTimer& T, uint64_t cellCoun
     return EM2_OK;
 }
 
-static int fetchCounters(em2_context* ctx)
+extern "C" {
+
+}  // extern "C"
+
+int em2::fetchCounters(em2_context* ctx)
 {
     uint64_t h[8] = {};
     EM2_CUDA(ctx, cudaMemcpyAsync(h, ctx->scratch[em2_context::S_COUNTERS].ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -427,7 +512,11 @@ static int fetchCounters(em2_context* ctx)
     return EM2_OK;
 }
 
-static int scanToHost(em2_context* ctx, StageTimer& T, const uint64_t* dSig, uint64_t cellCount, uint64_t lshCount,
+extern "C" {
+
+}  // extern "C"
+
+int em2::scanToHost(em2_context* ctx, StageTimer& T, const uint64_t* dSig, uint64_t cellCount, uint64_t lshCount,
                       uint64_t rowBegin, uint64_t rowEnd, uint64_t k, double similarityThreshold, int variant,
                       em2_pair* pairs, uint32_t* usedCount)
 {
@@ -443,8 +532,8 @@ static int scanToHost(em2_context* ctx, StageTimer& T, const uint64_t* dSig, uin
     EM2_TRY(launchScanTopK(ctx, dSig, cellCount, lshCount, rowBegin, rowEnd, k, mismatchMax, dLut, variant,
                            static_cast<em2_pair*>(dPairs), static_cast<uint32_t*>(dUsed), s));
     const int e1 = T.mark();
-    EM2_CUDA(ctx, cudaMemcpyAsync(pairs, dPairs, rows * k * sizeof(em2_pair), cudaMemcpyDeviceToHost, s));
-    EM2_CUDA(ctx, cudaMemcpyAsync(usedCount, dUsed, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    EM2_TRY(stageD2H(ctx, pairs, dPairs, rows * k * sizeof(em2_pair), s));
+    EM2_TRY(stageD2H(ctx, usedCount, dUsed, rows * sizeof(uint32_t), s));
     const int e2 = T.mark();
     EM2_CUDA(ctx, cudaStreamSynchronize(s));
     ctx->stats.d2h_bytes += rows * k * sizeof(em2_pair) + rows * sizeof(uint32_t);
@@ -452,6 +541,8 @@ static int scanToHost(em2_context* ctx, StageTimer& T, const uint64_t* dSig, uin
     ctx->stats.d2h_ms += T.ms(e1, e2);
     return EM2_OK;
 }
+
+extern "C" {
 
 int em2_compute_signatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                            const em2_count* counts, const double* lshVectors, uint64_t lshCount,
@@ -466,7 +557,7 @@ int em2_compute_signatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCo
     StageTimer T(ctx);
     uint64_t* dSig;
     double *dSum1, *dSum2;
-    EM2_TRY(signaturesOnDevice(ctx, T, cellCount, geneCount, toc, counts, lshVectors, lshCount, &dSig, &dSum1, &dSum2));
+    EM2_TRY(signaturesOnDevice(ctx, cellCount, geneCount, toc, counts, lshVectors, lshCount, &dSig, &dSum1, &dSum2));
     const uint64_t W = wordCount(lshCount);
     const int e0 = T.mark();
     EM2_CUDA(ctx, cudaMemcpyAsync(signatures, dSig, cellCount * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -523,7 +614,7 @@ int em2_lsh_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCou
     StageTimer T(ctx);
     uint64_t* dSig;
     double *dSum1, *dSum2;
-    EM2_TRY(signaturesOnDevice(ctx, T, cellCount, geneCount, toc, counts, lshVectors, lshCount, &dSig, &dSum1, &dSum2));
+    EM2_TRY(signaturesOnDevice(ctx, cellCount, geneCount, toc, counts, lshVectors, lshCount, &dSig, &dSum1, &dSum2));
     if (signaturesOut) {
         const uint64_t W = wordCount(lshCount);
         EM2_CUDA(ctx, cudaMemcpyAsync(signaturesOut, dSig, cellCount * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -535,8 +626,10 @@ int em2_lsh_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCou
     return EM2_OK;
 }
 
+}  // extern "C"
+
 // Selected cells' rows -> device, then the subset kernels.  Leaves the local CSR in S_TOC / S_COUNTS.
-static int subsetOnDevice(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc, const em2_count* globalCounts,
+int em2::subsetOnDevice(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc, const em2_count* globalCounts,
                           uint64_t globalGeneCount, const uint32_t* geneLocalId, uint64_t cellCount, const uint32_t* cellSet,
                           uint64_t** dTocOut, em2_count** dCountsOut, uint64_t* nnzLocal)
 {
@@ -559,15 +652,13 @@ static int subsetOnDevice(em2_context* ctx, uint64_t globalCellCount, const uint
     cudaStream_t s = ctx->stream;
     EM2_CUDA(ctx, cudaEventRecord(ctx->ev[14], s));
     EM2_CUDA(ctx, cudaMemcpyAsync(dSrcToc, srcToc, (cellCount + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    EM2_CUDA(ctx, cudaMemcpyAsync(dMap, geneLocalId, globalGeneCount * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    EM2_TRY(stageH2D(ctx, dMap, geneLocalId, globalGeneCount * sizeof(uint32_t), s));
     // runs of consecutive cells are contiguous in the global file: one copy per run
     for (uint64_t i = 0; i < cellCount;) {
         uint64_t j = i;
         while (j + 1 < cellCount && cellSet[j + 1] == cellSet[j] + 1) j++;
         const uint64_t b = globalToc[cellSet[i]], e = globalToc[cellSet[j] + 1];
-        if (e > b)
-            EM2_CUDA(ctx, cudaMemcpyAsync(static_cast<em2_count*>(dSrc) + srcToc[i], globalCounts + b, (e - b) * sizeof(em2_count),
-                                          cudaMemcpyHostToDevice, s));
+        if (e > b) EM2_TRY(stageH2D(ctx, static_cast<em2_count*>(dSrc) + srcToc[i], globalCounts + b, (e - b) * sizeof(em2_count), s));
         i = j + 1;
     }
     EM2_CUDA(ctx, cudaEventRecord(ctx->ev[15], s));
@@ -584,6 +675,8 @@ static int subsetOnDevice(em2_context* ctx, uint64_t globalCellCount, const uint
     *dCountsOut = static_cast<em2_count*>(dCounts);
     return EM2_OK;
 }
+
+extern "C" {
 
 int em2_subset(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc, const em2_count* globalCounts,
                uint64_t globalGeneCount, const uint32_t* geneLocalId, uint64_t cellCount, const uint32_t* cellSet,

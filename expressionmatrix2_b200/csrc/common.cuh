@@ -62,6 +62,8 @@ struct em2_context {
         S_INBOX,         // symmetric scan: column-direction candidates, uint64[N][inCap]
         S_COLLOG,        // symmetric scan: chunked log of column-direction survivors
         S_COLLOGFILL,    // symmetric scan: entries per log chunk + the chunk allocator
+        S_DIST0, S_DIST1, S_DIST2, S_DIST3,   // multi-GPU exchange buffers (multi.cu)
+        S_PERM,          // scan position -> cell id
         S_COUNT
     };
     int signatureMode = 0;   // 0 auto, 1 FP64 kernel only, 2 force the tensor-core filter path
@@ -82,6 +84,21 @@ struct em2_context {
     int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM
     em2::DeviceBuffer scratch[S_COUNT];
     em2::PinnedBuffer pinned[3];      // [2]: small read-back flags (symmetric scan)
+    // pageable host buffers (mmap regions) are staged through two pinned bounce buffers (capi.cu, stageH2D / stageD2H)
+    void* bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounceFree[2] = {nullptr, nullptr};
+    int bounceNext = 0;
+    int noBounce = 0;                  // option "no_bounce": 1 = hand pageable pointers straight to cudaMemcpyAsync
+    // multi-GPU (multi.cu): this context is rank `rank` of `world`; comm is an ncclComm_t
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    // called before every collective with this rank's status so far; returns non-zero if ANY rank failed (then nobody
+    // enters the collective).  Set by the in-process multi-GPU driver; null = no agreement step.
+    int (*agree)(void* user, int status) = nullptr;
+    void* agreeUser = nullptr;
+    bool distTimed = false;            // ev[12], ev[13] bracket the last signature all-gather
+    bool symExchangeTimed = false;     // ev[10], ev[11] bracket the symmetric scan's candidate exchange
+    int symNearHalfWidth = 0;          // option "sym_near_half_width": super blocks on each side of the near window (0 = automatic)
 };
 
 namespace em2 {
@@ -103,6 +120,42 @@ int reservePinned(em2_context* ctx, int which, size_t bytes, void** out);
         int rc__ = (call);            \
         if (rc__ != EM2_OK) return rc__; \
     } while (0)
+
+// events on the context stream, for the per-stage timings of em2_stats
+struct StageTimer {
+    em2_context* ctx;
+    int next = 0;
+    explicit StageTimer(em2_context* c) : ctx(c) {}
+    int mark()   // records an event on the context stream, returns its index
+    {
+        cudaEventRecord(ctx->ev[next], ctx->stream);
+        return next++;
+    }
+    double ms(int a, int b)
+    {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
+        return double(t);
+    }
+};
+
+// ---- helpers of the blocking host-buffer calls (capi.cu), shared with the multi-GPU driver (multi.cu) ----------
+double nowMs();
+int guardDevice(em2_context* ctx);
+void resetStats(em2_context* ctx);
+int uploadLut(em2_context* ctx, uint64_t lshCount, float** dLut);
+int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s);
+int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s);
+int fetchCounters(em2_context* ctx);
+int signaturesOnDevice(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc, const em2_count* counts,
+                       const double* U, uint64_t lshCount, uint64_t** dSigOut, double** dSum1Out, double** dSum2Out,
+                       uint64_t sigTotalRows = 0, uint64_t sigRowOffset = 0, const double* dUready = nullptr);
+int subsetOnDevice(em2_context* ctx, uint64_t globalCellCount, const uint64_t* globalToc, const em2_count* globalCounts,
+                   uint64_t globalGeneCount, const uint32_t* geneLocalId, uint64_t cellCount, const uint32_t* cellSet,
+                   uint64_t** dTocOut, em2_count** dCountsOut, uint64_t* nnzLocal);
+int scanToHost(em2_context* ctx, StageTimer& T, const uint64_t* dSig, uint64_t cellCount, uint64_t lshCount,
+               uint64_t rowBegin, uint64_t rowEnd, uint64_t k, double similarityThreshold, int variant,
+               em2_pair* pairs, uint32_t* usedCount);
 
 inline uint64_t wordCount(uint64_t lshCount) { return (lshCount - 1) / 64 + 1; }
 inline uint64_t roundUp(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
@@ -179,6 +232,23 @@ int launchMismatchBlock(em2_context* ctx, const uint64_t* signatures, uint64_t c
 int launchExact(em2_context* ctx, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
                 const em2_count* counts, const double* sum1, const double* sum2, uint64_t k,
                 double similarityThreshold, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);
+
+// ---- multi-GPU (multi.cu) -------------------------------------------------------------------------------------
+// Rank r owns the cells [r * shard, min(N, (r + 1) * shard)); shard is a multiple of 256 when there is more than one rank.
+struct DistPartition {
+    uint64_t shard, rowBegin, rowEnd;
+};
+DistPartition distPartition(uint64_t cellCount, int world, int rank);
+void commDestroy(em2_context* ctx);
+int distAgree(em2_context* ctx, int status);
+int distAllGather(em2_context* ctx, void* buffer, size_t count, size_t bytesPer, cudaStream_t s);
+int distAllToAll(em2_context* ctx, const void* send, const uint64_t* sendOffset, const uint64_t* sendBytes, void* recv,
+                 const uint64_t* recvOffset, const uint64_t* recvBytes, cudaStream_t s);
+void distCollectTimes(em2_context* ctx);
+// The symmetric scan over several GPUs (scan_mma.cu): allSig holds every cell's signature (after the all-gather).
+bool distSymmetricEligible(const em2_context* ctx, uint64_t cellCount, uint64_t lshCount, uint64_t k, int64_t mismatchMax, int variant);
+int launchScanSymDist(em2_context* ctx, const uint64_t* allSig, uint64_t cellCount, uint64_t lshCount, uint64_t k,
+                      int64_t mismatchMax, const float* lut, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s);
 
 // scan internals shared between the POPC and MMA variants
 // Work decomposition of a scan: rows are cut into blocks of rowsPerCta.  The first `mainBlocks` row blocks (a

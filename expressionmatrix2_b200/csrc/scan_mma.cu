@@ -617,23 +617,26 @@ constexpr int kSymMaxStages = 6;
 constexpr uint32_t kLogChunk = 64;
 constexpr uint32_t kPaceWindow = 256;      // tiles a CTA may run ahead of the slowest one (64 MB of distinct B tiles)
 constexpr uint32_t kSymSmallBytes = 192 + 2 * kSsTileN * 2 + 2 * (kSsTileN / 8) * 2 + kEpiThreads * 2;
+constexpr int kMaxInboxSources = 8;        // GPUs whose column-direction candidates a cell's merge reads
 
 struct SymParams {
-    uint64_t cellCount;            // N: rows == columns, in scan-position order
+    uint64_t cellCount;            // N: scan positions of the WHOLE job (all ranks); rows == columns
     uint32_t K, panels, stages;
     uint32_t mainBlocks, segments, items;
     uint64_t segmentCols;          // in virtual columns: offset * 256
     uint32_t superBlocks;          // S = ceil(N / 256)
-    uint32_t offsets;              // column tiles per row block: S / 2 + 1
     uint32_t halfOffset;           // S even: the offset visited by both owners (no column direction); else 0
-    uint32_t dBegin;               // this launch sweeps the offsets [dBegin, dBegin + offsetsHere)
+    int32_t dBegin;                // this launch sweeps the offsets [dBegin, dBegin + offsetsHere); negative in the near window
     uint32_t offsetsHere;
     uint32_t resume;               // 1: segment 0 of every row CONTINUES the row's streams of the previous launch
+    uint32_t rowOnly;              // 1: row direction only (the near window, which both owners of a tile pair visit)
+    uint32_t posBegin;             // first scan position of this GPU's rows (a multiple of 256)
+    uint32_t ownRows;              // rows of this GPU: positions [posBegin, posBegin + ownRows)
     uint32_t k, cap;
-    uint64_t* cand;
+    uint64_t* cand;                // [streams][ownRows][cap], indexed by position - posBegin
     uint32_t* candCount;
     unsigned long long* appendedTotal;   // both directions
-    uint32_t* limEx;               // per position: accept iff mismatch count < limEx
+    uint32_t* limEx;               // per position (all N): accept iff mismatch count < limEx
     ulonglong2* colLog;            // column-direction survivors {mismatch << 32 | row cell id, column position}: a pool of
     uint32_t* chunkFill;           //   64-entry chunks; a thread takes a chunk at a time (one atomic per 64 survivors);
     uint32_t* chunkNext;           //   chunkFill[c] = valid entries of chunk c; scattered to the inboxes afterwards
@@ -673,7 +676,9 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint64_t* aEmpty = bars + 5;     // every MMA of the item has read it
     uint64_t* full = bars + 6;       // [stages]
     uint64_t* empty = full + kSymMaxStages;
-    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(empty + kSymMaxStages);
+    uint64_t* thrFull = empty + kSymMaxStages;      // [2] the producer warp has staged the tile's column thresholds
+    uint64_t* thrEmpty = thrFull + 2;               // [2] every epilogue warp is done with them
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(thrEmpty + 2);
     int16_t* colThr = reinterpret_cast<int16_t*>(small + 192);          // [2][256] dot thresholds of the tile's columns
     int16_t* grpThr = colThr + 2 * kSsTileN;                             // [2][32]  loosest threshold of each 8 columns
     uint16_t* tauShare = reinterpret_cast<uint16_t*>(grpThr + 2 * (kSsTileN / 8));   // [kSubStreams][kRowsPerItem]
@@ -684,6 +689,8 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int i = 0; i < 2; i++) {
             mbarInit(accFull + i, 1);
             mbarInit(accEmpty + i, kEpiWarps * 32);
+            mbarInit(thrFull + i, 1);
+            mbarInit(thrEmpty + i, kEpiWarps);
         }
         mbarInit(aFull, 1);
         mbarInit(aEmpty, 1);
@@ -700,31 +707,43 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const uint32_t tmemBase = *tmemSlot;
     const uint32_t items = p.items;
     const uint64_t virtualCols = uint64_t(p.offsetsHere) * kSsTileN;
+    const uint32_t N = uint32_t(p.cellCount);
+    const uint32_t S = p.superBlocks;
+    const uint32_t firstBlock = p.posBegin / kRowsPerItem;
+    // column super block of offset d (may be negative) for the row super block `super`
+    auto colSuperOf = [S](uint32_t super, int32_t d) -> uint32_t {
+        int64_t c = (int64_t(super) - int64_t(d)) % int64_t(S);
+        return uint32_t(c < 0 ? c + S : c);
+    };
 
     if (warp == kEpiWarps) {
-        // ===================== TMA producer: A once per item, B per tile =====================
+        // ===================== producer warp: A once per item, B per tile (TMA), column thresholds per tile =====================
         // Lane 0 issues the loads; the whole warp takes part in the PACING of whole-sweep items: every CTA publishes how
         // far it is (in tiles) and none runs more than kPaceWindow tiles ahead of the slowest.  The B tiles of
         // neighbouring row blocks are the same blocks one step apart, so in step they are read from DRAM once and from
         // L2 147 times; without pacing a CTA that falls behind starts missing L2, gets slower still, and the sweep
         // settles DRAM-bound (1 M cells: 3.25 TB read from DRAM, L2 hit rate 33 %, tensor pipe 47 %).
-        uint32_t stage = 0, phase = 0, itemIter = 0;
+        // The warp also stages, per tile, the bounds of the tile's 256 column cells as dot-product thresholds (lane =
+        // one group of 8 columns) -- off the epilogue's critical path: with the 128 epilogue threads of a sub-stream
+        // doing it themselves behind a named barrier, 22 % of all warp samples sat at that barrier (ncu, 1 M cells).
+        uint32_t stage = 0, phase = 0, itemIter = 0, tileIter = 0;
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
             const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
-            const uint32_t super = it.rowBlock >> 1;
-            const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
-            const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+            const uint32_t super = (firstBlock + it.rowBlock) >> 1;
+            const int32_t d0 = p.dBegin + int32_t(it.colBegin / kSsTileN);
+            const int32_t d1 = p.dBegin + int32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
             const bool paced = p.progress != nullptr && item < p.mainBlocks;
             if (lane == 0) {
                 if (p.progress && !paced) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
                 mbarWait(aEmpty, (itemIter & 1) ^ 1);
                 mbarExpectTx(aFull, p.panels * kSsABytes);
                 for (uint32_t kc = 0; kc < p.panels; kc++)
-                    tmaLoad2d(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes), int32_t(it.rowBlock * kRowsPerItem));
+                    tmaLoad2d(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes),
+                              int32_t(p.posBegin + it.rowBlock * kRowsPerItem));
             }
-            for (uint32_t d = d0; d < d1; d++) {
-                if (paced && ((d - d0) & 7u) == 0) {
-                    const uint32_t vt = itemIter * p.offsetsHere + (d - d0);
+            for (int32_t d = d0; d < d1; d++, tileIter++) {
+                if (paced && ((d - d0) & 7) == 0) {
+                    const uint32_t vt = itemIter * p.offsetsHere + uint32_t(d - d0);
                     if (lane == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = vt;
                     for (int spin = 0; spin < 4000; spin++) {           // bounded: pacing is an optimisation, never a dependency
                         uint32_t slowest = 0xffffffffu;
@@ -735,8 +754,9 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         __nanosleep(500);
                     }
                 }
+                const uint32_t colSuper = colSuperOf(super, d);
                 if (lane == 0) {
-                    const int32_t col0 = int32_t(((super + p.superBlocks - d) % p.superBlocks) * kSsTileN);
+                    const int32_t col0 = int32_t(colSuper * kSsTileN);
                     for (uint32_t kc = 0; kc < p.panels; kc++) {
                         mbarWait(empty + stage, phase ^ 1);
                         mbarExpectTx(full + stage, kSsBBytes);
@@ -748,6 +768,28 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
                 __syncwarp();
+                if (!p.rowOnly) {
+                    const uint32_t slot = tileIter & 1;
+                    mbarWait(thrEmpty + slot, ((tileIter >> 1) & 1) ^ 1);
+                    const uint32_t pos0 = colSuper * kSsTileN + uint32_t(lane) * 8;
+                    int32_t t[8];
+                    int32_t loosest = 0x7fff;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t lim = pos0 + j < N ? __ldcg(p.limEx + pos0 + j) : 0u;      // padding columns: nothing passes
+                        t[j] = int32_t(p.K) - 2 * int32_t(lim);
+                        loosest = min(loosest, t[j]);
+                    }
+                    uint4 packed;
+                    packed.x = uint32_t(uint16_t(t[0])) | (uint32_t(uint16_t(t[1])) << 16);
+                    packed.y = uint32_t(uint16_t(t[2])) | (uint32_t(uint16_t(t[3])) << 16);
+                    packed.z = uint32_t(uint16_t(t[4])) | (uint32_t(uint16_t(t[5])) << 16);
+                    packed.w = uint32_t(uint16_t(t[6])) | (uint32_t(uint16_t(t[7])) << 16);
+                    *reinterpret_cast<uint4*>(colThr + slot * kSsTileN + lane * 8) = packed;
+                    grpThr[slot * (kSsTileN / 8) + lane] = int16_t(loosest);
+                    __syncwarp();
+                    if (lane == 0) mbarArrive(thrFull + slot);
+                }
             }
         }
         if (lane == 0 && p.progress) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
@@ -757,12 +799,11 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             uint32_t tileIter = 0, stage = 0, phase = 0, itemIter = 0;
             for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
                 const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
-                const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
-                const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+                const uint32_t tiles = uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN) - uint32_t(it.colBegin / kSsTileN);
                 mbarWait(aFull, itemIter & 1);
                 fenceAfter();
                 const uint32_t aBase = smemAddr(smA);
-                for (uint32_t d = d0; d < d1; d++, tileIter++) {
+                for (uint32_t t = 0; t < tiles; t++, tileIter++) {
                     const uint32_t buf = tileIter & 1;
                     mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
                     fenceAfter();
@@ -792,58 +833,47 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     } else {
         // ===================== epilogue: thread == (row == TMEM lane, 128-column sub-stream) =====================
         const uint32_t dotK = p.K;
-        const uint32_t N = uint32_t(p.cellCount);
         const uint32_t rowInItem = threadIdx.x & (kRowsPerItem - 1);
         const uint32_t sub = threadIdx.x / kRowsPerItem;
         constexpr int kSubCols = kSsTileN / kSubStreams;
         const uint32_t laneField = uint32_t((warp & 3) * 32) << 16;
+        const uint64_t streamStride = p.ownRows;
         uint32_t tileIter = 0;
         ulonglong2* logNext = nullptr;           // next free entry of the thread's current log chunk
         uint32_t logFill = kLogChunk;            // entries used in it (no chunk yet)
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
             const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
             const uint32_t seg = it.segment;
-            const uint32_t super = it.rowBlock >> 1;
-            const uint32_t d0 = p.dBegin + uint32_t(it.colBegin / kSsTileN);
-            const uint32_t d1 = p.dBegin + uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
-            const uint32_t rowPos = it.rowBlock * kRowsPerItem + rowInItem;
-            const bool valid = rowPos < N;
+            const uint32_t super = (firstBlock + it.rowBlock) >> 1;
+            const int32_t d0 = p.dBegin + int32_t(it.colBegin / kSsTileN);
+            const int32_t d1 = p.dBegin + int32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+            const uint32_t rowLocal = it.rowBlock * kRowsPerItem + rowInItem;
+            const bool valid = rowLocal < p.ownRows;
+            const uint32_t rowPos = p.posBegin + rowLocal;
             const uint32_t rowCell = !valid ? 0xffffffffu : p.perm ? p.perm[rowPos] : rowPos;
-            uint32_t* limPtr = p.limEx + (valid ? rowPos : 0);
+            uint32_t* limPtr = p.limEx + (valid ? rowPos : p.posBegin);
 
             RowState st;
-            st.rowId = rowPos;            // self test is on positions
+            st.rowId = valid ? rowPos : 0xffffffffu;            // self test is on positions
             // A stream that continues the previous launch's region keeps its k best so far: the next prune then yields
             // the k-th best of everything the row has seen.  (A fresh region needs ~2k survivors of the old bound
             // before its first prune tightens anything: measured 250 instead of ~65 row-direction survivors per cell.)
-            st.count = (p.resume && seg == 0 && valid) ? p.candCount[uint64_t(sub) * N + rowPos] : 0;
+            st.count = (p.resume && seg == 0 && valid) ? p.candCount[uint64_t(sub) * streamStride + rowLocal] : 0;
             st.appended = 0;
             st.tau = valid ? __ldcg(limPtr) : 0;
             st.lim = st.tau;
-            st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * N + (valid ? rowPos : 0)) * p.cap;
+            st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * streamStride + (valid ? rowLocal : 0)) * p.cap;
             tauShare[sub * kRowsPerItem + rowInItem] = 0xffffu;      // harmless for any row (see scanMmaKernel)
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.lim);      // mismatch < lim  <=>  dot > K - 2 lim
 
-            for (uint32_t d = d0; d < d1; d++, tileIter++) {
+            for (int32_t d = d0; d < d1; d++, tileIter++) {
                 const uint32_t buf = tileIter & 1;
-                const uint32_t colSuper = (super + p.superBlocks - d) % p.superBlocks;
-                const bool colDir = d != 0 && d != p.halfOffset;          // CTA-uniform
+                const uint32_t colSuper = colSuperOf(super, d);
+                const bool colDir = !p.rowOnly && d != 0 && uint32_t(d) != p.halfOffset;          // CTA-uniform
                 const int16_t* thr = colThr + buf * kSsTileN + sub * kSubCols;
                 const int16_t* grp = grpThr + buf * (kSsTileN / 8) + sub * (kSubCols / 8);
-                if (colDir) {
-                    // stage the bounds of this sub-stream's 128 columns (the same 128 threads use them)
-                    const uint32_t c = threadIdx.x;                       // == sub * 128 + rowInItem
-                    const uint32_t pos = colSuper * kSsTileN + c;
-                    const uint32_t lim = pos < N ? __ldcg(p.limEx + pos) : 0u;       // padding columns: nothing passes
-                    int32_t t = int32_t(dotK) - 2 * int32_t(lim);
-                    colThr[buf * kSsTileN + c] = int16_t(t);
-                    t = min(t, __shfl_xor_sync(0xffffffffu, t, 1));
-                    t = min(t, __shfl_xor_sync(0xffffffffu, t, 2));
-                    t = min(t, __shfl_xor_sync(0xffffffffu, t, 4));
-                    if ((lane & 7) == 0) grpThr[buf * (kSsTileN / 8) + (c >> 3)] = int16_t(t);
-                    asm volatile("bar.sync %0, %1;" ::"r"(2 + sub), "n"(kRowsPerItem) : "memory");
-                }
+                if (!p.rowOnly) mbarWait(thrFull + buf, (tileIter >> 1) & 1);
                 mbarWait(accFull + buf, (tileIter >> 1) & 1);
                 fenceAfter();
                 const uint32_t posBase = colSuper * kSsTileN + sub * kSubCols;
@@ -881,7 +911,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                 for (int j = 0; j < 8; j++) {
                                     const int32_t dv = int32_t(v[8 * g + j]);
                                     const uint32_t pos = posBase + c + 8 * g + j;
-                                    if (dv > dotThr && pos < N && pos != rowPos) {
+                                    if (dv > dotThr && pos < N && pos != st.rowId) {
                                         const uint32_t ham = uint32_t(int32_t(dotK) - dv) >> 1;
                                         st.buf[st.count++] = (uint64_t(ham) << 32) | pos;
                                         st.appended++;
@@ -918,9 +948,20 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
                 if (valid) tauShare[sub * kRowsPerItem + rowInItem] = uint16_t(min(st.tau, 0xffffu));
+                if (!p.rowOnly) {          // this warp is done with the tile's column thresholds
+                    __syncwarp();
+                    if (lane == 0) mbarArrive(thrEmpty + buf);
+                }
+            }
+            if (p.rowOnly) {
+                // End of a near-window item: every row publishes the bound it has learned -- the k-th best of each of its
+                // regions that holds k keys -- whether or not the region ever filled up.  The far sweep of EVERY GPU judges
+                // this cell by that bound.
+                __syncwarp();
+                warpPruneIfNeededAnyOrder(st, p.k, p.cap, limPtr, p.perm, true);
             }
             if (valid) {
-                p.candCount[uint64_t(seg * kSubStreams + sub) * N + rowPos] = st.count;
+                p.candCount[uint64_t(seg * kSubStreams + sub) * streamStride + rowLocal] = st.count;
                 if (p.appendedTotal && st.appended) atomicAdd(p.appendedTotal, (unsigned long long)st.appended);
             }
         }
@@ -933,51 +974,6 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     fenceBefore();
     __syncthreads();
     if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
-}
-
-// Sample rows of the encoded matrix (every stride-th scan position) as the column operand of the pre-pass, and for
-// every scan position its index in the sample (the pre-pass must not count a cell as its own neighbour).
-__global__ void sampleGatherKernel(const uint8_t* __restrict__ enc, uint32_t K, uint64_t cellCount, uint32_t stride,
-                                   uint32_t sampleCount, uint8_t* __restrict__ out, uint32_t* __restrict__ selfIndex)
-{
-    const uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    const uint32_t perRow = K / 16;
-    if (idx < uint64_t(sampleCount) * perRow) {
-        const uint64_t r = idx / perRow, o = idx % perRow;
-        reinterpret_cast<uint4*>(out + r * K)[o] = reinterpret_cast<const uint4*>(enc + r * stride * uint64_t(K))[o];
-    }
-    if (idx < cellCount) selfIndex[idx] = (idx % stride == 0 && idx / stride < sampleCount) ? uint32_t(idx / stride) : 0xffffffffu;
-}
-
-// Pre-pass result -> limEx: the k-th smallest mismatch count a cell has against the sample, plus one (exclusive
-// bound, ties still accepted); tau0 when the sample holds fewer than k admissible cells.  One warp per cell.
-__global__ void __launch_bounds__(128)
-sampleBoundKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k, const uint64_t* __restrict__ cand,
-                  const uint32_t* __restrict__ candCount, uint32_t tau0, uint32_t* __restrict__ limEx)
-{
-    const uint64_t row = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (row >= cellCount) return;
-    uint32_t n = 0;
-    for (uint32_t s = 0; s < streams; s++) n += candCount[uint64_t(s) * cellCount + row];
-    uint32_t bound = tau0;
-    if (n >= k && tau0 > 0) {
-        uint32_t lo = 0, hi = tau0 - 1;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            uint32_t c = 0;
-            for (uint32_t s = 0; s < streams; s++) {
-                const uint32_t cs = candCount[uint64_t(s) * cellCount + row];
-                const uint64_t* src = cand + (uint64_t(s) * cellCount + row) * cap;
-                for (uint32_t i = lane; i < cs; i += 32) c += (uint32_t(src[i] >> 32) <= mid);
-            }
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (c >= k) hi = mid;
-            else lo = mid + 1;
-        }
-        bound = lo + 1;
-    }
-    if (lane == 0) limEx[row] = bound;
 }
 
 // Files the column-direction log into per-cell inboxes of exactly the needed length (count -> exclusive scan -> fill,
@@ -1003,61 +999,84 @@ scatterLogKernel(const uint32_t* __restrict__ chunkNext, uint32_t chunkCap, cons
     }
 }
 
-// Merge of a cell's row streams and inbox (symmetric scan), one warp per cell.  Pass 1 finds h, the k-th smallest
-// mismatch count among the keys below the cell's final bound: their 16-bit counts are staged in shared memory for the
-// bisection when they fit, else (a cell with an unusually long inbox) every bisection step re-reads the regions.
-// Pass 2 stages the keys with count <= h -- k plus the ties at h -- which are ranked like in finalizeKernel
+// Merge of a cell's row streams and inboxes (symmetric scan), one warp per cell of THIS GPU.  A cell has one inbox per
+// GPU of the job (the column-direction candidates that GPU's rows produced for it; `sources`).  Pass 1 finds h, the
+// k-th smallest mismatch count among the keys below the cell's final bound: their 16-bit counts are staged in shared
+// memory for the bisection when they fit, else (a cell with an unusually long inbox) every bisection step re-reads the
+// regions.  Pass 2 stages the keys with count <= h -- k plus the ties at h -- which are ranked like in finalizeKernel
 // (scan_popc.cu).  Stream keys carry scan positions (translated here), inbox keys cell ids.
 constexpr int kSymFinalWarps = 4;
 
+struct InboxSources {
+    const uint64_t* keys[kMaxInboxSources];       // source s: the keys of local cell r are keys[s][offsets[s][r] .. offsets[s][r + 1])
+    const uint32_t* offsets[kMaxInboxSources];
+    uint32_t count;
+};
+
 __global__ void __launch_bounds__(kSymFinalWarps * 32)
-finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k, const uint64_t* __restrict__ cand,
-                  const uint32_t* __restrict__ candCount, const uint64_t* __restrict__ inbox, const uint32_t* __restrict__ inOffset,
-                  const uint32_t* __restrict__ limEx, const float* __restrict__ lut, em2_pair* __restrict__ pairs,
-                  uint32_t* __restrict__ usedCount, const uint32_t* __restrict__ perm, uint32_t* __restrict__ overflow,
-                  uint32_t hamsPerWarp, uint32_t keysPerWarp)
+finalizeSymKernel(uint32_t ownRows, uint32_t posBegin, uint32_t streams, uint32_t cap, uint32_t k, const uint64_t* __restrict__ cand,
+                  const uint32_t* __restrict__ candCount, const InboxSources in, const uint32_t* __restrict__ limEx,
+                  const float* __restrict__ lut, em2_pair* __restrict__ pairs, uint32_t* __restrict__ usedCount,
+                  const uint32_t* __restrict__ perm, uint32_t* __restrict__ overflow, uint32_t hamsPerWarp, uint32_t keysPerWarp)
 {
     extern __shared__ __align__(16) uint64_t skeys[];      // [warps][keysPerWarp] keys, then [warps][hamsPerWarp] uint16
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t row = uint64_t(blockIdx.x) * kSymFinalWarps + warp;
-    if (row >= cellCount) return;
+    if (row >= ownRows) return;
     uint64_t* keys = skeys + size_t(warp) * keysPerWarp;
     uint16_t* hams = reinterpret_cast<uint16_t*>(skeys + size_t(kSymFinalWarps) * keysPerWarp) + size_t(warp) * hamsPerWarp;
-    const uint32_t lim = limEx[row];
+    const uint32_t pos = posBegin + uint32_t(row);
+    const uint32_t lim = limEx[pos];
     const uint32_t lt = (1u << lane) - 1u;
-    const uint64_t* in = inbox + inOffset[row];
-    const uint32_t inboxCount = inOffset[row + 1] - inOffset[row];
-    uint32_t total = inboxCount;
-    for (uint32_t s = 0; s < streams; s++) total += candCount[uint64_t(s) * cellCount + row];
+    const uint32_t lists = streams + in.count;
+    // list i: a row stream (keys carry scan positions) or an inbox (keys carry cell ids)
+    auto listOf = [&](uint32_t i, const uint64_t*& src, uint32_t& c) {
+        if (i < streams) {
+            src = cand + (uint64_t(i) * ownRows + row) * cap;
+            c = candCount[uint64_t(i) * ownRows + row];
+        } else {
+            const uint32_t s = i - streams;
+            const uint32_t o = in.offsets[s][row];
+            src = in.keys[s] + o;
+            c = in.offsets[s][row + 1] - o;
+        }
+    };
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < lists; i++) {
+        const uint64_t* src;
+        uint32_t c;
+        listOf(i, src, c);
+        total += c;
+    }
     const bool staged = total <= hamsPerWarp;
     // ---- pass 1
     uint32_t n = 0;
-    auto stageHams = [&](const uint64_t* src, uint32_t c) {
+    for (uint32_t i = 0; i < lists; i++) {
+        const uint64_t* src;
+        uint32_t c;
+        listOf(i, src, c);
         for (uint32_t base = 0; base < c; base += 32) {
-            const uint32_t i = base + lane;
-            const uint32_t m = i < c ? uint32_t(src[i] >> 32) : 0xffffffffu;
+            const uint32_t e = base + lane;
+            const uint32_t m = e < c ? uint32_t(src[e] >> 32) : 0xffffffffu;
             const bool keep = m < lim;
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
             if (keep && staged) hams[n + __popc(mask & lt)] = uint16_t(m);
             n += __popc(mask);
         }
-    };
-    for (uint32_t s = 0; s < streams; s++)
-        stageHams(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row]);
-    stageHams(in, inboxCount);
+    }
     __syncwarp();
     auto countAtMost = [&](uint32_t mid) {
         uint32_t c = 0;
         if (staged) {
             for (uint32_t e = lane; e < n; e += 32) c += (hams[e] <= mid);
         } else {
-            for (uint32_t s = 0; s < streams; s++) {
-                const uint64_t* src = cand + (uint64_t(s) * cellCount + row) * cap;
-                const uint32_t cs = candCount[uint64_t(s) * cellCount + row];
-                for (uint32_t i = lane; i < cs; i += 32) c += (uint32_t(src[i] >> 32) <= mid);
+            for (uint32_t i = 0; i < lists; i++) {
+                const uint64_t* src;
+                uint32_t cs;
+                listOf(i, src, cs);
+                for (uint32_t e = lane; e < cs; e += 32) c += (uint32_t(src[e] >> 32) <= mid);
             }
-            for (uint32_t i = lane; i < inboxCount; i += 32) c += (uint32_t(in[i] >> 32) <= mid);
         }
         return __reduce_add_sync(0xffffffffu, c);
     };
@@ -1082,15 +1101,16 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
             const uint32_t r = k - less;              // ties that still fit (>= 1 by the choice of h)
             auto tiesUpTo = [&](uint32_t id) {
                 uint32_t c = 0;
-                for (uint32_t s = 0; s < streams; s++) {
-                    const uint64_t* src = cand + (uint64_t(s) * cellCount + row) * cap;
-                    const uint32_t cs = candCount[uint64_t(s) * cellCount + row];
-                    for (uint32_t i = lane; i < cs; i += 32) {
-                        const uint64_t key = src[i];
-                        if (uint32_t(key >> 32) == h) c += ((perm ? perm[uint32_t(key)] : uint32_t(key)) <= id);
+                for (uint32_t i = 0; i < lists; i++) {
+                    const uint64_t* src;
+                    uint32_t cs;
+                    listOf(i, src, cs);
+                    const bool positions = i < streams && perm;
+                    for (uint32_t e = lane; e < cs; e += 32) {
+                        const uint64_t key = src[e];
+                        if (uint32_t(key >> 32) == h) c += ((positions ? perm[uint32_t(key)] : uint32_t(key)) <= id);
                     }
                 }
-                for (uint32_t i = lane; i < inboxCount; i += 32) c += (uint32_t(in[i] >> 32) == h && uint32_t(in[i]) <= id);
                 return __reduce_add_sync(0xffffffffu, c);
             };
             uint32_t a = 0, b = 0xffffffffu;
@@ -1104,13 +1124,17 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
     }
     n = 0;
     bool over = false;
-    auto stageKeys = [&](const uint64_t* src, uint32_t c, bool positions) {
-        for (uint32_t base = 0; base < c && !over; base += 32) {
-            const uint32_t i = base + lane;
-            uint64_t key = i < c ? src[i] : ~0ull;
+    for (uint32_t i = 0; i < lists && !over; i++) {
+        const uint64_t* src;
+        uint32_t c;
+        listOf(i, src, c);
+        const bool positions = i < streams && perm;
+        for (uint32_t base = 0; base < c; base += 32) {
+            const uint32_t e = base + lane;
+            uint64_t key = e < c ? src[e] : ~0ull;
             const uint32_t m = uint32_t(key >> 32);
-            bool keep = i < c && m < lim && m <= h;
-            if (keep && positions && perm) key = (key & 0xffffffff00000000ull) | perm[uint32_t(key)];
+            bool keep = e < c && m < lim && m <= h;
+            if (keep && positions) key = (key & 0xffffffff00000000ull) | perm[uint32_t(key)];
             if (keep && m == h && uint32_t(key) > idCut) keep = false;
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
             if (n + __popc(mask) > keysPerWarp) {
@@ -1120,17 +1144,14 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
             if (keep) keys[n + __popc(mask & lt)] = key;
             n += __popc(mask);
         }
-    };
-    for (uint32_t s = 0; s < streams; s++)
-        stageKeys(cand + (uint64_t(s) * cellCount + row) * cap, candCount[uint64_t(s) * cellCount + row], true);
-    stageKeys(in, inboxCount, false);
+    }
     if (over) {
         if (lane == 0) atomicOr(overflow, 4u);      // bit 2: cannot happen (k <= keysPerWarp); kept as a guard
         return;
     }
     __syncwarp();
     const uint32_t used = n < k ? n : k;
-    const uint64_t outRow = perm ? uint64_t(perm[row]) : row;
+    const uint64_t outRow = perm ? uint64_t(perm[pos] - posBegin) : row;
     for (uint32_t e = lane; e < n; e += 32) {
         const uint64_t key = keys[e];
         uint32_t rank = 0;
@@ -1149,6 +1170,20 @@ finalizeSymKernel(uint64_t cellCount, uint32_t streams, uint32_t cap, uint32_t k
         pairs[outRow * k + i] = z;
     }
     if (lane == 0) usedCount[outRow] = used;
+}
+
+// Entries this GPU's log holds for every GPU of the job: row `rank` of the P x (P + 1) exchange matrix (the extra
+// column carries this GPU's overflow flag).  inOffset: exclusive scan of the per-position counts.
+__global__ void exchangeSizesKernel(const uint32_t* __restrict__ inOffset, uint64_t cellCount, uint64_t shard, uint32_t world,
+                                    uint32_t rank, const uint32_t* __restrict__ overflow, uint64_t* __restrict__ matrix)
+{
+    const uint32_t d = threadIdx.x;
+    if (d < world) {
+        const uint64_t b = min(cellCount, uint64_t(d) * shard), e = min(cellCount, uint64_t(d + 1) * shard);
+        matrix[uint64_t(rank) * (world + 1) + d] = uint64_t(inOffset[e]) - uint64_t(inOffset[b]);
+    } else if (d == world) {
+        matrix[uint64_t(rank) * (world + 1) + world] = *overflow;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1229,127 +1264,140 @@ __global__ void encodeKernel(const uint64_t* __restrict__ sig, uint32_t W, uint6
     *reinterpret_cast<uint4*>(enc + row * K + size_t(g) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-// Symmetric scan of the whole matrix; encP = encoded signatures in scan-position order (rows and columns),
-// perm = position -> cell id (nullptr: identity).  *overflowed != 0 means the log pool ran dry (bit 0) and NOTHING
-// that was written may be used: rerun one-directionally.
-int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, uint64_t cellCount, uint32_t K, uint64_t k,
-                 uint32_t tau0, const float* lut, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s, int* overflowed)
+__global__ void fillU32Kernel(uint32_t* __restrict__ dst, uint64_t n, uint32_t value)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i < n) dst[i] = value;
+}
+
+// Symmetric scan: every unordered pair of cells is evaluated once -- on one GPU or across the GPUs of a job.
+//   encP    encoded signatures of ALL N cells in scan-position order (rows and columns)
+//   perm    position -> cell id (nullptr: identity)
+//   this GPU owns the positions [posBegin, posBegin + ownRows) (posBegin = rank * shard, a multiple of 256; its cells
+//   are the SAME id range, permuted); pairs / usedCount hold its rows, indexed by cell id - posBegin.
+// Phases (the collectives only when ctx->world > 1; every rank runs the same sequence):
+//   1. near window   own row blocks x the column tiles within +-w super blocks of the row's own, row direction only --
+//                    both owners of such a tile pair visit it.  In grouped order a cell's neighbours sit next to it, so
+//                    this short launch (max(33 tiles, N/32 columns) per row block, ~3 % of the job at 1 M cells) leaves
+//                    every cell with a bound close to its final one; it replaces the sampling pre-pass of round 1.
+//   2. all-gather of the bounds (4 bytes per cell)
+//   3. far sweep     own row blocks x the offsets w+1 .. S/2, both directions; the column direction judges a cell by its
+//                    bound of phase 1 (cells of this GPU keep tightening theirs), survivors go to the log
+//   4. the log is filed by column position = by owner GPU (count -> scan -> fill); sizes are exchanged (one small
+//      all-gather, which also ORs the overflow flags), then the entries travel to their owners in ONE all-to-all
+//   5. merge per cell: own row streams + one inbox per GPU.
+// *overflowed != 0: a capacity ran out somewhere in the job and NOTHING that was written may be used -- every rank
+// reruns one-directionally (exactness never depends on the bounds being tight).
+int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, uint64_t cellCount, uint64_t posBegin, uint64_t ownRows,
+                 uint64_t shard, uint32_t K, uint64_t k, uint32_t tau0, const float* lut, em2_pair* pairs, uint32_t* usedCount,
+                 cudaStream_t s, int* overflowed)
 {
     const uint64_t N = cellCount;
+    const int P = ctx->world;
     const uint32_t panels = K / kChunkBytes;
-    // ---- sampling pre-pass: every cell against M ~ N/32 sample cells with the one-directional kernel
-    const uint32_t M = uint32_t(std::min<uint64_t>(N, std::max<uint64_t>(256, roundUp(N / 32, kSsTileN))));
-    const uint32_t stride = uint32_t(N / M);
-    ScanPlan pre = makeScanPlan(ctx, N, M, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
-    const uint32_t superBlocks = uint32_t((N + kSsTileN - 1) / kSsTileN);
-    const uint32_t offsets = superBlocks / 2 + 1;
-    // Two launches: the diagonal tiles first, for ALL row blocks (row direction only).  In grouped order a cell's
-    // nearest neighbours sit in its own super block, so after this short launch every cell's published bound is already
-    // tight on clustered data (the sample bound is the tight one on unstructured data) -- before any CTA of the long
-    // second launch compares the cell with its rows.
-    const uint32_t nearOffsets = 1;
-    ScanPlan nearPlan = makeScanPlan(ctx, N, uint64_t(nearOffsets) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
-    ScanPlan plan = nearPlan;
-    if (offsets > nearOffsets)
-        plan = makeScanPlan(ctx, N, uint64_t(offsets - nearOffsets) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
-    // small regions here: a cell's bound is published when its region is pruned, and the column direction of other CTAs
-    // lives on fresh bounds (with the one-directional kernels' 4k + 32 keys: 90 M instead of 70 M survivors at config 2)
-    nearPlan.cap = plan.cap = pre.cap = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
-    // stream pair 0 of a row is shared by the diagonal launch and segment 0 of the second launch (which continues it)
-    const uint32_t streams = std::max(nearPlan.segments, plan.segments) * kSubStreams;
-    const uint32_t maxSegments = std::max(pre.segments, streams / kSubStreams);
+    const uint32_t S = uint32_t((N + kSsTileN - 1) / kSsTileN);
+    uint32_t w = uint32_t(std::max<uint64_t>(16, (N / 32 + 2 * kSsTileN - 1) / (2 * kSsTileN)));
+    if (ctx->symNearHalfWidth > 0) w = uint32_t(ctx->symNearHalfWidth);
+    if (2 * uint64_t(w) + 1 > S) w = (S - 1) / 2;
+    const uint32_t nearCount = 2 * w + 1;
+    const uint32_t farBegin = w + 1;
+    const uint32_t farCount = S / 2 >= farBegin ? S / 2 - farBegin + 1 : 0;
+    *overflowed = 0;
 
-    void *cand = nullptr, *candCount = nullptr, *counters = nullptr, *sample = nullptr, *sym = nullptr, *inbox = nullptr;
-    EM2_TRY(reserve(ctx, em2_context::S_CAND, size_t(maxSegments) * kSubStreams * N * plan.cap * sizeof(uint64_t), &cand));
-    EM2_TRY(reserve(ctx, em2_context::S_CANDCOUNT, size_t(maxSegments) * kSubStreams * N * sizeof(uint32_t), &candCount));
-    EM2_TRY(reserve(ctx, em2_context::S_COUNTERS, 64, &counters));
-    EM2_TRY(reserve(ctx, em2_context::S_SAMPLE, size_t(M) * K, &sample));
-    // [limEx N][inCount N][selfIndex N][inOffset N + 1][overflow 1][pad][progress 1024]
-    EM2_TRY(reserve(ctx, em2_context::S_SYM, (4 * N + 8 + 1024) * sizeof(uint32_t), &sym));
-    // column-direction log pool: 24 k entries per cell (measured: 1.5-12 k per cell on clustered data); the inboxes are
-    // cut from a buffer of the same number of keys (count -> scan -> fill)
-    const uint64_t poolEntries = std::min<uint64_t>(0xf0000000ull, 24 * N * k + 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk);
+    ScanPlan nearPlan{}, farPlan{};
+    uint32_t cap = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
+    uint32_t streams = kSubStreams;
+    if (ownRows) {
+        nearPlan = makeScanPlan(ctx, ownRows, uint64_t(nearCount) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
+        farPlan = farCount ? makeScanPlan(ctx, ownRows, uint64_t(farCount) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams) : nearPlan;
+        // small regions here: a cell's bound is published when its region is pruned, and the column direction of other
+        // CTAs lives on fresh bounds (with the one-directional kernels' 4k + 32 keys: 90 M instead of 70 M survivors at config 2)
+        nearPlan.cap = farPlan.cap = cap;
+        // stream pair 0 of a row is shared by the near launch and segment 0 of the far launch (which continues it)
+        streams = std::max(nearPlan.segments, farPlan.segments) * kSubStreams;
+    }
+    const uint64_t Npad = uint64_t(P) * shard;      // every rank's slice of the per-position arrays has `shard` entries
+
+    // ---- scratch: everything is reserved before the first collective, then the ranks agree to go on
+    void *cand = nullptr, *candCount = nullptr, *counters = nullptr, *sym = nullptr, *outbox = nullptr, *colLog = nullptr,
+         *chunkFill = nullptr, *cubTemp = nullptr, *dist0 = nullptr, *dist2 = nullptr;
+    const uint64_t rowsAlloc = std::max<uint64_t>(ownRows, 1);
+    // column-direction log pool: 24 k entries per row on average (measured: 1.5-12 k per cell on clustered data); the
+    // outbox is cut from a buffer of the same number of keys (count -> scan -> fill)
+    const uint64_t poolEntries = std::min<uint64_t>(0xf0000000ull, 24 * rowsAlloc * k + 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk);
     const uint32_t chunkCap = uint32_t(poolEntries / kLogChunk);
-    EM2_TRY(reserve(ctx, em2_context::S_INBOX, size_t(chunkCap) * kLogChunk * sizeof(uint64_t), &inbox));
-    void *colLog = nullptr, *chunkFill = nullptr;
-    EM2_TRY(reserve(ctx, em2_context::S_COLLOG, (size_t(chunkCap) + 1) * kLogChunk * sizeof(ulonglong2), &colLog));   // + spill chunk
-    EM2_TRY(reserve(ctx, em2_context::S_COLLOGFILL, (size_t(chunkCap) + 4) * sizeof(uint32_t), &chunkFill));
+    size_t cubBytes = 0, cubBytes2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cubBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(N + 1), s);
+    cub::DeviceScan::ExclusiveSum(nullptr, cubBytes2, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(shard + 1), s);
+    int rc = EM2_OK;
+    auto res = [&](int which, size_t bytes, void** out) {
+        if (rc == EM2_OK) rc = reserve(ctx, which, bytes, out);
+    };
+    res(em2_context::S_CAND, size_t(streams) * rowsAlloc * cap * sizeof(uint64_t), &cand);
+    res(em2_context::S_CANDCOUNT, size_t(streams) * rowsAlloc * sizeof(uint32_t), &candCount);
+    res(em2_context::S_COUNTERS, 64, &counters);
+    // [limEx Npad][inCount Npad + 1][inOffset Npad + 1][overflow 4][progress 1024]
+    res(em2_context::S_SYM, (3 * Npad + 2 + 8 + 1024) * sizeof(uint32_t), &sym);
+    res(em2_context::S_INBOX, size_t(chunkCap) * kLogChunk * sizeof(uint64_t), &outbox);
+    res(em2_context::S_COLLOG, (size_t(chunkCap) + 1) * kLogChunk * sizeof(ulonglong2), &colLog);   // + spill chunk
+    res(em2_context::S_COLLOGFILL, (size_t(chunkCap) + 4) * sizeof(uint32_t), &chunkFill);
+    res(em2_context::S_MISC, std::max(cubBytes, cubBytes2), &cubTemp);
+    if (P > 1) {
+        // [recvCounts P x (shard + 1)][recvOffsets P x (shard + 1)]
+        res(em2_context::S_DIST0, 2 * size_t(P) * (shard + 1) * sizeof(uint32_t), &dist0);
+        res(em2_context::S_DIST2, size_t(P) * (P + 1) * sizeof(uint64_t), &dist2);
+    }
+    uint32_t* matrixHost = nullptr;
+    {
+        void* pin = nullptr;
+        if (rc == EM2_OK) rc = reservePinned(ctx, 2, std::max<size_t>(64, size_t(P) * (P + 1) * sizeof(uint64_t)), &pin);
+        matrixHost = static_cast<uint32_t*>(pin);
+    }
+    EM2_TRY(distAgree(ctx, rc));
+
+    uint32_t* limEx = static_cast<uint32_t*>(sym);
+    uint32_t* inCount = limEx + Npad;
+    uint32_t* inOffset = inCount + Npad + 1;
+    uint32_t* overflow = inOffset + Npad + 1;
+    uint32_t* progress = overflow + 8;
     uint32_t* chunkNext = static_cast<uint32_t*>(chunkFill) + chunkCap;
+    unsigned long long* appended = static_cast<unsigned long long*>(counters) + 1;
     EM2_CUDA(ctx, cudaMemsetAsync(chunkFill, 0, (size_t(chunkCap) + 4) * sizeof(uint32_t), s));
+    EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, (Npad + 1) * sizeof(uint32_t), s));
+    EM2_CUDA(ctx, cudaMemsetAsync(overflow, 0, 8 * sizeof(uint32_t), s));
+    EM2_CUDA(ctx, cudaMemsetAsync(candCount, 0, size_t(streams) * rowsAlloc * sizeof(uint32_t), s));   // untouched streams read as empty
+    if (ownRows) {
+        fillU32Kernel<<<unsigned((ownRows + 255) / 256), 256, 0, s>>>(limEx + posBegin, ownRows, tau0);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
     // debug_flags bit 3: report the candidate counters after every stage (synchronises)
     auto report = [&](const char* what) {
         if (!(ctx->debugFlags & 8)) return;
         unsigned long long v = 0;
         uint32_t chunksUsed = 0;
         cudaStreamSynchronize(s);
-        cudaMemcpy(&v, static_cast<unsigned long long*>(counters) + 1, sizeof(v), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&v, appended, sizeof(v), cudaMemcpyDeviceToHost);
         cudaMemcpy(&chunksUsed, chunkNext, sizeof(chunksUsed), cudaMemcpyDeviceToHost);
-        std::fprintf(stderr, "[em2 sym] after %s: row-direction candidates %llu, column-direction log chunks %u of %u\n", what, v,
+        std::fprintf(stderr, "[em2 sym rank %d] after %s: candidates so far %llu, column-direction log chunks %u of %u\n", ctx->rank, what, v,
                      chunksUsed, chunkCap);
     };
-    uint32_t* limEx = static_cast<uint32_t*>(sym);
-    uint32_t* inCount = limEx + N;
-    uint32_t* selfIndex = inCount + N;
-    uint32_t* inOffset = selfIndex + N;
-    uint32_t* overflow = inOffset + N + 1;
-    uint32_t* progress = overflow + 4;
-    EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, N * sizeof(uint32_t), s));
-    EM2_CUDA(ctx, cudaMemsetAsync(overflow, 0, sizeof(uint32_t), s));
-    {
-        const uint64_t threads = std::max<uint64_t>(uint64_t(M) * (K / 16), N);
-        sampleGatherKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(encP, K, N, stride, M, static_cast<uint8_t*>(sample), selfIndex);
-        EM2_CUDA(ctx, cudaGetLastError());
-    }
-    CUtensorMap mapA, mapB, mapS;
-    EM2_TRY(makeTensorMapU8(ctx, &mapA, encP, N, K, K, kRowsPerItem));
-    EM2_TRY(makeTensorMapU8(ctx, &mapB, encP, N, K, K, kSsTileN));
-    EM2_TRY(makeTensorMapU8(ctx, &mapS, sample, M, K, K, kSsTileN));
-    {
-        MmaParams q{};
-        q.cellCount = M;
-        q.rowBegin = 0;
-        q.rows = N;
-        q.K = K;
-        q.panels = panels;
-        q.mainBlocks = pre.mainBlocks;
-        q.segments = pre.segments;
-        q.items = pre.items;
-        q.segmentCols = pre.segmentCols;
-        q.k = uint32_t(k);
-        q.cap = pre.cap;
-        q.tau0 = tau0;
-        q.cand = static_cast<uint64_t*>(cand);
-        q.candCount = static_cast<uint32_t*>(candCount);
-        q.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
-        q.flags = uint32_t(ctx->debugFlags);
-        q.rowPerm = selfIndex;
-        if (pre.segments > 1)
-            EM2_CUDA(ctx, cudaMemsetAsync(candCount, 0, size_t(pre.segments) * kSubStreams * N * sizeof(uint32_t), s));
-        const size_t smem = 1024 + size_t(kSsStages) * kSsStageBytes + 256 + kShareBytes;
-        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSsKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        scanMmaSsKernel<false><<<unsigned(std::min<uint32_t>(pre.items, uint32_t(ctx->smCount))), kThreads, smem, s>>>(mapA, mapS, q);
-        EM2_CUDA(ctx, cudaGetLastError());
-        sampleBoundKernel<<<unsigned((N * 32 + 127) / 128), 128, 0, s>>>(N, pre.segments * kSubStreams, pre.cap, uint32_t(k), q.cand,
-                                                                         q.candCount, tau0, limEx);
-        EM2_CUDA(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches += 3;
-        report("pre-pass");
-    }
-    // ---- the symmetric sweep
+
     SymParams p{};
     p.cellCount = N;
     p.K = K;
     p.panels = panels;
     const size_t budget = 227 * 1024 - 1024 - kSymSmallBytes - size_t(panels) * kSsABytes;
     p.stages = uint32_t(std::min<size_t>(kSymMaxStages, budget / kSsBBytes));
-    p.superBlocks = superBlocks;
-    p.offsets = offsets;
-    p.halfOffset = superBlocks % 2 == 0 ? superBlocks / 2 : 0;
+    p.superBlocks = S;
+    p.halfOffset = S % 2 == 0 ? S / 2 : 0;
+    p.posBegin = uint32_t(posBegin);
+    p.ownRows = uint32_t(ownRows);
     p.k = uint32_t(k);
-    p.cap = plan.cap;
+    p.cap = cap;
     p.cand = static_cast<uint64_t*>(cand);
     p.candCount = static_cast<uint32_t*>(candCount);
-    p.appendedTotal = static_cast<unsigned long long*>(counters) + 1;
+    p.appendedTotal = appended;
     p.limEx = limEx;
     p.colLog = static_cast<ulonglong2*>(colLog);
     p.chunkFill = static_cast<uint32_t*>(chunkFill);
@@ -1358,71 +1406,161 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     p.overflow = overflow;
     p.perm = perm;
     p.flags = uint32_t(ctx->debugFlags);
-    EM2_CUDA(ctx, cudaMemsetAsync(candCount, 0, size_t(streams) * N * sizeof(uint32_t), s));   // untouched streams read as empty
-    {
-        const size_t smem = 1024 + size_t(panels) * kSsABytes + size_t(p.stages) * kSsBBytes + kSymSmallBytes;
-        EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        auto sweep = [&](const ScanPlan& pl, uint32_t dBegin, uint32_t count, uint32_t resume) -> int {
-            p.mainBlocks = pl.mainBlocks;
-            p.segments = pl.segments;
-            p.items = pl.items;
-            p.segmentCols = pl.segmentCols;
-            p.dBegin = dBegin;
-            p.offsetsHere = count;
-            p.resume = resume;
-            // only sweeps long enough for the CTAs to drift apart by more blocks than L2 holds (~490): paced at 200k cells
-            // (390 tiles per item) the sweep was 1.5x SLOWER, at 1 M cells (1953 tiles) 1.2x faster
-            p.progress = (count >= 768 && !(ctx->debugFlags & 16)) ? progress : nullptr;
-            if (p.progress) EM2_CUDA(ctx, cudaMemsetAsync(progress, 0, 1024 * sizeof(uint32_t), s));
-            scanMmaSymKernel<<<unsigned(std::min<uint32_t>(pl.items, uint32_t(ctx->smCount))), kThreads, smem, s>>>(mapA, mapB, p);
-            EM2_CUDA(ctx, cudaGetLastError());
-            ctx->stats.kernel_launches++;
+    CUtensorMap mapA, mapB;
+    EM2_TRY(makeTensorMapU8(ctx, &mapA, encP, N, K, K, kRowsPerItem));
+    EM2_TRY(makeTensorMapU8(ctx, &mapB, encP, N, K, K, kSsTileN));
+    const size_t smem = 1024 + size_t(panels) * kSsABytes + size_t(p.stages) * kSsBBytes + kSymSmallBytes;
+    EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    auto sweep = [&](const ScanPlan& pl, int32_t dBegin, uint32_t count, uint32_t resume, uint32_t rowOnly) -> int {
+        if (!ownRows || !count) return EM2_OK;
+        p.mainBlocks = pl.mainBlocks;
+        p.segments = pl.segments;
+        p.items = pl.items;
+        p.segmentCols = pl.segmentCols;
+        p.dBegin = dBegin;
+        p.offsetsHere = count;
+        p.resume = resume;
+        p.rowOnly = rowOnly;
+        // only sweeps long enough for the CTAs to drift apart by more blocks than L2 holds (~490): paced at 200k cells
+        // (390 tiles per item) the sweep was 1.5x SLOWER, at 1 M cells (1953 tiles) 1.2x faster
+        p.progress = (count >= 768 && !(ctx->debugFlags & 16)) ? progress : nullptr;
+        if (p.progress) EM2_CUDA(ctx, cudaMemsetAsync(progress, 0, 1024 * sizeof(uint32_t), s));
+        scanMmaSymKernel<<<unsigned(std::min<uint32_t>(pl.items, uint32_t(ctx->smCount))), kThreads, smem, s>>>(mapA, mapB, p);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        return EM2_OK;
+    };
+    // ---- 1. near window
+    EM2_TRY(sweep(nearPlan, -int32_t(w), nearCount, 0, 1));
+    report("near window");
+    // ---- 2. bounds of all cells
+    if (P > 1) EM2_TRY(distAllGather(ctx, limEx, shard, sizeof(uint32_t), s));
+    // ---- 3. far sweep
+    EM2_TRY(sweep(farPlan, int32_t(farBegin), farCount, 1, 0));
+    report("far sweep");
+    // ---- 4. log -> outbox in position order: count per column cell, exclusive scan, fill
+    scatterLogKernel<false><<<unsigned(ctx->smCount) * 8, 256, 0, s>>>(chunkNext, chunkCap, p.colLog, p.chunkFill, inCount, nullptr,
+                                                                      nullptr, appended);
+    EM2_CUDA(ctx, cudaGetLastError());
+    // inCount[N] is 0: inOffset[N] = total
+    EM2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cubTemp, cubBytes, inCount, inOffset, int(N + 1), s));
+    EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, N * sizeof(uint32_t), s));
+    scatterLogKernel<true><<<unsigned(ctx->smCount) * 8, 256, 0, s>>>(chunkNext, chunkCap, p.colLog, p.chunkFill, inCount, inOffset,
+                                                                     static_cast<uint64_t*>(outbox), appended);
+    EM2_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 2;      // + the scan's own kernels (library code, not counted)
+
+    InboxSources src{};
+    if (P == 1) {
+        src.count = 1;
+        src.keys[0] = static_cast<const uint64_t*>(outbox);
+        src.offsets[0] = inOffset;
+    } else {
+        // sizes (and overflow flags) of every rank for every rank
+        uint64_t* matrix = static_cast<uint64_t*>(dist2);
+        uint64_t* mh = reinterpret_cast<uint64_t*>(matrixHost);
+        exchangeSizesKernel<<<1, 32, 0, s>>>(inOffset, N, shard, uint32_t(P), uint32_t(ctx->rank), overflow, matrix);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        EM2_TRY(distAllGather(ctx, matrix, size_t(P + 1), sizeof(uint64_t), s));
+        EM2_CUDA(ctx, cudaMemcpyAsync(mh, matrix, size_t(P) * (P + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        EM2_CUDA(ctx, cudaStreamSynchronize(s));
+        uint64_t anyOverflow = 0, recvTotal = 0;
+        uint64_t sendOff[64], sendBytes[64], recvOff[64], recvBytes[64];
+        for (int r = 0; r < P; r++) anyOverflow |= mh[size_t(r) * (P + 1) + P];
+        if (anyOverflow) {
+            *overflowed = int(anyOverflow);
             return EM2_OK;
-        };
-        EM2_TRY(sweep(nearPlan, 0, nearOffsets, 0));
-        report("diagonal launch");
-        if (offsets > nearOffsets) EM2_TRY(sweep(plan, nearOffsets, offsets - nearOffsets, 1));
-        report("main sweep");
-        // inboxes: count the log entries per column cell, exclusive scan, fill
-        scatterLogKernel<false><<<unsigned(ctx->smCount) * 8, 256, 0, s>>>(chunkNext, chunkCap, p.colLog, p.chunkFill, inCount, nullptr,
-                                                                          nullptr, p.appendedTotal);
-        EM2_CUDA(ctx, cudaGetLastError());
-        {
-            size_t cubBytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, cubBytes, inCount, inOffset, int(N + 1), s);
-            void* cubTemp = nullptr;
-            EM2_TRY(reserve(ctx, em2_context::S_MISC, cubBytes, &cubTemp));
-            // inCount[N] is selfIndex[0]: only the first N + 1 outputs' prefix property matters, inOffset[N] = total
-            EM2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cubTemp, cubBytes, inCount, inOffset, int(N + 1), s));
         }
-        EM2_CUDA(ctx, cudaMemsetAsync(inCount, 0, N * sizeof(uint32_t), s));
-        scatterLogKernel<true><<<unsigned(ctx->smCount) * 8, 256, 0, s>>>(chunkNext, chunkCap, p.colLog, p.chunkFill, inCount, inOffset,
-                                                                         static_cast<uint64_t*>(inbox), p.appendedTotal);
-        EM2_CUDA(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches += 2;      // + the scan's own kernels (library code, not counted)
-        // staging: 16-bit mismatch counts of everything below the bound (cells with longer lists bisect in place), then
-        // the k best keys plus the ties at the k-th place
-        const uint32_t hamsPerWarp = uint32_t(roundUp(uint64_t(streams) * plan.cap + 40 * k + 256, 64));
+        uint64_t run = 0;
+        for (int d = 0; d < P; d++) {
+            sendOff[d] = run * sizeof(uint64_t);
+            sendBytes[d] = mh[size_t(ctx->rank) * (P + 1) + d] * sizeof(uint64_t);
+            run += mh[size_t(ctx->rank) * (P + 1) + d];
+            recvOff[d] = recvTotal * sizeof(uint64_t);
+            recvBytes[d] = mh[size_t(d) * (P + 1) + ctx->rank] * sizeof(uint64_t);
+            recvTotal += mh[size_t(d) * (P + 1) + ctx->rank];
+        }
+        void* recvKeys = nullptr;
+        EM2_TRY(distAgree(ctx, reserve(ctx, em2_context::S_DIST1, std::max<uint64_t>(recvTotal, 1) * sizeof(uint64_t), &recvKeys)));
+        uint32_t* recvCounts = static_cast<uint32_t*>(dist0);
+        uint32_t* recvOffsets = recvCounts + size_t(P) * (shard + 1);
+        EM2_CUDA(ctx, cudaMemsetAsync(recvCounts, 0, size_t(P) * (shard + 1) * sizeof(uint32_t), s));
+        cudaEvent_t x0 = ctx->ev[10], x1 = ctx->ev[11];
+        EM2_CUDA(ctx, cudaEventRecord(x0, s));
+        {
+            // per-cell counts: rank d gets my counts of ITS positions (equal sizes: `shard` entries each way)
+            uint64_t so[64], sb[64], ro[64], rb[64];
+            for (int d = 0; d < P; d++) {
+                so[d] = uint64_t(d) * shard * sizeof(uint32_t);
+                sb[d] = shard * sizeof(uint32_t);
+                ro[d] = uint64_t(d) * (shard + 1) * sizeof(uint32_t);
+                rb[d] = shard * sizeof(uint32_t);
+            }
+            EM2_TRY(distAllToAll(ctx, inCount, so, sb, recvCounts, ro, rb, s));
+        }
+        EM2_TRY(distAllToAll(ctx, outbox, sendOff, sendBytes, recvKeys, recvOff, recvBytes, s));
+        EM2_CUDA(ctx, cudaEventRecord(x1, s));
+        ctx->symExchangeTimed = true;
+        for (int d = 0; d < P; d++)
+            if (d != ctx->rank) ctx->stats.exchange_bytes += sendBytes[d] + shard * sizeof(uint32_t);
+        for (int r = 0; r < P; r++) {
+            EM2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cubTemp, cubBytes2, recvCounts + size_t(r) * (shard + 1),
+                                                        recvOffsets + size_t(r) * (shard + 1), int(shard + 1), s));
+            src.keys[r] = static_cast<const uint64_t*>(recvKeys) + recvOff[r] / sizeof(uint64_t);
+            src.offsets[r] = recvOffsets + size_t(r) * (shard + 1);
+        }
+        src.count = uint32_t(P);
+    }
+    // ---- 5. merge.  Staging: 16-bit mismatch counts of everything below the bound (cells with longer lists bisect in
+    // place), then the k best keys plus the ties at the k-th place
+    if (ownRows) {
+        const uint32_t hamsPerWarp = uint32_t(roundUp(uint64_t(streams) * cap + 40 * k + 256, 64));
         const uint32_t keysPerWarp = uint32_t(roundUp(2 * k + 256, 64));
         const size_t smemF = size_t(kSymFinalWarps) * (size_t(keysPerWarp) * sizeof(uint64_t) + size_t(hamsPerWarp) * sizeof(uint16_t));
         if (smemF > 200 * 1024) return fail(ctx, EM2_ERR_INVALID, "k too large for the symmetric finalize kernel");
         EM2_CUDA(ctx, cudaFuncSetAttribute(finalizeSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemF)));
-        finalizeSymKernel<<<unsigned((N + kSymFinalWarps - 1) / kSymFinalWarps), kSymFinalWarps * 32, smemF, s>>>(
-            N, streams, plan.cap, uint32_t(k), p.cand, p.candCount, static_cast<const uint64_t*>(inbox), inOffset, limEx, lut, pairs,
-            usedCount, perm, overflow, hamsPerWarp, keysPerWarp);
+        finalizeSymKernel<<<unsigned((ownRows + kSymFinalWarps - 1) / kSymFinalWarps), kSymFinalWarps * 32, smemF, s>>>(
+            uint32_t(ownRows), uint32_t(posBegin), streams, cap, uint32_t(k), p.cand, p.candCount, src, limEx, lut, pairs, usedCount, perm,
+            overflow, hamsPerWarp, keysPerWarp);
         EM2_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
     }
-    // the overflow flag decides whether the result stands
-    uint32_t* flagHost = nullptr;
-    {
-        void* pin = nullptr;
-        EM2_TRY(reservePinned(ctx, 2, 64, &pin));
-        flagHost = static_cast<uint32_t*>(pin);
-    }
-    EM2_CUDA(ctx, cudaMemcpyAsync(flagHost, overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    // the overflow flag decides whether the result stands (P > 1: the log pools were checked job-wide above; what is
+    // left is this rank's own merge guard)
+    EM2_CUDA(ctx, cudaMemcpyAsync(matrixHost, overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     EM2_CUDA(ctx, cudaStreamSynchronize(s));
-    *overflowed = int(*flagHost);
+    *overflowed = int(*matrixHost);
+    if (ctx->symExchangeTimed) {
+        ctx->symExchangeTimed = false;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]) == cudaSuccess) ctx->stats.exchange_ms += double(t);
+        else cudaGetLastError();
+    }
+    return EM2_OK;
+}
+
+// Scan order: rows [rowBegin, rowBegin + rows) sorted by (nearest of 256 pivot cells, cell id); see pivotAssignKernel.
+// perm[q] = cell id of scan position q (device, `rows` entries written at permOut).
+int groupRows(em2_context* ctx, const uint64_t* signatures, uint32_t W, uint64_t cellCount, uint64_t rowBegin, uint64_t rows,
+              uint32_t* permOut, cudaStream_t s)
+{
+    if (rows == 0) return EM2_OK;
+    size_t cubBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cubBytes, static_cast<const unsigned long long*>(nullptr),
+                                   static_cast<unsigned long long*>(nullptr), int(rows), 0, 40, s);
+    const size_t keyBytes = roundUp(rows * sizeof(unsigned long long), 256);
+    void* scratch = nullptr;
+    EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, 2 * keyBytes + cubBytes, &scratch));
+    auto* keysIn = static_cast<unsigned long long*>(scratch);
+    auto* keysOut = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(scratch) + keyBytes);
+    void* cubTemp = static_cast<uint8_t*>(scratch) + 2 * keyBytes;
+    pivotAssignKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(signatures, W, cellCount, rowBegin, rows, keysIn);
+    EM2_CUDA(ctx, cudaGetLastError());
+    EM2_CUDA(ctx, cub::DeviceRadixSort::SortKeys(cubTemp, cubBytes, keysIn, keysOut, int(rows), 0, 40, s));
+    keysToPermKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(keysOut, rows, permOut);
+    EM2_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 2;      // + the radix sort's own passes (library code, not counted)
     return EM2_OK;
 }
 
@@ -1455,27 +1593,16 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     const uint8_t* encRows = static_cast<const uint8_t*>(enc) + rowBegin * uint64_t(K);
     const uint32_t* rowPerm = nullptr;
     if (grouped) {
-        size_t cubBytes = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, cubBytes, static_cast<const unsigned long long*>(nullptr),
-                                       static_cast<unsigned long long*>(nullptr), int(rows), 0, 40, s);
-        const size_t keyBytes = roundUp(rows * sizeof(unsigned long long), 256);
-        void* scratch = nullptr;
-        EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, 2 * keyBytes + roundUp(rows * 4, 256) + cubBytes, &scratch));
-        auto* keysIn = static_cast<unsigned long long*>(scratch);
-        auto* keysOut = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(scratch) + keyBytes);
-        auto* perm = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(scratch) + 2 * keyBytes);
-        void* cubTemp = static_cast<uint8_t*>(scratch) + 2 * keyBytes + roundUp(rows * 4, 256);
-        pivotAssignKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(signatures, W, cellCount, rowBegin, rows, keysIn);
-        EM2_CUDA(ctx, cudaGetLastError());
-        EM2_CUDA(ctx, cub::DeviceRadixSort::SortKeys(cubTemp, cubBytes, keysIn, keysOut, int(rows), 0, 40, s));
-        keysToPermKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(keysOut, rows, perm);
-        EM2_CUDA(ctx, cudaGetLastError());
+        void* permBuf = nullptr;
+        EM2_TRY(reserve(ctx, em2_context::S_PERM, rows * sizeof(uint32_t), &permBuf));
+        uint32_t* perm = static_cast<uint32_t*>(permBuf);
+        EM2_TRY(groupRows(ctx, signatures, W, cellCount, rowBegin, rows, perm, s));
         void* er = nullptr;
         EM2_TRY(reserve(ctx, em2_context::S_ENCROWS, rows * uint64_t(K), &er));
         const uint64_t threads = rows * (K / 16);
         encodeKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(signatures, W, rows, K, static_cast<uint8_t*>(er), perm);
         EM2_CUDA(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches += 4;      // + the radix sort's own passes (library code, not counted)
+        ctx->stats.kernel_launches++;
         encRows = static_cast<const uint8_t*>(er);
         rowPerm = perm;
     }
@@ -1503,9 +1630,9 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
             if (cudaMemGetInfo(&freeBytes, &totalBytes) != cudaSuccess) freeBytes = 0;
             automatic = want <= have + freeBytes / 10 * 9;
         }
-        if (eligible && (ctx->scanSymmetric == 2 || automatic)) {
+        if (eligible && ctx->world == 1 && (ctx->scanSymmetric == 2 || automatic)) {
             int overflowed = 0;
-            EM2_TRY(runSymmetric(ctx, encRows, rowPerm, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
+            EM2_TRY(runSymmetric(ctx, encRows, rowPerm, cellCount, 0, cellCount, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
             ctx->stats.scan_symmetric = overflowed ? 2 + 16 * overflowed : 1;      // 2 + 16 * (which capacity ran out)
             if (!overflowed) return EM2_OK;
         }
@@ -1632,6 +1759,76 @@ int launchScanMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCou
 {
     return runMma(ctx, signatures, cellCount, lshCount, rowBegin, rowEnd, k, mismatchMax, lut, pairs, usedCount,
                   nullptr, s);
+}
+
+// Whether a multi-GPU job runs the symmetric scan.  Every rank evaluates this on the same arguments and options, so
+// every rank takes the same branch (the branches differ in their collectives).
+bool distSymmetricEligible(const em2_context* ctx, uint64_t cellCount, uint64_t lshCount, uint64_t k, int64_t mismatchMax, int variant)
+{
+    if (ctx->world < 1 || ctx->world > kMaxInboxSources) return false;
+    if (variant == EM2_VARIANT_POPC) return false;
+    if (variant == EM2_VARIANT_AUTO && !(lshCount >= 256 && double(cellCount) * double(cellCount) / ctx->world >= 1e7)) return false;
+    const uint32_t K = uint32_t(roundUp(lshCount, kChunkBytes));
+    const bool streamed = K > kMaxPanels * kChunkBytes || ctx->mmaKernel == 2 || (ctx->mmaKernel == 0 && K >= 512);
+    const uint32_t capSym = scanCandidateCapacity(uint32_t(k), uint32_t(ctx->candCapExtra));
+    const bool eligible = streamed && K <= kMaxPanels * kChunkBytes && capSym <= 32 * kPruneRegsPerLane && cellCount >= 1024 &&
+                          cellCount <= 0x7fffff00ull && mismatchMax >= 0 && k <= 1024;
+    if (!eligible || ctx->scanSymmetric == 1) return false;
+    if (ctx->scanSymmetric == 2) return true;
+    return cellCount >= 400000 && cellCount <= 2000000ull * uint64_t(ctx->world);
+}
+
+__global__ void iotaKernel(uint32_t* __restrict__ dst, uint64_t n, uint32_t first)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i < n) dst[i] = first + uint32_t(i);
+}
+
+// Symmetric scan of a multi-GPU job; allSig: the signatures of all cells (after the all-gather).  Collective.
+int launchScanSymDist(em2_context* ctx, const uint64_t* allSig, uint64_t cellCount, uint64_t lshCount, uint64_t k,
+                      int64_t mismatchMax, const float* lut, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s)
+{
+    const DistPartition part = distPartition(cellCount, ctx->world, ctx->rank);
+    const uint64_t rows = part.rowEnd - part.rowBegin;
+    const uint32_t W = uint32_t(wordCount(lshCount));
+    const uint32_t K = uint32_t(roundUp(lshCount, kChunkBytes));
+    const uint32_t tau0 = uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
+    ctx->stats.variant_used = EM2_VARIANT_MMA_I8;
+    void *permBuf = nullptr, *enc = nullptr;
+    int rc = reserve(ctx, em2_context::S_PERM, uint64_t(ctx->world) * part.shard * sizeof(uint32_t), &permBuf);
+    if (rc == EM2_OK) rc = reserve(ctx, em2_context::S_ENC, cellCount * K, &enc);
+    EM2_TRY(distAgree(ctx, rc));
+    uint32_t* perm = static_cast<uint32_t*>(permBuf);
+    // scan order: every GPU groups ITS cells (similar rows into the same warps, similar columns into the same tiles);
+    // positions [rank * shard, ...) hold a permutation of the same range of cell ids
+    if (rows) {
+        if (ctx->rowGrouping == 1) {
+            iotaKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(perm + part.rowBegin, rows, uint32_t(part.rowBegin));
+            EM2_CUDA(ctx, cudaGetLastError());
+            ctx->stats.kernel_launches++;
+        } else {
+            EM2_TRY(groupRows(ctx, allSig, W, cellCount, part.rowBegin, rows, perm + part.rowBegin, s));
+        }
+    }
+    EM2_TRY(distAllGather(ctx, perm, part.shard, sizeof(uint32_t), s));
+    {
+        const uint64_t threads = cellCount * (K / 16);
+        encodeKernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(allSig, W, cellCount, K, static_cast<uint8_t*>(enc), perm);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    int overflowed = 0;
+    EM2_TRY(runSymmetric(ctx, static_cast<const uint8_t*>(enc), perm, cellCount, part.rowBegin, rows, part.shard, K, k, tau0, lut, pairs,
+                         usedCount, s, &overflowed));
+    if (!overflowed) {
+        ctx->stats.scan_symmetric = 1;
+        return EM2_OK;
+    }
+    // a capacity ran out somewhere in the job: every rank scans its rows one-directionally (no collective involved)
+    EM2_TRY(launchScanTopK(ctx, allSig, cellCount, lshCount, part.rowBegin, part.rowEnd, k, mismatchMax, lut, EM2_VARIANT_MMA_I8, pairs,
+                           usedCount, s));
+    ctx->stats.scan_symmetric = 2 + 16 * overflowed;
+    return EM2_OK;
 }
 
 int launchMismatchBlockMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,

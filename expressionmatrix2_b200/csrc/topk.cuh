@@ -260,10 +260,12 @@ static __device__ __noinline__ uint32_t warpPruneRegsAnyOrder(uint64_t* buf, uin
 
 // Call with the warp converged; regions of at most 32 * kPruneRegsPerLane keys.  The owner's new bound is also
 // published (atomicMin) to *shared, the row's entry of a global bound array read by other CTAs.
+// force: prune every region that holds at least k keys (end of the near window: every row publishes the bound it has
+// learned, whether or not its region ever filled up).
 static __device__ __forceinline__ void warpPruneIfNeededAnyOrder(RowState& st, uint32_t k, uint32_t cap, uint32_t* shared,
-                                                                 const uint32_t* __restrict__ idOf)
+                                                                 const uint32_t* __restrict__ idOf, bool force = false)
 {
-    uint32_t need = __ballot_sync(0xffffffffu, st.count + kPruneSlack > cap);
+    uint32_t need = __ballot_sync(0xffffffffu, force ? (st.count >= k) : (st.count + kPruneSlack > cap));
     if (need) __syncwarp();
     while (need) {
         const int src = __ffs(int(need)) - 1;

@@ -24,8 +24,12 @@ class Partition:
 
     @property
     def shard(self) -> int:
-        """Rows per rank (the last rank may own fewer real cells; shards are padded to this size)."""
-        return (self.cell_count + self.world_size - 1) // self.world_size
+        """Rows per rank (the last rank may own fewer real cells; shards are padded to this size).  The rule of
+        em2_dist_partition (csrc/multi.cu): whole super blocks of 256 cells per rank when there is more than one."""
+        if self.world_size <= 1:
+            return self.cell_count
+        per = (self.cell_count + self.world_size - 1) // self.world_size
+        return (per + 255) // 256 * 256
 
     @property
     def row_begin(self) -> int:

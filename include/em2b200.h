@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define EM2_ABI_VERSION 1
+#define EM2_ABI_VERSION 2
 
 enum em2_status {
     EM2_OK = 0,
@@ -100,6 +100,12 @@ typedef struct em2_stats {
     uint64_t filter_uncertain;    /* projections the filter could not decide (recomputed exactly in FP64) */
     int32_t variant_used;     /* em2_variant actually run                                */
     int32_t scan_symmetric;   /* 1 = the scan evaluated every unordered pair once; 2 + 16 f = it tried, a capacity ran out (f: 1 log, 2 inbox, 4 merge staging), rerun one-directionally */
+    uint64_t bounced_bytes;   /* bytes of pageable host memory staged through the library's pinned bounce buffers */
+    double allgather_ms;      /* multi-GPU: the signature all-gather                                               */
+    double exchange_ms;       /* multi-GPU symmetric scan: all-to-all of the column-direction candidates          */
+    uint64_t exchange_bytes;  /* bytes this rank sent in that exchange                                             */
+    int32_t world_size;       /* ranks of the last collective call (1 = single GPU)                                */
+    int32_t rank;
 } em2_stats;
 
 /* ------------------------------------------------------------------------------------------------
@@ -128,6 +134,9 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
  *   "cand_cap_extra"   candidate regions hold (2 + n) k + 32 keys;  "popc_csa" carry-save levels of the POPC scan (0..2)
  *   "exact_matrix_bytes" budget of the exact path's similarity matrix (default 48 GiB);  "exact_cta_pair" 1 = CTA-pair GEMM
  *   "exact_general"    1 = force the exact path's general FP64 kernel
+ *   "sym_near_half_width" symmetric scan: super blocks (256 cells) on each side of a row's own that the near window covers
+ *                      (0 = automatic: max(16, N / 32 columns in total))
+ *   "no_bounce"        1 = pageable host buffers go straight to cudaMemcpyAsync instead of through the pinned bounce buffers
  *   "debug_flags"      bit 0: no bound sharing between the MMA scan's sub-streams */
 int em2_set_option(em2_context* ctx, const char* name, int64_t value);
 
@@ -276,6 +285,58 @@ int em2_mismatch_counts_device(em2_context* ctx, const uint64_t* signatures, uin
  * (uint16 out[(rowEnd-rowBegin)*cellCount]); used by the parity tests to check the MMA path bit-exactly. */
 int em2_mismatch_block_device(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
                               uint64_t rowBegin, uint64_t rowEnd, int variant, uint16_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU (BASELINE.json north star: "partitioned across the 8 B200s of one box by cell-row blocks:
+ * signatures are all-gathered once with NCCL over NVLink, each GPU scans its row block against all cells").
+ * The reference's entry is ONE blocking call from one host thread (src/ExpressionMatrixLsh.cpp:155-303), so the
+ * library drives all GPUs itself: em2_multi owns one context + one worker thread per device; a call partitions the
+ * cells into contiguous row blocks (em2_dist_partition), every GPU copies ITS rows' counts from the caller's buffers
+ * (1/P of the hyperplanes each, completed by an all-gather over NVLink), builds its signatures, takes part in the
+ * signature all-gather, scans, and writes ITS rows of pairs / usedCount straight into the caller's arrays -- with
+ * pairs pointing at the mapped SimilarPairs-<name>-Pairs payload every GPU fills its own byte range of the file.
+ * For whole-matrix tcgen05 scans the symmetric kernel is used across the GPUs too (every unordered pair once;
+ * column-direction candidates reach their owner in one all-to-all), with results identical to the single-GPU call.
+ * Calls are blocking and not re-entrant per em2_multi.  NCCL is bound at run time (libnccl.so.2; EM2_NCCL_LIB overrides).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct em2_multi em2_multi;
+/* devices: CUDA device indices (NULL: 0 .. deviceCount-1); deviceCount <= 0: every visible device. */
+int em2_multi_create(const int* devices, int deviceCount, em2_multi** multi);
+void em2_multi_destroy(em2_multi* multi);
+/* multi may be NULL: message of the last failed em2_multi_create on this thread. */
+const char* em2_multi_last_error(const em2_multi* multi);
+int em2_multi_device_count(const em2_multi* multi);
+em2_context* em2_multi_context(em2_multi* multi, int index);   /* the per-device context (options, device name) */
+int em2_multi_set_option(em2_multi* multi, const char* name, int64_t value);   /* em2_set_option on every device */
+/* index >= 0: that device's stats of the last call; index < 0: the job's (times = max over devices, counters = sums). */
+int em2_multi_get_stats(const em2_multi* multi, int index, em2_stats* stats);
+/* Same arguments, results and errors as em2_find_similar_pairs (all rows) / em2_lsh_similar_pairs /
+ * em2_lsh_similar_pairs_subset; all buffers are host buffers. */
+int em2_multi_find_similar_pairs(em2_multi* multi, const uint64_t* signatures, uint64_t cellCount, uint64_t lshCount,
+                                 uint64_t k, double similarityThreshold, int variant, em2_pair* pairs, uint32_t* usedCount);
+int em2_multi_lsh_similar_pairs(em2_multi* multi, uint64_t cellCount, uint64_t geneCount, const uint64_t* toc,
+                                const em2_count* counts, const double* lshVectors, uint64_t lshCount, uint64_t k,
+                                double similarityThreshold, int variant, em2_pair* pairs, uint32_t* usedCount,
+                                uint64_t* signaturesOut /* may be NULL */);
+int em2_multi_lsh_similar_pairs_subset(em2_multi* multi, uint64_t globalCellCount, const uint64_t* globalToc,
+                                       const em2_count* globalCounts, uint64_t globalGeneCount, const uint32_t* geneLocalId,
+                                       uint64_t geneCount, uint64_t cellCount, const uint32_t* cellSet, const double* lshVectors,
+                                       uint64_t lshCount, uint64_t k, double similarityThreshold, int variant, em2_pair* pairs,
+                                       uint32_t* usedCount, uint64_t* signaturesOut /* may be NULL */);
+
+/* One process per GPU (bench.py under torchrun, MPI hosts): each process creates its own em2_context; rank 0 makes an
+ * id with em2_comm_unique_id, the host program broadcasts its EM2_COMM_ID_BYTES bytes, every rank calls em2_comm_init.
+ * em2_scan_topk_dist_device is then COLLECTIVE: every rank passes the signatures of its own row block
+ * (em2_dist_partition; device pointer, rows x W words) and receives the lists of its rows (device pointers, rows x k
+ * pairs, rows counts); the all-gather and, for the symmetric scan, the candidate exchange run on NCCL inside. */
+#define EM2_COMM_ID_BYTES 128
+int em2_comm_unique_id(void* id /* EM2_COMM_ID_BYTES */);
+int em2_comm_init(em2_context* ctx, const void* id, int rank, int worldSize);
+/* Row block of a rank: [*rowBegin, *rowEnd); *shardRows = rows per rank (a multiple of 256 when worldSize > 1). */
+int em2_dist_partition(uint64_t cellCount, int worldSize, int rank, uint64_t* rowBegin, uint64_t* rowEnd, uint64_t* shardRows);
+int em2_scan_topk_dist_device(em2_context* ctx, const uint64_t* localSignatures, uint64_t cellCount, uint64_t lshCount,
+                              uint64_t k, int64_t mismatchMax, const float* similarityTable, int variant, em2_pair* pairs,
+                              uint32_t* usedCount, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,12 +26,12 @@ def test_library_exports_every_declared_symbol(em2):
     L = ctypes.CDLL(em2.LIB_PATH)
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert em2.lib().em2_abi_version() == 1
+    assert em2.lib().em2_abi_version() == 2
 
 
 def test_struct_layouts_match_reference_types(em2):
     assert em2.PAIR_DTYPE.itemsize == 8 and em2.SIMPAIR_DTYPE.itemsize == 8   # pair<uint32,float>
-    assert ctypes.sizeof(em2.Stats) == 8 * 8 + 7 * 8 + 8
+    assert ctypes.sizeof(em2.Stats) == 8 * 8 + 7 * 8 + 8 + 8 + 2 * 8 + 8 + 8
 
 
 @pytest.mark.parametrize("name", golden_cases())
