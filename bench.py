@@ -422,6 +422,9 @@ def run_b200(args, w):
         eng.set_option("scan_symmetric", 2)
     if args.one_directional:
         eng.set_option("scan_symmetric", 1)
+    for nv in args.option:
+        name, value = nv.split("=")
+        eng.set_option(name, int(value))
     stream = torch.cuda.current_stream().cuda_stream
     peaks = load_peaks()
     pairs_total = N * (N - 1) / 2
@@ -618,6 +621,9 @@ def run_b200(args, w):
                 runner.set_option("scan_symmetric", 2)
             if args.one_directional:
                 runner.set_option("scan_symmetric", 1)
+            for nv in args.option:
+                name, value = nv.split("=")
+                runner.set_option(name, int(value))
             if kind == "lsh":
                 a_toc, a_counts, a_U = p_toc.numpy().view(np.uint64), p_counts.numpy().view(em2.PAIR_DTYPE), p_U.numpy()
                 call = lambda: runner.lsh_similar_pairs_into(a_toc, a_counts, a_U, k, thr, o_pairs, o_used, variant=variant)
@@ -731,6 +737,8 @@ def main():
                     help="whole-matrix scans evaluate every unordered pair once (em2_set_option scan_symmetric = 2; N = 1 only)")
     ap.add_argument("--one-directional", action="store_true", help="never use the symmetric scan (scan_symmetric = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="em2_set_option on the engine (tuning / diagnosis runs), e.g. --option debug_flags=8")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

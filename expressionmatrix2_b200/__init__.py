@@ -345,7 +345,7 @@ class Engine:
         pairs["similarity"] = sims
         used = np.ascontiguousarray(used, np.uint32)
         vertex_of = np.ascontiguousarray(vertex_of, np.uint32)
-        cap = max(1, n * min(k, max_connectivity))
+        cap = max(1, n * (min(k, max_connectivity) if max_connectivity else k))
         out = np.zeros(cap, EDGE_DTYPE)
         count = C.c_uint64(0)
         self._check(self._L.em2_cell_graph_edges(self._h, n, k, _ptr(pairs), _ptr(used), _ptr(vertex_of), similarity_threshold,

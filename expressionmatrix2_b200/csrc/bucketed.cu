@@ -204,6 +204,13 @@ int launchBucketedSearch(em2_context* ctx, const uint64_t* sig, uint64_t cellCou
                          uint32_t mismatchThreshold, const float* lut, const int32_t* sliceLengths, uint64_t sliceLengthCount,
                          uint32_t maxCheck, uint32_t log2BucketCount, em2_pair* pairs, uint32_t* usedCount, cudaStream_t s)
 {
+    // The reference's `size() == maxCheck` stop never fires for 0 or for values beyond the cell count: both mean "no
+    // limit", which is N - 1 candidates at most -- the workspace below is sized by it.
+    if (cellCount > 0x7fffffffull) return fail(ctx, EM2_ERR_INVALID, "em2_find_similar_pairs7: more than 2^31 - 1 cells");
+    {
+        const uint64_t most = cellCount > 1 ? cellCount - 1 : 1;
+        if (maxCheck == 0 || maxCheck > most) maxCheck = uint32_t(most);
+    }
     const uint64_t N = cellCount;
     const uint32_t W = uint32_t(wordCount(lshCount));
     struct Table {

@@ -187,6 +187,16 @@ int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
     return EM2_OK;
 }
 
+// Argument limits of every blocking entry point, checked BEFORE the first allocation or copy (sizes below are
+// computed from lshCount: 0 would underflow the word count).
+int checkScanArguments(em2_context* ctx, uint64_t cellCount, uint64_t lshCount, uint64_t k)
+{
+    if (lshCount == 0 || lshCount > 65535) return fail(ctx, EM2_ERR_INVALID, "lshCount must be in [1, 65535]");
+    if (k == 0 || k > 1024) return fail(ctx, EM2_ERR_INVALID, "k must be in [1, 1024]");
+    if (cellCount > 0xfffffff0ull) return fail(ctx, EM2_ERR_INVALID, "cellCount exceeds the 32-bit CellId range");
+    return EM2_OK;
+}
+
 int uploadLut(em2_context* ctx, uint64_t lshCount, float** dLut)
 {
     std::vector<double> t(lshCount + 1);
@@ -551,6 +561,7 @@ int em2_compute_signatures(em2_context* ctx, uint64_t cellCount, uint64_t geneCo
     EM2_TRY(guardDevice(ctx));
     if (!toc || !lshVectors || !signatures || (!counts && cellCount && toc[cellCount]))
         return fail(ctx, EM2_ERR_INVALID, "em2_compute_signatures: null pointer");
+    EM2_TRY(checkScanArguments(ctx, cellCount, lshCount, 1));
     resetStats(ctx);
     const double t0 = nowMs();
     if (cellCount == 0) return EM2_OK;
@@ -579,6 +590,7 @@ int em2_find_similar_pairs(em2_context* ctx, const uint64_t* signatures, uint64_
     EM2_TRY(guardDevice(ctx));
     if (!signatures || !pairs || !usedCount) return fail(ctx, EM2_ERR_INVALID, "em2_find_similar_pairs: null pointer");
     if (rowEnd > cellCount || rowBegin > rowEnd) return fail(ctx, EM2_ERR_INVALID, "row range outside [0, cellCount]");
+    EM2_TRY(checkScanArguments(ctx, cellCount, lshCount, k));
     resetStats(ctx);
     const double t0 = nowMs();
     if (rowEnd == rowBegin) return EM2_OK;
@@ -608,6 +620,7 @@ int em2_lsh_similar_pairs(em2_context* ctx, uint64_t cellCount, uint64_t geneCou
     EM2_TRY(guardDevice(ctx));
     if (!toc || !lshVectors || !pairs || !usedCount || (!counts && cellCount && toc[cellCount]))
         return fail(ctx, EM2_ERR_INVALID, "em2_lsh_similar_pairs: null pointer");
+    EM2_TRY(checkScanArguments(ctx, cellCount, lshCount, k));
     resetStats(ctx);
     const double t0 = nowMs();
     if (cellCount == 0) return EM2_OK;
@@ -721,6 +734,7 @@ int em2_lsh_similar_pairs_subset(em2_context* ctx, uint64_t globalCellCount, con
     EM2_TRY(guardDevice(ctx));
     if (!globalToc || !geneLocalId || !lshVectors || !pairs || !usedCount || (cellCount && !cellSet))
         return fail(ctx, EM2_ERR_INVALID, "em2_lsh_similar_pairs_subset: null pointer");
+    EM2_TRY(checkScanArguments(ctx, cellCount, lshCount, k));
     resetStats(ctx);
     const double t0 = nowMs();
     if (cellCount == 0) return EM2_OK;
@@ -807,7 +821,6 @@ int em2_find_similar_pairs7(em2_context* ctx, const uint64_t* signatures, uint64
         return fail(ctx, EM2_ERR_INVALID, "em2_find_similar_pairs7: null pointer");
     if (lshCount == 0 || lshCount > 65535) return fail(ctx, EM2_ERR_INVALID, "lshCount must be in [1, 65535]");
     if (k == 0 || k > 1024) return fail(ctx, EM2_ERR_INVALID, "k must be in [1, 1024]");
-    if (maxCheck == 0) return fail(ctx, EM2_ERR_INVALID, "maxCheck must be positive");
     if (log2BucketCount == 0 || log2BucketCount > 32) return fail(ctx, EM2_ERR_INVALID, "log2BucketCount must be in [1, 32]");
     if (cellCount > 0xfffffff0ull) return fail(ctx, EM2_ERR_INVALID, "cellCount exceeds the 32-bit CellId range");
     for (uint64_t i = 0; i < sliceLengthCount; i++) {

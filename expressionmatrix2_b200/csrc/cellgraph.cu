@@ -25,7 +25,7 @@ constexpr uint32_t kNoVertex = 0xffffffffu;
 // pass 1: count the records of each cell;  pass 2 (records != nullptr): write them at offsets[cell]
 __global__ void edgeRecordsKernel(uint64_t cellCount, uint64_t k, const em2_pair* __restrict__ pairs,
                                   const uint32_t* __restrict__ usedCount, const uint32_t* __restrict__ vertexOf,
-                                  float similarityThreshold, uint32_t maxConnectivity, uint64_t* __restrict__ counts,
+                                  double similarityThreshold, uint32_t maxConnectivity, uint64_t* __restrict__ counts,
                                   const uint64_t* __restrict__ offsets, unsigned long long* __restrict__ edgeKeys,
                                   unsigned long long* __restrict__ orderKeys, float* __restrict__ sims)
 {
@@ -43,7 +43,7 @@ __global__ void edgeRecordsKernel(uint64_t cellCount, uint64_t k, const em2_pair
         uint64_t out = offsets ? offsets[c] : 0;
         for (uint32_t i = 0; i < used && n < maxConnectivity; i++) {
             const em2_pair p = row[i];
-            if (p.similarity < similarityThreshold) break;            // rows are sorted by decreasing similarity
+            if (double(p.similarity) < similarityThreshold) break;    // float promoted to double, as in the reference (CellGraph.cpp:84); rows are sorted by decreasing similarity
             const uint32_t v1 = vertexOf[p.cell];
             if (v1 == kNoVertex) continue;
             if (edgeKeys) {
@@ -130,10 +130,13 @@ int launchCellGraphEdges(em2_context* ctx, uint64_t cellCount, uint64_t k, const
         *edgeCountHost = 0;
         return EM2_OK;
     }
+    // maxConnectivity == 0 never stops the reference's loop (its `pairs.size() == maxConnectivity` test follows a
+    // push_back, CellGraph.cpp:93-95): every stored neighbour counts, i.e. k of them
+    if (maxConnectivity == 0) maxConnectivity = k;
     if (cellCount * std::min<uint64_t>(maxConnectivity, k) > 0x7fffffffull)
         return fail(ctx, EM2_ERR_INVALID, "em2_cell_graph_edges: more than 2^31 candidate edges");
     const uint32_t maxConn = uint32_t(std::min<uint64_t>(maxConnectivity, k));
-    const float thr = float(similarityThreshold);       // the reference compares the stored float with a float parameter
+    const double thr = similarityThreshold;             // the reference compares the stored float, promoted, with its double parameter
     const unsigned blocks = unsigned((cellCount + 1 + 255) / 256);
     // offsets
     size_t scanBytes = 0, sortBytes = 0;

@@ -144,6 +144,7 @@ double nowMs();
 int guardDevice(em2_context* ctx);
 void resetStats(em2_context* ctx);
 int uploadLut(em2_context* ctx, uint64_t lshCount, float** dLut);
+int checkScanArguments(em2_context* ctx, uint64_t cellCount, uint64_t lshCount, uint64_t k);
 int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s);
 int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s);
 int fetchCounters(em2_context* ctx);

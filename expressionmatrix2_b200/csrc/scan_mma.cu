@@ -34,8 +34,11 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 namespace em2 {
@@ -629,6 +632,7 @@ struct SymParams {
     int32_t dBegin;                // this launch sweeps the offsets [dBegin, dBegin + offsetsHere); negative in the near window
     uint32_t offsetsHere;
     uint32_t resume;               // 1: segment 0 of every row CONTINUES the row's streams of the previous launch
+    uint32_t segBase;              // stream slot of segment g > 0 is segBase + g (the far sweep's extra segments come after the near window's)
     uint32_t rowOnly;              // 1: row direction only (the near window, which both owners of a tile pair visit)
     uint32_t posBegin;             // first scan position of this GPU's rows (a multiple of 256)
     uint32_t ownRows;              // rows of this GPU: positions [posBegin, posBegin + ownRows)
@@ -858,11 +862,12 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             // A stream that continues the previous launch's region keeps its k best so far: the next prune then yields
             // the k-th best of everything the row has seen.  (A fresh region needs ~2k survivors of the old bound
             // before its first prune tightens anything: measured 250 instead of ~65 row-direction survivors per cell.)
+            const uint32_t slot = seg == 0 ? 0u : p.segBase + seg;          // stream pair of this (row, segment)
             st.count = (p.resume && seg == 0 && valid) ? p.candCount[uint64_t(sub) * streamStride + rowLocal] : 0;
             st.appended = 0;
             st.tau = valid ? __ldcg(limPtr) : 0;
             st.lim = st.tau;
-            st.buf = p.cand + (uint64_t(seg * kSubStreams + sub) * streamStride + (valid ? rowLocal : 0)) * p.cap;
+            st.buf = p.cand + (uint64_t(slot * kSubStreams + sub) * streamStride + (valid ? rowLocal : 0)) * p.cap;
             tauShare[sub * kRowsPerItem + rowInItem] = 0xffffu;      // harmless for any row (see scanMmaKernel)
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             int32_t dotThr = int32_t(dotK) - 2 * int32_t(st.lim);      // mismatch < lim  <=>  dot > K - 2 lim
@@ -961,7 +966,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 warpPruneIfNeededAnyOrder(st, p.k, p.cap, limPtr, p.perm, true);
             }
             if (valid) {
-                p.candCount[uint64_t(seg * kSubStreams + sub) * streamStride + rowLocal] = st.count;
+                p.candCount[uint64_t(slot * kSubStreams + sub) * streamStride + rowLocal] = st.count;
                 if (p.appendedTotal && st.appended) atomicAdd(p.appendedTotal, (unsigned long long)st.appended);
             }
         }
@@ -1191,43 +1196,128 @@ __global__ void exchangeSizesKernel(const uint32_t* __restrict__ inOffset, uint6
 // 32-column chunk holds a passing column for SOME lane and the selection code runs with two or three lanes
 // active (ncu: ~90 % of the chunks, 10 of 32 threads per instruction on clustered data).  Rows that are
 // similar to each other pass on the SAME columns, so putting similar rows into the same warp makes most chunks
-// miss for the whole warp and the rest hit with most lanes active.  Only the ORDER IN WHICH ROWS ARE SCANNED
-// changes: columns stay in cell-id order (the tie-break of topk.cuh needs that), every row still sees every
-// column, results are identical.  Grouping = nearest of 256 pivot cells by Hamming distance on the first
-// <= 512 bits, then a radix sort of (pivot, cell id).
+// miss for the whole warp and the rest hit with most lanes active.  The symmetric scan goes further: it visits a
+// cell's neighbourhood in scan order FIRST (the near window), so that the cell's bound is final before the bulk of
+// the matrix is judged by it -- which only works if a cell's neighbours really are its neighbours in scan order.
+// Only the ORDER IN WHICH CELLS ARE SCANNED changes: every row still sees every column, results are identical.
+//
+// Grouping = leader clustering on the signatures, then a radix sort of (leader, cell id).  Leaders ("pivots") are
+// found in rounds: a cell is COVERED when some pivot lies within the radius r = min(threshold, L/2 - 2 sqrt(L)) bits;
+// every round draws up to 64 evenly spaced candidates from the cells that are still uncovered, keeps those that no
+// earlier pivot (of this or a previous round) covers, and re-assigns every cell to its nearest pivot.  Pivots drawn
+// from the uncovered cells always open a NEW cluster, so a cluster gets one pivot (a fixed set of 256 random pivots --
+// round 1 of this work -- left the cells of every cluster without a pivot of its own scattered over the scan order:
+// at 1 M cells / 512 clusters the far sweep then met ~2000 survivors per cell and direction instead of a few dozen).
+// Up to 16 rounds / 1024 pivots, no host synchronisation; ~1e9 word popcounts per round at 1 M cells.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kPivots = 256;
-constexpr int kPivotWords = 8;        // 512 bits are plenty to tell clusters apart; halves the assignment pass
+constexpr int kMaxPivots = 1024;
+constexpr int kPivotRound = 64;       // candidates per round
+constexpr int kPivotRounds = 16;
+constexpr int kPivotWords = 16;       // signature words compared (the first 1024 bits)
 
-__global__ void __launch_bounds__(256)
-pivotAssignKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t cellCount, uint64_t rowBegin, uint64_t rows,
-                  unsigned long long* __restrict__ keys)
+struct PivotState {
+    uint32_t count;                   // pivots so far
+    uint32_t newBegin;                // pivots [newBegin, count) were added by the last round
+    uint32_t uncovered;               // cells no pivot covers (written by the select of each round)
+    uint32_t candidates;              // candidates of the current round
+};
+
+// Evenly spaced candidates from the list of uncovered rows (round 0: all rows are uncovered).
+__global__ void pivotCandidatesKernel(const uint32_t* __restrict__ uncoveredRows, PivotState* __restrict__ st, uint32_t* __restrict__ cand)
 {
-    __shared__ uint64_t piv[kPivots][kPivotWords];
+    const uint32_t n = st->uncovered;
+    const uint32_t want = min(uint32_t(kPivotRound), min(n, uint32_t(kMaxPivots) - st->count));
+    const uint32_t i = threadIdx.x;
+    if (i < want) cand[i] = uncoveredRows[uint64_t(i) * n / want];
+    if (i == 0) st->candidates = want;
+}
+
+// One CTA: candidates are taken in order; one that an accepted pivot (earlier rounds or this one) covers is dropped.
+__global__ void __launch_bounds__(256)
+pivotAcceptKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t rowBegin, const uint32_t* __restrict__ cand,
+                  PivotState* __restrict__ st, uint64_t* __restrict__ pivotSig, uint32_t radius)
+{
+    __shared__ uint32_t best;
     const uint32_t wp = W < kPivotWords ? W : kPivotWords;
-    for (uint32_t i = threadIdx.x; i < kPivots * wp; i += blockDim.x) {
-        const uint32_t pv = i / wp, w = i % wp;
-        const uint64_t cell = uint64_t(pv) * cellCount / kPivots;
-        piv[pv][w] = sig[cell * W + w];
+    uint32_t count = st->count;
+    const uint32_t first = count;
+    const uint32_t nc = st->candidates;
+    for (uint32_t c = 0; c < nc && count < kMaxPivots; c++) {
+        const uint64_t* x = sig + (rowBegin + cand[c]) * W;
+        if (threadIdx.x == 0) best = 0xffffffffu;
+        __syncthreads();
+        uint32_t mine = 0xffffffffu;
+        for (uint32_t pv = threadIdx.x; pv < count; pv += blockDim.x) {
+            uint32_t d = 0;
+            for (uint32_t w = 0; w < wp; w++) d += __popcll(x[w] ^ pivotSig[uint64_t(pv) * kPivotWords + w]);
+            mine = min(mine, d);
+        }
+        if (mine != 0xffffffffu) atomicMin(&best, mine);
+        __syncthreads();
+        if (best > radius) {            // nobody covers it: a new pivot
+            for (uint32_t w = threadIdx.x; w < kPivotWords; w += blockDim.x) pivotSig[uint64_t(count) * kPivotWords + w] = w < wp ? x[w] : 0;
+            count++;
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        st->newBegin = first;
+        st->count = count;
+    }
+}
+
+// Every row against the pivots of the last round: nearest pivot, its distance, and the "still uncovered" flag.
+__global__ void __launch_bounds__(256)
+pivotAssignKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t rowBegin, uint64_t rows, const PivotState* __restrict__ st,
+                  const uint64_t* __restrict__ pivotSig, uint32_t radius, uint32_t* __restrict__ nearest, uint32_t* __restrict__ nearestDist,
+                  uint8_t* __restrict__ uncoveredFlag)
+{
+    __shared__ uint64_t piv[kPivotRound][kPivotWords];
+    const uint32_t b = st->newBegin, e = st->count;
+    const uint32_t wp = W < kPivotWords ? W : kPivotWords;
+    for (uint32_t i = threadIdx.x; i < (e - b) * kPivotWords; i += blockDim.x) piv[i / kPivotWords][i % kPivotWords] = pivotSig[uint64_t(b) * kPivotWords + i];
     __syncthreads();
     const uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if (q >= rows) return;
+    if (q >= rows || e == b) return;
     uint64_t x[kPivotWords];
 #pragma unroll
     for (int w = 0; w < kPivotWords; w++) x[w] = uint32_t(w) < wp ? sig[(rowBegin + q) * W + w] : 0;
-    uint32_t best = 0xffffffffu, bestPivot = 0;
-    for (int pv = 0; pv < kPivots; pv++) {
+    uint32_t best = nearestDist[q], bestPivot = nearest[q];
+    for (uint32_t pv = 0; pv < e - b; pv++) {
         uint32_t d = 0;
 #pragma unroll
-        for (int w = 0; w < kPivotWords; w++)
-            if (uint32_t(w) < wp) d += __popcll(x[w] ^ piv[pv][w]);
+        for (int w = 0; w < kPivotWords; w++) d += __popcll(x[w] ^ piv[pv][w]);
         if (d < best) {
             best = d;
-            bestPivot = pv;
+            bestPivot = b + pv;
         }
     }
-    keys[q] = (uint64_t(bestPivot) << 32) | uint32_t(rowBegin + q);
+    nearest[q] = bestPivot;
+    nearestDist[q] = best;
+    uncoveredFlag[q] = best > radius;
+}
+
+__global__ void pivotInitKernel(uint64_t rows, uint32_t* __restrict__ nearest, uint32_t* __restrict__ nearestDist,
+                                uint8_t* __restrict__ uncoveredFlag, PivotState* __restrict__ st)
+{
+    const uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (q < rows) {
+        nearest[q] = 0;
+        nearestDist[q] = 0xffffffffu;
+        uncoveredFlag[q] = 1;
+    }
+    if (q == 0) {
+        st->count = 0;
+        st->newBegin = 0;
+        st->uncovered = 0;
+        st->candidates = 0;
+    }
+}
+
+__global__ void pivotKeysKernel(uint64_t rowBegin, uint64_t rows, const uint32_t* __restrict__ nearest, unsigned long long* __restrict__ keys)
+{
+    const uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (q < rows) keys[q] = (uint64_t(nearest[q]) << 32) | uint32_t(rowBegin + q);
 }
 
 __global__ void keysToPermKernel(const unsigned long long* __restrict__ keys, uint64_t rows, uint32_t* __restrict__ perm)
@@ -1313,8 +1403,9 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
         // small regions here: a cell's bound is published when its region is pruned, and the column direction of other
         // CTAs lives on fresh bounds (with the one-directional kernels' 4k + 32 keys: 90 M instead of 70 M survivors at config 2)
         nearPlan.cap = farPlan.cap = cap;
-        // stream pair 0 of a row is shared by the near launch and segment 0 of the far launch (which continues it)
-        streams = std::max(nearPlan.segments, farPlan.segments) * kSubStreams;
+        // stream pair 0 of a row is shared by the near launch and segment 0 of the far launch (which continues it); the
+        // other segments of the two launches own their pairs
+        streams = (nearPlan.segments + (farCount ? farPlan.segments - 1 : 0)) * kSubStreams;
     }
     const uint64_t Npad = uint64_t(P) * shard;      // every rank's slice of the per-position arrays has `shard` entries
 
@@ -1413,6 +1504,7 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     auto sweep = [&](const ScanPlan& pl, int32_t dBegin, uint32_t count, uint32_t resume, uint32_t rowOnly) -> int {
         if (!ownRows || !count) return EM2_OK;
+        p.segBase = resume ? nearPlan.segments - 1 : 0;
         p.mainBlocks = pl.mainBlocks;
         p.segments = pl.segments;
         p.items = pl.items;
@@ -1540,27 +1632,61 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     return EM2_OK;
 }
 
-// Scan order: rows [rowBegin, rowBegin + rows) sorted by (nearest of 256 pivot cells, cell id); see pivotAssignKernel.
-// perm[q] = cell id of scan position q (device, `rows` entries written at permOut).
-int groupRows(em2_context* ctx, const uint64_t* signatures, uint32_t W, uint64_t cellCount, uint64_t rowBegin, uint64_t rows,
-              uint32_t* permOut, cudaStream_t s)
+// Scan order: rows [rowBegin, rowBegin + rows) sorted by (leader, cell id); see "Row grouping" above.
+// perm[q] = cell id of scan position q (device, `rows` entries written at permOut).  tau0: the scan's initial
+// exclusive bound in bits (mismatchMax + 1), which caps the cover radius.
+int groupRows(em2_context* ctx, const uint64_t* signatures, uint32_t W, uint64_t lshCount, uint32_t tau0, uint64_t rowBegin,
+              uint64_t rows, uint32_t* permOut, cudaStream_t s)
 {
     if (rows == 0) return EM2_OK;
-    size_t cubBytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, cubBytes, static_cast<const unsigned long long*>(nullptr),
-                                   static_cast<unsigned long long*>(nullptr), int(rows), 0, 40, s);
+    // distances are taken over the first min(L, 1024) bits
+    const double bits = double(std::min<uint64_t>(lshCount, 64ull * kPivotWords));
+    const double scaledTau = double(tau0 > 0 ? tau0 - 1 : 0) * bits / double(lshCount);
+    const uint32_t radius = uint32_t(std::max(0.0, std::min(scaledTau, bits / 2 - 2 * std::sqrt(bits))));
+    size_t sortBytes = 0, selectBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, static_cast<const unsigned long long*>(nullptr),
+                                   static_cast<unsigned long long*>(nullptr), int(rows), 0, 44, s);
+    cub::CountingInputIterator<uint32_t> rowIds(0);
+    cub::DeviceSelect::Flagged(nullptr, selectBytes, rowIds, static_cast<const uint8_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                               static_cast<uint32_t*>(nullptr), int(rows), s);
+    const size_t cubBytes = roundUp(std::max(sortBytes, selectBytes), 256);
     const size_t keyBytes = roundUp(rows * sizeof(unsigned long long), 256);
+    const size_t u32Bytes = roundUp(rows * sizeof(uint32_t), 256);
+    const size_t pivotBytes = roundUp(size_t(kMaxPivots) * kPivotWords * sizeof(uint64_t), 256);
     void* scratch = nullptr;
-    EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, 2 * keyBytes + cubBytes, &scratch));
-    auto* keysIn = static_cast<unsigned long long*>(scratch);
-    auto* keysOut = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(scratch) + keyBytes);
-    void* cubTemp = static_cast<uint8_t*>(scratch) + 2 * keyBytes;
-    pivotAssignKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(signatures, W, cellCount, rowBegin, rows, keysIn);
+    // [keysIn][keysOut][nearest][nearestDist][uncoveredRows][flags][pivotSig][cand][state][cub]
+    EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, 2 * keyBytes + 3 * u32Bytes + roundUp(rows, 256) + pivotBytes + 1024 + cubBytes, &scratch));
+    uint8_t* base = static_cast<uint8_t*>(scratch);
+    auto* keysIn = reinterpret_cast<unsigned long long*>(base);
+    auto* keysOut = reinterpret_cast<unsigned long long*>(base + keyBytes);
+    auto* nearest = reinterpret_cast<uint32_t*>(base + 2 * keyBytes);
+    auto* nearestDist = reinterpret_cast<uint32_t*>(base + 2 * keyBytes + u32Bytes);
+    auto* uncoveredRows = reinterpret_cast<uint32_t*>(base + 2 * keyBytes + 2 * u32Bytes);
+    auto* flags = base + 2 * keyBytes + 3 * u32Bytes;
+    auto* pivotSig = reinterpret_cast<uint64_t*>(flags + roundUp(rows, 256));
+    auto* cand = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(pivotSig) + pivotBytes);
+    auto* state = reinterpret_cast<PivotState*>(cand + kPivotRound);
+    void* cubTemp = reinterpret_cast<uint8_t*>(cand) + 1024;
+    const unsigned blocks = unsigned((rows + 255) / 256);
+    pivotInitKernel<<<blocks, 256, 0, s>>>(rows, nearest, nearestDist, flags, state);
     EM2_CUDA(ctx, cudaGetLastError());
-    EM2_CUDA(ctx, cub::DeviceRadixSort::SortKeys(cubTemp, cubBytes, keysIn, keysOut, int(rows), 0, 40, s));
-    keysToPermKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(keysOut, rows, permOut);
+    for (int round = 0; round < kPivotRounds; round++) {
+        size_t bytes = selectBytes;
+        EM2_CUDA(ctx, cub::DeviceSelect::Flagged(cubTemp, bytes, rowIds, flags, uncoveredRows, &state->uncovered, int(rows), s));
+        pivotCandidatesKernel<<<1, kPivotRound, 0, s>>>(uncoveredRows, state, cand);
+        pivotAcceptKernel<<<1, 256, 0, s>>>(signatures, W, rowBegin, cand, state, pivotSig, radius);
+        pivotAssignKernel<<<blocks, 256, 0, s>>>(signatures, W, rowBegin, rows, state, pivotSig, radius, nearest, nearestDist, flags);
+        EM2_CUDA(ctx, cudaGetLastError());
+    }
+    pivotKeysKernel<<<blocks, 256, 0, s>>>(rowBegin, rows, nearest, keysIn);
     EM2_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += 2;      // + the radix sort's own passes (library code, not counted)
+    {
+        size_t bytes = sortBytes;
+        EM2_CUDA(ctx, cub::DeviceRadixSort::SortKeys(cubTemp, bytes, keysIn, keysOut, int(rows), 0, 44, s));
+    }
+    keysToPermKernel<<<blocks, 256, 0, s>>>(keysOut, rows, permOut);
+    EM2_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 3 + 3 * kPivotRounds;      // + the select / sort passes (library code, not counted)
     return EM2_OK;
 }
 
@@ -1588,7 +1714,8 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         EM2_CUDA(ctx, cudaGetLastError());
     }
 
-    // 1b. the scanned rows in grouped order (see pivotAssignKernel) and their encoded signatures by scan position
+    // 1b. the scanned rows in grouped order (see "Row grouping") and their encoded signatures by scan position
+    const uint32_t tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
     const bool grouped = !dump && (ctx->rowGrouping == 2 || (ctx->rowGrouping == 0 && rows >= 8192));
     const uint8_t* encRows = static_cast<const uint8_t*>(enc) + rowBegin * uint64_t(K);
     const uint32_t* rowPerm = nullptr;
@@ -1596,7 +1723,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         void* permBuf = nullptr;
         EM2_TRY(reserve(ctx, em2_context::S_PERM, rows * sizeof(uint32_t), &permBuf));
         uint32_t* perm = static_cast<uint32_t*>(permBuf);
-        EM2_TRY(groupRows(ctx, signatures, W, cellCount, rowBegin, rows, perm, s));
+        EM2_TRY(groupRows(ctx, signatures, W, lshCount, tau0, rowBegin, rows, perm, s));
         void* er = nullptr;
         EM2_TRY(reserve(ctx, em2_context::S_ENCROWS, rows * uint64_t(K), &er));
         const uint64_t threads = rows * (K / 16);
@@ -1609,7 +1736,6 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
 
     // 1c. whole-matrix jobs, on request: every unordered pair once (scanMmaSymKernel); falls through to the
     //     one-directional kernels if a capacity ran out (nothing of the symmetric attempt is kept)
-    const uint32_t tau0 = mismatchMax < 0 ? 0u : uint32_t(std::min<int64_t>(mismatchMax, int64_t(lshCount)) + 1);
     ctx->stats.scan_symmetric = 0;
     {
         const uint32_t capSym = scanCandidateCapacity(uint32_t(k), uint32_t(ctx->candCapExtra));
@@ -1807,7 +1933,7 @@ int launchScanSymDist(em2_context* ctx, const uint64_t* allSig, uint64_t cellCou
             EM2_CUDA(ctx, cudaGetLastError());
             ctx->stats.kernel_launches++;
         } else {
-            EM2_TRY(groupRows(ctx, allSig, W, cellCount, part.rowBegin, rows, perm + part.rowBegin, s));
+            EM2_TRY(groupRows(ctx, allSig, W, lshCount, tau0, part.rowBegin, rows, perm + part.rowBegin, s));
         }
     }
     EM2_TRY(distAllGather(ctx, perm, part.shard, sizeof(uint32_t), s));

@@ -176,20 +176,31 @@ void ExpressionMatrix::findSimilarPairs4(std::ostream& out, const std::string& g
     std::copy(geneSet.localIds().begin(), geneSet.localIds().begin() + std::min<size_t>(geneSet.localIds().size(), localIds.size()),
               localIds.begin());
 
+    // Limits of the device path that the reference does not have: checked before anything is written to the data directory.
+    if (k == 0 || k > 1024) throw std::runtime_error("findSimilarPairs4: k must be in [1, 1024] on the GPU path.");
+    if (lshCount == 0 || lshCount > 65535) throw std::runtime_error("findSimilarPairs4: lshCount must be in [1, 65535] on the GPU path.");
+
     out << timestamp << "Initializing SimilarPairs object." << std::endl;
     SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
 
-    Gpu& gpu = Gpu::instance();
+    GpuSet& gpu = GpuSet::instance();
     out << timestamp << "Expression matrix subset, LSH signatures and all cell pairs on " << gpu.name() << "." << std::endl;
     static_assert(sizeof(std::pair<GeneId, float>) == sizeof(em2_count), "pair<GeneId,float> must be 8 bytes");
     static_assert(sizeof(SimilarPairs::Pair) == sizeof(em2_pair), "pair<CellId,float> must be 8 bytes");
     std::vector<uint32_t> used(n);
-    gpu.check(em2_lsh_similar_pairs_subset(gpu.context(), cellExpressionCounts.size(), cellExpressionCounts.tocBegin(),
-                                           reinterpret_cast<const em2_count*>(cellExpressionCounts.dataBegin()), geneCount(),
-                                           localIds.data(), geneSet.size(), n, cellSet.begin(), lshVectors.data(), lshCount, k,
-                                           similarityThreshold, scanVariant,
-                                           reinterpret_cast<em2_pair*>(similarPairs.begin(0)), used.data(), nullptr),
-              "em2_lsh_similar_pairs_subset");
+    try {
+        // every GPU copies its cells' rows out of the mapped CellExpressionCounts file and writes its rows of the result
+        // straight into the mapped SimilarPairs-<name>-Pairs payload (both through the library's pinned bounce buffers)
+        gpu.check(em2_multi_lsh_similar_pairs_subset(gpu.handle(), cellExpressionCounts.size(), cellExpressionCounts.tocBegin(),
+                                                     reinterpret_cast<const em2_count*>(cellExpressionCounts.dataBegin()), geneCount(),
+                                                     localIds.data(), geneSet.size(), n, cellSet.begin(), lshVectors.data(), lshCount, k,
+                                                     similarityThreshold, scanVariant,
+                                                     reinterpret_cast<em2_pair*>(similarPairs.begin(0)), used.data(), nullptr),
+                  "em2_multi_lsh_similar_pairs_subset");
+    } catch (...) {
+        similarPairs.remove();      // no empty but valid-looking SimilarPairs-<name> set stays behind a failed call
+        throw;
+    }
     similarPairs.setUsedCounts(used);
     const em2_stats st = gpu.stats();
     lastSignatureMs = st.signatures_ms;
@@ -238,7 +249,12 @@ void ExpressionMatrix::findSimilarPairs7(const std::string& geneSetName, const s
     SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
     std::cout << "Mismatch count threshold is " << lsh.computeMismatchCountThresholdFromSimilarityThreshold(similarityThreshold)
               << std::endl;
-    lsh.findSimilarPairs7(similarPairs, k, similarityThreshold, lshSliceLengths, maxCheck, log2BucketCount);
+    try {
+        lsh.findSimilarPairs7(similarPairs, k, similarityThreshold, lshSliceLengths, maxCheck, log2BucketCount);
+    } catch (...) {
+        similarPairs.remove();
+        throw;
+    }
     std::cout << timestamp << "ExpressionMatrix::findSimilarPairs7 ends." << std::endl;
 }
 
@@ -247,6 +263,7 @@ void ExpressionMatrix::findSimilarPairs0(std::ostream& out, const std::string& g
                                          size_t k, double similarityThreshold)
 {
     if (similarityThreshold > 1.) throw std::runtime_error("similarityThreshold must not exceed 1.");
+    if (k == 0 || k > 1024) throw std::runtime_error("findSimilarPairs0: k must be in [1, 1024] on the GPU path.");
     const GeneSet& geneSet = findGeneSet(geneSetName);
     const CellSet& cellSet = findCellSet(cellSetName);
     SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
@@ -256,10 +273,15 @@ void ExpressionMatrix::findSimilarPairs0(std::ostream& out, const std::string& g
     const size_t n = subset.cellCount();
     std::vector<uint32_t> used(n);
     Gpu& gpu = Gpu::instance();
-    gpu.check(em2_exact_similar_pairs(gpu.context(), n, subset.geneCount(), subset.toc(),
-                                      reinterpret_cast<const em2_count*>(subset.data()), k, similarityThreshold,
-                                      reinterpret_cast<em2_pair*>(similarPairs.begin(0)), used.data()),
-              "em2_exact_similar_pairs");
+    try {
+        gpu.check(em2_exact_similar_pairs(gpu.context(), n, subset.geneCount(), subset.toc(),
+                                          reinterpret_cast<const em2_count*>(subset.data()), k, similarityThreshold,
+                                          reinterpret_cast<em2_pair*>(similarPairs.begin(0)), used.data()),
+                  "em2_exact_similar_pairs");
+    } catch (...) {
+        similarPairs.remove();
+        throw;
+    }
     similarPairs.setUsedCounts(used);
     lastScanMs = gpu.stats().scan_ms;
     out << "Time for all pairs: " << 1e-3 * lastScanMs << " s." << std::endl;

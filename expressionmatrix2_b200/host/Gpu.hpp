@@ -24,5 +24,23 @@ private:
     em2_context* ctx_ = nullptr;
 };
 
+// Every GPU of the box behind one blocking call (em2_multi): what findSimilarPairs4 runs on.  The devices are
+// $EM2_DEVICES (comma separated indices) or, by default, all visible ones; with a single device it is the same
+// code path minus the collectives.
+class GpuSet {
+public:
+    static GpuSet& instance();
+    em2_multi* handle() { return multi_; }
+    int deviceCount() const;
+    std::string name();                  // "8 x NVIDIA B200"
+    em2_stats stats();                   // of the whole job (times: max over the devices)
+    void check(int status, const char* what);
+    ~GpuSet();
+
+private:
+    GpuSet();
+    em2_multi* multi_ = nullptr;
+};
+
 }  // namespace ExpressionMatrix2
 }  // namespace ChanZuckerberg

@@ -304,14 +304,15 @@ def ref_subset(toc, gene_ids, counts, gene_count: int, gene_set, cell_set):
 
 def cell_graph_edges(ids, sims, used, vertex_of, similarity_threshold: float, max_connectivity: int):
     """The edge loop of CellGraph::CellGraph (reference src/CellGraph.cpp:60-107), restated literally over a
-    SimilarPairs payload: cells in order; per cell walk the row, `break` at the first similarity < threshold (float
-    compare, as the reference's `float similarity < similarityThreshold`), skip neighbours that are not vertices, stop
-    at max_connectivity kept neighbours; add the edge unless it exists.  vertex_of[c] = vertex index or 0xFFFFFFFF.
+    SimilarPairs payload: cells in order; per cell walk the row, `break` at the first similarity < threshold (the
+    stored float promoted to double against the double parameter, CellGraph.cpp:84), skip neighbours that are not
+    vertices, stop when the kept neighbours number max_connectivity (tested after the push_back, so 0 never stops);
+    add the edge unless it exists.  vertex_of[c] = vertex index or 0xFFFFFFFF.
     Returns (vertex0 uint32[E], vertex1 uint32[E], similarity float32[E]) in insertion order.
     (The reference's CellGraph itself needs Boost.Graph and cannot be compiled here: restatement only.)"""
     ids = np.asarray(ids)
     sims = np.asarray(sims, np.float32)
-    thr = np.float32(similarity_threshold)
+    thr = float(similarity_threshold)
     seen = set()
     v0s, v1s, ss = [], [], []
     for c in range(len(used)):
@@ -320,7 +321,7 @@ def cell_graph_edges(ids, sims, used, vertex_of, similarity_threshold: float, ma
             continue
         kept = []
         for i in range(int(used[c])):
-            if sims[c, i] < thr:
+            if float(sims[c, i]) < thr:
                 break
             v1 = int(vertex_of[int(ids[c, i])])
             if v1 == 0xFFFFFFFF:
@@ -617,6 +618,27 @@ def ref_write_similar_pairs(directory: str, name: str, gene_count: int, ids, sim
     n, k = ids.shape
     _check(rlib().em2ref_write_similar_pairs(directory.encode(), name.encode(), n, gene_count, k, _ptr(ids, u32p),
                                              _ptr(sims, f32p), _ptr(used, u32p)))
+
+
+def ref_cell_graph_edges(ids, sims, used, cell_set, similarity_threshold: float, max_connectivity: int, gene_count: int = 4):
+    """Edges of the reference's OWN CellGraph constructor (src/CellGraph.cpp:33-117, compiled unmodified into
+    oracle/_ref against the Boost.Graph stand-in of boost_shim/) for a SimilarPairs payload over cells 0..N-1 and the
+    graph cell set `cell_set` (sorted cell ids).  Returns (vertex0, vertex1, similarity) in the graph's edge order,
+    vertices as positions in cell_set."""
+    cell_set = _c(cell_set, np.uint32)
+    with tempfile.TemporaryDirectory(prefix="em2ref-") as d:
+        ref_write_similar_pairs(d, "P", gene_count, ids, sims, used)
+        cap = max(1, len(cell_set) * ids.shape[1])
+        v0 = np.zeros(cap, np.uint32)
+        v1 = np.zeros(cap, np.uint32)
+        ss = np.zeros(cap, np.float32)
+        n = C.c_uint64(0)
+        rlib().em2ref_cell_graph_edges.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, u32p, C.c_double, C.c_uint64, C.c_uint64,
+                                                   u32p, u32p, f32p, u64p]
+        _check(rlib().em2ref_cell_graph_edges(d.encode(), b"P", len(cell_set), _ptr(cell_set, u32p), similarity_threshold,
+                                              max_connectivity, cap, _ptr(v0, u32p), _ptr(v1, u32p), _ptr(ss, f32p), C.byref(n)))
+    m = int(n.value)
+    return v0[:m].copy(), v1[:m].copy(), ss[:m].copy()
 
 
 def ref_read_similar_pairs(directory: str, name: str):

@@ -53,6 +53,8 @@
 #include "orderPairs.hpp"
 #include "filesystem.hpp"
 #include "MurmurHash2.hpp"
+#include "CellGraph.hpp"
+#include <boost/graph/iteration_macros.hpp>
 
 using namespace ChanZuckerberg;
 using namespace ExpressionMatrix2;
@@ -486,6 +488,39 @@ int em2ref_read_similar_pairs(const char* dir, const char* name, uint64_t* kOut,
                 sims[size_t(c) * sp.k() + i] = p[i].second;
             }
         }
+    });
+}
+
+// The reference's OWN CellGraph constructor (src/CellGraph.cpp:33-117, compiled unmodified against the Boost.Graph
+// stand-in of boost_shim/) on a SimilarPairs object written by em2ref_write_similar_pairs: the graph's cell set is
+// `cellSet` (sorted cell ids); edges come back in the graph's edge order (= insertion order) as vertex indices
+// (positions in cellSet) plus the stored similarity.  *edgeCount receives the number of edges; the arrays may be
+// null for a size query.
+int em2ref_cell_graph_edges(const char* dir, const char* similarPairsName, uint64_t cellSetSize, const uint32_t* cellSet,
+                            double similarityThreshold, uint64_t maxConnectivity, uint64_t capacity, uint32_t* vertex0,
+                            uint32_t* vertex1, float* similarity, uint64_t* edgeCount)
+{
+    return guarded([&] {
+        MemoryMapped::Vector<CellId> cells;
+        const std::string name = std::string(dir) + "/tmp-CellGraphCellSet";
+        cells.createNew(name, cellSetSize);
+        for (uint64_t i = 0; i < cellSetSize; i++) cells[i] = cellSet[i];
+        {
+            CellGraph graph(cells, dir, similarPairsName, similarityThreshold, size_t(maxConnectivity));
+            std::map<CellId, uint32_t> indexOf;
+            for (uint64_t i = 0; i < cellSetSize; i++) indexOf[cellSet[i]] = uint32_t(i);
+            uint64_t n = 0;
+            BGL_FORALL_EDGES(e, graph, CellGraph) {
+                if (vertex0 && n < capacity) {
+                    vertex0[n] = indexOf[graph[source(e, graph)].cellId];
+                    vertex1[n] = indexOf[graph[target(e, graph)].cellId];
+                    similarity[n] = graph[e].similarity;
+                }
+                n++;
+            }
+            *edgeCount = n;
+        }
+        cells.remove();
     });
 }
 

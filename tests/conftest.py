@@ -33,6 +33,15 @@ def golden_bucketed_cases():
                int(g[f"c{i}_max_check"]), int(g[f"c{i}_log2b"]), g[f"c{i}_ids"], g[f"c{i}_sims"], g[f"c{i}_used"])
 
 
+def golden_cellgraph_cases():
+    """(ids, sims, used, cell_set, thr, max_conn, v0, v1, sim) of tests/golden/next_cellgraph.npz: edges built by the
+    reference's own CellGraph constructor (tests/golden/make_golden_next_rows.py)."""
+    g = load_golden("next_cellgraph")
+    for i in range(int(g["cases"])):
+        yield (g["ids"], g["sims"], g["used"], g[f"c{i}_cell_set"], float(g[f"c{i}_thr"]), int(g[f"c{i}_max_conn"]),
+               g[f"c{i}_v0"], g[f"c{i}_v1"], g[f"c{i}_sim"])
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import oracle as O

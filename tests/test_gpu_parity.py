@@ -6,7 +6,7 @@ deterministic oracle (ids, order, usedCount), similarity floats 0 ULP."""
 import numpy as np
 import pytest
 
-from conftest import golden_bucketed_cases, golden_cases, load_golden
+from conftest import golden_bucketed_cases, golden_cases, golden_cellgraph_cases, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -573,6 +573,19 @@ def test_cell_graph_edges_match_the_reference_loop(engine, oracle, thr, max_conn
     assert np.array_equal(e["similarity"].view(np.uint32), ws.view(np.uint32))
 
 
+def test_cell_graph_edges_equal_the_reference_constructor(engine):
+    """Golden edges produced by the reference's OWN CellGraph constructor (src/CellGraph.cpp compiled unmodified into
+    oracle/_ref; tests/golden/next_cellgraph.npz): cells outside the graph's cell set, a threshold equal to a stored
+    float (the reference compares float < double), maxConnectivity 0 (never stops the reference's loop)."""
+    for ids, sims, used, cell_set, thr, max_conn, v0, v1, sim in golden_cellgraph_cases():
+        vertex_of = np.full(len(used), 0xFFFFFFFF, np.uint32)
+        vertex_of[cell_set] = np.arange(len(cell_set), dtype=np.uint32)
+        e = engine.cell_graph_edges(ids, sims, used, vertex_of, thr, max_conn)
+        assert len(e) == len(v0)
+        assert np.array_equal(e["vertex0"], v0) and np.array_equal(e["vertex1"], v1)
+        assert np.array_equal(e["similarity"].view(np.uint32), sim.view(np.uint32))
+
+
 def test_cell_graph_edges_degenerate(engine, oracle):
     ids = np.zeros((4, 3), np.uint32)
     sims = np.zeros((4, 3), np.float32)
@@ -777,6 +790,15 @@ def test_bucketed_search_equals_the_reference_loops(engine, oracle):
             want = ref.find_similar_pairs7(k, thr, slices, max_check, log2b)
         got = engine.find_similar_pairs7(sig, L, k, thr, slices, max_check, log2b)
         _check_lists(got, want)
+
+
+def test_bucketed_search_without_a_candidate_limit(engine, oracle):
+    """maxCheck = 0 or UINT32_MAX means "no limit" in the reference (its size() == maxCheck test never fires): same lists
+    as maxCheck = N - 1, and the workspace is sized by the cell count, not by the argument."""
+    sig = synthetic.gen_signatures(1200, 128, seed=31, clusters=6)
+    want = engine.find_similar_pairs7(sig, 128, 8, 0.3, [16, 8], 1199, 9)
+    for max_check in (0, 0xFFFFFFFF, 5000):
+        _check_lists(engine.find_similar_pairs7(sig, 128, 8, 0.3, [16, 8], max_check, 9), want)
 
 
 def test_bucketed_search_argument_checks(engine):

@@ -172,6 +172,21 @@ def test_signature_graph_restatement_matches_reference_bitsets():
     assert order.tolist() == [0, 2, 1] and offsets.tolist() == [0, 2, 3] and edges.tolist() == [[0, 1]]
 
 
+def test_cell_graph_restatement_matches_reference_constructor():
+    """oracle.cell_graph_edges (numpy restatement of src/CellGraph.cpp:60-112) against the reference's OWN CellGraph
+    constructor (compiled unmodified into oracle/_ref), and against the committed golden edges it produced."""
+    import oracle
+    from conftest import golden_cellgraph_cases
+    for ids, sims, used, cell_set, thr, max_conn, v0, v1, sim in golden_cellgraph_cases():
+        vertex_of = np.full(len(used), 0xFFFFFFFF, np.uint32)
+        vertex_of[cell_set] = np.arange(len(cell_set), dtype=np.uint32)
+        w0, w1, ws = oracle.cell_graph_edges(ids, sims, used, vertex_of, thr, max_conn)
+        assert np.array_equal(w0, v0) and np.array_equal(w1, v1) and np.array_equal(ws.view(np.uint32), sim.view(np.uint32))
+        if oracle.have_ref():
+            r0, r1, rs = oracle.ref_cell_graph_edges(ids, sims, used, cell_set, thr, max_conn)
+            assert np.array_equal(r0, v0) and np.array_equal(r1, v1) and np.array_equal(rs.view(np.uint32), sim.view(np.uint32))
+
+
 def test_golden_vectors_of_the_next_rows_are_reproduced():
     """tests/golden/next_*.npz (made by the reference's own classes): the numpy restatement of the SignatureGraph loops
     reproduces the stored graph, and -- where oracle/_ref is present -- so do the reference-class drivers themselves."""
