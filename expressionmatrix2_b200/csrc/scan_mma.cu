@@ -621,6 +621,7 @@ constexpr uint32_t kLogChunk = 64;
 constexpr uint32_t kPaceWindow = 256;      // tiles a CTA may run ahead of the slowest one (64 MB of distinct B tiles)
 constexpr uint32_t kSymSmallBytes = 192 + 2 * kSsTileN * 2 + 2 * (kSsTileN / 8) * 2 + kEpiThreads * 2;
 constexpr int kMaxInboxSources = 8;        // GPUs whose column-direction candidates a cell's merge reads
+constexpr int kSymThreads = kThreads + 32;  // + one warp that stages the column thresholds
 
 struct SymParams {
     uint64_t cellCount;            // N: scan positions of the WHOLE job (all ranks); rows == columns
@@ -666,7 +667,7 @@ static __device__ __noinline__ ulonglong2* nextLogChunk(uint32_t* chunkFill, uin
     return pool + uint64_t(c) * kLogChunk;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kSymThreads, 1)
 scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SymParams p)
 {
     extern __shared__ uint8_t smemRaw[];
@@ -727,9 +728,6 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // neighbouring row blocks are the same blocks one step apart, so in step they are read from DRAM once and from
         // L2 147 times; without pacing a CTA that falls behind starts missing L2, gets slower still, and the sweep
         // settles DRAM-bound (1 M cells: 3.25 TB read from DRAM, L2 hit rate 33 %, tensor pipe 47 %).
-        // The warp also stages, per tile, the bounds of the tile's 256 column cells as dot-product thresholds (lane =
-        // one group of 8 columns) -- off the epilogue's critical path: with the 128 epilogue threads of a sub-stream
-        // doing it themselves behind a named barrier, 22 % of all warp samples sat at that barrier (ncu, 1 M cells).
         uint32_t stage = 0, phase = 0, itemIter = 0, tileIter = 0;
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
             const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
@@ -772,16 +770,33 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
                 __syncwarp();
-                if (!p.rowOnly) {
+            }
+        }
+        if (lane == 0 && p.progress) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
+    } else if (warp == kEpiWarps + 2) {
+        // ===================== threshold warp: the bounds of every tile's 256 column cells as dot-product thresholds =====================
+        // lane = one group of 8 columns.  Runs up to two tiles ahead of the epilogue (two slots), so the L2 round trip
+        // of the bounds is off everybody's critical path: done by the 128 epilogue threads of a sub-stream behind a
+        // named barrier it cost 22 % of all warp samples (ncu, 1 M cells); done by the producer warp between two tiles'
+        // TMA loads it starved the 3-stage B ring (tensor pipe 45 %, 62 % of the samples waiting for thresholds).
+        if (!p.rowOnly) {
+            uint32_t tileIter = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
+                const uint32_t super = (firstBlock + it.rowBlock) >> 1;
+                const int32_t d0 = p.dBegin + int32_t(it.colBegin / kSsTileN);
+                const int32_t d1 = p.dBegin + int32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
+                for (int32_t d = d0; d < d1; d++, tileIter++) {
                     const uint32_t slot = tileIter & 1;
-                    mbarWait(thrEmpty + slot, ((tileIter >> 1) & 1) ^ 1);
-                    const uint32_t pos0 = colSuper * kSsTileN + uint32_t(lane) * 8;
+                    const uint32_t pos0 = colSuperOf(super, d) * kSsTileN + uint32_t(lane) * 8;
+                    uint32_t lim[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) lim[j] = pos0 + j < N ? __ldcg(p.limEx + pos0 + j) : 0u;      // padding columns: nothing passes
                     int32_t t[8];
                     int32_t loosest = 0x7fff;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        const uint32_t lim = pos0 + j < N ? __ldcg(p.limEx + pos0 + j) : 0u;      // padding columns: nothing passes
-                        t[j] = int32_t(p.K) - 2 * int32_t(lim);
+                        t[j] = int32_t(p.K) - 2 * int32_t(lim[j]);
                         loosest = min(loosest, t[j]);
                     }
                     uint4 packed;
@@ -789,6 +804,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     packed.y = uint32_t(uint16_t(t[2])) | (uint32_t(uint16_t(t[3])) << 16);
                     packed.z = uint32_t(uint16_t(t[4])) | (uint32_t(uint16_t(t[5])) << 16);
                     packed.w = uint32_t(uint16_t(t[6])) | (uint32_t(uint16_t(t[7])) << 16);
+                    mbarWait(thrEmpty + slot, ((tileIter >> 1) & 1) ^ 1);      // every epilogue warp is done with the slot's last tile
                     *reinterpret_cast<uint4*>(colThr + slot * kSsTileN + lane * 8) = packed;
                     grpThr[slot * (kSsTileN / 8) + lane] = int16_t(loosest);
                     __syncwarp();
@@ -796,7 +812,6 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
             }
         }
-        if (lane == 0 && p.progress) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
     } else if (warp == kEpiWarps + 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
@@ -1233,36 +1248,70 @@ __global__ void pivotCandidatesKernel(const uint32_t* __restrict__ uncoveredRows
 }
 
 // One CTA: candidates are taken in order; one that an accepted pivot (earlier rounds or this one) covers is dropped.
+// Distances are computed in parallel (candidate x existing pivot, candidate x earlier candidate); only the greedy
+// pass over the <= 64 candidates is sequential.
 __global__ void __launch_bounds__(256)
 pivotAcceptKernel(const uint64_t* __restrict__ sig, uint32_t W, uint64_t rowBegin, const uint32_t* __restrict__ cand,
                   PivotState* __restrict__ st, uint64_t* __restrict__ pivotSig, uint32_t radius)
 {
-    __shared__ uint32_t best;
+    __shared__ uint64_t cs[kPivotRound][kPivotWords];
+    __shared__ uint32_t minOld[kPivotRound];
+    __shared__ unsigned long long nearEarlier[kPivotRound];
+    __shared__ uint32_t slotOf[kPivotRound];
+    static_assert(kPivotRound <= 64, "one bit per candidate");
     const uint32_t wp = W < kPivotWords ? W : kPivotWords;
-    uint32_t count = st->count;
-    const uint32_t first = count;
+    const uint32_t count0 = st->count;
     const uint32_t nc = st->candidates;
-    for (uint32_t c = 0; c < nc && count < kMaxPivots; c++) {
-        const uint64_t* x = sig + (rowBegin + cand[c]) * W;
-        if (threadIdx.x == 0) best = 0xffffffffu;
-        __syncthreads();
-        uint32_t mine = 0xffffffffu;
-        for (uint32_t pv = threadIdx.x; pv < count; pv += blockDim.x) {
-            uint32_t d = 0;
-            for (uint32_t w = 0; w < wp; w++) d += __popcll(x[w] ^ pivotSig[uint64_t(pv) * kPivotWords + w]);
-            mine = min(mine, d);
-        }
-        if (mine != 0xffffffffu) atomicMin(&best, mine);
-        __syncthreads();
-        if (best > radius) {            // nobody covers it: a new pivot
-            for (uint32_t w = threadIdx.x; w < kPivotWords; w += blockDim.x) pivotSig[uint64_t(count) * kPivotWords + w] = w < wp ? x[w] : 0;
-            count++;
-        }
-        __syncthreads();
+    if (nc == 0) {
+        if (threadIdx.x == 0) st->newBegin = count0;
+        return;
     }
+    for (uint32_t i = threadIdx.x; i < nc * kPivotWords; i += blockDim.x) {
+        const uint32_t c = i / kPivotWords, w = i % kPivotWords;
+        cs[c][w] = w < wp ? sig[(rowBegin + cand[c]) * W + w] : 0;
+    }
+    if (threadIdx.x < kPivotRound) {
+        minOld[threadIdx.x] = 0xffffffffu;
+        nearEarlier[threadIdx.x] = 0;
+        slotOf[threadIdx.x] = 0xffffffffu;
+    }
+    __syncthreads();
+    for (uint32_t pv = threadIdx.x; pv < count0; pv += blockDim.x) {        // existing pivots: one per thread, all candidates
+        uint64_t x[kPivotWords];
+#pragma unroll
+        for (int w = 0; w < kPivotWords; w++) x[w] = pivotSig[uint64_t(pv) * kPivotWords + w];
+        for (uint32_t c = 0; c < nc; c++) {
+            uint32_t d = 0;
+#pragma unroll
+            for (int w = 0; w < kPivotWords; w++) d += __popcll(x[w] ^ cs[c][w]);
+            if (d <= radius) atomicMin(&minOld[c], d);
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < nc * nc; i += blockDim.x) {            // candidate pairs (c, earlier e)
+        const uint32_t c = i / nc, e = i % nc;
+        if (e >= c) continue;
+        uint32_t d = 0;
+#pragma unroll
+        for (int w = 0; w < kPivotWords; w++) d += __popcll(cs[c][w] ^ cs[e][w]);
+        if (d <= radius) atomicOr(&nearEarlier[c], 1ull << e);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        st->newBegin = first;
+        unsigned long long accepted = 0;
+        uint32_t count = count0;
+        for (uint32_t c = 0; c < nc && count < kMaxPivots; c++) {
+            if (minOld[c] == 0xffffffffu && !(nearEarlier[c] & accepted)) {   // nobody covers it: a new pivot
+                accepted |= 1ull << c;
+                slotOf[c] = count++;
+            }
+        }
+        st->newBegin = count0;
         st->count = count;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nc * kPivotWords; i += blockDim.x) {
+        const uint32_t c = i / kPivotWords, w = i % kPivotWords;
+        if (slotOf[c] != 0xffffffffu) pivotSig[uint64_t(slotOf[c]) * kPivotWords + w] = cs[c][w];
     }
 }
 
@@ -1517,7 +1566,7 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
         // (390 tiles per item) the sweep was 1.5x SLOWER, at 1 M cells (1953 tiles) 1.2x faster
         p.progress = (count >= 768 && !(ctx->debugFlags & 16)) ? progress : nullptr;
         if (p.progress) EM2_CUDA(ctx, cudaMemsetAsync(progress, 0, 1024 * sizeof(uint32_t), s));
-        scanMmaSymKernel<<<unsigned(std::min<uint32_t>(pl.items, uint32_t(ctx->smCount))), kThreads, smem, s>>>(mapA, mapB, p);
+        scanMmaSymKernel<<<unsigned(std::min<uint32_t>(pl.items, uint32_t(ctx->smCount))), kSymThreads, smem, s>>>(mapA, mapB, p);
         EM2_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
         return EM2_OK;
@@ -1923,19 +1972,21 @@ int launchScanSymDist(em2_context* ctx, const uint64_t* allSig, uint64_t cellCou
     void *permBuf = nullptr, *enc = nullptr;
     int rc = reserve(ctx, em2_context::S_PERM, uint64_t(ctx->world) * part.shard * sizeof(uint32_t), &permBuf);
     if (rc == EM2_OK) rc = reserve(ctx, em2_context::S_ENC, cellCount * K, &enc);
-    EM2_TRY(distAgree(ctx, rc));
     uint32_t* perm = static_cast<uint32_t*>(permBuf);
     // scan order: every GPU groups ITS cells (similar rows into the same warps, similar columns into the same tiles);
     // positions [rank * shard, ...) hold a permutation of the same range of cell ids
-    if (rows) {
+    if (rc == EM2_OK && rows) {
         if (ctx->rowGrouping == 1) {
             iotaKernel<<<unsigned((rows + 255) / 256), 256, 0, s>>>(perm + part.rowBegin, rows, uint32_t(part.rowBegin));
-            EM2_CUDA(ctx, cudaGetLastError());
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, EM2_ERR_CUDA, "iotaKernel launch failed");
             ctx->stats.kernel_launches++;
         } else {
-            EM2_TRY(groupRows(ctx, allSig, W, lshCount, tau0, part.rowBegin, rows, perm + part.rowBegin, s));
+            rc = groupRows(ctx, allSig, W, lshCount, tau0, part.rowBegin, rows, perm + part.rowBegin, s);
         }
     }
+    // In the one-process driver no rank allocates device memory between an agreement and the collective behind it: an
+    // allocation may wait for OTHER devices (peer mappings), whose NCCL kernels wait for this rank's.
+    EM2_TRY(distAgree(ctx, rc));
     EM2_TRY(distAllGather(ctx, perm, part.shard, sizeof(uint32_t), s));
     {
         const uint64_t threads = cellCount * (K / 16);

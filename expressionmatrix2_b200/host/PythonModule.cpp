@@ -122,5 +122,5 @@ PYBIND11_MODULE(ExpressionMatrix2, module)
     module.def("readSimilarPairs", &readSimilarPairs, arg("directoryName"), arg("similarPairsName"));
     module.def("writeSimilarPairs", &writeSimilarPairs, arg("directoryName"), arg("similarPairsName"),
                arg("geneSetName"), arg("cellSetName"), arg("ids"), arg("similarities"), arg("usedCount"));
-    module.def("gpuName", [] { return Gpu::instance().name(); }, "Name of the CUDA device the engine runs on.");
+    module.def("gpuName", [] { return GpuSet::instance().name(); }, "The CUDA devices the engine runs on (all visible ones, or $EM2_DEVICES).");
 }
