@@ -62,6 +62,23 @@ __device__ __forceinline__ void prefetchMap(const CUtensorMap* map)
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// One lane of the (converged) warp: the issue loops of the MMA warps run on all 32 lanes with uniform control flow and
+// only the tcgen05 instructions sit behind this predicate -- inside an `if (lane == 0)` region the compiler cannot keep
+// the descriptors in uniform registers and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+// (~20 SASS instructions per MMA from one thread: as long as the MMA itself at K = 32).
+__device__ __forceinline__ bool electOne()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 -----------------------------------------------------------------------------------
 __device__ __forceinline__ void fenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

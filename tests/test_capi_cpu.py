@@ -71,3 +71,29 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "em2_oracle" not in text and "libem2ref" not in text, f
+
+
+def test_dist_partition_rule(em2):
+    """em2_dist_partition (no GPU needed): rank r owns [r S, (r + 1) S) with S a multiple of 256 when there is more than
+    one rank; the Python mirror used by bench.py / the gloo tests (parallel.Partition) follows the same rule."""
+    from expressionmatrix2_b200.parallel import Partition
+    for N in (0, 1, 255, 256, 257, 1000, 100_000, 1_000_000, 1_300_000):
+        for P in (1, 2, 3, 4, 8):
+            covered = 0
+            for r in range(P):
+                b, e, sh = em2.dist_partition(N, P, r)
+                assert b == covered and b <= e <= N and e - b <= sh
+                assert P == 1 or sh % 256 == 0
+                part = Partition(N, P, r)
+                assert (part.row_begin, part.row_end, part.shard) == (b, e, sh)
+                covered = e
+            assert covered == N
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_gpu(em2):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(em2.Em2Error) as e:
+        em2.MultiEngine()
+    assert "no CPU fallback" in str(e.value)
