@@ -449,35 +449,35 @@ scanMmaSsKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else if (warp == kEpiWarps + 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t tileIter = 0, stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
-                const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
-                const uint32_t tiles = uint32_t((it.colEnd - it.colBegin + kSsTileN - 1) / kSsTileN);
-                for (uint32_t t = 0; t < tiles; t++, tileIter++) {
-                    const uint32_t buf = tileIter & 1;
-                    mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
+        // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues (tc05.cuh, electOne) =====================
+        uint32_t tileIter = 0, stage = 0, phase = 0;
+        const uint32_t ringBase = smemAddr(ring);
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, p.cellCount);
+            const uint32_t tiles = uint32_t((it.colEnd - it.colBegin + kSsTileN - 1) / kSsTileN);
+            for (uint32_t t = 0; t < tiles; t++, tileIter++) {
+                const uint32_t buf = tileIter & 1;
+                mbarWait(accEmpty + buf, ((tileIter >> 1) & 1) ^ 1);
+                fenceAfter();
+                const uint32_t tmemD = tmemBase + buf * kSsTileN;
+                for (uint32_t kc = 0; kc < p.panels; kc++) {
+                    mbarWait(full + stage, phase);
                     fenceAfter();
-                    const uint32_t tmemD = tmemBase + buf * kSsTileN;
-                    uint32_t accumulate = 0;
-                    for (uint32_t kc = 0; kc < p.panels; kc++) {
-                        mbarWait(full + stage, phase);
-                        fenceAfter();
-                        const uint32_t aAddr = smemAddr(ring + size_t(stage) * kSsStageBytes);
-                        const uint32_t bAddr = aAddr + kSsABytes;
+                    const uint64_t descA = makeSmemDesc(ringBase + stage * kSsStageBytes);
+                    const uint64_t descB = makeSmemDesc(ringBase + stage * kSsStageBytes + kSsABytes);
+                    if (electOne()) {
 #pragma unroll
-                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++) {
-                            mmaI8Ss(tmemD, makeSmemDesc(aAddr + ks * kUmmaK), makeSmemDesc(bAddr + ks * kUmmaK), kInstrDescSs, accumulate);
-                            accumulate = 1;
-                        }
+                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++)      // + 32 bytes along K = + 2 in the descriptor's address field
+                            mmaI8Ss(tmemD, descA + uint64_t(ks * (kUmmaK >> 4)), descB + uint64_t(ks * (kUmmaK >> 4)), kInstrDescSs,
+                                    (kc | uint32_t(ks)) != 0 ? 1u : 0u);
                         commit(empty + stage);
-                        if (++stage == kSsStages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        if (kc + 1 == p.panels) commit(accFull + buf);
                     }
-                    commit(accFull + buf);
+                    __syncwarp();
+                    if (++stage == kSsStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }

@@ -335,33 +335,35 @@ sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, tileIter = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, tileIter++) {
-                mbarWait(accEmpty, (tileIter & 1) ^ 1);
+        // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues (tc05.cuh, electOne) =====================
+        uint32_t stage = 0, phase = 0, tileIter = 0;
+        const uint32_t ringBase = smemAddr(ring);
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, tileIter++) {
+            mbarWait(accEmpty, (tileIter & 1) ^ 1);
+            fenceAfter();
+            const uint32_t tmemD = tmemBase;
+            for (uint32_t kc = 0; kc < p.kChunks; kc++) {
+                mbarWait(full + stage, phase);
                 fenceAfter();
-                const uint32_t tmemD = tmemBase;
-                uint32_t accumulate = 0;
-                for (uint32_t kc = 0; kc < p.kChunks; kc++) {
-                    mbarWait(full + stage, phase);
-                    fenceAfter();
-                    const uint32_t aAddr = smemAddr(ring + size_t(stage) * kFStageBytes);
-                    const uint32_t bAddr = aAddr + kFABytes;
+                const uint32_t aAddr = ringBase + stage * kFStageBytes;
+                const uint64_t descA = makeSmemDesc(aAddr);
+                const uint64_t descB0 = makeSmemDesc(aAddr + kFABytes);
+                const uint64_t descB1 = makeSmemDesc(aAddr + kFABytes + 256 * kFChunk);
+                if (electOne()) {
 #pragma unroll
-                    for (int ks = 0; ks < kFChunk / 32; ks++) {
-                        const uint64_t descA = makeSmemDesc(aAddr + ks * 32);
-                        mmaI8Ss(tmemD, descA, makeSmemDesc(bAddr + ks * 32), p.idesc256, accumulate);
-                        mmaI8Ss(tmemD + 256, descA, makeSmemDesc(bAddr + 256 * kFChunk + ks * 32), p.idesc128, accumulate);
-                        accumulate = 1;
+                    for (int ks = 0; ks < kFChunk / 32; ks++) {      // + 32 bytes along K = + 2 in the descriptor's address field
+                        const uint32_t accumulate = (kc | uint32_t(ks)) != 0 ? 1u : 0u;
+                        mmaI8Ss(tmemD, descA + uint64_t(2 * ks), descB0 + uint64_t(2 * ks), p.idesc256, accumulate);
+                        mmaI8Ss(tmemD + 256, descA + uint64_t(2 * ks), descB1 + uint64_t(2 * ks), p.idesc128, accumulate);
                     }
                     commit(empty + stage);
-                    if (++stage == kFStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    if (kc + 1 == p.kChunks) commit(accFull);
                 }
-                commit(accFull);
+                __syncwarp();
+                if (++stage == kFStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
         }
     } else {
