@@ -375,9 +375,11 @@ def _scan_roofline(em2, eng, peaks, variant, variant_used, rows, N, L, W, k, wor
             pass
         popc_peak = popc_peak or 4.6e12
         # algorithmic unit = one unordered pair = 2W 32-bit popcount-words
+        # the kernel folds three words into two POPCs with carry-save adders: (2W * 2 / 3, rounded up) + 1 POPC per ordered pair
+        popc_per_pair = (2 * W * 2 + 2) // 3 + 1
         roof = dict(bound="alu", unit="Gpopc32/s", achieved=alg_pairs * 2 * W / scan_s / 1e9, peak=popc_peak / 1e9,
                     peak_source="POPC.b32 issue rate measured by tools/microbench.cu on this GPU",
-                    executed=ordered * 2 * W / scan_s / 1e9)
+                    executed=ordered * popc_per_pair / scan_s / 1e9)
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["executed_frac"] = roof["executed"] / roof["peak"]
     roof["kernel"] = "scan_topk (encode + scanMmaKernel/scanPopc*Kernel + finalize)"

@@ -9,10 +9,96 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 namespace em2 {
 
 static thread_local std::string g_createError;
+
+// Helper threads of the pageable-memory staging: one memcpy thread moves ~8-10 GB/s out of the page cache, a PCIe 5 x16
+// link takes 55 -- a piece is cut into slices copied side by side (1 M-cell job through the C++ host layer: 12 GB of
+// mapped counts, 1.4 s single threaded).
+class ParallelCopier {
+public:
+    explicit ParallelCopier(int helpers)
+    {
+        for (int i = 0; i < helpers; i++) threads_.emplace_back([this, i] { loop(i); });
+    }
+    ~ParallelCopier()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            quit_ = true;
+        }
+        cvJob_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+        const size_t parts = threads_.size() + 1;
+        if (bytes < (size_t(1) << 20) || parts == 1) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t slice = ((bytes + parts - 1) / parts + 4095) & ~size_t(4095);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            dst_ = static_cast<char*>(dst);
+            src_ = static_cast<const char*>(src);
+            bytes_ = bytes;
+            slice_ = slice;
+            pending_ = int(threads_.size());
+            generation_++;
+        }
+        cvJob_.notify_all();
+        const size_t b = std::min(bytes, slice * threads_.size());      // the caller takes the last slice
+        if (b < bytes) std::memcpy(static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, bytes - b);
+        std::unique_lock<std::mutex> lock(m_);
+        cvDone_.wait(lock, [this] { return pending_ == 0; });
+    }
+
+private:
+    void loop(int index)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lock(m_);
+            cvJob_.wait(lock, [&] { return quit_ || generation_ != seen; });
+            if (quit_) return;
+            seen = generation_;
+            char* dst = dst_;
+            const char* src = src_;
+            const size_t b = std::min(bytes_, slice_ * size_t(index)), e = std::min(bytes_, b + slice_);
+            lock.unlock();
+            if (e > b) std::memcpy(dst + b, src + b, e - b);
+            lock.lock();
+            if (--pending_ == 0) cvDone_.notify_all();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cvJob_, cvDone_;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0, slice_ = 0;
+    int pending_ = 0;
+    uint64_t generation_ = 0;
+    bool quit_ = false;
+};
+
+static ParallelCopier* copierOf(em2_context* ctx)
+{
+    if (!ctx->copier) ctx->copier = new ParallelCopier(ctx->stageThreads > 0 ? ctx->stageThreads - 1 : 3);
+    return static_cast<ParallelCopier*>(ctx->copier);
+}
+
+void destroyCopier(em2_context* ctx)
+{
+    delete static_cast<ParallelCopier*>(ctx->copier);
+    ctx->copier = nullptr;
+}
 
 int fail(em2_context* ctx, int code, const std::string& message)
 {
@@ -89,6 +175,8 @@ int makeTensorMapU8(em2_context* ctx, CUtensorMap* map, const void* base, uint64
     return EM2_OK;
 }
 
+constexpr size_t kBouncePiece = size_t(32) << 20;
+
 double nowMs()
 {
     return 1e-6 * double(std::chrono::duration_cast<std::chrono::nanoseconds>(
@@ -112,7 +200,7 @@ void resetStats(em2_context* ctx)
 // memory -- the usual case: the C++ host layer hands over mmap regions of MemoryMapped::Vector files, whose pages
 // cannot be pinned reliably ("Ownership") -- is staged through two library-owned pinned bounce buffers:
 // the host thread copies piece i + 1 into one buffer while the copy engine moves piece i out of the other, so the
-// transfer is asynchronous to the compute stream either way.
+// transfer is asynchronous to the compute stream either way.  The host-side copy runs on `stage_threads` threads (default 4).
 int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s)
 {
     if (bytes == 0) return EM2_OK;
@@ -124,7 +212,7 @@ int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
         EM2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
         return EM2_OK;
     }
-    constexpr size_t kPiece = size_t(16) << 20;
+    constexpr size_t kPiece = kBouncePiece;
     if (!ctx->bounce[0]) {
         for (int i = 0; i < 2; i++) {
             EM2_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], kPiece));
@@ -134,7 +222,7 @@ int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
     for (size_t off = 0, i = ctx->bounceNext; off < bytes; off += kPiece, i ^= 1, ctx->bounceNext = int(i)) {
         const size_t n = std::min(kPiece, bytes - off);
         EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[i]));      // the copy that last read this buffer is done
-        std::memcpy(ctx->bounce[i], static_cast<const char*>(src) + off, n);
+        copierOf(ctx)->copy(ctx->bounce[i], static_cast<const char*>(src) + off, n);
         EM2_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(dst) + off, ctx->bounce[i], n, cudaMemcpyHostToDevice, s));
         EM2_CUDA(ctx, cudaEventRecord(ctx->bounceFree[i], s));
         ctx->stats.bounced_bytes += n;
@@ -154,7 +242,7 @@ int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
         EM2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
         return EM2_OK;
     }
-    constexpr size_t kPiece = size_t(16) << 20;
+    constexpr size_t kPiece = kBouncePiece;
     if (!ctx->bounce[0]) {
         for (int i = 0; i < 2; i++) {
             EM2_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], kPiece));
@@ -170,7 +258,7 @@ int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
         const size_t n = std::min(kPiece, bytes - off);
         if (pendingBytes[i]) {
             EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[i]));
-            std::memcpy(static_cast<char*>(dst) + pendingOff[i], ctx->bounce[i], pendingBytes[i]);
+            copierOf(ctx)->copy(static_cast<char*>(dst) + pendingOff[i], ctx->bounce[i], pendingBytes[i]);
         }
         EM2_CUDA(ctx, cudaMemcpyAsync(ctx->bounce[i], static_cast<const char*>(src) + off, n, cudaMemcpyDeviceToHost, s));
         EM2_CUDA(ctx, cudaEventRecord(ctx->bounceFree[i], s));
@@ -181,7 +269,7 @@ int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
     for (int j = 0; j < 2; j++, i ^= 1)
         if (pendingBytes[i]) {
             EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[i]));
-            std::memcpy(static_cast<char*>(dst) + pendingOff[i], ctx->bounce[i], pendingBytes[i]);
+            copierOf(ctx)->copy(static_cast<char*>(dst) + pendingOff[i], ctx->bounce[i], pendingBytes[i]);
         }
     ctx->bounceNext = i;
     return EM2_OK;
@@ -282,6 +370,7 @@ void em2_destroy(em2_context* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     commDestroy(ctx);
+    destroyCopier(ctx);
     for (int i = 0; i < 2; i++) {
         if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
         if (ctx->bounceFree[i]) cudaEventDestroy(ctx->bounceFree[i]);
@@ -346,7 +435,12 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     else if (n == "mma_kernel" && value >= 0 && value <= 2) ctx->mmaKernel = int(value);
     else if (n == "mma_cta_pair" && value >= 0 && value <= 1) ctx->mmaCtaPair = int(value);
     else if (n == "exact_matrix_bytes" && value >= 0) ctx->exactMatrixBytes = uint64_t(value);
+    else if (n == "sym_cta_pair" && value >= 0 && value <= 1) ctx->symCtaPair = int(value);
     else if (n == "sym_near_half_width" && value >= 0 && value <= 100000) ctx->symNearHalfWidth = int(value);
+    else if (n == "stage_threads" && value >= 0 && value <= 64) {
+        destroyCopier(ctx);
+        ctx->stageThreads = int(value);
+    }
     else if (n == "no_bounce" && value >= 0 && value <= 1) ctx->noBounce = int(value);
     else if (n == "filter_uncertain_cap" && value >= 0 && value <= (1 << 28)) ctx->filterUncertainCap = uint32_t(value);
     else return fail(ctx, EM2_ERR_INVALID, "em2_set_option: unknown option or value out of range: " + n);

@@ -78,7 +78,7 @@ struct em2_context {
     int debugFlags = 0;                // bit 0: no bound sharing between MMA sub-streams; bit 1: memory prune
     int rowGrouping = 0;               // MMA scan: 0 auto (group similar rows into the same warps), 1 off, 2 on
     int mmaKernel = 0;                 // MMA scan kernel: 0 auto, 1 A operand resident in TMEM (L <= 1024), 2 streamed operands
-    int scanSymmetric = 0;             // whole-matrix MMA scans, symmetric kernel (every unordered pair once): 0 auto (400k..2M cells), 1 off, 2 whenever eligible
+    int scanSymmetric = 0;             // whole-matrix MMA scans, symmetric kernel (every unordered pair once): 0 auto (65,536..2M cells), 1 off, 2 whenever eligible
     int mmaCtaPair = 0;                // 1: the MMA scan runs on CTA pairs (cta_group::2, M = 256)
     int denseWarpKernel = 0;           // 1: dense expansion of the filter path with the warp-per-cell kernel (tests / comparison)
     int filterCountsSigned = 0;   // 1: dense counts as s8 (<= 127) instead of u8 (<= 255) in the filter GEMM
@@ -89,6 +89,8 @@ struct em2_context {
     cudaEvent_t bounceFree[2] = {nullptr, nullptr};
     int bounceNext = 0;
     int noBounce = 0;                  // option "no_bounce": 1 = hand pageable pointers straight to cudaMemcpyAsync
+    void* copier = nullptr;            // helper threads of the host-side staging copies (capi.cu, ParallelCopier)
+    int stageThreads = 0;              // option "stage_threads": threads per staging copy (0 = 4)
     // multi-GPU (multi.cu): this context is rank `rank` of `world`; comm is an ncclComm_t
     void* comm = nullptr;
     int rank = 0, world = 1;
@@ -98,6 +100,7 @@ struct em2_context {
     void* agreeUser = nullptr;
     bool distTimed = false;            // ev[12], ev[13] bracket the last signature all-gather
     bool symExchangeTimed = false;     // ev[10], ev[11] bracket the symmetric scan's candidate exchange
+    int symCtaPair = 0;                // option "sym_cta_pair": symmetric scan on CTA pairs (cta_group::2): 0 = yes, 1 = single CTAs
     int symNearHalfWidth = 0;          // option "sym_near_half_width": super blocks on each side of the near window (0 = automatic)
 };
 

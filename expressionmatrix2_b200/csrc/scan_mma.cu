@@ -622,6 +622,7 @@ constexpr uint32_t kPaceWindow = 256;      // tiles a CTA may run ahead of the s
 constexpr uint32_t kSymSmallBytes = 192 + 2 * kSsTileN * 2 + 2 * (kSsTileN / 8) * 2 + kEpiThreads * 2;
 constexpr int kMaxInboxSources = 8;        // GPUs whose column-direction candidates a cell's merge reads
 constexpr int kSymThreads = kThreads + 32;  // + one warp that stages the column thresholds
+constexpr uint32_t kInstrDescSsPair = (kInstrDescSs & ~(0x1Fu << 24)) | (uint32_t(kPairRows >> 4) << 24);   // M = 256 over two CTAs, N = 256
 
 struct SymParams {
     uint64_t cellCount;            // N: scan positions of the WHOLE job (all ranks); rows == columns
@@ -667,13 +668,22 @@ static __device__ __noinline__ ulonglong2* nextLogChunk(uint32_t* chunkFill, uin
     return pool + uint64_t(c) * kLogChunk;
 }
 
+// PAIR: the two CTAs of a cluster (the two SMs of a TPC) take the two row blocks of ONE super block and run every tile
+// as one M = 256 instruction (tcgen05.mma.cta_group::2): each CTA keeps its own 128 rows of A and of the accumulators and
+// streams HALF of every B tile (its 128 columns; 16 KB per K chunk), the leader (cluster rank 0) issues.  Per 128 x 256 x 32
+// MMA an SM then reads 8 KB of shared memory instead of 12 KB -- the operand traffic of the TMEM-operand form, whose
+// issue rate is 4223 TOP/s against the 3414 of the single-CTA shared-memory form -- and the L2 -> SM traffic halves.
+// Barriers: full[] / accEmpty[] / aFull live in the leader (both CTAs' TMA bytes and epilogue warps arrive there),
+// empty[] / accFull[] / aEmpty are per CTA and receive the leader's multicast commits.
+template <bool PAIR>
 __global__ void __launch_bounds__(kSymThreads, 1)
 scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SymParams p)
 {
+    constexpr uint32_t kBStageBytes = PAIR ? kSsBBytes / 2 : kSsBBytes;      // PAIR: this CTA's 128 columns of a K chunk
     extern __shared__ uint8_t smemRaw[];
     uint8_t* smA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = smA + size_t(p.panels) * kSsABytes;
-    uint8_t* small = ring + size_t(p.stages) * kSsBBytes;
+    uint8_t* small = ring + size_t(p.stages) * kBStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(small);
     uint64_t* accFull = bars + 0;    // [2]
     uint64_t* accEmpty = bars + 2;   // [2]
@@ -690,10 +700,13 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? clusterRank() : 0;
+    const uint32_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+    const uint32_t workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
             mbarInit(accFull + i, 1);
-            mbarInit(accEmpty + i, kEpiWarps * 32);
+            mbarInit(accEmpty + i, PAIR ? 2 * kEpiWarps : kEpiWarps * 32);      // PAIR: one arrival per epilogue warp of either CTA
             mbarInit(thrFull + i, 1);
             mbarInit(thrEmpty + i, kEpiWarps);
         }
@@ -705,9 +718,13 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         mbarInitFence();
     }
-    if (warp == kEpiWarps) tmemAlloc(tmemSlot, 512);
+    if (warp == kEpiWarps) {
+        if (PAIR) tmemAllocPair(tmemSlot, 512);
+        else tmemAlloc(tmemSlot, 512);
+    }
     fenceBefore();
-    __syncthreads();
+    if (PAIR) clusterSync();      // barriers of both CTAs are initialised before anyone signals across
+    else __syncthreads();
     fenceAfter();
     const uint32_t tmemBase = *tmemSlot;
     const uint32_t items = p.items;
@@ -715,6 +732,8 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const uint32_t N = uint32_t(p.cellCount);
     const uint32_t S = p.superBlocks;
     const uint32_t firstBlock = p.posBegin / kRowsPerItem;
+    // row block of an item within this GPU's rows: PAIR items are super blocks, this CTA takes half `rank`
+    auto rowBlockOf = [rank](const ScanItem& it) -> uint32_t { return PAIR ? 2 * it.rowBlock + rank : it.rowBlock; };
     // column super block of offset d (may be negative) for the row super block `super`
     auto colSuperOf = [S](uint32_t super, int32_t d) -> uint32_t {
         int64_t c = (int64_t(super) - int64_t(d)) % int64_t(S);
@@ -729,27 +748,34 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // L2 147 times; without pacing a CTA that falls behind starts missing L2, gets slower still, and the sweep
         // settles DRAM-bound (1 M cells: 3.25 TB read from DRAM, L2 hit rate 33 %, tensor pipe 47 %).
         uint32_t stage = 0, phase = 0, itemIter = 0, tileIter = 0;
-        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+        for (uint32_t item = worker; item < items; item += workers, itemIter++) {
             const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
-            const uint32_t super = (firstBlock + it.rowBlock) >> 1;
+            const uint32_t super = (firstBlock + rowBlockOf(it)) >> 1;
             const int32_t d0 = p.dBegin + int32_t(it.colBegin / kSsTileN);
             const int32_t d1 = p.dBegin + int32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
-            const bool paced = p.progress != nullptr && item < p.mainBlocks;
+            // PAIR: the leader paces for the pair (its partner cannot run ahead of the leader's MMAs anyway)
+            const bool paced = p.progress != nullptr && item < p.mainBlocks && rank == 0;
             if (lane == 0) {
-                if (p.progress && !paced) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
+                if (p.progress && !paced && rank == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + worker) = 0xffffffffu;
                 mbarWait(aEmpty, (itemIter & 1) ^ 1);
-                mbarExpectTx(aFull, p.panels * kSsABytes);
-                for (uint32_t kc = 0; kc < p.panels; kc++)
-                    tmaLoad2d(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes),
-                              int32_t(p.posBegin + it.rowBlock * kRowsPerItem));
+                const int32_t rowA = int32_t(p.posBegin + rowBlockOf(it) * kRowsPerItem);
+                if (PAIR) {
+                    if (rank == 0) mbarExpectTx(aFull, 2 * p.panels * kSsABytes);      // both CTAs' bytes
+                    for (uint32_t kc = 0; kc < p.panels; kc++)
+                        tmaLoad2dPair(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes), rowA);
+                } else {
+                    mbarExpectTx(aFull, p.panels * kSsABytes);
+                    for (uint32_t kc = 0; kc < p.panels; kc++)
+                        tmaLoad2d(smA + size_t(kc) * kSsABytes, &mapA, aFull, int32_t(kc * kChunkBytes), rowA);
+                }
             }
             for (int32_t d = d0; d < d1; d++, tileIter++) {
                 if (paced && ((d - d0) & 7) == 0) {
                     const uint32_t vt = itemIter * p.offsetsHere + uint32_t(d - d0);
-                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = vt;
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + worker) = vt;
                     for (int spin = 0; spin < 4000; spin++) {           // bounded: pacing is an optimisation, never a dependency
                         uint32_t slowest = 0xffffffffu;
-                        for (uint32_t c = lane; c < gridDim.x; c += 32)
+                        for (uint32_t c = lane; c < workers; c += 32)
                             slowest = min(slowest, *reinterpret_cast<volatile const uint32_t*>(p.progress + c));
                         slowest = __reduce_min_sync(0xffffffffu, slowest);
                         if (slowest >= vt || slowest + kPaceWindow >= vt) break;
@@ -758,11 +784,16 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
                 const uint32_t colSuper = colSuperOf(super, d);
                 if (lane == 0) {
-                    const int32_t col0 = int32_t(colSuper * kSsTileN);
+                    const int32_t col0 = int32_t(colSuper * kSsTileN + (PAIR ? rank * (kSsTileN / 2) : 0));
                     for (uint32_t kc = 0; kc < p.panels; kc++) {
                         mbarWait(empty + stage, phase ^ 1);
-                        mbarExpectTx(full + stage, kSsBBytes);
-                        tmaLoad2d(ring + size_t(stage) * kSsBBytes, &mapB, full + stage, int32_t(kc * kChunkBytes), col0);
+                        if (PAIR) {      // this CTA's 128 columns (mapA's box is 128 rows); the leader's barrier collects both halves
+                            if (rank == 0) mbarExpectTx(full + stage, 2 * kBStageBytes);
+                            tmaLoad2dPair(ring + size_t(stage) * kBStageBytes, &mapA, full + stage, int32_t(kc * kChunkBytes), col0);
+                        } else {
+                            mbarExpectTx(full + stage, kSsBBytes);
+                            tmaLoad2d(ring + size_t(stage) * kSsBBytes, &mapB, full + stage, int32_t(kc * kChunkBytes), col0);
+                        }
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -772,7 +803,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 __syncwarp();
             }
         }
-        if (lane == 0 && p.progress) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.x) = 0xffffffffu;
+        if (lane == 0 && p.progress && rank == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + worker) = 0xffffffffu;
     } else if (warp == kEpiWarps + 2) {
         // ===================== threshold warp: the bounds of every tile's 256 column cells as dot-product thresholds =====================
         // lane = one group of 8 columns.  Runs up to two tiles ahead of the epilogue (two slots), so the L2 round trip
@@ -781,9 +812,9 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // TMA loads it starved the 3-stage B ring (tensor pipe 45 %, 62 % of the samples waiting for thresholds).
         if (!p.rowOnly) {
             uint32_t tileIter = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            for (uint32_t item = worker; item < items; item += workers) {
                 const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
-                const uint32_t super = (firstBlock + it.rowBlock) >> 1;
+                const uint32_t super = (firstBlock + rowBlockOf(it)) >> 1;
                 const int32_t d0 = p.dBegin + int32_t(it.colBegin / kSsTileN);
                 const int32_t d1 = p.dBegin + int32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
                 for (int32_t d = d0; d < d1; d++, tileIter++) {
@@ -817,7 +848,7 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         uint32_t tileIter = 0, stage = 0, phase = 0, itemIter = 0;
         const uint32_t aBase = smemAddr(smA);
         const uint32_t ringBase = smemAddr(ring);
-        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, itemIter++) {
+        for (uint32_t item = worker; item < items && rank == 0; item += workers, itemIter++) {
             const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
             const uint32_t tiles = uint32_t((it.colEnd + kSsTileN - 1) / kSsTileN) - uint32_t(it.colBegin / kSsTileN);
             mbarWait(aFull, itemIter & 1);
@@ -831,18 +862,28 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     mbarWait(full + stage, phase);
                     fenceAfter();
                     const uint64_t descA = makeSmemDesc(aBase + kc * kSsABytes);
-                    const uint64_t descB = makeSmemDesc(ringBase + stage * kSsBBytes);
+                    const uint64_t descB = makeSmemDesc(ringBase + stage * kBStageBytes);
                     if (electOne()) {
 #pragma unroll
-                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++)      // + 32 bytes along K = + 2 in the descriptor's address field
-                            mmaI8Ss(tmemD, descA + uint64_t(ks * (kUmmaK >> 4)), descB + uint64_t(ks * (kUmmaK >> 4)), kInstrDescSs,
-                                    (kc | uint32_t(ks)) != 0 ? 1u : 0u);
-                        commit(empty + stage);
-                        // the same lane commits everything it issued: the tile's accumulator, and after the item's last
-                        // tile the A operand (the producer may then overwrite it)
-                        if (kc + 1 == p.panels) {
-                            commit(accFull + buf);
-                            if (t + 1 == tiles) commit(aEmpty);
+                        for (int ks = 0; ks < kChunkBytes / kUmmaK; ks++) {      // + 32 bytes along K = + 2 in the descriptor's address field
+                            const uint32_t accumulate = (kc | uint32_t(ks)) != 0 ? 1u : 0u;
+                            if (PAIR) mmaI8SsPair(tmemD, descA + uint64_t(ks * (kUmmaK >> 4)), descB + uint64_t(ks * (kUmmaK >> 4)), kInstrDescSsPair, accumulate);
+                            else mmaI8Ss(tmemD, descA + uint64_t(ks * (kUmmaK >> 4)), descB + uint64_t(ks * (kUmmaK >> 4)), kInstrDescSs, accumulate);
+                        }
+                        // the same lane commits everything it issued: the ring stage, the tile's accumulator, and after the
+                        // item's last tile the A operand (the producer may then overwrite it); PAIR: in both CTAs
+                        if (PAIR) {
+                            commitPair(empty + stage);
+                            if (kc + 1 == p.panels) {
+                                commitPair(accFull + buf);
+                                if (t + 1 == tiles) commitPair(aEmpty);
+                            }
+                        } else {
+                            commit(empty + stage);
+                            if (kc + 1 == p.panels) {
+                                commit(accFull + buf);
+                                if (t + 1 == tiles) commit(aEmpty);
+                            }
                         }
                     }
                     __syncwarp();
@@ -864,13 +905,13 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         uint32_t tileIter = 0;
         ulonglong2* logNext = nullptr;           // next free entry of the thread's current log chunk
         uint32_t logFill = kLogChunk;            // entries used in it (no chunk yet)
-        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+        for (uint32_t item = worker; item < items; item += workers) {
             const ScanItem it = decodeScanItem(item, p.mainBlocks, p.segments, p.segmentCols, virtualCols);
             const uint32_t seg = it.segment;
-            const uint32_t super = (firstBlock + it.rowBlock) >> 1;
+            const uint32_t super = (firstBlock + rowBlockOf(it)) >> 1;
             const int32_t d0 = p.dBegin + int32_t(it.colBegin / kSsTileN);
             const int32_t d1 = p.dBegin + int32_t((it.colEnd + kSsTileN - 1) / kSsTileN);
-            const uint32_t rowLocal = it.rowBlock * kRowsPerItem + rowInItem;
+            const uint32_t rowLocal = rowBlockOf(it) * kRowsPerItem + rowInItem;
             const bool valid = rowLocal < p.ownRows;
             const uint32_t rowPos = p.posBegin + rowLocal;
             const uint32_t rowCell = !valid ? 0xffffffffu : p.perm ? p.perm[rowPos] : rowPos;
@@ -916,7 +957,12 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tmemLoadWait();
                     if (c + 32 == kSubCols) {          // last chunk is in registers: hand the accumulator back
                         fenceBefore();
-                        mbarArrive(accEmpty + buf);
+                        if (PAIR) {
+                            __syncwarp();
+                            if (lane == 0) mbarArriveLeader(accEmpty + buf);
+                        } else {
+                            mbarArrive(accEmpty + buf);
+                        }
                     }
                     int32_t m[4];
 #pragma unroll
@@ -996,8 +1042,13 @@ scanMmaSymKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     }
     fenceBefore();
-    __syncthreads();
-    if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
+    if (PAIR) {
+        clusterSync();        // neither CTA may retire while its partner can still signal into it
+        if (warp == kEpiWarps) tmemDeallocPair(tmemBase, 512);
+    } else {
+        __syncthreads();
+        if (warp == kEpiWarps) tmemDealloc(tmemBase, 512);
+    }
 }
 
 // Files the column-direction log into per-cell inboxes of exactly the needed length (count -> exclusive scan -> fill,
@@ -1450,9 +1501,13 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     ScanPlan nearPlan{}, farPlan{};
     uint32_t cap = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
     uint32_t streams = kSubStreams;
+    // CTA pairs (cta_group::2; an item = one super block of 256 rows) unless option "sym_cta_pair" = 1
+    const bool pair = ctx->symCtaPair != 1 && ctx->smCount >= 2;
+    const uint32_t rowsPerItem = pair ? kPairRows : kRowsPerItem;
+    const uint32_t slots = pair ? uint32_t(ctx->smCount / 2) : uint32_t(ctx->smCount);
     if (ownRows) {
-        nearPlan = makeScanPlan(ctx, ownRows, uint64_t(nearCount) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams);
-        farPlan = farCount ? makeScanPlan(ctx, ownRows, uint64_t(farCount) * kSsTileN, k, kSsTileN, kRowsPerItem, 1, kSubStreams) : nearPlan;
+        nearPlan = makeScanPlan(ctx, ownRows, uint64_t(nearCount) * kSsTileN, k, kSsTileN, rowsPerItem, 1, kSubStreams, slots);
+        farPlan = farCount ? makeScanPlan(ctx, ownRows, uint64_t(farCount) * kSsTileN, k, kSsTileN, rowsPerItem, 1, kSubStreams, slots) : nearPlan;
         // small regions here: a cell's bound is published when its region is pruned, and the column direction of other
         // CTAs lives on fresh bounds (with the one-directional kernels' 4k + 32 keys: 90 M instead of 70 M survivors at config 2)
         nearPlan.cap = farPlan.cap = cap;
@@ -1532,7 +1587,8 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     p.K = K;
     p.panels = panels;
     const size_t budget = 227 * 1024 - 1024 - kSymSmallBytes - size_t(panels) * kSsABytes;
-    p.stages = uint32_t(std::min<size_t>(kSymMaxStages, budget / kSsBBytes));
+    const size_t bStageBytes = pair ? kSsBBytes / 2 : kSsBBytes;
+    p.stages = uint32_t(std::min<size_t>(kSymMaxStages, budget / bStageBytes));
     p.superBlocks = S;
     p.halfOffset = S % 2 == 0 ? S / 2 : 0;
     p.posBegin = uint32_t(posBegin);
@@ -1553,8 +1609,9 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
     CUtensorMap mapA, mapB;
     EM2_TRY(makeTensorMapU8(ctx, &mapA, encP, N, K, K, kRowsPerItem));
     EM2_TRY(makeTensorMapU8(ctx, &mapB, encP, N, K, K, kSsTileN));
-    const size_t smem = 1024 + size_t(panels) * kSsABytes + size_t(p.stages) * kSsBBytes + kSymSmallBytes;
-    EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSymKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const size_t smem = 1024 + size_t(panels) * kSsABytes + size_t(p.stages) * bStageBytes + kSymSmallBytes;
+    EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSymKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    EM2_CUDA(ctx, cudaFuncSetAttribute(scanMmaSymKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     auto sweep = [&](const ScanPlan& pl, int32_t dBegin, uint32_t count, uint32_t resume, uint32_t rowOnly) -> int {
         if (!ownRows || !count) return EM2_OK;
         p.segBase = resume ? nearPlan.segments - 1 : 0;
@@ -1570,7 +1627,23 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
         // (390 tiles per item) the sweep was 1.5x SLOWER, at 1 M cells (1953 tiles) 1.2x faster
         p.progress = (count >= 768 && !(ctx->debugFlags & 16)) ? progress : nullptr;
         if (p.progress) EM2_CUDA(ctx, cudaMemsetAsync(progress, 0, 1024 * sizeof(uint32_t), s));
-        scanMmaSymKernel<<<unsigned(std::min<uint32_t>(pl.items, uint32_t(ctx->smCount))), kSymThreads, smem, s>>>(mapA, mapB, p);
+        if (pair) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(kSymThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;      // the two CTAs of a pair: one TPC
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cfg.gridDim = dim3(2 * std::min<uint32_t>(pl.items, slots));
+            EM2_CUDA(ctx, cudaLaunchKernelEx(&cfg, scanMmaSymKernel<true>, mapA, mapB, p));
+        } else {
+            scanMmaSymKernel<false><<<unsigned(std::min<uint32_t>(pl.items, slots)), kSymThreads, smem, s>>>(mapA, mapB, p);
+        }
         EM2_CUDA(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
         return EM2_OK;
@@ -1794,11 +1867,10 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         const uint32_t capSym = scanCandidateCapacity(uint32_t(k), uint32_t(ctx->candCapExtra));
         const bool eligible = streamed && !dump && K <= kMaxPanels * kChunkBytes && rowBegin == 0 && rows == cellCount &&
                               capSym <= 32 * kPruneRegsPerLane && cellCount >= 1024 && tau0 > 0;
-        // "scan_symmetric" = 2 asks for the symmetric kernel whenever it is eligible.  AUTO takes it for 400k..2M cells:
-        // there the one-directional sweep sits at the power cap and the paced symmetric sweep is 1.3x faster (1 M clustered
-        // cells: 570 vs 756 ms); around 100k densely clustered cells it is 5-15 % slower -- the selection epilogue, not
-        // the MMA pipe, is what the sweep waits for -- and above 2 M cells its logs outgrow the memory.
-        bool automatic = ctx->scanSymmetric == 0 && cellCount >= 400000 && cellCount <= 2000000;
+        // "scan_symmetric" = 2 asks for the symmetric kernel whenever it is eligible.  AUTO takes it from 65,536 cells: with
+        // the near window and the leader-clustering scan order it wins from config 2's 100k cells on (8.2 vs 8.7 ms) and by
+        // 1.9x at 1 M cells; above 2 M cells per GPU its logs outgrow the memory.
+        bool automatic = ctx->scanSymmetric == 0 && cellCount >= 65536 && cellCount <= 2000000;
         if (automatic) {
             // its scratch (log pool 16 B + inbox 8 B per entry, 24 k entries per cell; candidate regions; sample) must fit
             // beside what is already allocated -- otherwise stay with the one-directional kernels instead of failing
@@ -1954,7 +2026,7 @@ bool distSymmetricEligible(const em2_context* ctx, uint64_t cellCount, uint64_t 
                           cellCount <= 0x7fffff00ull && mismatchMax >= 0 && k <= 1024;
     if (!eligible || ctx->scanSymmetric == 1) return false;
     if (ctx->scanSymmetric == 2) return true;
-    return cellCount >= 400000 && cellCount <= 2000000ull * uint64_t(ctx->world);
+    return cellCount >= 65536 && cellCount <= 2000000ull * uint64_t(ctx->world);
 }
 
 __global__ void iotaKernel(uint32_t* __restrict__ dst, uint64_t n, uint32_t first)

@@ -129,13 +129,15 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
  *   "mma_cta_pair"     1 = the TMEM-resident scan kernel runs on CTA pairs (cta_group::2)
  *   "row_grouping"     MMA scan: 1 = scan rows in cell order, 2 = always group similar rows into the same warps
  *   "scan_symmetric"   whole-matrix MMA scans (L <= 1024, k <= 112) that evaluate every unordered pair once: 0 = automatic
- *                      (400k..2M cells), 1 = never, 2 = whenever eligible (faster when the similarity threshold rejects
+ *                      (65,536..2M cells per GPU), 1 = never, 2 = whenever eligible (faster when the similarity threshold rejects
  *                      most pairs and on large jobs, 5-15 % slower on ~100k densely clustered cells)
  *   "cand_cap_extra"   candidate regions hold (2 + n) k + 32 keys;  "popc_csa" carry-save levels of the POPC scan (0..2)
  *   "exact_matrix_bytes" budget of the exact path's similarity matrix (default 48 GiB);  "exact_cta_pair" 1 = CTA-pair GEMM
  *   "exact_general"    1 = force the exact path's general FP64 kernel
+ *   "sym_cta_pair"     1 = the symmetric scan runs on single CTAs instead of CTA pairs (cta_group::2, M = 256)
  *   "sym_near_half_width" symmetric scan: super blocks (256 cells) on each side of a row's own that the near window covers
  *                      (0 = automatic: max(16, N / 32 columns in total))
+ *   "stage_threads"    host threads that copy a pageable buffer into / out of the pinned bounce buffers (0 = 4)
  *   "no_bounce"        1 = pageable host buffers go straight to cudaMemcpyAsync instead of through the pinned bounce buffers
  *   "debug_flags"      bit 0: no bound sharing between the MMA scan's sub-streams */
 int em2_set_option(em2_context* ctx, const char* name, int64_t value);
