@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--dir", default=None)
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--k", type=int, default=50)
+    ap.add_argument("--out", default=None, help="write the JSON line here (the C++ layer prints its progress to stdout)")
     args = ap.parse_args()
     w = SHAPES[args.workload]
     base = args.dir or ("/dev/shm/em2-e2e" if os.path.isdir("/dev/shm") else "/tmp/em2-e2e")
@@ -68,7 +69,12 @@ def main():
                mean_neighbours_stored=float(np.asarray(used).mean()),
                includes="hyperplane generation, SimilarPairs file creation, H2D from the mapped counts file and D2H into the mapped "
                         "Pairs file through pinned bounce buffers, msync on close")
-    print(json.dumps(out))
+    if args.out:
+        with open(args.out, "w") as f:
+            f.write(json.dumps(out) + "\n")
+    else:
+        sys.stdout.flush()
+        print(json.dumps(out), flush=True)
     shutil.rmtree(base, ignore_errors=True)
 
 
