@@ -100,6 +100,7 @@ struct em2_context {
     void* agreeUser = nullptr;
     bool distTimed = false;            // ev[12], ev[13] bracket the last signature all-gather
     bool symExchangeTimed = false;     // ev[10], ev[11] bracket the symmetric scan's candidate exchange
+    int lastNearHalfWidth = 0;         // near-window half width the last symmetric scan used (reported by debug_flags bit 3)
     int symCtaPair = 0;                // option "sym_cta_pair": symmetric scan on CTA pairs (cta_group::2): 0 = yes, 1 = single CTAs
     int symNearHalfWidth = 0;          // option "sym_near_half_width": super blocks on each side of the near window (0 = automatic)
 };

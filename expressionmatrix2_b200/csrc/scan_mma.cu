@@ -1424,6 +1424,28 @@ __global__ void pivotKeysKernel(uint64_t rowBegin, uint64_t rows, const uint32_t
     if (q < rows) keys[q] = (uint64_t(nearest[q]) << 32) | uint32_t(rowBegin + q);
 }
 
+// Cluster statistics of a grouping: cells per pivot (histogram), then the largest cluster, the number of cells no pivot
+// covers and the pivot count -> stats[0..2].  The symmetric scan sizes its near window by them.
+__global__ void pivotHistKernel(uint64_t rows, const uint32_t* __restrict__ nearest, const uint8_t* __restrict__ uncoveredFlag,
+                                uint32_t* __restrict__ hist, uint32_t* __restrict__ stats)
+{
+    const uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (q >= rows) return;
+    atomicAdd(hist + nearest[q], 1u);
+    if (uncoveredFlag[q]) atomicAdd(stats + 1, 1u);
+}
+
+__global__ void pivotStatsKernel(const uint32_t* __restrict__ hist, const PivotState* __restrict__ st, uint32_t* __restrict__ stats)
+{
+    uint32_t m = 0;
+    for (uint32_t i = threadIdx.x; i < kMaxPivots; i += blockDim.x) m = max(m, hist[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (threadIdx.x == 0) {
+        stats[0] = m;
+        stats[2] = st->count;
+    }
+}
+
 __global__ void keysToPermKernel(const unsigned long long* __restrict__ keys, uint64_t rows, uint32_t* __restrict__ perm)
 {
     const uint64_t q = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -1482,21 +1504,49 @@ __global__ void fillU32Kernel(uint32_t* __restrict__ dst, uint64_t n, uint32_t v
 //   5. merge per cell: own row streams + one inbox per GPU.
 // *overflowed != 0: a capacity ran out somewhere in the job and NOTHING that was written may be used -- every rank
 // reruns one-directionally (exactness never depends on the bounds being tight).
-int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, uint64_t cellCount, uint64_t posBegin, uint64_t ownRows,
-                 uint64_t shard, uint32_t K, uint64_t k, uint32_t tau0, const float* lut, em2_pair* pairs, uint32_t* usedCount,
-                 cudaStream_t s, int* overflowed)
+int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, const uint32_t* groupStats, bool grouped, uint64_t cellCount,
+                 uint64_t posBegin, uint64_t ownRows, uint64_t shard, uint32_t K, uint64_t k, uint32_t tau0, const float* lut,
+                 em2_pair* pairs, uint32_t* usedCount, cudaStream_t s, int* overflowed)
 {
     const uint64_t N = cellCount;
     const int P = ctx->world;
     const uint32_t panels = K / kChunkBytes;
     const uint32_t S = uint32_t((N + kSsTileN - 1) / kSsTileN);
+    *overflowed = 0;
+    // Half width of the near window, in super blocks.  Default: N/32 columns in total (what a sample must hold for the
+    // k-th best of unstructured data to be a useful bound).  When the scan order is a clustering that covers nearly every
+    // cell, a cell's neighbours lie inside its own cluster -- a contiguous run of the order -- and the window only has to
+    // span the largest cluster (1 M cells in 512 clusters: 11 super blocks instead of 61).  Every GPU of a job must choose
+    // the same width: the statistics are all-gathered.
     uint32_t w = uint32_t(std::max<uint64_t>(16, (N / 32 + 2 * kSsTileN - 1) / (2 * kSsTileN)));
+    if (grouped && ctx->symNearHalfWidth == 0) {
+        void *gathered = nullptr, *pin = nullptr;
+        int rc0 = reserve(ctx, em2_context::S_DIST3, size_t(P) * 4 * sizeof(uint32_t), &gathered);
+        if (rc0 == EM2_OK) rc0 = reservePinned(ctx, 2, std::max<size_t>(64, size_t(P) * (P + 1) * sizeof(uint64_t)), &pin);
+        EM2_TRY(distAgree(ctx, rc0));
+        uint32_t* mine = static_cast<uint32_t*>(gathered) + size_t(ctx->rank) * 4;
+        if (groupStats) EM2_CUDA(ctx, cudaMemcpyAsync(mine, groupStats, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        else EM2_CUDA(ctx, cudaMemsetAsync(mine, 0, 4 * sizeof(uint32_t), s));      // a rank without cells
+        EM2_TRY(distAllGather(ctx, gathered, 4, sizeof(uint32_t), s));
+        uint32_t* host = static_cast<uint32_t*>(pin);
+        EM2_CUDA(ctx, cudaMemcpyAsync(host, gathered, size_t(P) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        EM2_CUDA(ctx, cudaStreamSynchronize(s));
+        uint64_t largest = 0, uncovered = 0;
+        for (int r = 0; r < P; r++) {
+            largest = std::max<uint64_t>(largest, host[4 * r]);
+            uncovered += host[4 * r + 1];
+        }
+        if (largest > 0 && uncovered * 20 <= N) {
+            const uint32_t wCluster = uint32_t((largest + kSsTileN - 1) / kSsTileN) + 2;
+            w = std::min(w, std::max<uint32_t>(8, wCluster));
+        }
+    }
     if (ctx->symNearHalfWidth > 0) w = uint32_t(ctx->symNearHalfWidth);
     if (2 * uint64_t(w) + 1 > S) w = (S - 1) / 2;
     const uint32_t nearCount = 2 * w + 1;
     const uint32_t farBegin = w + 1;
     const uint32_t farCount = S / 2 >= farBegin ? S / 2 - farBegin + 1 : 0;
-    *overflowed = 0;
+    ctx->lastNearHalfWidth = int(w);
 
     ScanPlan nearPlan{}, farPlan{};
     uint32_t cap = candidateCapacity(uint32_t(k)) + uint32_t(k) * uint32_t(ctx->candCapExtra);
@@ -1578,8 +1628,8 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
         cudaStreamSynchronize(s);
         cudaMemcpy(&v, appended, sizeof(v), cudaMemcpyDeviceToHost);
         cudaMemcpy(&chunksUsed, chunkNext, sizeof(chunksUsed), cudaMemcpyDeviceToHost);
-        std::fprintf(stderr, "[em2 sym rank %d] after %s: candidates so far %llu, column-direction log chunks %u of %u\n", ctx->rank, what, v,
-                     chunksUsed, chunkCap);
+        std::fprintf(stderr, "[em2 sym rank %d] after %s: candidates so far %llu, column-direction log chunks %u of %u (near half width %d of %u super blocks)\n",
+                     ctx->rank, what, v, chunksUsed, chunkCap, ctx->lastNearHalfWidth, S);
     };
 
     SymParams p{};
@@ -1762,8 +1812,9 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, ui
 // perm[q] = cell id of scan position q (device, `rows` entries written at permOut).  tau0: the scan's initial
 // exclusive bound in bits (mismatchMax + 1), which caps the cover radius.
 int groupRows(em2_context* ctx, const uint64_t* signatures, uint32_t W, uint64_t lshCount, uint32_t tau0, uint64_t rowBegin,
-              uint64_t rows, uint32_t* permOut, cudaStream_t s)
+              uint64_t rows, uint32_t* permOut, cudaStream_t s, uint32_t** statsOut = nullptr)
 {
+    if (statsOut) *statsOut = nullptr;
     if (rows == 0) return EM2_OK;
     // distances are taken over the first min(L, 1024) bits
     const double bits = double(std::min<uint64_t>(lshCount, 64ull * kPivotWords));
@@ -1781,7 +1832,7 @@ int groupRows(em2_context* ctx, const uint64_t* signatures, uint32_t W, uint64_t
     const size_t pivotBytes = roundUp(size_t(kMaxPivots) * kPivotWords * sizeof(uint64_t), 256);
     void* scratch = nullptr;
     // [keysIn][keysOut][nearest][nearestDist][uncoveredRows][flags][pivotSig][cand][state][cub]
-    EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, 2 * keyBytes + 3 * u32Bytes + roundUp(rows, 256) + pivotBytes + 1024 + cubBytes, &scratch));
+    EM2_TRY(reserve(ctx, em2_context::S_ROWPERM, 2 * keyBytes + 3 * u32Bytes + roundUp(rows, 256) + pivotBytes + 1024 + cubBytes + (kMaxPivots + 64) * sizeof(uint32_t), &scratch));
     uint8_t* base = static_cast<uint8_t*>(scratch);
     auto* keysIn = reinterpret_cast<unsigned long long*>(base);
     auto* keysOut = reinterpret_cast<unsigned long long*>(base + keyBytes);
@@ -1793,6 +1844,8 @@ int groupRows(em2_context* ctx, const uint64_t* signatures, uint32_t W, uint64_t
     auto* cand = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(pivotSig) + pivotBytes);
     auto* state = reinterpret_cast<PivotState*>(cand + kPivotRound);
     void* cubTemp = reinterpret_cast<uint8_t*>(cand) + 1024;
+    auto* hist = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(cubTemp) + cubBytes);      // [kMaxPivots] + stats [4]
+    uint32_t* stats = hist + kMaxPivots;
     const unsigned blocks = unsigned((rows + 255) / 256);
     pivotInitKernel<<<blocks, 256, 0, s>>>(rows, nearest, nearestDist, flags, state);
     EM2_CUDA(ctx, cudaGetLastError());
@@ -1806,6 +1859,14 @@ int groupRows(em2_context* ctx, const uint64_t* signatures, uint32_t W, uint64_t
     }
     pivotKeysKernel<<<blocks, 256, 0, s>>>(rowBegin, rows, nearest, keysIn);
     EM2_CUDA(ctx, cudaGetLastError());
+    if (statsOut) {
+        EM2_CUDA(ctx, cudaMemsetAsync(hist, 0, (kMaxPivots + 4) * sizeof(uint32_t), s));
+        pivotHistKernel<<<blocks, 256, 0, s>>>(rows, nearest, flags, hist, stats);
+        pivotStatsKernel<<<1, 32, 0, s>>>(hist, state, stats);
+        EM2_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 2;
+        *statsOut = stats;
+    }
     {
         size_t bytes = sortBytes;
         EM2_CUDA(ctx, cub::DeviceRadixSort::SortKeys(cubTemp, bytes, keysIn, keysOut, int(rows), 0, 44, s));
@@ -1845,11 +1906,12 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
     const bool grouped = !dump && (ctx->rowGrouping == 2 || (ctx->rowGrouping == 0 && rows >= 8192));
     const uint8_t* encRows = static_cast<const uint8_t*>(enc) + rowBegin * uint64_t(K);
     const uint32_t* rowPerm = nullptr;
+    uint32_t* groupStats = nullptr;
     if (grouped) {
         void* permBuf = nullptr;
         EM2_TRY(reserve(ctx, em2_context::S_PERM, rows * sizeof(uint32_t), &permBuf));
         uint32_t* perm = static_cast<uint32_t*>(permBuf);
-        EM2_TRY(groupRows(ctx, signatures, W, lshCount, tau0, rowBegin, rows, perm, s));
+        EM2_TRY(groupRows(ctx, signatures, W, lshCount, tau0, rowBegin, rows, perm, s, &groupStats));
         void* er = nullptr;
         EM2_TRY(reserve(ctx, em2_context::S_ENCROWS, rows * uint64_t(K), &er));
         const uint64_t threads = rows * (K / 16);
@@ -1883,7 +1945,7 @@ int runMma(em2_context* ctx, const uint64_t* signatures, uint64_t cellCount, uin
         }
         if (eligible && ctx->world == 1 && (ctx->scanSymmetric == 2 || automatic)) {
             int overflowed = 0;
-            EM2_TRY(runSymmetric(ctx, encRows, rowPerm, cellCount, 0, cellCount, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
+            EM2_TRY(runSymmetric(ctx, encRows, rowPerm, groupStats, grouped, cellCount, 0, cellCount, cellCount, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
             ctx->stats.scan_symmetric = overflowed ? 2 + 16 * overflowed : 1;      // 2 + 16 * (which capacity ran out)
             if (!overflowed) return EM2_OK;
         }
@@ -2049,6 +2111,7 @@ int launchScanSymDist(em2_context* ctx, const uint64_t* allSig, uint64_t cellCou
     int rc = reserve(ctx, em2_context::S_PERM, uint64_t(ctx->world) * part.shard * sizeof(uint32_t), &permBuf);
     if (rc == EM2_OK) rc = reserve(ctx, em2_context::S_ENC, cellCount * K, &enc);
     uint32_t* perm = static_cast<uint32_t*>(permBuf);
+    uint32_t* groupStats = nullptr;
     // scan order: every GPU groups ITS cells (similar rows into the same warps, similar columns into the same tiles);
     // positions [rank * shard, ...) hold a permutation of the same range of cell ids
     if (rc == EM2_OK && rows) {
@@ -2057,7 +2120,7 @@ int launchScanSymDist(em2_context* ctx, const uint64_t* allSig, uint64_t cellCou
             if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, EM2_ERR_CUDA, "iotaKernel launch failed");
             ctx->stats.kernel_launches++;
         } else {
-            rc = groupRows(ctx, allSig, W, lshCount, tau0, part.rowBegin, rows, perm + part.rowBegin, s);
+            rc = groupRows(ctx, allSig, W, lshCount, tau0, part.rowBegin, rows, perm + part.rowBegin, s, &groupStats);
         }
     }
     // In the one-process driver no rank allocates device memory between an agreement and the collective behind it: an
@@ -2071,8 +2134,8 @@ int launchScanSymDist(em2_context* ctx, const uint64_t* allSig, uint64_t cellCou
         ctx->stats.kernel_launches++;
     }
     int overflowed = 0;
-    EM2_TRY(runSymmetric(ctx, static_cast<const uint8_t*>(enc), perm, cellCount, part.rowBegin, rows, part.shard, K, k, tau0, lut, pairs,
-                         usedCount, s, &overflowed));
+    EM2_TRY(runSymmetric(ctx, static_cast<const uint8_t*>(enc), perm, groupStats, ctx->rowGrouping != 1, cellCount, part.rowBegin, rows,
+                         part.shard, K, k, tau0, lut, pairs, usedCount, s, &overflowed));
     if (!overflowed) {
         ctx->stats.scan_symmetric = 1;
         return EM2_OK;
