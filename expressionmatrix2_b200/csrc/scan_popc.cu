@@ -474,8 +474,24 @@ ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount,
         const uint32_t maxSeg = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(32, maxStreams / streamsPerSegment),
                                                                                   cellCount / (4 * tileCols))));
         if (p.mainBlocks) {
-            seg = std::max<uint32_t>(1, std::min<uint32_t>(slots / tail, maxSeg));
-            if (tail * 10 >= slots * 9) seg = 1;      // a tail that nearly fills a wave is better left whole
+            // A small tail is cut so that its pieces fill one wave.  A tail of more than half a wave costs
+            // ceil(tail * seg / slots) waves of 1/seg of a full sweep each: take the cheapest split (one GPU's share of an
+            // 8-GPU job has ~7 waves, so a tail wave at 60 % occupancy is 5 % of its scan), with a small charge per extra
+            // candidate stream; a tail that nearly fills a wave is left whole.
+            if (slots / tail >= 2) {
+                seg = std::max<uint32_t>(1, std::min<uint32_t>(slots / tail, maxSeg));
+            } else {
+                double best = 1e30;
+                for (uint32_t c = 1; c <= std::min<uint32_t>(maxSeg, 8); c++) {
+                    const uint64_t items = uint64_t(tail) * c;
+                    const double cost = double((items + slots - 1) / slots) / double(c) + 0.01 * double(c - 1);
+                    if (cost < best - 1e-9) {
+                        best = cost;
+                        seg = c;
+                    }
+                }
+            }
+            if (tail * 10 >= slots * 9) seg = 1;
         } else {
             // fewer row blocks than CTA slots (small jobs, or one rank's share of a multi-GPU job): the smallest
             // number of segments whose items fill their waves to >= 90 %, else the best found
