@@ -654,6 +654,20 @@ def test_symmetric_scan_equals_oracle(engine, oracle, N, L, k, thr, clusters):
     _check_lists(_sym(engine, sig, L, k, thr, row_grouping=1), want)
 
 
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("near", [0, 1, 3, 40])
+def test_symmetric_scan_forms_and_near_window_widths(engine, oracle, pair, near):
+    """Both forms of the symmetric kernel -- CTA pairs (cta_group::2, the default) and single CTAs -- and near windows
+    from one super block each side to wider than the matrix (then the near window IS the scan) give the oracle's lists."""
+    N, L, k, thr = 7000, 1024, 30, 0.2
+    sig = synthetic.gen_signatures(N, L, seed=41, clusters=9)
+    want = oracle.topk(sig, L, k, thr)[:3]
+    _check_lists(_sym(engine, sig, L, k, thr, sym_cta_pair=pair, sym_near_half_width=near), want)
+    sig = synthetic.gen_signatures(4000, 512, seed=42)          # unstructured, no threshold: every bound comes from the k-th best
+    want = oracle.topk(sig, 512, 20, -1.0)[:3]
+    _check_lists(_sym(engine, sig, 512, 20, -1.0, sym_cta_pair=pair, sym_near_half_width=near), want)
+
+
 def test_symmetric_scan_ties_resolve_by_cell_id(engine, oracle):
     """Candidates do not arrive in id order (cyclic column order, grouped positions, inbox appends from many CTAs):
     ties at the k-th place must still go to the smaller cell id.  Few distinct signatures = ties everywhere, but
