@@ -1576,8 +1576,23 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, co
     const uint64_t rowsAlloc = std::max<uint64_t>(ownRows, 1);
     // column-direction log pool: 24 k entries per row on average (measured: 1.5-12 k per cell on clustered data); the
     // outbox is cut from a buffer of the same number of keys (count -> scan -> fill)
-    const uint64_t poolEntries = std::min<uint64_t>(0xf0000000ull, 24 * rowsAlloc * k + 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk);
-    const uint32_t chunkCap = uint32_t(poolEntries / kLogChunk);
+    // 24 k entries per row at least, up to 64 k when memory allows (a third of what is free; log 16 B + outbox 8 B per
+    // entry).  Measured needs: 0.8 k per cell on the 1 M-cell bench workload, 25 k per cell on config 3 (64 loose clusters
+    // of 20k cells spread over 8 GPUs: a rank's near window only sees its own eighth of a cluster) -- which overflowed a
+    // 24 k pool and fell back to the one-directional kernels (296 instead of 116 ms).  Buffers only grow.
+    uint64_t perRow = 24;
+    {
+        size_t freeBytes = 0, totalBytes = 0;
+        if (cudaMemGetInfo(&freeBytes, &totalBytes) != cudaSuccess) {
+            cudaGetLastError();
+            freeBytes = 0;
+        }
+        const size_t have = ctx->scratch[em2_context::S_COLLOG].bytes + ctx->scratch[em2_context::S_INBOX].bytes;
+        const uint64_t affordable = (uint64_t(freeBytes) / 3 + have) / 24 / std::max<uint64_t>(1, rowsAlloc * k);
+        perRow = std::min<uint64_t>(64, std::max<uint64_t>(24, affordable));
+    }
+    const uint64_t poolEntries = std::min<uint64_t>(0xf0000000ull * uint64_t(kLogChunk) / 64, perRow * rowsAlloc * k + 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk);
+    const uint32_t chunkCap = uint32_t(std::min<uint64_t>(0xfffffff0ull, poolEntries / kLogChunk));
     size_t cubBytes = 0, cubBytes2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cubBytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(N + 1), s);
     cub::DeviceScan::ExclusiveSum(nullptr, cubBytes2, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), int(shard + 1), s);

@@ -480,6 +480,8 @@ ScanPlan makeScanPlan(const em2_context* ctx, uint64_t rows, uint64_t cellCount,
             // candidate stream; a tail that nearly fills a wave is left whole.
             if (slots / tail >= 2) {
                 seg = std::max<uint32_t>(1, std::min<uint32_t>(slots / tail, maxSeg));
+            } else if (p.mainBlocks / slots >= 16) {
+                seg = 1;      // many waves: the tail wave is a few per mille, and every extra stream costs the merge of ALL rows
             } else {
                 double best = 1e30;
                 for (uint32_t c = 1; c <= std::min<uint32_t>(maxSeg, 8); c++) {
