@@ -180,10 +180,11 @@ void ExpressionMatrix::findSimilarPairs4(std::ostream& out, const std::string& g
     if (k == 0 || k > 1024) throw std::runtime_error("findSimilarPairs4: k must be in [1, 1024] on the GPU path.");
     if (lshCount == 0 || lshCount > 65535) throw std::runtime_error("findSimilarPairs4: lshCount must be in [1, 65535] on the GPU path.");
 
+    GpuSet& gpu = GpuSet::instance();      // throws without a device: before anything is written to the data directory
+
     out << timestamp << "Initializing SimilarPairs object." << std::endl;
     SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
 
-    GpuSet& gpu = GpuSet::instance();
     out << timestamp << "Expression matrix subset, LSH signatures and all cell pairs on " << gpu.name() << "." << std::endl;
     static_assert(sizeof(std::pair<GeneId, float>) == sizeof(em2_count), "pair<GeneId,float> must be 8 bytes");
     static_assert(sizeof(SimilarPairs::Pair) == sizeof(em2_pair), "pair<CellId,float> must be 8 bytes");
@@ -266,13 +267,13 @@ void ExpressionMatrix::findSimilarPairs0(std::ostream& out, const std::string& g
     if (k == 0 || k > 1024) throw std::runtime_error("findSimilarPairs0: k must be in [1, 1024] on the GPU path.");
     const GeneSet& geneSet = findGeneSet(geneSetName);
     const CellSet& cellSet = findCellSet(cellSetName);
+    Gpu& gpu = Gpu::instance();            // throws without a device: before anything is written to the data directory
     SimilarPairs similarPairs(directoryName, similarPairsName, geneSetName, cellSetName, k);
     ExpressionMatrixSubset subset(directoryName + "/tmp-ExpressionMatrixSubset-" + similarPairsName, geneSet, cellSet,
                                   cellExpressionCounts);
     out << timestamp << "Begin computing similarities for all cell pairs." << std::endl;
     const size_t n = subset.cellCount();
     std::vector<uint32_t> used(n);
-    Gpu& gpu = Gpu::instance();
     try {
         gpu.check(em2_exact_similar_pairs(gpu.context(), n, subset.geneCount(), subset.toc(),
                                           reinterpret_cast<const em2_count*>(subset.data()), k, similarityThreshold,

@@ -90,6 +90,25 @@ def test_lookup_errors_match_the_reference(M, tmp_path):
         e.findSimilarPairs4(cellSetName="Empty", similarPairsName="x")
 
 
+def test_device_limits_are_checked_before_anything_is_written(M, tmp_path):
+    """k <= 1024 and lshCount <= 65535 are limits of the device path the reference does not have: the host layer refuses
+    them BEFORE it creates the SimilarPairs object, and a call that fails on the device removes the object it created
+    (here: no GPU) -- no empty but valid-looking SimilarPairs-<name> set stays in the data directory."""
+    import glob
+    e, _ = _make_matrix(M, tmp_path / "data", N=20, G=10)
+    with pytest.raises(RuntimeError, match="k must be in"):
+        e.findSimilarPairs4(similarPairsName="TooWide", k=5000)
+    with pytest.raises(RuntimeError, match="lshCount must be in"):
+        e.findSimilarPairs4(similarPairsName="TooLong", lshCount=70000)
+    with pytest.raises(RuntimeError, match="k must be in"):
+        e.findSimilarPairs0(similarPairsName="TooWide0", k=0)
+    import torch
+    if not torch.cuda.is_available():      # the device call itself fails: the object it created must be gone again
+        with pytest.raises(RuntimeError, match="GPU"):
+            e.findSimilarPairs4(similarPairsName="NoDevice", k=5)
+    assert glob.glob(str(tmp_path / "data" / "SimilarPairs-*")) == []
+
+
 def test_reopen_existing_directory(M, tmp_path):
     e, _ = _make_matrix(M, tmp_path / "data", N=30, G=12)
     e.createGeneSet("Some", [1, 5, 7])
