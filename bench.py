@@ -735,6 +735,22 @@ def run_b200(args, w):
                     gpu_launches=int(launches), clocks=clocks)
         if sig_roof:
             line["signature_roofline"] = sig_roof
+        if world == 1 and kind == "lsh" and hashed and not args.no_e2e and not args.no_api_e2e:
+            # the reference's own call on a data directory, everything it contains inside the timed region (tools/e2e_host.py;
+            # a subprocess: the C++ layer prints its progress to stdout, and a failure here must not cost the bench line)
+            api_out = os.path.join(ROOT, "gpurun_out", "e2e_api.json") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "/tmp/e2e_api.json"
+            try:
+                torch.cuda.empty_cache()
+                subprocess.run([sys.executable, os.path.join(ROOT, "tools", "e2e_host.py"), "--workload", args.workload, "--repeat", "2",
+                                "--out", api_out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=420, check=True,
+                               env=dict(os.environ, EM2_DEVICES=str(local_rank)))
+                api = json.load(open(api_out))
+                line["e2e_api"] = dict(value=api["cell_pairs_per_s"], unit="cell-pairs/s", ms=1e3 * api["best_seconds"], api=api["api"],
+                                       includes=api["includes"], runs=api["runs"],
+                                       note="ingest (addCells into the mapped CellExpressionCounts file) is outside the timed region, as in the "
+                                            "reference; `e2e` above is the same job through the C-ABI call on pinned host buffers")
+            except Exception as ex:      # noqa: BLE001
+                line["e2e_api"] = dict(error=f"{type(ex).__name__}: {ex}"[:300])
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
@@ -767,6 +783,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="em2_set_option on the engine (tuning / diagnosis runs), e.g. --option debug_flags=8")
+    ap.add_argument("--no-api-e2e", action="store_true", help="skip the API-level leg (tools/e2e_host.py on a data directory)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

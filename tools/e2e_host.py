@@ -25,6 +25,8 @@ SHAPES = {
     "c1": dict(cells=10_000, genes=20_000, nnz_per_cell=1000, clusters=64),
     "c2": dict(cells=100_000, genes=30_000, nnz_per_cell=1500, clusters=64),
     "m1": dict(cells=1_000_000, genes=30_000, nnz_per_cell=1500, clusters=512),
+    "m1s": dict(cells=60_000, genes=30_000, nnz_per_cell=1500, clusters=32),
+    "c3": dict(cells=1_300_000, genes=28_000, nnz_per_cell=2000, clusters=64),
 }
 
 
