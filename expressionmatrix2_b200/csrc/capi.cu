@@ -207,7 +207,8 @@ int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
     cudaPointerAttributes attr{};
     const cudaError_t pe = cudaPointerGetAttributes(&attr, src);
     if (pe != cudaSuccess) cudaGetLastError();
-    const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    // anything the driver knows (pinned / registered host memory, managed or device memory) needs no staging
+    const bool pinned = pe == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
     if (pinned || ctx->noBounce) {
         EM2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
         return EM2_OK;
@@ -237,7 +238,8 @@ int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
     cudaPointerAttributes attr{};
     const cudaError_t pe = cudaPointerGetAttributes(&attr, dst);
     if (pe != cudaSuccess) cudaGetLastError();
-    const bool pinned = pe == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    // anything the driver knows (pinned / registered host memory, managed or device memory) needs no staging
+    const bool pinned = pe == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
     if (pinned || ctx->noBounce) {
         EM2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
         return EM2_OK;
