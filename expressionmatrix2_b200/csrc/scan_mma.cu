@@ -1639,7 +1639,19 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, co
         ctx->stats.kernel_launches++;
     }
     // debug_flags bit 3: report the candidate counters after every stage (synchronises)
+    // debug_flags bit 5: wall-clock time of every phase (synchronises the stream at each mark) -- how a rank's scan
+    // divides into sweeps, collectives and waiting for the other ranks
+    const double phaseT0 = nowMs();
+    double phaseLast = phaseT0;
+    auto phase = [&](const char* what) {
+        if (!(ctx->debugFlags & 32)) return;
+        cudaStreamSynchronize(s);
+        const double t = nowMs();
+        std::fprintf(stderr, "[em2 sym rank %d] %-22s %8.3f ms (at %8.3f)\n", ctx->rank, what, t - phaseLast, t - phaseT0);
+        phaseLast = t;
+    };
     auto report = [&](const char* what) {
+        phase(what);
         if (!(ctx->debugFlags & 8)) return;
         unsigned long long v = 0;
         uint32_t chunksUsed = 0;
@@ -1716,11 +1728,13 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, co
         ctx->stats.kernel_launches++;
         return EM2_OK;
     };
+    phase("set-up");
     // ---- 1. near window
     EM2_TRY(sweep(nearPlan, -int32_t(w), nearCount, 0, 1));
     report("near window");
     // ---- 2. bounds of all cells
     if (P > 1) EM2_TRY(distAllGather(ctx, limEx, shard, sizeof(uint32_t), s));
+    phase("bounds all-gather");
     // ---- 3. far sweep
     EM2_TRY(sweep(farPlan, int32_t(farBegin), farCount, 1, 0));
     report("far sweep");
@@ -1735,6 +1749,7 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, co
                                                                      static_cast<uint64_t*>(outbox), appended);
     EM2_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 2;      // + the scan's own kernels (library code, not counted)
+    phase("log filing");
 
     InboxSources src{};
     if (P == 1) {
@@ -1797,6 +1812,7 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, co
             src.offsets[r] = recvOffsets + size_t(r) * (shard + 1);
         }
         src.count = uint32_t(P);
+        phase("candidate exchange");
     }
     // ---- 5. merge.  Staging: 16-bit mismatch counts of everything below the bound (cells with longer lists bisect in
     // place), then the k best keys plus the ties at the k-th place
@@ -1817,6 +1833,7 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, co
     EM2_CUDA(ctx, cudaMemcpyAsync(matrixHost, overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     EM2_CUDA(ctx, cudaStreamSynchronize(s));
     *overflowed = int(*matrixHost);
+    phase("merge");
     if (ctx->symExchangeTimed) {
         ctx->symExchangeTimed = false;
         float t = 0.f;

@@ -139,7 +139,8 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
  *                      (0 = automatic: max(16, N / 32 columns in total))
  *   "stage_threads"    host threads that copy a pageable buffer into / out of the pinned bounce buffers (0 = 4)
  *   "no_bounce"        1 = pageable host buffers go straight to cudaMemcpyAsync instead of through the pinned bounce buffers
- *   "debug_flags"      bit 0: no bound sharing between the MMA scan's sub-streams */
+ *   "debug_flags"      bit 0: no bound sharing between the MMA scan's sub-streams; bit 3: candidate counters of the
+ *                      symmetric scan's phases; bit 5: wall-clock time of its phases (both print to stderr and synchronise) */
 int em2_set_option(em2_context* ctx, const char* name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------
