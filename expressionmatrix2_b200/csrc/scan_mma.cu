@@ -1582,14 +1582,22 @@ int runSymmetric(em2_context* ctx, const uint8_t* encP, const uint32_t* perm, co
     // 24 k pool and fell back to the one-directional kernels (296 instead of 116 ms).  Buffers only grow.
     uint64_t perRow = 24;
     {
-        size_t freeBytes = 0, totalBytes = 0;
-        if (cudaMemGetInfo(&freeBytes, &totalBytes) != cudaSuccess) {
-            cudaGetLastError();
-            freeBytes = 0;
+        const uint64_t slack = 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk + kLogChunk;
+        const uint64_t haveEntries = std::min<uint64_t>(ctx->scratch[em2_context::S_COLLOG].bytes / sizeof(ulonglong2),
+                                                        ctx->scratch[em2_context::S_INBOX].bytes / sizeof(uint64_t));
+        if (haveEntries >= 24 * rowsAlloc * k + slack) {
+            // buffers of an earlier call are large enough: use what they hold (cudaMemGetInfo costs milliseconds)
+            perRow = std::min<uint64_t>(64, (haveEntries - slack) / (rowsAlloc * k));
+        } else {
+            size_t freeBytes = 0, totalBytes = 0;
+            if (cudaMemGetInfo(&freeBytes, &totalBytes) != cudaSuccess) {
+                cudaGetLastError();
+                freeBytes = 0;
+            }
+            const size_t have = ctx->scratch[em2_context::S_COLLOG].bytes + ctx->scratch[em2_context::S_INBOX].bytes;
+            const uint64_t affordable = (uint64_t(freeBytes) / 3 + have) / 24 / std::max<uint64_t>(1, rowsAlloc * k);
+            perRow = std::min<uint64_t>(64, std::max<uint64_t>(24, affordable));
         }
-        const size_t have = ctx->scratch[em2_context::S_COLLOG].bytes + ctx->scratch[em2_context::S_INBOX].bytes;
-        const uint64_t affordable = (uint64_t(freeBytes) / 3 + have) / 24 / std::max<uint64_t>(1, rowsAlloc * k);
-        perRow = std::min<uint64_t>(64, std::max<uint64_t>(24, affordable));
     }
     const uint64_t poolEntries = std::min<uint64_t>(0xf0000000ull * uint64_t(kLogChunk) / 64, perRow * rowsAlloc * k + 2 * uint64_t(ctx->smCount) * kEpiThreads * kLogChunk);
     const uint32_t chunkCap = uint32_t(std::min<uint64_t>(0xfffffff0ull, poolEntries / kLogChunk));
