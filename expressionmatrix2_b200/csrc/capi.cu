@@ -429,6 +429,7 @@ int em2_set_option(em2_context* ctx, const char* name, int64_t value)
     else if (n == "exact_general" && value >= 0 && value <= 1) ctx->exactGeneral = int(value);
     else if (n == "exact_cta_pair" && value >= 0 && value <= 1) ctx->exactCtaPair = int(value);
     else if (n == "filter_parts" && value >= 0 && value <= 64) ctx->filterParts = int(value);
+    else if (n == "filter_cta_pair" && value >= 0 && value <= 1) ctx->filterCtaPair = int(value);
     else if (n == "cand_cap_extra" && value >= 0 && value <= 14) ctx->candCapExtra = int(value);
     else if (n == "debug_flags" && value >= 0 && value <= 255) ctx->debugFlags = int(value);
     else if (n == "row_grouping" && value >= 0 && value <= 2) ctx->rowGrouping = int(value);

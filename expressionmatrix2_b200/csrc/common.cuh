@@ -74,6 +74,7 @@ struct em2_context {
     int exactGeneral = 0;              // 1: force the general FP64 kernel of the exact path (tests)
     int exactCtaPair = 0;              // 1: the one-digit exact GEMM runs on CTA pairs (cta_group::2, M = 256)
     int filterParts = 0;               // test knob: chunks per filter call (0 = automatic)
+    int filterCtaPair = 0;             // filter GEMM: 0 = CTA pairs (cta_group::2, M = 256), 1 = one CTA per tile
     int candCapExtra = 0;              // candidate regions hold (2 + candCapExtra) * k + 32 keys
     int debugFlags = 0;                // bit 0: no bound sharing between MMA sub-streams; bit 1: memory prune
     int rowGrouping = 0;               // MMA scan: 0 auto (group similar rows into the same warps), 1 off, 2 on

@@ -28,6 +28,12 @@
 // and one N=128 instruction per 32 genes), K = genes in 128-byte chunks, both operands by TMA (128B swizzle)
 // through a 3-stage ring of 64 KB stages, accumulators in 384 TMEM columns (the epilogue is ~1 % of a tile's
 // 235-chunk main loop, so it is not double buffered).
+// PAIR form (default): the two CTAs of a cluster (the two SMs of a TPC) take 256 cells x 128 hyperplanes as ONE
+// cta_group::2 tile (M = 256): each CTA streams its own 128 cells of A and HALF of every B tile (digit 0 or digit 1 of
+// the N=256 instruction, 64 of digit 2's 128 rows for the N=128 one) -- 40 KB per K chunk and SM instead of 64, five
+// stages, and per MMA 8 / 6 KB of shared-memory operand reads per SM instead of 12 / 8.  With both operands in shared
+// memory and one CTA per tile the pipe tops out at 0.81 (N=256) / 0.64 (N=128) of its peak (tools/mma_peak.cu); the
+// single-CTA kernel sat at that ceiling (ncu: tensor pipe 73 % at 1 M cells).
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -49,6 +55,9 @@ constexpr uint32_t kFABytes = kFM * kFChunk;
 constexpr uint32_t kFBBytes = kFN * kFChunk;
 constexpr uint32_t kFStageBytes = kFABytes + kFBBytes;     // 64 KB
 constexpr int kFThreads = 192;
+constexpr int kFPairStages = 5;
+constexpr uint32_t kFPairBBytes = (kFN / 2) * kFChunk;                 // this CTA's half of the B rows: 128 + 64
+constexpr uint32_t kFPairStageBytes = kFABytes + kFPairBBytes;          // 40 KB
 constexpr double kQuantMax = 2080768.;   // |q| <= 127 * 128 * 128
 constexpr double kNearZeroEps = 1e-12;
 constexpr double kMaxSum1 = 1.6e7;    // keeps |sum c * qh| <= 127 * sum1 below 2^31
@@ -279,35 +288,50 @@ struct FilterParams {
     uint32_t uncertainCap;
 };
 
+// PAIR: mapB64 is mapB with a 64-row box (this CTA's half of digit 2); the leader (cluster rank 0) owns the barriers the
+// MMA issuer waits on (full, accEmpty) and issues for the pair; empty / accFull are signalled in both CTAs (commitPair).
+template <bool PAIR>
 __global__ void __launch_bounds__(kFThreads, 1)
-sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const FilterParams p)
+sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapB64, const FilterParams p)
 {
+    constexpr int kNumStages = PAIR ? kFPairStages : kFStages;
+    constexpr uint32_t kStageSz = PAIR ? kFPairStageBytes : kFStageBytes;
     extern __shared__ uint8_t smemRaw[];
     uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smemRaw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(kFStages) * kFStageBytes);
-    uint64_t* full = bars;                   // [stages]  TMA -> MMA
-    uint64_t* empty = bars + kFStages;       // [stages]  MMA -> TMA
-    uint64_t* accFull = bars + 2 * kFStages; // MMA -> epilogue
-    uint64_t* accEmpty = accFull + 1;        // epilogue -> MMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + size_t(kNumStages) * kStageSz);
+    uint64_t* full = bars;                     // [stages]  TMA -> MMA
+    uint64_t* empty = bars + kNumStages;       // [stages]  MMA -> TMA
+    uint64_t* accFull = bars + 2 * kNumStages; // MMA -> epilogue
+    uint64_t* accEmpty = accFull + 1;          // epilogue -> MMA
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(accEmpty + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? clusterRank() : 0;
+    const uint32_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+    const uint32_t workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kFStages; i++) {
+        for (int i = 0; i < kNumStages; i++) {
             mbarInit(full + i, 1);
             mbarInit(empty + i, 1);
         }
         mbarInit(accFull, 1);
-        mbarInit(accEmpty, 128);
+        mbarInit(accEmpty, PAIR ? 8 : 128);      // PAIR: one arrival per epilogue warp of either CTA
         mbarInitFence();
     }
-    if (warp == 4) tmemAlloc(tmemSlot, 512);
+    if (warp == 4) {
+        if (PAIR) tmemAllocPair(tmemSlot, 512);
+        else tmemAlloc(tmemSlot, 512);
+    }
     fenceBefore();
-    __syncthreads();
+    if (PAIR) clusterSync();      // barriers of both CTAs are initialised before anyone signals across
+    else __syncthreads();
     fenceAfter();
     const uint32_t tmemBase = *tmemSlot;
-    const uint32_t items = p.mBlocks * p.nBlocks;
+    // PAIR: an item is 256 cells (m-blocks 2 q and 2 q + 1; an odd last block reads zeros and writes nothing)
+    const uint32_t mItems = PAIR ? (p.mBlocks + 1) / 2 : p.mBlocks;
+    const uint32_t items = mItems * p.nBlocks;
 
     if (warp == 4) {
         // ===================== TMA producer =====================
@@ -315,19 +339,30 @@ sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             prefetchMap(&mapA);
             prefetchMap(&mapB);
             uint32_t stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
-                const int32_t rowA = int32_t((item / p.nBlocks) * kFM);
+            if (PAIR) prefetchMap(&mapB64);
+            for (uint32_t item = worker; item < items; item += workers) {
+                const int32_t rowA = int32_t(((item / p.nBlocks) * (PAIR ? 2 : 1) + rank) * kFM);
                 const int32_t rowB = int32_t((item % p.nBlocks) * kFN);
                 for (uint32_t kc = 0; kc < p.kChunks; kc++) {
                     mbarWait(empty + stage, phase ^ 1);
-                    mbarExpectTx(full + stage, kFStageBytes);
-                    uint8_t* dst = ring + size_t(stage) * kFStageBytes;
-                    tmaLoad2d(dst, &mapA, full + stage, int32_t(kc * kFChunk), rowA);
+                    uint8_t* dst = ring + size_t(stage) * kStageSz;
+                    if (PAIR) {
+                        // this CTA's cells, its digit (0 or 1) of the N=256 instruction, its 64 rows of digit 2;
+                        // the leader's barrier collects both CTAs' bytes
+                        if (rank == 0) mbarExpectTx(full + stage, 2 * kFPairStageBytes);
+                        tmaLoad2dPair(dst, &mapA, full + stage, int32_t(kc * kFChunk), rowA);
+                        tmaLoad2dPair(dst + kFABytes, &mapB, full + stage, int32_t(kc * kFChunk), rowB + int32_t(rank) * kFHyper);
+                        tmaLoad2dPair(dst + kFABytes + kFHyper * kFChunk, &mapB64, full + stage, int32_t(kc * kFChunk),
+                                      rowB + 2 * kFHyper + int32_t(rank) * (kFHyper / 2));
+                    } else {
+                        mbarExpectTx(full + stage, kFStageBytes);
+                        tmaLoad2d(dst, &mapA, full + stage, int32_t(kc * kFChunk), rowA);
 #pragma unroll
-                    for (int d = 0; d < kFDigits; d++)
-                        tmaLoad2d(dst + kFABytes + d * kFHyper * kFChunk, &mapB, full + stage, int32_t(kc * kFChunk),
-                                  rowB + d * kFHyper);
-                    if (++stage == kFStages) {
+                        for (int d = 0; d < kFDigits; d++)
+                            tmaLoad2d(dst + kFABytes + d * kFHyper * kFChunk, &mapB, full + stage, int32_t(kc * kFChunk),
+                                      rowB + d * kFHyper);
+                    }
+                    if (++stage == kNumStages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -338,29 +373,40 @@ sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues (tc05.cuh, electOne) =====================
         uint32_t stage = 0, phase = 0, tileIter = 0;
         const uint32_t ringBase = smemAddr(ring);
-        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, tileIter++) {
+        for (uint32_t item = worker; item < items && rank == 0; item += workers, tileIter++) {
             mbarWait(accEmpty, (tileIter & 1) ^ 1);
             fenceAfter();
             const uint32_t tmemD = tmemBase;
             for (uint32_t kc = 0; kc < p.kChunks; kc++) {
                 mbarWait(full + stage, phase);
                 fenceAfter();
-                const uint32_t aAddr = ringBase + stage * kFStageBytes;
+                const uint32_t aAddr = ringBase + stage * kStageSz;
                 const uint64_t descA = makeSmemDesc(aAddr);
                 const uint64_t descB0 = makeSmemDesc(aAddr + kFABytes);
-                const uint64_t descB1 = makeSmemDesc(aAddr + kFABytes + 256 * kFChunk);
+                // second instruction's B rows: digit 2 (PAIR: this CTA's 64 of them, behind its 128 rows of digit 0 / 1)
+                const uint64_t descB1 = makeSmemDesc(aAddr + kFABytes + (PAIR ? kFHyper : 2 * kFHyper) * kFChunk);
                 if (electOne()) {
 #pragma unroll
                     for (int ks = 0; ks < kFChunk / 32; ks++) {      // + 32 bytes along K = + 2 in the descriptor's address field
                         const uint32_t accumulate = (kc | uint32_t(ks)) != 0 ? 1u : 0u;
-                        mmaI8Ss(tmemD, descA + uint64_t(2 * ks), descB0 + uint64_t(2 * ks), p.idesc256, accumulate);
-                        mmaI8Ss(tmemD + 256, descA + uint64_t(2 * ks), descB1 + uint64_t(2 * ks), p.idesc128, accumulate);
+                        if (PAIR) {
+                            mmaI8SsPair(tmemD, descA + uint64_t(2 * ks), descB0 + uint64_t(2 * ks), p.idesc256, accumulate);
+                            mmaI8SsPair(tmemD + 256, descA + uint64_t(2 * ks), descB1 + uint64_t(2 * ks), p.idesc128, accumulate);
+                        } else {
+                            mmaI8Ss(tmemD, descA + uint64_t(2 * ks), descB0 + uint64_t(2 * ks), p.idesc256, accumulate);
+                            mmaI8Ss(tmemD + 256, descA + uint64_t(2 * ks), descB1 + uint64_t(2 * ks), p.idesc128, accumulate);
+                        }
                     }
-                    commit(empty + stage);
-                    if (kc + 1 == p.kChunks) commit(accFull);
+                    if (PAIR) {      // in both CTAs: the stage is free, the accumulator halves are complete
+                        commitPair(empty + stage);
+                        if (kc + 1 == p.kChunks) commitPair(accFull);
+                    } else {
+                        commit(empty + stage);
+                        if (kc + 1 == p.kChunks) commit(accFull);
+                    }
                 }
                 __syncwarp();
-                if (++stage == kFStages) {
+                if (++stage == kNumStages) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -370,8 +416,8 @@ sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // ===================== epilogue: thread == cell == TMEM lane =====================
         const uint32_t laneField = uint32_t(warp * 32) << 16;
         uint32_t tileIter = 0;
-        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, tileIter++) {
-            const uint32_t mb = item / p.nBlocks, nb = item % p.nBlocks;
+        for (uint32_t item = worker; item < items; item += workers, tileIter++) {
+            const uint32_t mb = (item / p.nBlocks) * (PAIR ? 2 : 1) + rank, nb = item % p.nBlocks;
             const uint32_t wLocal = mb * kFM + threadIdx.x;
             const bool valid = wLocal < p.chunkCells && p.flags[wLocal] != 0;
             const uint64_t cell = p.chunkBegin + (wLocal < p.chunkCells ? wLocal : 0);
@@ -408,7 +454,12 @@ sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 masks[q] = mask;
             }
             fenceBefore();
-            mbarArrive(accEmpty);
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbarArriveLeader(accEmpty);
+            } else {
+                mbarArrive(accEmpty);
+            }
             if (valid) {
                 const uint32_t w0 = nb * 2;
                 uint64_t* out = p.signatures + cell * p.wordsPerCell;
@@ -418,8 +469,13 @@ sigFilterKernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     }
     fenceBefore();
-    __syncthreads();
-    if (warp == 4) tmemDealloc(tmemBase, 512);
+    if (PAIR) {
+        clusterSync();        // neither CTA may retire while its partner can still signal into it
+        if (warp == 4) tmemDeallocPair(tmemBase, 512);
+    } else {
+        __syncthreads();
+        if (warp == 4) tmemDealloc(tmemBase, 512);
+    }
 }
 
 // Exact FP64 evaluation of the listed (cell, hyperplane) projections: the reference's operation sequence
@@ -556,10 +612,13 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
     const uint64_t cellCount = cellEnd;
 
     const bool unsignedCounts = ctx->filterCountsSigned == 0;
-    const size_t smem = 1024 + size_t(kFStages) * kFStageBytes + 256;
-    EM2_CUDA(ctx, cudaFuncSetAttribute(sigFilterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    CUtensorMap mapB;
+    const bool pair = ctx->filterCtaPair != 1 && ctx->smCount >= 2;
+    const size_t smem = 1024 + (pair ? size_t(kFPairStages) * kFPairStageBytes : size_t(kFStages) * kFStageBytes) + 256;
+    EM2_CUDA(ctx, cudaFuncSetAttribute(sigFilterKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    EM2_CUDA(ctx, cudaFuncSetAttribute(sigFilterKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CUtensorMap mapB, mapB64;
     EM2_TRY(makeTensorMapU8(ctx, &mapB, uq, uint64_t(nBlocks) * kFN, gPad, gPad, 128));
+    EM2_TRY(makeTensorMapU8(ctx, &mapB64, uq, uint64_t(nBlocks) * kFN, gPad, gPad, 64));
 
     // the dense expansion runs ahead on its own stream; it only needs the CSR, which everything enqueued on `s` so far provides
     cudaStream_t d = ctx->auxStream2;
@@ -605,8 +664,8 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
         p.nBlocks = nBlocks;
         p.lshCount = uint32_t(lshCount);
         p.wordsPerCell = uint32_t(W);
-        p.idesc256 = instrDescI8(!unsignedCounts, true, kFM, 256);
-        p.idesc128 = instrDescI8(!unsignedCounts, true, kFM, 128);
+        p.idesc256 = instrDescI8(!unsignedCounts, true, pair ? 2 * kFM : kFM, 256);
+        p.idesc128 = instrDescI8(!unsignedCounts, true, pair ? 2 * kFM : kFM, 128);
         p.toc = toc;
         p.sum1 = sum1;
         p.flags = dFlags;
@@ -620,10 +679,27 @@ int launchSignaturesFiltered(em2_context* ctx, const SignaturePlan& pl, const ui
         p.uncertainCap = uncertainCap;
         CUtensorMap mapA;
         EM2_TRY(makeTensorMapU8(ctx, &mapA, dense, chunkCells, gPad, gPad, kFM));
-        const uint32_t items = p.mBlocks * p.nBlocks;
-        const unsigned grid = std::min<uint32_t>(items, uint32_t(ctx->smCount));
         if (pl.prepOnAux) EM2_CUDA(ctx, cudaStreamWaitEvent(s, ctx->evPrep, 0));
-        sigFilterKernel<<<grid, kFThreads, smem, s>>>(mapA, mapB, p);
+        if (pair) {
+            const uint32_t items = ((p.mBlocks + 1) / 2) * p.nBlocks;
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(kFThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;      // the two CTAs of a pair: one TPC
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cfg.gridDim = dim3(2 * std::min<uint32_t>(items, uint32_t(ctx->smCount / 2)));
+            EM2_CUDA(ctx, cudaLaunchKernelEx(&cfg, sigFilterKernel<true>, mapA, mapB, mapB64, p));
+        } else {
+            const uint32_t items = p.mBlocks * p.nBlocks;
+            const unsigned grid = std::min<uint32_t>(items, uint32_t(ctx->smCount));
+            sigFilterKernel<false><<<grid, kFThreads, smem, s>>>(mapA, mapB, mapB64, p);
+        }
         ctx->stats.kernel_launches++;
         EM2_CUDA(ctx, cudaGetLastError());
 

@@ -124,6 +124,7 @@ int em2_get_stats(const em2_context* ctx, em2_stats* stats);
  *   "filter_counts_signed" 1 = the filter GEMM takes counts as s8 <= 127 instead of u8 <= 255
  *   "dense_warp_kernel" 1 = the filter's dense expansion uses the warp-per-cell kernel instead of the shared-memory one
  *   "filter_uncertain_cap" capacity of the filter's uncertain list;  "filter_parts" chunks of cells per filter call
+ *   "filter_cta_pair"  1 = the filter GEMM runs one CTA per 128-cell tile instead of CTA pairs (cta_group::2, M = 256)
  *   "h2d_chunk_bytes"  CSR bytes per PCIe chunk of the blocking calls (default 256 MiB)
  *   "mma_kernel"       tcgen05 scan kernel: 1 = A operand resident in tensor memory (L <= 1024), 2 = both operands streamed
  *   "mma_cta_pair"     1 = the TMEM-resident scan kernel runs on CTA pairs (cta_group::2)

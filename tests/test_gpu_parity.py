@@ -244,6 +244,11 @@ def test_filter_signatures_bit_exact(engine, oracle, N, G, dens, L, mode):
     sig_s8 = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes),
                         filter_counts_signed=1)
     assert np.array_equal(sig_s8, want)
+    # the GEMM's two forms: CTA pairs (default; an odd last 128-cell block has no partner) and one CTA per tile
+    for signed in (0, 1):
+        single = _with_mode(engine, 2, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes),
+                            filter_cta_pair=1, filter_counts_signed=signed)
+        assert np.array_equal(single, want) and engine.stats()["filter_cells"] == N
 
 
 def test_filter_ineligible_cells_and_overflow(engine, oracle):
@@ -281,6 +286,8 @@ def test_filter_equals_fp64_at_scale(engine, oracle):
     fp64 = _with_mode(engine, 1, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes))
     assert engine.stats()["filter_cells"] == 0
     assert np.array_equal(auto, fp64)
+    single = _with_mode(engine, 0, lambda: engine.compute_signatures(toc, counts, U, gene_ids=genes), filter_cta_pair=1)
+    assert engine.stats()["filter_cells"] == N and np.array_equal(single, fp64)
     e = int(toc[64])
     s1, _ = oracle.cell_sums(toc[:65], counts[:e])
     want, _ = oracle.signatures(toc[:65], genes[:e], counts[:e], s1, U)
