@@ -156,14 +156,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 int makeTensorMapU8(em2_context* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t widthBytes,
                     uint64_t pitchBytes, uint32_t boxRows)
 {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
+    // looked up once per process; the initialisation of a function-local static is thread safe (em2_multi's workers)
+    static const EncodeTiledFn fn = [] {
         void* f = nullptr;
         cudaDriverEntryPointQueryResult q;
-        EM2_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
-        if (!f || q != cudaDriverEntryPointSuccess) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
-        fn = reinterpret_cast<EncodeTiledFn>(f);
-    }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    if (!fn) return fail(ctx, EM2_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
     const cuuint64_t dims[2] = {widthBytes, rows};
     const cuuint64_t strides[1] = {pitchBytes};
     const cuuint32_t box[2] = {128u, boxRows};
@@ -201,6 +205,15 @@ void resetStats(em2_context* ctx)
 // cannot be pinned reliably ("Ownership") -- is staged through two library-owned pinned bounce buffers:
 // the host thread copies piece i + 1 into one buffer while the copy engine moves piece i out of the other, so the
 // transfer is asynchronous to the compute stream either way.  The host-side copy runs on `stage_threads` threads (default 4).
+static int ensureBounceBuffers(em2_context* ctx)
+{
+    for (int i = 0; i < 2; i++) {      // whichever is missing: a failed first attempt may have left one behind
+        if (!ctx->bounce[i]) EM2_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], kBouncePiece));
+        if (!ctx->bounceFree[i]) EM2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bounceFree[i], cudaEventDisableTiming));
+    }
+    return EM2_OK;
+}
+
 int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s)
 {
     if (bytes == 0) return EM2_OK;
@@ -214,12 +227,7 @@ int stageH2D(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
         return EM2_OK;
     }
     constexpr size_t kPiece = kBouncePiece;
-    if (!ctx->bounce[0]) {
-        for (int i = 0; i < 2; i++) {
-            EM2_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], kPiece));
-            EM2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bounceFree[i], cudaEventDisableTiming));
-        }
-    }
+    EM2_TRY(ensureBounceBuffers(ctx));
     for (size_t off = 0, i = ctx->bounceNext; off < bytes; off += kPiece, i ^= 1, ctx->bounceNext = int(i)) {
         const size_t n = std::min(kPiece, bytes - off);
         EM2_CUDA(ctx, cudaEventSynchronize(ctx->bounceFree[i]));      // the copy that last read this buffer is done
@@ -245,12 +253,7 @@ int stageD2H(em2_context* ctx, void* dst, const void* src, size_t bytes, cudaStr
         return EM2_OK;
     }
     constexpr size_t kPiece = kBouncePiece;
-    if (!ctx->bounce[0]) {
-        for (int i = 0; i < 2; i++) {
-            EM2_CUDA(ctx, cudaMallocHost(&ctx->bounce[i], kPiece));
-            EM2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bounceFree[i], cudaEventDisableTiming));
-        }
-    }
+    EM2_TRY(ensureBounceBuffers(ctx));
     // piece i + 1 crosses PCIe while the host thread copies piece i out of its bounce buffer
     size_t pendingOff[2] = {0, 0}, pendingBytes[2] = {0, 0};
     int i = ctx->bounceNext;
